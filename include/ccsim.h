@@ -1,0 +1,263 @@
+/*
+ * ccsim.h — C-ABI of the B200 cluster-capacity hot path ("libccsim.so").
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b): plain pointers and sizes, no torch / C++ types.
+ * It replaces, for the simulated pod stream, what the reference drives through the embedded
+ * kube-scheduler:
+ *
+ *   ccsim_load_nodes      <- NodeInfo / Resource built by SetNode + AddPodInfo/update
+ *                            (vendor/k8s.io/kubernetes/pkg/scheduler/framework/types.go:160-200,333-343,409-427,461-465)
+ *                            in nodeTree.list() order (backend/cache/node_tree.go:119-143)
+ *   ccsim_set_templates   <- per-pod PreFilter/PreScore state (noderesources/fit.go:224-233,
+ *                            resource_allocation.go:118-140, tainttoleration, nodeaffinity, nodeports,
+ *                            podtopologyspread/filtering.go:235-308, interpodaffinity/filtering.go:274-309)
+ *   ccsim_run             <- ClusterCapacity.Run: the ScheduleOne loop
+ *                            (pkg/framework/simulator.go:356-381; scheduler/schedule_one.go:66-148,430-478),
+ *                            the ClusterCapacityBinder commit (pkg/framework/plugins/clustercapacitybinder/plugin.go:34-53)
+ *                            and the postBindHook limit check (pkg/framework/simulator.go:297-312)
+ *   ccsim_result          <- Status{Pods, StopReason} (pkg/framework/simulator.go:90-93) + the FitError
+ *                            reason histogram (framework/types.go:787-838) + the preemption suffix counts
+ *                            (framework/preemption/preemption.go:234-279)
+ *
+ * All strings (node names, label keys, reasons) stay on the host: the device sees ids and bitmasks only.
+ * The host side that produces these arrays from Node/Pod objects is include/cchost.h.
+ *
+ * Conventions: every function returns 0 on success or a negative CCSIM_E* code; ccsim_last_error(h)
+ * gives text. A handle is not thread-safe (one Run at a time, like the reference). Input arrays are
+ * caller-owned HOST memory and are copied (H2D) before the call returns. No exceptions cross the ABI.
+ */
+#ifndef CCSIM_H
+#define CCSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCSIM_ABI_VERSION 1
+
+/* ---- limits (compile-time, shared by host encoder, oracle and kernels) ---- */
+#define CCSIM_MAX_TAINT_WORDS   4   /* 64-bit words of the taint dictionary mask per node  */
+#define CCSIM_MAX_STATIC_WORDS  4   /* 64-bit words of static node-predicate bits per node */
+#define CCSIM_MAX_SCALARS       4   /* extended/scalar resources referenced by templates    */
+#define CCSIM_MAX_AFF_TERMS     8   /* required nodeAffinity terms (ORed)                   */
+#define CCSIM_MAX_PTS           8   /* hard topology-spread constraints                     */
+#define CCSIM_MAX_IPA           8   /* distinct topology keys of required (anti-)affinity   */
+#define CCSIM_MAX_TOPO_COLS     16  /* topology domain-id columns                           */
+#define CCSIM_MAX_COUNTERS      24  /* per-domain counters (PTS + IPA)                      */
+#define CCSIM_MAX_TEMPLATES     64
+#define CCSIM_MAX_CLASSES       8   /* distinct PreferNoSchedule intolerable-taint counts   */
+
+/* bit 63 of taint word 0 is node.Spec.Unschedulable (nodeunschedulable/node_unschedulable.go:133-150) */
+#define CCSIM_TAINT_UNSCHEDULABLE_BIT 63
+
+/* ---- error codes ---- */
+#define CCSIM_OK             0
+#define CCSIM_EINVAL        -1
+#define CCSIM_ENOMEM        -2
+#define CCSIM_ECUDA         -3
+#define CCSIM_EUNSUPPORTED  -4
+#define CCSIM_ESTATE        -5
+#define CCSIM_ENCCL         -6
+
+/* ---- template flags ---- */
+#define CCSIM_TF_TOLERATES_UNSCHEDULABLE  (1u << 0)  /* pod tolerates node.kubernetes.io/unschedulable:NoSchedule */
+#define CCSIM_TF_HAS_NODE_SELECTOR        (1u << 1)  /* NodeAffinity filter not skipped (node_affinity.go:147-155) */
+#define CCSIM_TF_HAS_AFFINITY_TERMS       (1u << 2)  /* spec.affinity.nodeAffinity.required present                */
+#define CCSIM_TF_HAS_HOST_PORTS           (1u << 3)  /* NodePorts not skipped (node_ports.go:68-76)                */
+#define CCSIM_TF_FIT_ALL_ZERO             (1u << 4)  /* cpu=mem=eph=0 and no scalars: fit.go:578-583 early-out     */
+#define CCSIM_TF_BALANCED_SKIP            (1u << 5)  /* best-effort pod: BalancedAllocation PreScore Skip (:68-73) */
+#define CCSIM_TF_AFF_SELF_MATCH_ALL       (1u << 6)  /* pod matches all of its own required affinity terms          */
+#define CCSIM_TF_PREFILTER_NODES          (1u << 7)  /* NodeAffinity PreFilterResult.NodeNames (node_affinity.go:164-194) */
+
+/* ---- plugin enable bits (filter_enable / score_enable); default profile = all ---- */
+#define CCSIM_PL_NODE_UNSCHEDULABLE (1u << 0)
+#define CCSIM_PL_NODE_NAME          (1u << 1)
+#define CCSIM_PL_TAINT_TOLERATION   (1u << 2)
+#define CCSIM_PL_NODE_AFFINITY      (1u << 3)
+#define CCSIM_PL_NODE_PORTS         (1u << 4)
+#define CCSIM_PL_FIT                (1u << 5)
+#define CCSIM_PL_POD_TOPOLOGY_SPREAD (1u << 6)
+#define CCSIM_PL_INTER_POD_AFFINITY (1u << 7)
+#define CCSIM_PL_BALANCED           (1u << 8)   /* score only */
+#define CCSIM_PL_IMAGE_LOCALITY     (1u << 9)   /* score only; contributes weight*0 on snapshots without images */
+#define CCSIM_PL_ALL                0x3ffu
+
+/* ---- FitError reason ids (framework/types.go:787-838 builds "<count> <reason>" from these) ---- */
+enum {
+  CCSIM_R_UNSCHEDULABLE = 0,      /* "node(s) were unschedulable"                                      */
+  CCSIM_R_NODE_NAME,              /* "node(s) didn't match the requested node name"                    */
+  CCSIM_R_NODE_AFFINITY,          /* "node(s) didn't match Pod's node affinity/selector"               */
+  CCSIM_R_NODE_PORTS,             /* "node(s) didn't have free ports for the requested pod ports"      */
+  CCSIM_R_TOO_MANY_PODS,          /* "Too many pods"                                                   */
+  CCSIM_R_INSUFFICIENT_CPU,       /* "Insufficient cpu"                                                */
+  CCSIM_R_INSUFFICIENT_MEMORY,    /* "Insufficient memory"                                             */
+  CCSIM_R_INSUFFICIENT_EPHEMERAL, /* "Insufficient ephemeral-storage"                                  */
+  CCSIM_R_PTS_MISSING_LABEL,      /* "node(s) didn't match pod topology spread constraints (missing required label)" */
+  CCSIM_R_PTS_SKEW,               /* "node(s) didn't match pod topology spread constraints"            */
+  CCSIM_R_IPA_AFFINITY,           /* "node(s) didn't match pod affinity rules"                         */
+  CCSIM_R_IPA_ANTI_AFFINITY,      /* "node(s) didn't match pod anti-affinity rules"                    */
+  CCSIM_R_IPA_EXISTING_ANTI,      /* "node(s) didn't satisfy existing pods anti-affinity rules"        */
+  CCSIM_R_PREFILTER_NODES,        /* "node(s) didn't satisfy plugin(s) [NodeAffinity]"                 */
+  CCSIM_R_FIXED_COUNT,
+  /* then CCSIM_MAX_SCALARS entries "Insufficient <scalar name>", then one per taint-dictionary id:
+     "node(s) had untolerated taint {key: value}" */
+  CCSIM_R_SCALAR0 = CCSIM_R_FIXED_COUNT,
+  CCSIM_R_TAINT0  = CCSIM_R_SCALAR0 + CCSIM_MAX_SCALARS,
+  CCSIM_R_TOTAL   = CCSIM_R_TAINT0 + 64 * CCSIM_MAX_TAINT_WORDS
+};
+
+/* stop codes: pkg/framework/simulator.go:300-305 (LimitReached) and :327-342 (Unschedulable) */
+#define CCSIM_STOP_UNSCHEDULABLE 0
+#define CCSIM_STOP_LIMIT_REACHED 1
+
+/* engine selection */
+#define CCSIM_ENGINE_AUTO        0  /* batched tie-run waves when provably order-equivalent, else sequential */
+#define CCSIM_ENGINE_SEQUENTIAL  1  /* one winner per wave (always valid; evals = (placed+1)*N)               */
+#define CCSIM_ENGINE_BATCHED     2  /* error if the templates are not eligible                               */
+
+typedef struct ccsim_config {
+  int32_t abi_version;      /* CCSIM_ABI_VERSION */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t engine;           /* CCSIM_ENGINE_* */
+  int32_t rank, world;      /* node-axis shard of a multi-GPU run; world=1 for a single GPU */
+  int32_t reserved[3];
+} ccsim_config;
+
+/*
+ * Node columns (SoA), all length n_nodes, in nodeTree.list() order. A1 of SURVEY.md §8(a).
+ * Bitmask columns are word-major: word w of node i is mask[w * n_nodes + i] (coalesced per word).
+ */
+typedef struct ccsim_nodes {
+  int32_t n_nodes;
+  int32_t n_scalars;        /* <= CCSIM_MAX_SCALARS */
+  int32_t taint_words;      /* 1..CCSIM_MAX_TAINT_WORDS (word 0 always present: carries the unschedulable bit) */
+  int32_t static_words;     /* 0..CCSIM_MAX_STATIC_WORDS */
+  int32_t n_topo_cols;      /* <= CCSIM_MAX_TOPO_COLS */
+  int32_t has_placed_mask;  /* 1 if any template has hostPorts: engine keeps a per-node "templates placed here" mask */
+  /* Allocatable (types.go:461-465) */
+  const int64_t *alloc_cpu, *alloc_mem, *alloc_eph;
+  const int32_t *alloc_pods;
+  /* Requested / NonZeroRequested / len(Pods) (types.go:409-427) */
+  const int64_t *req_cpu, *req_mem, *req_eph;
+  const int32_t *npods;
+  const int64_t *nz_cpu, *nz_mem;
+  const int64_t *alloc_scalar[CCSIM_MAX_SCALARS];
+  const int64_t *req_scalar[CCSIM_MAX_SCALARS];
+  /* taint dictionary mask: bit t of word w <=> node carries taint id 64*w+t (any effect); bit 63 of word 0 = Spec.Unschedulable */
+  const uint64_t *taint_mask;
+  /* static node-predicate bits (label requirements, existing hostPort conflicts, existing-pod anti-affinity, ...) */
+  const uint64_t *static_mask;
+  /* topology domain ids per column: >=0 domain id, -1 = node lacks the key */
+  const int32_t *topo[CCSIM_MAX_TOPO_COLS];
+  /* taint-dictionary effect masks (global, taint_words each): NoSchedule|NoExecute and PreferNoSchedule entries */
+  uint64_t taint_nosched[CCSIM_MAX_TAINT_WORDS];
+  uint64_t taint_prefer[CCSIM_MAX_TAINT_WORDS];
+  /* per node: taint ids in node.Spec.Taints list order, CSR, used only by the terminal diagnosis pass
+     (FindMatchingUntoleratedTaint returns the FIRST untolerated taint: component-helpers/scheduling/corev1/helpers.go:78-101) */
+  const int32_t *taint_list_off;  /* n_nodes+1 */
+  const uint8_t *taint_list;      /* taint ids (<256) */
+} ccsim_nodes;
+
+/* One per-domain counter of the (single) template: a PTS constraint or an IPA topology key. */
+typedef struct ccsim_counter {
+  int32_t topo_col;      /* index into ccsim_nodes.topo, or -1: node-local (every node its own domain, e.g. unique hostnames) */
+  int32_t n_domains;     /* D; for node-local counters = n_nodes */
+  int32_t n_present;     /* PTS only: domains [0,n_present) are in TpValueToMatchNum (take part in the global min) */
+  int32_t inc;           /* added to the winner's domain at every commit (self-match count) */
+  const int32_t *init;   /* [n_domains] counts from pre-existing pods */
+} ccsim_counter;
+
+typedef struct ccsim_pts {
+  int32_t counter;       /* index into counters */
+  int32_t max_skew;
+  int32_t self_match;    /* 1 if the pod's own labels match the constraint selector (filtering.go:341-344) */
+  int32_t min_zero;      /* 1 if #domains < minDomains: global minimum treated as 0 (filtering.go:56-69) */
+} ccsim_pts;
+
+typedef struct ccsim_template {
+  /* A2: request vectors (fit.go:224-233; types.go:700-734; resource_allocation.go:118-140) */
+  int64_t req_cpu, req_mem, req_eph;
+  int64_t req_scalar[CCSIM_MAX_SCALARS];
+  int64_t nz_cpu, nz_mem;         /* Non0CPU / Non0Mem added to NonZeroRequested at commit */
+  int64_t least_cpu, least_mem;   /* LeastAllocated pod request (useRequested=false)        */
+  int64_t bal_cpu, bal_mem;       /* BalancedAllocation pod request (useRequested=true)     */
+  uint32_t flags;                 /* CCSIM_TF_*  */
+  uint32_t filter_enable;         /* CCSIM_PL_*  */
+  uint32_t score_enable;          /* CCSIM_PL_*  */
+  int32_t nodename_idx;           /* -1: spec.nodeName empty (always, for generated pods: podgenerator.go:31) */
+  /* weights (default_plugins.go:38-50) */
+  int32_t w_taint, w_node_affinity, w_fit, w_pts, w_ipa, w_balanced, w_image;
+  int32_t least_w_cpu, least_w_mem;  /* NodeResourcesFitArgs.ScoringStrategy.Resources weights (defaults.go:229-245) */
+  /* TaintToleration */
+  uint64_t tol_nosched[CCSIM_MAX_TAINT_WORDS];  /* dictionary taints (NoSchedule/NoExecute) tolerated by the pod */
+  uint64_t tol_prefer[CCSIM_MAX_TAINT_WORDS];   /* PreferNoSchedule taints tolerated (taint_toleration.go:129-137) */
+  /* NodeAffinity: nodeSelector AND (OR over terms); static bits */
+  uint64_t sel_mask[CCSIM_MAX_STATIC_WORDS];
+  int32_t n_aff_terms;
+  int32_t prefilter_bit;          /* static bit "node name is in PreFilterResult.NodeNames", -1 none */
+  uint64_t aff_term_mask[CCSIM_MAX_AFF_TERMS][CCSIM_MAX_STATIC_WORDS];
+  /* NodePorts */
+  uint64_t port_static_mask[CCSIM_MAX_STATIC_WORDS]; /* static bits: an existing pod on the node conflicts with a wanted hostPort */
+  uint64_t port_tmpl_conflict;    /* templates whose hostPorts conflict with this one's (bit = template index) */
+  /* InterPodAffinity: static bit(s) "an existing pod's required anti-affinity term matches this pod in one of the node's topology pairs" */
+  uint64_t existing_anti_mask[CCSIM_MAX_STATIC_WORDS];
+  /* PodTopologySpread hard constraints, in spec order */
+  int32_t n_pts;
+  ccsim_pts pts[CCSIM_MAX_PTS];
+  /* InterPodAffinity required terms, grouped by topology key */
+  int32_t n_aff;                  /* affinity keys  */
+  int32_t aff_counter[CCSIM_MAX_IPA];
+  int32_t n_anti;                 /* anti-affinity keys */
+  int32_t anti_counter[CCSIM_MAX_IPA];
+  int64_t aff_total_init;         /* sum of all affinity counts (len(affinityCounts)==0 test, filtering.go:396-405) */
+} ccsim_template;
+
+typedef struct ccsim_result {
+  int64_t placed;                 /* len(status.Pods) */
+  int32_t stop_code;              /* CCSIM_STOP_* */
+  int32_t n_nodes;
+  int64_t waves;                  /* grid-wide waves executed */
+  int64_t evals;                  /* (pod attempt, node) pairs pushed through the fused Filter pass on the device */
+  int64_t reason_hist[CCSIM_R_TOTAL]; /* terminal FitError histogram (zero when stop_code == LIMIT_REACHED) */
+  int64_t preempt_no_victims;     /* nodes whose terminal status code is Unschedulable ("No preemption victims found for incoming pod") */
+  int64_t preempt_not_helpful;    /* the rest ("Preemption is not helpful for scheduling") */
+  double  run_ms;                 /* device time of the run (CUDA events on the engine stream) */
+  const int32_t *pod_node;        /* [placed] node index of pod k, host memory owned by the handle until the next run/destroy */
+} ccsim_result;
+
+typedef struct ccsim_handle ccsim_handle;
+
+/* lifecycle */
+int  ccsim_create(const ccsim_config *cfg, ccsim_handle **out);
+void ccsim_destroy(ccsim_handle *h);
+const char *ccsim_last_error(const ccsim_handle *h);  /* h may be NULL: last create error */
+int  ccsim_abi_version(void);
+
+/* snapshot upload (H2D inside the call) */
+int  ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nodes);
+int  ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const ccsim_template *templates,
+                         int32_t n_counters, const ccsim_counter *counters);
+
+/* Run: place pods k = 0,1,2,... (template k % n_templates) until one does not fit or max_pods (>0) are placed.
+ * Restores the loaded snapshot first, so it can be called repeatedly. Blocking. */
+int  ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out);
+
+/* per-node number of placed pods of template t after the last run (device histogram; report.go:146-180 without the O(P*nodes) scan)
+ * and the index of the first pod placed on each node (-1 none): ReplicasOnNodes is ordered by first placement. */
+int  ccsim_node_counts(ccsim_handle *h, int32_t t, int32_t *counts /*[n_nodes]*/, int64_t *first_pod /*[n_nodes]*/);
+
+/* multi-GPU (node-axis shards): NCCL unique id exchange is done by the caller (torch.distributed) */
+int  ccsim_nccl_unique_id(uint8_t id_out[128]);
+int  ccsim_comm_init(ccsim_handle *h, const uint8_t id[128]);
+
+/* introspection for tests / bench */
+int  ccsim_device_info(ccsim_handle *h, int32_t *sm_count, int32_t *grid, int32_t *block, int64_t *l2_bytes);
+int64_t ccsim_kernel_launches(const ccsim_handle *h);  /* kernels launched by this handle so far */
+int  ccsim_flush_l2(ccsim_handle *h);                  /* writes a buffer larger than L2 (bench hygiene) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCSIM_H */
