@@ -1,0 +1,816 @@
+// ccsim_engine.cu — libccsim.so: the B200 cluster-capacity hot path behind the C-ABI of include/ccsim.h.
+//
+// Replaces the reference's sequential schedule-one-pod-then-update loop
+// (pkg/framework/simulator.go:356-381 driving vendor/k8s.io/kubernetes/pkg/scheduler/schedule_one.go:66-148) by ONE
+// persistent cooperative kernel per Run:
+//
+//   wave k (pod k, template k % M):
+//     every CTA owns a contiguous tile of nodes and pushes each through the fused Filter+Score pass (eval_node),
+//     warp-shuffle + shared-memory arg-max over packed (score, ~index) keys,
+//     all-to-all exchange of one 64-bit tagged key per CTA (and per normalisation class) through L2 — this is the
+//     only grid-wide synchronisation of the wave (no atomics, no fences: the tag makes each word self-validating),
+//     every CTA redundantly reduces the 148 keys, the owner CTA commits the winner row (NodeInfo.update,
+//     framework/types.go:409-427), every CTA updates its replica of the per-domain counters.
+//
+// The node state is mutated in place in HBM/L2; only the owner CTA ever reads or writes a given row, so no
+// inter-CTA ordering is needed beyond the key exchange.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+#include "ccsim_device.cuh"
+
+#define BLOCK_THREADS 512
+#define MAX_WARPS (BLOCK_THREADS / 32)
+#define SMEM_CNT_MAX_INTS 16384      /* 64 KB of replicated counters in shared memory; above that: global replicas */
+#define WATCHDOG_SPINS (1u << 24)
+
+// ------------------------------------------------------------------------------------------------------------------
+// slot exchange primitives: relaxed 64-bit accesses that bypass L1 (the tag inside the word carries the ordering)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_slot(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_slot(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other > v ? other : v;
+  }
+  return v;
+}
+
+struct __align__(16) WaveShared {
+  ccsim_template tmpl;                              // current template
+  unsigned long long warp_best[MAX_WARPS][CCSIM_MAX_CLASSES];
+  int32_t ptsmin[CCSIM_MAX_PTS];
+  int32_t ptsnum[CCSIM_MAX_PTS];
+  long long aff_total;
+  int32_t winner;        // global node index, -1 = none
+  int32_t stop;          // 0 continue, 1 unschedulable, 2 limit, 3 error
+  int32_t scratch[MAX_WARPS];
+};
+
+// recount of a PTS constraint's minimum and its multiplicity over the present domains (all threads of the CTA)
+__device__ void pts_recount(const DevParams &p, WaveShared &ws, const int32_t *smem_cnt, int c) {
+  const ccsim_pts &pc = ws.tmpl.pts[c];
+  const DevCounter &dc = p.counters[pc.counter];
+  const int32_t *cnt = counter_base(p, pc.counter, smem_cnt);
+  int32_t m = INT32_MAX;
+  for (int d = threadIdx.x; d < dc.n_present; d += blockDim.x) m = min(m, cnt[d]);
+  for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) ws.scratch[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = INT32_MAX;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = min(m, ws.scratch[w]);
+  __syncthreads();
+  int32_t num = 0;
+  for (int d = threadIdx.x; d < dc.n_present; d += blockDim.x) num += (cnt[d] == m);
+  for (int o = 16; o > 0; o >>= 1) num += __shfl_xor_sync(0xffffffffu, num, o);
+  if ((threadIdx.x & 31) == 0) ws.scratch[threadIdx.x >> 5] = num;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += ws.scratch[w];
+    ws.ptsmin[c] = pc.min_zero ? 0 : m;    // filtering.go:56-69: fewer domains than minDomains -> global minimum 0
+    ws.ptsnum[c] = s;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The persistent wave kernel (sequential engine: one winner per wave; always a valid execution of the reference loop)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WaveShared &ws = *reinterpret_cast<WaveShared *>(smem_raw);
+  int32_t *smem_cnt = reinterpret_cast<int32_t *>(smem_raw + sizeof(WaveShared));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x;
+  const int32_t lo = min(p.n, cta * p.chunk), hi = min(p.n, lo + p.chunk);
+  const int ncls = p.n_classes;
+
+  // ---- prologue: template 0, replicated counters, PTS minima ----
+  for (int k = tid; k < (int)(sizeof(ccsim_template) / 8); k += blockDim.x)
+    reinterpret_cast<unsigned long long *>(&ws.tmpl)[k] = reinterpret_cast<const unsigned long long *>(&p.templates[0])[k];
+  for (int j = 0; j < p.n_counters; j++) {
+    const DevCounter &dc = p.counters[j];
+    if (dc.topo_col < 0) continue;   // node-local columns are restored by the host before the launch
+    int32_t *dst = dc.smem_off >= 0 ? smem_cnt + dc.smem_off : dc.work + (size_t)cta * dc.n_domains;
+    for (int d = tid; d < dc.n_domains; d += blockDim.x) dst[d] = dc.init[d];
+  }
+  if (tid == 0) { ws.aff_total = p.templates[0].aff_total_init; ws.winner = -1; ws.stop = 0; }
+  __syncthreads();
+  for (int c = 0; c < ws.tmpl.n_pts; c++) pts_recount(p, ws, smem_cnt, c);
+
+  long long k = 0;
+  for (;; k++) {
+    // postBindHook limit (pkg/framework/simulator.go:300-305): checked after the k-th pod was bound
+    if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ws.stop = 2; __syncthreads(); break; }
+    if (p.n_templates > 1) {
+      const ccsim_template *src = &p.templates[k % p.n_templates];
+      for (int q = tid; q < (int)(sizeof(ccsim_template) / 8); q += blockDim.x)
+        reinterpret_cast<unsigned long long *>(&ws.tmpl)[q] = reinterpret_cast<const unsigned long long *>(src)[q];
+      __syncthreads();
+    }
+    const ccsim_template &t = ws.tmpl;
+
+    // ---- fused Filter + Score over this CTA's tile ----
+    unsigned long long best[CCSIM_MAX_CLASSES];
+    #pragma unroll
+    for (int c = 0; c < CCSIM_MAX_CLASSES; c++) best[c] = 0ull;
+    for (int32_t i = lo + tid; i < hi; i += blockDim.x) {
+      int cls; int64_t sc;
+      if (eval_node(p, t, smem_cnt, ws.ptsmin, ws.aff_total, i, cls, sc)) {
+        const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
+        if (ncls == 1) best[0] = key > best[0] ? key : best[0];
+        else {
+          #pragma unroll
+          for (int c = 0; c < CCSIM_MAX_CLASSES; c++) if (c == cls) best[c] = key > best[c] ? key : best[c];
+        }
+      }
+    }
+    for (int c = 0; c < ncls; c++) {
+      unsigned long long v = 0ull;
+      #pragma unroll
+      for (int q = 0; q < CCSIM_MAX_CLASSES; q++) if (q == c) v = best[q];
+      v = warp_max_u64(v);
+      if (lane == 0) ws.warp_best[warp][c] = v;
+    }
+    __syncthreads();                                                    // S1
+
+    if (warp == 0) {
+      const unsigned long long tag = (unsigned long long)(k % 4095) + 1ull;   // 1..4095; waves k and k+2 (same parity buffer) differ
+      const unsigned long long tagbits = tag << KEY_TAG_SHIFT;
+      unsigned long long *myslots = p.slots + ((size_t)(k & 1) * p.grid + cta) * CCSIM_MAX_CLASSES;
+      // CTA arg-max per class, published as one tagged word each
+      for (int c = 0; c < ncls; c++) {
+        unsigned long long v = (lane < (int)(blockDim.x >> 5)) ? ws.warp_best[lane][c] : 0ull;
+        v = warp_max_u64(v);
+        if (lane == 0) st_slot(&myslots[c], v | tagbits);
+      }
+      // gather every CTA's word (poll until its tag is this wave's)
+      const unsigned long long *all = p.slots + (size_t)(k & 1) * p.grid * CCSIM_MAX_CLASSES;
+      unsigned long long cbest[CCSIM_MAX_CLASSES];
+      bool dead = false;
+      for (int c = 0; c < ncls; c++) {
+        unsigned long long m = 0ull;
+        for (int b = lane; b < p.grid; b += 32) {
+          unsigned long long v;
+          unsigned spins = 0;
+          do {
+            v = ld_slot(&all[(size_t)b * CCSIM_MAX_CLASSES + c]);
+            if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+          } while ((v >> KEY_TAG_SHIFT) != tag);
+          v &= KEY_BODY_MASK;
+          m = v > m ? v : m;
+        }
+        cbest[c] = warp_max_u64(m);
+      }
+      dead = __any_sync(0xffffffffu, dead);
+      // prioritizeNodes + selectHost over the class winners (schedule_one.go:776-941)
+      int maxraw = 0;
+      for (int c = 0; c < ncls; c++) if (cbest[c] != 0ull) maxraw = c;
+      unsigned long long wkey = 0ull;
+      for (int c = 0; c < ncls; c++) {
+        if (cbest[c] == 0ull) continue;
+        int64_t total = key_score(cbest[c]);
+        if (t.score_enable & CCSIM_PL_TAINT_TOLERATION) total += (int64_t)t.w_taint * taint_norm(c, maxraw);
+        const unsigned long long kk = pack_key(total, key_index(cbest[c]));
+        wkey = kk > wkey ? kk : wkey;
+      }
+      if (lane == 0) {
+        if (dead) { ws.stop = 3; ws.winner = -1; }
+        else if (wkey == 0ull) { ws.stop = 1; ws.winner = -1; }
+        else ws.winner = (int32_t)key_index(wkey);
+      }
+      __syncwarp();
+      // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
+      if (!dead && wkey != 0ull) {
+        const int32_t g = (int32_t)key_index(wkey);
+        const int32_t w = g - p.node_base;
+        const bool mine = (w >= lo && w < hi);
+        if (mine && lane == 0) {
+          p.req_cpu[w] += t.req_cpu; p.req_mem[w] += t.req_mem; p.req_eph[w] += t.req_eph;
+          for (int q = 0; q < p.n_scalars; q++) p.req_scalar[q][w] += t.req_scalar[q];
+          p.nz_cpu[w] += t.nz_cpu; p.nz_mem[w] += t.nz_mem;
+          p.npods[w] += 1;
+          if (p.placed_mask) p.placed_mask[w] |= 1ull << (k % p.n_templates);
+          // ClusterCapacityBinder.Bind + postBindHook: record pod k -> node (plugin.go:34-53; simulator.go:297-312)
+          if (k < p.pod_cap) p.pod_node[k] = g; else ws.stop = 3;
+        }
+        // per-domain counters: every CTA applies the same update to its own replica
+        // (the next cycle's PreFilter recount would see this clone: podtopologyspread/filtering.go:255-289,
+        //  interpodaffinity/filtering.go:234-271)
+        if (lane == 0) {
+          for (int j = 0; j < p.n_counters; j++) {
+            const DevCounter &dc = p.counters[j];
+            if (dc.inc == 0) continue;
+            if (dc.is_aff && !(t.flags & CCSIM_TF_AFF_SELF_MATCH_ALL)) continue;
+            if (dc.topo_col < 0) { if (mine) dc.work[w] += dc.inc; if (dc.is_aff) ws.aff_total += dc.inc; continue; }
+            const int32_t dom = p.topo[dc.topo_col][w];   // single-GPU: the winner is always a local node
+            if (dom < 0) continue;
+            int32_t *cnt = dc.smem_off >= 0 ? smem_cnt + dc.smem_off : dc.work + (size_t)cta * dc.n_domains;
+            const int32_t old = cnt[dom];
+            cnt[dom] = old + dc.inc;
+            if (dc.is_aff) ws.aff_total += dc.inc;
+            for (int c = 0; c < t.n_pts; c++) {
+              if (t.pts[c].counter != j || t.pts[c].min_zero) continue;
+              if (dom < dc.n_present && old == ws.ptsmin[c]) ws.ptsnum[c] -= 1;   // left the minimum level
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                                    // S2
+    if (ws.stop) break;
+    // a PTS minimum whose last domain moved up: recount (rare: once per n_present commits at that level)
+    for (int c = 0; c < t.n_pts; c++)
+      if (!t.pts[c].min_zero && ws.ptsnum[c] <= 0 && p.counters[t.pts[c].counter].n_present > 0) pts_recount(p, ws, smem_cnt, c);
+  }
+
+  // ---- epilogue ----
+  if (cta == 0) {
+    for (int j = 0; j < p.n_counters; j++) {
+      const DevCounter &dc = p.counters[j];
+      if (dc.topo_col < 0) continue;
+      const int32_t *src = dc.smem_off >= 0 ? smem_cnt + dc.smem_off : dc.work;
+      for (int d = tid; d < dc.n_domains; d += blockDim.x) p.final_cnt[p.final_off[j] + d] = src[d];
+    }
+    if (tid == 0) {
+      DevOut *o = p.out;
+      o->placed = k;
+      o->stop_code = (ws.stop == 2) ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
+      o->error = (ws.stop == 3) ? 1 : 0;
+      o->waves = (ws.stop == 2) ? k : k + 1;
+      o->evals = o->waves * (long long)p.n;
+      for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ws.ptsmin[c];
+      o->aff_total = ws.aff_total;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Terminal diagnosis: FitError histogram of the pod that did not fit (framework/types.go:787-838) and the status codes
+// the DefaultPreemption PostFilter groups nodes by (preemption/preemption.go:309-331). Runs once per Run.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void ccsim_diag_kernel(const DevParams p, int tmpl_index) {
+  const ccsim_template &t = p.templates[tmpl_index];
+  DevOut *o = p.out;
+  const int32_t n = p.n;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int st = ST_OK;
+    int reasons[8 + CCSIM_MAX_SCALARS]; int nr = 0;
+    const uint64_t taint0 = p.taint_mask[i];
+    do {
+      if ((t.flags & CCSIM_TF_PREFILTER_NODES) && t.prefilter_bit >= 0) {
+        const int b = t.prefilter_bit;
+        if (!((p.static_mask[(size_t)(b >> 6) * n + i] >> (b & 63)) & 1ull)) { reasons[nr++] = CCSIM_R_PREFILTER_NODES; st = ST_UNRESOLVABLE; break; }
+      }
+      if ((t.filter_enable & CCSIM_PL_NODE_UNSCHEDULABLE) && ((taint0 >> CCSIM_TAINT_UNSCHEDULABLE_BIT) & 1ull) &&
+          !(t.flags & CCSIM_TF_TOLERATES_UNSCHEDULABLE)) { reasons[nr++] = CCSIM_R_UNSCHEDULABLE; st = ST_UNRESOLVABLE; break; }
+      if ((t.filter_enable & CCSIM_PL_NODE_NAME) && t.nodename_idx >= 0 && t.nodename_idx != p.node_base + i) {
+        reasons[nr++] = CCSIM_R_NODE_NAME; st = ST_UNRESOLVABLE; break; }
+      if (t.filter_enable & CCSIM_PL_TAINT_TOLERATION) {
+        uint64_t untol_any = 0; int low = -1;
+        for (int w = 0; w < p.taint_words; w++) {
+          const uint64_t m = p.taint_mask[(size_t)w * n + i] & p.taint_nosched[w] & ~t.tol_nosched[w];
+          if (m && low < 0) low = 64 * w + __ffsll((long long)m) - 1;
+          untol_any |= m;
+        }
+        if (untol_any) {
+          int id = -1;
+          if (p.taint_list_off) {   // first untolerated taint in node.Spec.Taints order (corev1/helpers.go:78-101)
+            for (int32_t q = p.taint_list_off[i]; q < p.taint_list_off[i + 1]; q++) {
+              const int tid = p.taint_list[q];
+              if (((p.taint_nosched[tid >> 6] >> (tid & 63)) & 1ull) && !((t.tol_nosched[tid >> 6] >> (tid & 63)) & 1ull)) { id = tid; break; }
+            }
+          }
+          if (id < 0) id = low;
+          reasons[nr++] = CCSIM_R_TAINT0 + id; st = ST_UNRESOLVABLE; break;
+        }
+      }
+      uint64_t sw[CCSIM_MAX_STATIC_WORDS];
+      for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) sw[w] = (w < p.static_words) ? p.static_mask[(size_t)w * n + i] : 0ull;
+      if ((t.filter_enable & CCSIM_PL_NODE_AFFINITY) && (t.flags & (CCSIM_TF_HAS_NODE_SELECTOR | CCSIM_TF_HAS_AFFINITY_TERMS))) {
+        bool m = true;
+        for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) m &= ((sw[w] & t.sel_mask[w]) == t.sel_mask[w]);
+        if (m && (t.flags & CCSIM_TF_HAS_AFFINITY_TERMS)) {
+          bool any = false;
+          for (int k = 0; k < t.n_aff_terms; k++) {
+            bool tm = true;
+            for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) tm &= ((sw[w] & t.aff_term_mask[k][w]) == t.aff_term_mask[k][w]);
+            any |= tm;
+          }
+          m = any;
+        }
+        if (!m) { reasons[nr++] = CCSIM_R_NODE_AFFINITY; st = ST_UNRESOLVABLE; break; }
+      }
+      if ((t.filter_enable & CCSIM_PL_NODE_PORTS) && (t.flags & CCSIM_TF_HAS_HOST_PORTS)) {
+        uint64_t c = 0;
+        for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) c |= sw[w] & t.port_static_mask[w];
+        if (p.placed_mask && (p.placed_mask[i] & t.port_tmpl_conflict)) c = 1;
+        if (c) { reasons[nr++] = CCSIM_R_NODE_PORTS; st = ST_UNSCHEDULABLE; break; }
+      }
+      if (t.filter_enable & CCSIM_PL_FIT) {
+        bool fail = false, unres = false;
+        if (p.npods[i] + 1 > p.alloc_pods[i]) { fail = true; reasons[nr++] = CCSIM_R_TOO_MANY_PODS; }
+        if (!(t.flags & CCSIM_TF_FIT_ALL_ZERO)) {
+          if (t.req_cpu > 0 && t.req_cpu > p.alloc_cpu[i] - p.req_cpu[i]) { fail = true; unres |= t.req_cpu > p.alloc_cpu[i]; reasons[nr++] = CCSIM_R_INSUFFICIENT_CPU; }
+          if (t.req_mem > 0 && t.req_mem > p.alloc_mem[i] - p.req_mem[i]) { fail = true; unres |= t.req_mem > p.alloc_mem[i]; reasons[nr++] = CCSIM_R_INSUFFICIENT_MEMORY; }
+          if (t.req_eph > 0 && t.req_eph > p.alloc_eph[i] - p.req_eph[i]) { fail = true; unres |= t.req_eph > p.alloc_eph[i]; reasons[nr++] = CCSIM_R_INSUFFICIENT_EPHEMERAL; }
+          for (int k = 0; k < p.n_scalars; k++) {
+            const int64_t q = t.req_scalar[k];
+            if (q == 0) continue;
+            if (q > p.alloc_scalar[k][i] - p.req_scalar[k][i]) { fail = true; unres |= q > p.alloc_scalar[k][i]; reasons[nr++] = CCSIM_R_SCALAR0 + k; }
+          }
+        }
+        if (fail) { st = unres ? ST_UNRESOLVABLE : ST_UNSCHEDULABLE; break; }
+      }
+      if (t.filter_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) {
+        bool done = false;
+        for (int c = 0; c < t.n_pts && !done; c++) {
+          const ccsim_pts &pc = t.pts[c];
+          const DevCounter &dc = p.counters[pc.counter];
+          const int32_t dom = dc.topo_col < 0 ? i : p.topo[dc.topo_col][i];
+          if (dom < 0) { reasons[nr++] = CCSIM_R_PTS_MISSING_LABEL; st = ST_UNRESOLVABLE; done = true; break; }
+          const int32_t cv = dc.topo_col < 0 ? dc.work[i] : p.final_cnt[p.final_off[pc.counter] + dom];
+          const long long skew = (long long)cv + pc.self_match - (long long)o->ptsmin[c];
+          if (skew > pc.max_skew) { reasons[nr++] = CCSIM_R_PTS_SKEW; st = ST_UNSCHEDULABLE; done = true; }
+        }
+        if (done) break;
+      }
+      if (t.filter_enable & CCSIM_PL_INTER_POD_AFFINITY) {
+        bool pods_exist = true, missing = false;
+        for (int a = 0; a < t.n_aff; a++) {
+          const DevCounter &dc = p.counters[t.aff_counter[a]];
+          const int32_t dom = dc.topo_col < 0 ? i : p.topo[dc.topo_col][i];
+          if (dom < 0) { missing = true; break; }
+          const int32_t cv = dc.topo_col < 0 ? dc.work[i] : p.final_cnt[p.final_off[t.aff_counter[a]] + dom];
+          if (cv <= 0) pods_exist = false;
+        }
+        if (t.n_aff > 0 && (missing || (!pods_exist && !(o->aff_total == 0 && (t.flags & CCSIM_TF_AFF_SELF_MATCH_ALL))))) {
+          reasons[nr++] = CCSIM_R_IPA_AFFINITY; st = ST_UNRESOLVABLE; break; }
+        bool anti = false;
+        for (int a = 0; a < t.n_anti; a++) {
+          const DevCounter &dc = p.counters[t.anti_counter[a]];
+          const int32_t dom = dc.topo_col < 0 ? i : p.topo[dc.topo_col][i];
+          if (dom < 0) continue;
+          const int32_t cv = dc.topo_col < 0 ? dc.work[i] : p.final_cnt[p.final_off[t.anti_counter[a]] + dom];
+          if (cv > 0) anti = true;
+        }
+        if (anti) { reasons[nr++] = CCSIM_R_IPA_ANTI_AFFINITY; st = ST_UNSCHEDULABLE; break; }
+        uint64_t c = 0;
+        for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) c |= sw[w] & t.existing_anti_mask[w];
+        if (c) { reasons[nr++] = CCSIM_R_IPA_EXISTING_ANTI; st = ST_UNSCHEDULABLE; break; }
+      }
+    } while (0);
+    for (int q = 0; q < nr; q++) atomicAdd(&o->reason_hist[reasons[q]], 1ull);
+    if (st == ST_UNSCHEDULABLE) atomicAdd(&o->preempt_no_victims, 1ull);
+    atomicAdd(&o->n_diag, 1ull);
+  }
+}
+
+// per-node replica counts of template t and first-placement index (report.go:146-180 without the O(P*nodes) scan)
+__global__ void ccsim_count_kernel(const int32_t *pod_node, long long placed, int n_templates, int t,
+                                   int32_t *counts, unsigned long long *first) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < placed; k += (long long)gridDim.x * blockDim.x) {
+    if ((int)(k % n_templates) != t) continue;
+    const int32_t w = pod_node[k];
+    atomicAdd(&counts[w], 1);
+    atomicMin(&first[w], (unsigned long long)k);
+  }
+}
+
+__global__ void ccsim_flush_kernel(unsigned long long *buf, size_t n, unsigned long long v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = v + i;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side of the C-ABI
+// ------------------------------------------------------------------------------------------------------------------
+struct ccsim_handle {
+  ccsim_config cfg;
+  int sm_count = 0;
+  size_t l2_bytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // snapshot
+  bool have_nodes = false, have_templates = false;
+  int32_t n = 0, n_global = 0, node_base = 0;
+  ccsim_nodes meta;            // scalar members only
+  std::vector<void *> allocs;  // every device allocation, freed in destroy / reload
+  std::vector<void *> tmpl_allocs;
+  // device columns: snapshot copies and working copies of the mutable ones
+  int64_t *d_alloc_cpu = nullptr, *d_alloc_mem = nullptr, *d_alloc_eph = nullptr;
+  int32_t *d_alloc_pods = nullptr;
+  int64_t *d_alloc_scalar[CCSIM_MAX_SCALARS] = {};
+  uint64_t *d_taint = nullptr, *d_static = nullptr;
+  int32_t *d_topo[CCSIM_MAX_TOPO_COLS] = {};
+  int64_t *s_req_cpu = nullptr, *s_req_mem = nullptr, *s_req_eph = nullptr, *s_nz_cpu = nullptr, *s_nz_mem = nullptr;
+  int32_t *s_npods = nullptr;
+  int64_t *s_req_scalar[CCSIM_MAX_SCALARS] = {};
+  int64_t *w_req_cpu = nullptr, *w_req_mem = nullptr, *w_req_eph = nullptr, *w_nz_cpu = nullptr, *w_nz_mem = nullptr;
+  int32_t *w_npods = nullptr;
+  int64_t *w_req_scalar[CCSIM_MAX_SCALARS] = {};
+  uint64_t *w_placed = nullptr;
+  int32_t *d_taint_off = nullptr; uint8_t *d_taint_list = nullptr;
+  int64_t pod_bound = 0;       // sum over nodes of max(0, alloc_pods - npods): no run can place more
+  int max_prefer_pop = 0;      // max over nodes of popcount(taint & prefer): number of normalisation classes - 1
+  // templates
+  int32_t n_templates = 0, n_counters = 0;
+  std::vector<ccsim_template> h_templates;
+  ccsim_template *d_templates = nullptr;
+  DevCounter counters[CCSIM_MAX_COUNTERS];
+  int32_t *d_final_cnt = nullptr; int32_t final_off[CCSIM_MAX_COUNTERS] = {}; int32_t final_total = 0;
+  int32_t smem_cnt_ints = 0;
+  // run state
+  int grid = 0;
+  unsigned long long *d_slots = nullptr;
+  int32_t *d_pod_node = nullptr; int64_t pod_cap = 0;
+  std::vector<int32_t> h_pod_node;
+  DevOut *d_out = nullptr;
+  int64_t last_placed = 0;
+  void *d_flush = nullptr; size_t flush_bytes = 0;
+};
+
+static std::string g_create_err;
+
+static int fail(ccsim_handle *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (h) h->err = buf; else g_create_err = buf;
+  return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, CCSIM_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <typename T> static int dev_alloc(ccsim_handle *h, std::vector<void *> &pool, T **out, size_t count) {
+  void *p = nullptr;
+  size_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(h, CCSIM_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  pool.push_back(p);
+  *out = (T *)p;
+  return 0;
+}
+template <typename T> static int dev_upload(ccsim_handle *h, std::vector<void *> &pool, T **out, const T *src, size_t count) {
+  int rc = dev_alloc(h, pool, out, count);
+  if (rc) return rc;
+  if (count) CK(cudaMemcpyAsync(*out, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+static void free_pool(std::vector<void *> &pool) { for (void *p : pool) cudaFree(p); pool.clear(); }
+
+extern "C" int ccsim_abi_version(void) { return CCSIM_ABI_VERSION; }
+
+extern "C" const char *ccsim_last_error(const ccsim_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
+  ccsim_handle *h = nullptr;
+  if (!cfg || !out) return fail(h, CCSIM_EINVAL, "null argument");
+  if (cfg->abi_version != CCSIM_ABI_VERSION) return fail(h, CCSIM_EINVAL, "abi_version %d != %d", cfg->abi_version, CCSIM_ABI_VERSION);
+  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(h, CCSIM_EINVAL, "bad rank/world");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, CCSIM_ECUDA, "no CUDA device: %s (libccsim has no CPU fallback)", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(h, CCSIM_EINVAL, "device %d out of range (%d)", cfg->device, ndev);
+  h = new ccsim_handle();
+  h->cfg = *cfg;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) {
+    fail(nullptr, CCSIM_ECUDA, "cudaSetDevice/GetDeviceProperties: %s", cudaGetErrorString(e));
+    delete h; return CCSIM_ECUDA;
+  }
+  if (!prop.cooperativeLaunch) { fail(nullptr, CCSIM_EUNSUPPORTED, "device lacks cooperative launch"); delete h; return CCSIM_EUNSUPPORTED; }
+  h->sm_count = prop.multiProcessorCount;
+  h->l2_bytes = (size_t)prop.l2CacheSize;
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  cudaMalloc((void **)&h->d_out, sizeof(DevOut));
+  cudaMalloc((void **)&h->d_slots, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * CCSIM_MAX_CLASSES);
+  cudaFuncSetAttribute(ccsim_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(sizeof(WaveShared) + SMEM_CNT_MAX_INTS * sizeof(int32_t)));
+  *out = h;
+  return CCSIM_OK;
+}
+
+extern "C" void ccsim_destroy(ccsim_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  free_pool(h->allocs); free_pool(h->tmpl_allocs);
+  cudaFree(h->d_out); cudaFree(h->d_slots); cudaFree(h->d_pod_node); cudaFree(h->d_flush);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nd) {
+  if (!h || !nd) return fail(h, CCSIM_EINVAL, "null argument");
+  if (nd->n_nodes < 0 || nd->n_scalars < 0 || nd->n_scalars > CCSIM_MAX_SCALARS || nd->taint_words < 1 ||
+      nd->taint_words > CCSIM_MAX_TAINT_WORDS || nd->static_words < 0 || nd->static_words > CCSIM_MAX_STATIC_WORDS ||
+      nd->n_topo_cols < 0 || nd->n_topo_cols > CCSIM_MAX_TOPO_COLS)
+    return fail(h, CCSIM_EINVAL, "ccsim_nodes dimensions out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  free_pool(h->allocs);
+  h->have_nodes = false; h->have_templates = false;
+  const int32_t N = nd->n_nodes;
+  // node-axis shard of this rank: contiguous block of the nodeTree order
+  const int32_t per = (N + h->cfg.world - 1) / h->cfg.world;
+  const int32_t lo = std::min<int64_t>((int64_t)per * h->cfg.rank, N), hi = std::min<int64_t>((int64_t)lo + per, N);
+  const int32_t n = hi - lo;
+  h->n = n; h->n_global = N; h->node_base = lo;
+  h->meta = *nd;
+  int rc;
+#define UP(dst, src, T) if ((rc = dev_upload<T>(h, h->allocs, &h->dst, (src) ? (src) + lo : (const T *)nullptr, (src) ? (size_t)n : 0))) return rc
+  if (N > 0 && (!nd->alloc_cpu || !nd->alloc_mem || !nd->alloc_eph || !nd->alloc_pods || !nd->req_cpu || !nd->req_mem ||
+                !nd->req_eph || !nd->npods || !nd->nz_cpu || !nd->nz_mem || !nd->taint_mask))
+    return fail(h, CCSIM_EINVAL, "null core column");
+  UP(d_alloc_cpu, nd->alloc_cpu, int64_t); UP(d_alloc_mem, nd->alloc_mem, int64_t); UP(d_alloc_eph, nd->alloc_eph, int64_t);
+  UP(d_alloc_pods, nd->alloc_pods, int32_t);
+  UP(s_req_cpu, nd->req_cpu, int64_t); UP(s_req_mem, nd->req_mem, int64_t); UP(s_req_eph, nd->req_eph, int64_t);
+  UP(s_nz_cpu, nd->nz_cpu, int64_t); UP(s_nz_mem, nd->nz_mem, int64_t); UP(s_npods, nd->npods, int32_t);
+  for (int k = 0; k < nd->n_scalars; k++) {
+    if (!nd->alloc_scalar[k] || !nd->req_scalar[k]) return fail(h, CCSIM_EINVAL, "null scalar column %d", k);
+    UP(d_alloc_scalar[k], nd->alloc_scalar[k], int64_t); UP(s_req_scalar[k], nd->req_scalar[k], int64_t);
+  }
+#undef UP
+  // word-major bitmask columns: copy the shard slice of each word
+  if ((rc = dev_alloc(h, h->allocs, &h->d_taint, (size_t)nd->taint_words * n))) return rc;
+  for (int w = 0; w < nd->taint_words && n; w++)
+    CK(cudaMemcpyAsync(h->d_taint + (size_t)w * n, nd->taint_mask + (size_t)w * N + lo, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = dev_alloc(h, h->allocs, &h->d_static, (size_t)nd->static_words * n))) return rc;
+  if (nd->static_words && N > 0 && !nd->static_mask) return fail(h, CCSIM_EINVAL, "null static_mask");
+  for (int w = 0; w < nd->static_words && n; w++)
+    CK(cudaMemcpyAsync(h->d_static + (size_t)w * n, nd->static_mask + (size_t)w * N + lo, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  for (int k = 0; k < nd->n_topo_cols; k++) {
+    if (!nd->topo[k] && N > 0) return fail(h, CCSIM_EINVAL, "null topo column %d", k);
+    if ((rc = dev_upload<int32_t>(h, h->allocs, &h->d_topo[k], nd->topo[k] ? nd->topo[k] + lo : nullptr, (size_t)n))) return rc;
+  }
+  // working copies
+#define WK(dst, T) if ((rc = dev_alloc<T>(h, h->allocs, &h->dst, (size_t)n))) return rc
+  WK(w_req_cpu, int64_t); WK(w_req_mem, int64_t); WK(w_req_eph, int64_t); WK(w_nz_cpu, int64_t); WK(w_nz_mem, int64_t); WK(w_npods, int32_t);
+  for (int k = 0; k < nd->n_scalars; k++) WK(w_req_scalar[k], int64_t);
+  h->w_placed = nullptr;
+  if (nd->has_placed_mask) WK(w_placed, uint64_t);
+#undef WK
+  h->d_taint_off = nullptr; h->d_taint_list = nullptr;
+  if (nd->taint_list_off && nd->taint_list && n > 0) {
+    std::vector<int32_t> off(n + 1);
+    const int32_t base = nd->taint_list_off[lo];
+    for (int32_t i = 0; i <= n; i++) off[i] = nd->taint_list_off[lo + i] - base;
+    if ((rc = dev_upload<int32_t>(h, h->allocs, &h->d_taint_off, off.data(), (size_t)n + 1))) return rc;
+    if ((rc = dev_upload<uint8_t>(h, h->allocs, &h->d_taint_list, nd->taint_list + base, (size_t)off[n]))) return rc;
+    CK(cudaStreamSynchronize(h->stream));   // off[] is a local
+  }
+  // host-side bounds used to size outputs / classes
+  int64_t bound = 0; int maxpop = 0;
+  for (int32_t i = 0; i < N; i++) {
+    const int64_t free_pods = (int64_t)nd->alloc_pods[i] - nd->npods[i];
+    if (free_pods > 0) bound += free_pods;
+    int pc = 0;
+    for (int w = 0; w < nd->taint_words; w++) pc += __builtin_popcountll(nd->taint_mask[(size_t)w * N + i] & nd->taint_prefer[w]);
+    if (pc > maxpop) maxpop = pc;
+  }
+  h->pod_bound = bound; h->max_prefer_pop = maxpop;
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_nodes = true;
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const ccsim_template *templates,
+                                   int32_t n_counters, const ccsim_counter *counters) {
+  if (!h || !templates) return fail(h, CCSIM_EINVAL, "null argument");
+  if (!h->have_nodes) return fail(h, CCSIM_ESTATE, "ccsim_load_nodes must come first");
+  if (n_templates < 1 || n_templates > CCSIM_MAX_TEMPLATES) return fail(h, CCSIM_EINVAL, "n_templates out of range");
+  if (n_counters < 0 || n_counters > CCSIM_MAX_COUNTERS || (n_counters && !counters)) return fail(h, CCSIM_EINVAL, "n_counters out of range");
+  if (n_templates > 1 && n_counters > 0)
+    return fail(h, CCSIM_EUNSUPPORTED, "PodTopologySpread/InterPodAffinity templates are single-template only");
+  CK(cudaSetDevice(h->cfg.device));
+  free_pool(h->tmpl_allocs);
+  h->have_templates = false;
+  const ccsim_nodes &nd = h->meta;
+  for (int t = 0; t < n_templates; t++) {
+    const ccsim_template &T = templates[t];
+    if (T.n_pts < 0 || T.n_pts > CCSIM_MAX_PTS || T.n_aff < 0 || T.n_aff > CCSIM_MAX_IPA || T.n_anti < 0 || T.n_anti > CCSIM_MAX_IPA ||
+        T.n_aff_terms < 0 || T.n_aff_terms > CCSIM_MAX_AFF_TERMS)
+      return fail(h, CCSIM_EINVAL, "template %d: term counts out of range", t);
+    for (int c = 0; c < T.n_pts; c++) {
+      if (T.pts[c].counter < 0 || T.pts[c].counter >= n_counters) return fail(h, CCSIM_EINVAL, "template %d: pts counter index", t);
+      if (counters[T.pts[c].counter].topo_col < 0)
+        return fail(h, CCSIM_EUNSUPPORTED, "topology spread over a node-local (hostname) domain is not supported yet");
+    }
+    for (int a = 0; a < T.n_aff; a++) if (T.aff_counter[a] < 0 || T.aff_counter[a] >= n_counters) return fail(h, CCSIM_EINVAL, "aff counter index");
+    for (int a = 0; a < T.n_anti; a++) if (T.anti_counter[a] < 0 || T.anti_counter[a] >= n_counters) return fail(h, CCSIM_EINVAL, "anti counter index");
+    if ((T.flags & CCSIM_TF_PREFILTER_NODES) && (T.prefilter_bit < 0 || T.prefilter_bit >= 64 * nd.static_words))
+      return fail(h, CCSIM_EINVAL, "template %d: prefilter_bit", t);
+  }
+  if (h->max_prefer_pop + 1 > CCSIM_MAX_CLASSES)
+    return fail(h, CCSIM_EUNSUPPORTED, "a node carries %d PreferNoSchedule taints (max %d)", h->max_prefer_pop, CCSIM_MAX_CLASSES - 1);
+  h->h_templates.assign(templates, templates + n_templates);
+  int rc;
+  if ((rc = dev_upload<ccsim_template>(h, h->tmpl_allocs, &h->d_templates, templates, (size_t)n_templates))) return rc;
+  // counters: small domain sets live replicated in shared memory, large ones as per-CTA replicas in global memory
+  h->smem_cnt_ints = 0; h->final_total = 0;
+  const int grid_max = std::min(h->sm_count, CCSIM_MAX_GRID);
+  for (int j = 0; j < n_counters; j++) {
+    const ccsim_counter &c = counters[j];
+    DevCounter &d = h->counters[j];
+    d.topo_col = c.topo_col; d.inc = c.inc; d.n_present = c.n_present; d.is_aff = 0; d.smem_off = -1; d.work = nullptr;
+    for (int a = 0; a < templates[0].n_aff; a++) if (templates[0].aff_counter[a] == j) d.is_aff = 1;
+    if (c.topo_col >= nd.n_topo_cols) return fail(h, CCSIM_EINVAL, "counter %d: topo_col", j);
+    if (c.topo_col < 0) {
+      // node-local: init is a whole-cluster column; keep this shard's slice
+      if (c.n_domains != h->n_global) return fail(h, CCSIM_EINVAL, "counter %d: node-local counter needs n_domains == n_nodes", j);
+      d.n_domains = h->n;
+      if ((rc = dev_upload<int32_t>(h, h->tmpl_allocs, &d.init, c.init + h->node_base, (size_t)h->n))) return rc;
+      if ((rc = dev_alloc<int32_t>(h, h->tmpl_allocs, &d.work, (size_t)h->n))) return rc;
+    } else {
+      if (c.n_domains < 0 || c.n_present < 0 || c.n_present > c.n_domains) return fail(h, CCSIM_EINVAL, "counter %d: domains", j);
+      d.n_domains = c.n_domains;
+      if ((rc = dev_upload<int32_t>(h, h->tmpl_allocs, &d.init, c.init, (size_t)c.n_domains))) return rc;
+      if (h->smem_cnt_ints + c.n_domains <= SMEM_CNT_MAX_INTS) { d.smem_off = h->smem_cnt_ints; h->smem_cnt_ints += c.n_domains; }
+      else if ((rc = dev_alloc<int32_t>(h, h->tmpl_allocs, &d.work, (size_t)grid_max * c.n_domains))) return rc;
+      h->final_off[j] = h->final_total; h->final_total += c.n_domains;
+    }
+  }
+  if ((rc = dev_alloc<int32_t>(h, h->tmpl_allocs, &h->d_final_cnt, (size_t)h->final_total))) return rc;
+  h->n_templates = n_templates; h->n_counters = n_counters;
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_templates = true;
+  return CCSIM_OK;
+}
+
+static void fill_params(ccsim_handle *h, DevParams &p, int64_t max_pods) {
+  memset(&p, 0, sizeof(p));
+  const ccsim_nodes &nd = h->meta;
+  p.n = h->n; p.n_global = h->n_global; p.node_base = h->node_base;
+  p.n_scalars = nd.n_scalars; p.taint_words = nd.taint_words; p.static_words = nd.static_words; p.n_topo = nd.n_topo_cols;
+  p.n_templates = h->n_templates; p.n_counters = h->n_counters;
+  p.n_classes = h->max_prefer_pop + 1;
+  p.rank = h->cfg.rank; p.world = h->cfg.world;
+  p.alloc_cpu = h->d_alloc_cpu; p.alloc_mem = h->d_alloc_mem; p.alloc_eph = h->d_alloc_eph; p.alloc_pods = h->d_alloc_pods;
+  for (int k = 0; k < nd.n_scalars; k++) { p.alloc_scalar[k] = h->d_alloc_scalar[k]; p.req_scalar[k] = h->w_req_scalar[k]; }
+  p.taint_mask = h->d_taint; p.static_mask = h->d_static;
+  for (int k = 0; k < nd.n_topo_cols; k++) p.topo[k] = h->d_topo[k];
+  p.req_cpu = h->w_req_cpu; p.req_mem = h->w_req_mem; p.req_eph = h->w_req_eph; p.nz_cpu = h->w_nz_cpu; p.nz_mem = h->w_nz_mem;
+  p.npods = h->w_npods; p.placed_mask = h->w_placed;
+  for (int w = 0; w < CCSIM_MAX_TAINT_WORDS; w++) { p.taint_nosched[w] = nd.taint_nosched[w]; p.taint_prefer[w] = nd.taint_prefer[w]; }
+  p.templates = h->d_templates;
+  for (int j = 0; j < h->n_counters; j++) { p.counters[j] = h->counters[j]; p.final_off[j] = h->final_off[j]; }
+  p.final_cnt = h->d_final_cnt;
+  p.slots = h->d_slots;
+  p.pod_node = h->d_pod_node; p.pod_cap = h->pod_cap; p.max_pods = max_pods;
+  p.out = h->d_out;
+  p.taint_list_off = h->d_taint_off; p.taint_list = h->d_taint_list;
+}
+
+extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
+  if (!h || !out) return fail(h, CCSIM_EINVAL, "null argument");
+  if (!h->have_nodes || !h->have_templates) return fail(h, CCSIM_ESTATE, "load_nodes and set_templates must come first");
+  if (h->cfg.world > 1) return fail(h, CCSIM_EUNSUPPORTED, "multi-GPU run: use ccsim_comm_init + sharded run (not in this build)");
+  CK(cudaSetDevice(h->cfg.device));
+  memset(out, 0, sizeof(*out));
+  out->n_nodes = h->n_global;
+  const int32_t n = h->n;
+  // output capacity: no run can place more than sum(max(0, alloc_pods - npods)) pods (fit.go:567-576)
+  int64_t cap = h->pod_bound + 1;
+  if (max_pods > 0 && max_pods < cap) cap = max_pods;
+  if (cap > h->pod_cap) {
+    cudaFree(h->d_pod_node); h->d_pod_node = nullptr; h->pod_cap = 0;
+    CK(cudaMalloc((void **)&h->d_pod_node, (size_t)cap * sizeof(int32_t)));
+    h->pod_cap = cap;
+  }
+  // restore the working copies of the mutable columns from the snapshot (a Run never changes the loaded snapshot)
+  cudaStream_t s = h->stream;
+  if (n) {
+    CK(cudaMemcpyAsync(h->w_req_cpu, h->s_req_cpu, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->w_req_mem, h->s_req_mem, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->w_req_eph, h->s_req_eph, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->w_nz_cpu, h->s_nz_cpu, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->w_nz_mem, h->s_nz_mem, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->w_npods, h->s_npods, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    for (int k = 0; k < h->meta.n_scalars; k++)
+      CK(cudaMemcpyAsync(h->w_req_scalar[k], h->s_req_scalar[k], (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    if (h->w_placed) CK(cudaMemsetAsync(h->w_placed, 0, (size_t)n * 8, s));
+    for (int j = 0; j < h->n_counters; j++)
+      if (h->counters[j].topo_col < 0)
+        CK(cudaMemcpyAsync(h->counters[j].work, h->counters[j].init, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  CK(cudaMemsetAsync(h->d_out, 0, sizeof(DevOut), s));
+  CK(cudaMemsetAsync(h->d_slots, 0, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * CCSIM_MAX_CLASSES, s));
+
+  if (n == 0) {   // ErrNoNodesAvailable (scheduler.go:68): nothing to evaluate; the host formats the message
+    out->placed = 0; out->stop_code = CCSIM_STOP_UNSCHEDULABLE; out->pod_node = nullptr;
+    CK(cudaStreamSynchronize(s));
+    return CCSIM_OK;
+  }
+  // grid: one persistent CTA per SM (fewer for tiny clusters: the exchange cost grows with the CTA count)
+  int grid = std::min(h->sm_count, CCSIM_MAX_GRID);
+  const int want = (n + BLOCK_THREADS - 1) / BLOCK_THREADS;
+  if (want < grid) grid = want;
+  if (grid < 1) grid = 1;
+  h->grid = grid;
+  DevParams p;
+  fill_params(h, p, max_pods);
+  p.grid = grid;
+  p.chunk = (n + grid - 1) / grid;
+  const size_t smem = sizeof(WaveShared) + (size_t)h->smem_cnt_ints * sizeof(int32_t);
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel, BLOCK_THREADS, smem));
+  if (occ < 1 || occ * h->sm_count < grid) return fail(h, CCSIM_ECUDA, "persistent grid %d does not fit (occupancy %d x %d SMs)", grid, occ, h->sm_count);
+  void *args[] = { (void *)&p };
+  CK(cudaEventRecord(h->ev0, s));
+  CK(cudaLaunchCooperativeKernel((const void *)ccsim_wave_kernel, dim3(grid), dim3(BLOCK_THREADS), args, smem, s));
+  h->launches++;
+  CK(cudaEventRecord(h->ev1, s));
+  DevOut ho;
+  CK(cudaMemcpyAsync(&ho, h->d_out, sizeof(DevOut), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (ho.error) return fail(h, CCSIM_ECUDA, "wave kernel aborted (error %d: %s)", ho.error, ho.error == 1 ? "exchange watchdog / output overflow" : "?");
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  out->placed = ho.placed; out->stop_code = ho.stop_code; out->waves = ho.waves; out->evals = ho.evals; out->run_ms = ms;
+  h->last_placed = ho.placed;
+  if (ho.stop_code == CCSIM_STOP_UNSCHEDULABLE) {
+    const int ti = (int)(ho.placed % h->n_templates);
+    ccsim_diag_kernel<<<std::min(4 * h->sm_count, (n + 255) / 256), 256, 0, s>>>(p, ti);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&ho, h->d_out, sizeof(DevOut), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int r = 0; r < CCSIM_R_TOTAL; r++) out->reason_hist[r] = (int64_t)ho.reason_hist[r];
+    out->preempt_no_victims = (int64_t)ho.preempt_no_victims;
+    out->preempt_not_helpful = (int64_t)h->n_global - (int64_t)ho.preempt_no_victims;
+  }
+  h->h_pod_node.resize((size_t)ho.placed);
+  if (ho.placed) CK(cudaMemcpyAsync(h->h_pod_node.data(), h->d_pod_node, (size_t)ho.placed * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  out->pod_node = h->h_pod_node.data();
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_node_counts(ccsim_handle *h, int32_t t, int32_t *counts, int64_t *first_pod) {
+  if (!h || !counts || !first_pod) return fail(h, CCSIM_EINVAL, "null argument");
+  if (!h->have_templates || t < 0 || t >= h->n_templates) return fail(h, CCSIM_EINVAL, "template index");
+  CK(cudaSetDevice(h->cfg.device));
+  const int32_t N = h->n_global;
+  int32_t *d_counts = nullptr; unsigned long long *d_first = nullptr;
+  CK(cudaMalloc((void **)&d_counts, (size_t)(N ? N : 1) * 4));
+  CK(cudaMalloc((void **)&d_first, (size_t)(N ? N : 1) * 8));
+  CK(cudaMemsetAsync(d_counts, 0, (size_t)N * 4, h->stream));
+  CK(cudaMemsetAsync(d_first, 0xFF, (size_t)N * 8, h->stream));
+  if (h->last_placed > 0) {
+    ccsim_count_kernel<<<std::min<long long>(4 * h->sm_count, (h->last_placed + 255) / 256), 256, 0, h->stream>>>(
+        h->d_pod_node, h->last_placed, h->n_templates, t, d_counts, d_first);
+    h->launches++;
+  }
+  CK(cudaMemcpyAsync(counts, d_counts, (size_t)N * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(first_pod, d_first, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_counts); cudaFree(d_first);
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_device_info(ccsim_handle *h, int32_t *sm_count, int32_t *grid, int32_t *block, int64_t *l2_bytes) {
+  if (!h) return CCSIM_EINVAL;
+  if (sm_count) *sm_count = h->sm_count;
+  if (grid) *grid = h->grid;
+  if (block) *block = BLOCK_THREADS;
+  if (l2_bytes) *l2_bytes = (int64_t)h->l2_bytes;
+  return CCSIM_OK;
+}
+
+extern "C" int64_t ccsim_kernel_launches(const ccsim_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int ccsim_flush_l2(ccsim_handle *h) {
+  if (!h) return CCSIM_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t bytes = std::max<size_t>(2 * h->l2_bytes, (size_t)256 << 20);
+  if (h->flush_bytes < bytes) {
+    cudaFree(h->d_flush); h->d_flush = nullptr; h->flush_bytes = 0;
+    CK(cudaMalloc(&h->d_flush, bytes));
+    h->flush_bytes = bytes;
+  }
+  ccsim_flush_kernel<<<h->sm_count * 4, 512, 0, h->stream>>>((unsigned long long *)h->d_flush, bytes / 8, (unsigned long long)h->launches);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_nccl_unique_id(uint8_t id_out[128]) { (void)id_out; return CCSIM_EUNSUPPORTED; }
+extern "C" int ccsim_comm_init(ccsim_handle *h, const uint8_t id[128]) { (void)id; return fail(h, CCSIM_EUNSUPPORTED, "multi-GPU not built yet"); }

@@ -1,0 +1,144 @@
+"""GPU: the CUDA hot path (through the C-ABI) against the CPU oracle — bit-exact placement sequence, stop code and
+FitError histogram on the same seeded snapshots. Sizes are chosen so the single-thread oracle finishes in seconds."""
+import importlib
+
+import numpy as np
+import pytest
+
+abi = importlib.import_module("cluster-capacity_b200._abi")
+synth = importlib.import_module("cluster-capacity_b200.synth")
+from oracle import binding as oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GiB, MiB = 1 << 30, 1 << 20
+
+
+def gpu_run(snap, tmpl, ctr=(), max_pods=0):
+    engine = importlib.import_module("cluster-capacity_b200.engine")
+    with engine.Engine(device=0) as eng:
+        eng.load_nodes(snap)
+        eng.set_templates(tmpl, ctr)
+        res = eng.run(max_pods)
+        counts, first = eng.node_counts(0)
+    return res, counts, first
+
+
+def check(snap, tmpl, ctr=(), max_pods=0, threads=4):
+    got, counts, first = gpu_run(snap, tmpl, ctr, max_pods)
+    want = oracle.run(snap, tmpl, ctr, max_pods=max_pods, threads=threads)
+    assert got.placed == want.placed
+    assert got.stop_code == want.stop_code
+    assert np.array_equal(got.pod_node, want.pod_node)
+    assert np.array_equal(got.reason_hist, want.reason_hist)
+    assert (got.preempt_no_victims, got.preempt_not_helpful) == (want.preempt_no_victims, want.preempt_not_helpful)
+    assert got.evals == want.evals and got.waves == want.waves
+    if len(tmpl) == 1:
+        assert np.array_equal(counts, np.bincount(want.pod_node, minlength=snap.n))
+        # ReplicasOnNodes order = order of first placement (report.go:157-171)
+        seen = {}
+        for k, w in enumerate(want.pod_node.tolist()):
+            seen.setdefault(w, k)
+        for w, k in seen.items():
+            assert first[w] == k
+    return got
+
+
+def test_c1_readme(built):
+    got = check(*synth.c1())
+    assert got.placed == 52
+
+
+def test_c1_limit(built):
+    snap, tmpl, ctr = synth.c1()
+    got = check(snap, tmpl, ctr, max_pods=5)
+    assert got.stop_code == abi.STOP_LIMIT_REACHED and got.placed == 5
+
+
+def test_testprediction_nodes(built):
+    snap = abi.Snapshot(3, np.array([300, 400, 1200]), np.array([10**9, 2 * 10**9, 10**9]), np.array([3, 3, 3]))
+    t = abi.default_template(100, 5 * 10**6)
+    assert check(snap, [t]).placed == 9
+    assert check(snap, [t], max_pods=6).stop_code == abi.STOP_LIMIT_REACHED
+
+
+@pytest.mark.parametrize("n", [1, 31, 513, 2000])
+def test_c2_fit_only(built, n):
+    check(*synth.c2(n=n, seed=n))
+
+
+def test_c2_default_profile(built):
+    check(*synth.c2(n=1500, fit_only=False))
+
+
+@pytest.mark.parametrize("prefer", [False, True])
+def test_c3_full_filter_set(built, prefer):
+    got = check(*synth.c3(n=4000, prefer_taints=prefer))
+    assert got.reason_hist[abi.R_NODE_AFFINITY] > 0 and got.reason_hist[abi.R_UNSCHEDULABLE] > 0
+
+
+def test_c4_spread_and_anti_affinity(built):
+    got = check(*synth.c4(n=4000, n_existing=8000, zones=8, racks=64, regions=4))
+    assert got.placed > 100
+
+
+def test_c4_large_domain_set_uses_global_replicas(built):
+    # 20000 racks > the 16384-int shared-memory counter area: per-CTA replicas in global memory
+    check(*synth.c4(n=30000, n_existing=30000, zones=16, racks=20000, regions=4), max_pods=300)
+
+
+def test_c5_multi_template_round_robin(built):
+    snap, tmpl, ctr = synth.c5(n=3000, n_templates=7)
+    check(snap, tmpl, ctr, max_pods=4000)
+
+
+def test_colocation_affinity(built):
+    zone = [0, 0, 0, 1, 1, 1, 2, 2, 2]
+    snap = abi.Snapshot(9, np.full(9, 1000), np.full(9, 1000), np.full(9, 30), topo=[np.asarray(zone, np.int32)])
+    t = abi.default_template(10, 10)
+    t.flags |= abi.TF_AFF_SELF_MATCH_ALL
+    t.n_aff = 1
+    t.aff_counter[0] = 0
+    ctr = [abi.make_counter(0, np.zeros(3, np.int32), inc=1)]
+    got = check(snap, [t], ctr, max_pods=100)
+    assert got.placed == 90 and len({zone[i] for i in got.pod_node.tolist()}) == 1
+
+
+def test_scalar_resources_and_ephemeral(built):
+    rng = np.random.default_rng(7)
+    n = 700
+    snap = abi.Snapshot(n, np.full(n, 64000), np.full(n, 256 * GiB), np.full(n, 110),
+                        alloc_eph=rng.integers(10, 100, n) * GiB,
+                        scalars=[(rng.integers(0, 9, n), rng.integers(0, 3, n))])
+    t = abi.default_template(500, 1 * GiB, eph=7 * GiB)
+    t.req_scalar[0] = 2
+    got = check(snap, [t])
+    assert got.reason_hist[abi.R_SCALAR0] > 0
+
+
+def test_best_effort_pod(built):
+    n = 300
+    snap = abi.Snapshot(n, np.full(n, 4000), np.full(n, 8 * GiB), np.random.default_rng(3).integers(0, 20, n))
+    check(snap, [abi.default_template(0, 0)])
+
+
+def test_host_ports_one_clone_per_node(built):
+    n = 200
+    static = (np.random.default_rng(5).random(n) < 0.3).astype(np.uint64)
+    snap = abi.Snapshot(n, np.full(n, 4000), np.full(n, 8 * GiB), np.full(n, 110), static_mask=static.reshape(1, n),
+                        has_placed_mask=True)
+    t = abi.default_template(100, 100 * MiB)
+    t.flags |= abi.TF_HAS_HOST_PORTS
+    t.port_static_mask[0] = 1
+    t.port_tmpl_conflict = 1
+    got = check(snap, [t])
+    assert got.placed == int((static == 0).sum())
+    assert got.reason_hist[abi.R_NODE_PORTS] == n
+
+
+def test_full_size_c2_properties(built):
+    """BASELINE config C2 at full size (10k nodes): closed-form count and per-node distribution (KA5), no oracle run."""
+    snap, tmpl, ctr = synth.c2()
+    got, counts, _ = gpu_run(snap, tmpl, ctr)
+    cap = synth.closed_form_capacity(snap, tmpl[0])
+    assert got.placed == int(cap.sum()) and np.array_equal(counts, cap)
+    assert got.evals == (got.placed + 1) * snap.n
