@@ -9,9 +9,11 @@
 // round-to-nearest intrinsics so that nothing is contracted into an FMA.
 #pragma once
 #include <stdint.h>
+#include <limits.h>
 #include "../../include/ccsim.h"
 
 #define CCSIM_MAX_GRID 160  /* >= SM count of the part (B200: 148) */
+#define SLOT_STRIDE 16      /* 64-bit words per CTA slot: one 128-byte L2 line per CTA (sharing a line between writers costs ~2x) */
 
 struct DevCounter {
   int32_t topo_col;   // -1: node-local column
@@ -35,6 +37,7 @@ struct DevOut {
   unsigned long long reason_hist[CCSIM_R_TOTAL];
   unsigned long long preempt_no_victims;
   unsigned long long n_diag;
+  long long phase_cycles[8];       // CCSIM_PHASE_TIMERS builds only: CTA 0's cycles per phase
 };
 
 struct DevParams {
@@ -56,6 +59,11 @@ struct DevParams {
   int32_t *npods;
   int64_t *req_scalar[CCSIM_MAX_SCALARS];
   uint64_t *placed_mask;   // nullptr unless a template has hostPorts
+  int32_t *score_cache;    // memoised node-local score per node, -1 = stale (streaming mode; resident mode keeps it in the tile)
+  int32_t tile_resident;   // 1: the CTA's node tile is staged into shared memory once and stays there for the whole run
+  int32_t chunk_pad;       // chunk rounded up to a multiple of 4 (tile column stride)
+  int32_t n_local;         // node-local counters (each gets a tile column in resident mode)
+  int32_t smem_cnt_ints;   // size of the shared replicated-counter area
   uint64_t taint_nosched[CCSIM_MAX_TAINT_WORDS], taint_prefer[CCSIM_MAX_TAINT_WORDS];
   const ccsim_template *templates;
   DevCounter counters[CCSIM_MAX_COUNTERS];
@@ -71,6 +79,7 @@ struct DevParams {
   DevOut *out;
   const int32_t *taint_list_off;
   const uint8_t *taint_list;
+  const DevParams *self;   // device-memory copy of this struct, for the out-of-line slow paths
 };
 
 // ---- key packing ----------------------------------------------------------------------------------------------
@@ -98,29 +107,32 @@ __device__ __forceinline__ int64_t least_requested_score(int64_t requested, int6
   return q;
 }
 
-// Fit.Score with LeastAllocated over cpu,mem: resource_allocation.go:48-114 + least_allocated.go:30-48
-__device__ __forceinline__ int64_t score_least(int64_t a_cpu, int64_t a_mem, int64_t nz_cpu, int64_t nz_mem,
-                                               const ccsim_template &t) {
+struct ScoreWeights { int32_t w_fit, w_balanced, least_w_cpu, least_w_mem; };
+
+// Fit.Score with LeastAllocated over cpu,mem: resource_allocation.go:48-114 + least_allocated.go:30-48.
+// q_* = NonZeroRequested + the pod's non-zero request.
+__device__ __forceinline__ int64_t score_least(int64_t a_cpu, int64_t a_mem, int64_t q_cpu, int64_t q_mem,
+                                               int32_t w_cpu, int32_t w_mem) {
   int64_t node_score = 0, wsum = 0;
-  if (a_cpu != 0) { node_score += least_requested_score(nz_cpu + t.least_cpu, a_cpu) * t.least_w_cpu; wsum += t.least_w_cpu; }
-  if (a_mem != 0) { node_score += least_requested_score(nz_mem + t.least_mem, a_mem) * t.least_w_mem; wsum += t.least_w_mem; }
+  if (a_cpu != 0) { node_score += least_requested_score(q_cpu, a_cpu) * w_cpu; wsum += w_cpu; }
+  if (a_mem != 0) { node_score += least_requested_score(q_mem, a_mem) * w_mem; wsum += w_mem; }
   if (wsum == 0) return 0;
   if (wsum == 2) return node_score >> 1;   // both weights 1 (default): node_score >= 0
   return node_score / wsum;
 }
 
 // balancedResourceScorer over cpu,mem (balanced_allocation.go:146-180): float64, one rounding per operation.
-__device__ __forceinline__ int64_t score_balanced(int64_t a_cpu, int64_t a_mem, int64_t r_cpu, int64_t r_mem,
-                                                  const ccsim_template &t) {
+// q_* = Requested + the pod's request.
+__device__ __noinline__ int64_t score_balanced_f64(int64_t a_cpu, int64_t a_mem, int64_t q_cpu, int64_t q_mem) {
   double f0 = 0.0, f1 = 0.0;
   int nf = 0;
   if (a_cpu != 0) {
-    double fr = __ddiv_rn((double)(r_cpu + t.bal_cpu), (double)a_cpu);
+    double fr = __ddiv_rn((double)q_cpu, (double)a_cpu);
     if (fr > 1.0) fr = 1.0;
     f0 = fr; nf = 1;
   }
   if (a_mem != 0) {
-    double fr = __ddiv_rn((double)(r_mem + t.bal_mem), (double)a_mem);
+    double fr = __ddiv_rn((double)q_mem, (double)a_mem);
     if (fr > 1.0) fr = 1.0;
     if (nf == 0) f0 = fr; else f1 = fr;
     nf++;
@@ -129,20 +141,122 @@ __device__ __forceinline__ int64_t score_balanced(int64_t a_cpu, int64_t a_mem, 
   if (nf == 2) sd = fabs(__dmul_rn(__dsub_rn(f0, f1), 0.5));   // (f0-f1)/2: exact scaling by a power of two
   return (int64_t)__dmul_rn(__dsub_rn(1.0, sd), 100.0);
 }
+// The float64 result is int64((1-std)*100). An fp32 estimate of (1-std)*100 is within 1e-3 of the float64 value
+// (three fp32 roundings + two approximate divides on operands in [0,1]); when the estimate is at least 1/64 away from
+// an integer boundary the truncation is decided and the float64 sequence is skipped. Otherwise (ties, f0==f1, clipped
+// fractions) the exact float64 path runs. Bit-exactness is therefore never estimated, only the fast path's eligibility.
+__device__ __forceinline__ int64_t score_balanced(int64_t a_cpu, int64_t a_mem, int64_t q_cpu, int64_t q_mem) {
+  if (a_cpu > 0 && a_mem > 0 && q_cpu >= 0 && q_mem >= 0) {
+    const float g0 = fminf(__fdividef((float)q_cpu, (float)a_cpu), 1.0f);
+    const float g1 = fminf(__fdividef((float)q_mem, (float)a_mem), 1.0f);
+    const float v = (1.0f - fabsf(g0 - g1) * 0.5f) * 100.0f;
+    const float fl = floorf(v);
+    const float fr = v - fl;
+    if (fr > 0.015625f && fr < 0.984375f) return (int64_t)fl;
+  }
+  return score_balanced_f64(a_cpu, a_mem, q_cpu, q_mem);
+}
 
-// ---- per-CTA view of the dynamic cross-node state -------------------------------------------------------------
-struct CtaState {
-  int32_t *smem_cnt;                // replicated counters (shared memory area)
-  int32_t ptsmin[CCSIM_MAX_PTS];    // (in shared memory) global minimum per PTS constraint
-  int32_t ptsnum[CCSIM_MAX_PTS];    // number of present domains at the minimum
-  long long aff_total;
+// ---- per-wave constants of the fused Filter pass (shared memory; rebuilt when the template or a PTS minimum changes) ----
+// Everything that depends only on the template is folded into a handful of masks / thresholds so that the per-node
+// work is: 7 coalesced loads, ~10 integer ops, plus one (load, shared-memory counter read, compare) per coupled term.
+#define CCSIM_X_TAINT_WORDS   (1u << 0)   /* taint dictionary wider than one word                   */
+#define CCSIM_X_STATIC_WORDS  (1u << 1)   /* static bits wider than one word / nodeAffinity terms   */
+#define CCSIM_X_SCALARS       (1u << 2)   /* extended resources requested                           */
+#define CCSIM_X_NODENAME      (1u << 3)
+#define CCSIM_X_PREFILTER     (1u << 4)
+#define CCSIM_X_PLACED        (1u << 5)   /* hostPorts vs. clones already placed                    */
+#define CCSIM_X_EPH           (1u << 6)
+
+struct CoupledTerm {
+  const int32_t *col;   // topology column (nullptr: node-local, the counter is indexed by the node itself)
+  const int32_t *cnt;   // counter base (shared or global replica, or the node-local working column)
 };
 
-__device__ __forceinline__ const int32_t *counter_base(const DevParams &p, int j, const int32_t *smem_cnt) {
-  const DevCounter &c = p.counters[j];
-  if (c.topo_col < 0) return c.work;
-  if (c.smem_off >= 0) return smem_cnt + c.smem_off;
-  return c.work + (size_t)blockIdx.x * c.n_domains;
+struct FilterConsts {
+  unsigned long long taint_bad0;   // word 0: untolerated NoSchedule/NoExecute entries | unschedulable bit
+  unsigned long long prefer0;      // word 0: PreferNoSchedule entries not tolerated (score classes)
+  unsigned long long sel0;         // static word 0: bits that must all be set (nodeSelector)
+  unsigned long long forbid0;      // static word 0: bits that must all be clear (port conflicts, existing anti-affinity)
+  long long eq_cpu, eq_mem, eq_eph; // effective requests (LLONG_MIN: check disabled)
+  int32_t fit_pods;                // 1: npods + 1 > allowedPodNumber rejects
+  uint32_t extras;                 // CCSIM_X_*
+  int32_t n_pts, n_aff, n_anti, aff_bypass;
+  int32_t tmpl_index;
+  int32_t pts_lim[CCSIM_MAX_PTS];  // reject when cnt > lim  (lim = maxSkew - selfMatch + globalMin)
+  CoupledTerm pts[CCSIM_MAX_PTS], aff[CCSIM_MAX_IPA], anti[CCSIM_MAX_IPA];
+};
+
+// Node tile of a CTA. Every pointer is pre-offset so that [i] with the shard-local node index i works, whether the
+// tile lives in shared memory (resident mode) or is the global column itself (streaming mode).
+// Resident mode keeps the three Fit inputs as differences (free = allocatable - requested: fit.go:585-616 compares the
+// pod request against exactly this difference), updated at commit, next to the raw columns the scorers need.
+struct Tile {
+  const unsigned long long *taint0, *static0;
+  const int32_t *alloc_pods;
+  int32_t *npods;
+  const long long *alloc_cpu, *alloc_mem;
+  long long *req_cpu, *req_mem, *nz_cpu, *nz_mem;
+  long long *free_cpu, *free_mem;   // resident mode only
+  int32_t *free_pods;               // resident mode only: allowedPodNumber - len(Pods)
+  int32_t *score;     // memoised node-local score, -1 = stale
+};
+
+// one thread: fold template t into FilterConsts. topo_ptr[k] / cnt_ptr[j] are the (pre-offset) bases of topology
+// column k and of counter j as this CTA sees them.
+__device__ void build_filter_consts(const DevParams &p, const ccsim_template &t, int32_t ti, const int32_t *const *topo_ptr,
+                                    int32_t *const *cnt_ptr, const int32_t *ptsmin, long long aff_total, FilterConsts &fc) {
+  const uint32_t fe = t.filter_enable, fl = t.flags;
+  fc.tmpl_index = ti;
+  unsigned long long tb = 0ull;
+  if (fe & CCSIM_PL_TAINT_TOLERATION) tb |= p.taint_nosched[0] & ~t.tol_nosched[0] & ~(1ull << CCSIM_TAINT_UNSCHEDULABLE_BIT);
+  if ((fe & CCSIM_PL_NODE_UNSCHEDULABLE) && !(fl & CCSIM_TF_TOLERATES_UNSCHEDULABLE)) tb |= 1ull << CCSIM_TAINT_UNSCHEDULABLE_BIT;
+  fc.taint_bad0 = tb;
+  fc.prefer0 = (t.score_enable & CCSIM_PL_TAINT_TOLERATION) ? (p.taint_prefer[0] & ~t.tol_prefer[0]) : 0ull;
+  const bool aff_on = (fe & CCSIM_PL_NODE_AFFINITY) && (fl & (CCSIM_TF_HAS_NODE_SELECTOR | CCSIM_TF_HAS_AFFINITY_TERMS));
+  fc.sel0 = (aff_on && p.static_words > 0) ? t.sel_mask[0] : 0ull;
+  unsigned long long fb = 0ull;
+  if (p.static_words > 0) {
+    if ((fe & CCSIM_PL_NODE_PORTS) && (fl & CCSIM_TF_HAS_HOST_PORTS)) fb |= t.port_static_mask[0];
+    if (fe & CCSIM_PL_INTER_POD_AFFINITY) fb |= t.existing_anti_mask[0];
+  }
+  fc.forbid0 = fb;
+  const bool fit = (fe & CCSIM_PL_FIT) != 0, nz = fit && !(fl & CCSIM_TF_FIT_ALL_ZERO);
+  fc.fit_pods = fit ? 1 : 0;
+  fc.eq_cpu = (nz && t.req_cpu > 0) ? t.req_cpu : LLONG_MIN;
+  fc.eq_mem = (nz && t.req_mem > 0) ? t.req_mem : LLONG_MIN;
+  fc.eq_eph = (nz && t.req_eph > 0) ? t.req_eph : LLONG_MIN;
+  uint32_t x = 0;
+  if (p.taint_words > 1) x |= CCSIM_X_TAINT_WORDS;
+  if (p.static_words > 1 || (aff_on && (fl & CCSIM_TF_HAS_AFFINITY_TERMS))) x |= CCSIM_X_STATIC_WORDS;
+  if (nz) for (int k = 0; k < p.n_scalars; k++) if (t.req_scalar[k] != 0) x |= CCSIM_X_SCALARS;
+  if ((fe & CCSIM_PL_NODE_NAME) && t.nodename_idx >= 0) x |= CCSIM_X_NODENAME;
+  if (fl & CCSIM_TF_PREFILTER_NODES) x |= CCSIM_X_PREFILTER;
+  if ((fe & CCSIM_PL_NODE_PORTS) && (fl & CCSIM_TF_HAS_HOST_PORTS) && p.placed_mask) x |= CCSIM_X_PLACED;
+  if (fc.eq_eph != LLONG_MIN) x |= CCSIM_X_EPH;
+  fc.extras = x;
+  fc.n_pts = (fe & CCSIM_PL_POD_TOPOLOGY_SPREAD) ? t.n_pts : 0;
+  for (int c = 0; c < fc.n_pts; c++) {
+    const DevCounter &dc = p.counters[t.pts[c].counter];
+    fc.pts[c].col = dc.topo_col < 0 ? nullptr : topo_ptr[dc.topo_col];
+    fc.pts[c].cnt = cnt_ptr[t.pts[c].counter];
+    const long long lim = (long long)t.pts[c].max_skew - t.pts[c].self_match + (long long)ptsmin[c];
+    fc.pts_lim[c] = lim > INT32_MAX ? INT32_MAX : (lim < INT32_MIN ? INT32_MIN : (int32_t)lim);
+  }
+  const bool ipa = (fe & CCSIM_PL_INTER_POD_AFFINITY) != 0;
+  fc.n_aff = ipa ? t.n_aff : 0;
+  fc.n_anti = ipa ? t.n_anti : 0;
+  for (int a = 0; a < fc.n_aff; a++) {
+    const DevCounter &dc = p.counters[t.aff_counter[a]];
+    fc.aff[a].col = dc.topo_col < 0 ? nullptr : topo_ptr[dc.topo_col];
+    fc.aff[a].cnt = cnt_ptr[t.aff_counter[a]];
+  }
+  for (int a = 0; a < fc.n_anti; a++) {
+    const DevCounter &dc = p.counters[t.anti_counter[a]];
+    fc.anti[a].col = dc.topo_col < 0 ? nullptr : topo_ptr[dc.topo_col];
+    fc.anti[a].cnt = cnt_ptr[t.anti_counter[a]];
+  }
+  fc.aff_bypass = (aff_total == 0 && (fl & CCSIM_TF_AFF_SELF_MATCH_ALL)) ? 1 : 0;
 }
 
 // status codes for the diagnosis pass
@@ -150,60 +264,29 @@ __device__ __forceinline__ const int32_t *counter_base(const DevParams &p, int j
 #define ST_UNSCHEDULABLE 1
 #define ST_UNRESOLVABLE 2
 
-// Hot path: is node i (local index) feasible for template t, and if so its class (raw PreferNoSchedule intolerable
-// count) and node-local score. Returns false if any enabled Filter plugin rejects the node.
-__device__ __forceinline__ bool eval_node(const DevParams &p, const ccsim_template &t, const int32_t *smem_cnt,
-                                          const int32_t *ptsmin, long long aff_total, int32_t i,
-                                          int &cls, int64_t &score) {
+// the uncommon predicates (wide dictionaries, nodeAffinity terms, extended resources, nodeName, hostPorts vs clones)
+__device__ __noinline__ bool filter_extras(const DevParams *pp, int32_t ti, uint32_t extras, int32_t i) {
+  const DevParams &p = *pp;
+  const ccsim_template &t = p.templates[ti];
   const int32_t n = p.n;
-  // -- loads issued up front (coalesced: consecutive threads -> consecutive nodes) --
-  const uint64_t taint0 = p.taint_mask[i];
-  const int32_t a_pods = p.alloc_pods[i];
-  const int32_t npods = p.npods[i];
-  const int64_t a_cpu = p.alloc_cpu[i], a_mem = p.alloc_mem[i];
-  const int64_t r_cpu = p.req_cpu[i], r_mem = p.req_mem[i];
-  const int64_t z_cpu = p.nz_cpu[i], z_mem = p.nz_mem[i];
   bool ok = true;
-
-  if (t.flags & CCSIM_TF_PREFILTER_NODES) {
+  if (extras & CCSIM_X_PREFILTER) {
     const int b = t.prefilter_bit;
     ok &= (bool)((p.static_mask[(size_t)(b >> 6) * n + i] >> (b & 63)) & 1ull);
   }
-  // NodeUnschedulable (node_unschedulable.go:133-150)
-  if (t.filter_enable & CCSIM_PL_NODE_UNSCHEDULABLE)
-    ok &= !(((taint0 >> CCSIM_TAINT_UNSCHEDULABLE_BIT) & 1ull) && !(t.flags & CCSIM_TF_TOLERATES_UNSCHEDULABLE));
-  // NodeName (node_name.go:81-83)
-  if ((t.filter_enable & CCSIM_PL_NODE_NAME) && t.nodename_idx >= 0) ok &= (t.nodename_idx == p.node_base + i);
-  // TaintToleration filter (taint_toleration.go:111-122) + raw score (taint_toleration.go:154-182)
-  int raw = 0;
-  {
-    uint64_t untol = 0;
-    #pragma unroll
-    for (int w = 0; w < CCSIM_MAX_TAINT_WORDS; w++) {
-      if (w < p.taint_words) {
-        const uint64_t m = (w == 0) ? taint0 : p.taint_mask[(size_t)w * n + i];
-        untol |= m & p.taint_nosched[w] & ~t.tol_nosched[w];
-        raw += __popcll(m & p.taint_prefer[w] & ~t.tol_prefer[w]);
-      }
-    }
-    if (t.filter_enable & CCSIM_PL_TAINT_TOLERATION) ok &= (untol == 0);
-    if (!(t.score_enable & CCSIM_PL_TAINT_TOLERATION)) raw = 0;
-  }
-  // static-bit predicates: NodeAffinity (node_affinity.go:206-227), NodePorts (node_ports.go:157-185),
-  // existing pods' anti-affinity (interpodaffinity/filtering.go:352-364)
-  if (p.static_words > 0) {
+  if (extras & CCSIM_X_NODENAME) ok &= (t.nodename_idx == p.node_base + i);
+  if ((extras & CCSIM_X_TAINT_WORDS) && (t.filter_enable & CCSIM_PL_TAINT_TOLERATION))
+    for (int w = 1; w < p.taint_words; w++) ok &= ((p.taint_mask[(size_t)w * n + i] & p.taint_nosched[w] & ~t.tol_nosched[w]) == 0);
+  if (extras & CCSIM_X_STATIC_WORDS) {
     uint64_t sw[CCSIM_MAX_STATIC_WORDS];
-    #pragma unroll
     for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) sw[w] = (w < p.static_words) ? p.static_mask[(size_t)w * n + i] : 0ull;
     if ((t.filter_enable & CCSIM_PL_NODE_AFFINITY) && (t.flags & (CCSIM_TF_HAS_NODE_SELECTOR | CCSIM_TF_HAS_AFFINITY_TERMS))) {
       bool m = true;
-      #pragma unroll
-      for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) m &= ((sw[w] & t.sel_mask[w]) == t.sel_mask[w]);
-      if (t.flags & CCSIM_TF_HAS_AFFINITY_TERMS) {
+      for (int w = 1; w < CCSIM_MAX_STATIC_WORDS; w++) m &= ((sw[w] & t.sel_mask[w]) == t.sel_mask[w]);
+      if (t.flags & CCSIM_TF_HAS_AFFINITY_TERMS) {   // terms are ORed; zero terms match nothing
         bool any = false;
         for (int k = 0; k < t.n_aff_terms; k++) {
           bool tm = true;
-          #pragma unroll
           for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) tm &= ((sw[w] & t.aff_term_mask[k][w]) == t.aff_term_mask[k][w]);
           any |= tm;
         }
@@ -211,73 +294,129 @@ __device__ __forceinline__ bool eval_node(const DevParams &p, const ccsim_templa
       }
       ok &= m;
     }
-    if ((t.filter_enable & CCSIM_PL_NODE_PORTS) && (t.flags & CCSIM_TF_HAS_HOST_PORTS)) {
-      uint64_t c = 0;
-      #pragma unroll
-      for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) c |= sw[w] & t.port_static_mask[w];
-      ok &= (c == 0);
-    }
-    if (t.filter_enable & CCSIM_PL_INTER_POD_AFFINITY) {
-      uint64_t c = 0;
-      #pragma unroll
-      for (int w = 0; w < CCSIM_MAX_STATIC_WORDS; w++) c |= sw[w] & t.existing_anti_mask[w];
-      ok &= (c == 0);
-    }
+    uint64_t c = 0;
+    if ((t.filter_enable & CCSIM_PL_NODE_PORTS) && (t.flags & CCSIM_TF_HAS_HOST_PORTS))
+      for (int w = 1; w < CCSIM_MAX_STATIC_WORDS; w++) c |= sw[w] & t.port_static_mask[w];
+    if (t.filter_enable & CCSIM_PL_INTER_POD_AFFINITY)
+      for (int w = 1; w < CCSIM_MAX_STATIC_WORDS; w++) c |= sw[w] & t.existing_anti_mask[w];
+    ok &= (c == 0);
   }
-  if ((t.filter_enable & CCSIM_PL_NODE_PORTS) && (t.flags & CCSIM_TF_HAS_HOST_PORTS) && p.placed_mask)
-    ok &= ((p.placed_mask[i] & t.port_tmpl_conflict) == 0);
-  // NodeResourcesFit (fit.go:564-660)
-  if (t.filter_enable & CCSIM_PL_FIT) {
-    ok &= !(npods + 1 > a_pods);
-    if (!(t.flags & CCSIM_TF_FIT_ALL_ZERO)) {
-      ok &= !(t.req_cpu > 0 && t.req_cpu > a_cpu - r_cpu);
-      ok &= !(t.req_mem > 0 && t.req_mem > a_mem - r_mem);
-      if (t.req_eph > 0) ok &= !(t.req_eph > p.alloc_eph[i] - p.req_eph[i]);
-      for (int k = 0; k < p.n_scalars; k++) {
-        const int64_t q = t.req_scalar[k];
-        if (q != 0) ok &= !(q > p.alloc_scalar[k][i] - p.req_scalar[k][i]);
-      }
+  if (extras & CCSIM_X_PLACED) ok &= ((p.placed_mask[i] & t.port_tmpl_conflict) == 0);
+  if (extras & CCSIM_X_EPH) ok &= !(t.req_eph > p.alloc_eph[i] - p.req_eph[i]);
+  if (extras & CCSIM_X_SCALARS)
+    for (int k = 0; k < p.n_scalars; k++) {
+      const int64_t q = t.req_scalar[k];
+      if (q != 0) ok &= !(q > p.alloc_scalar[k][i] - p.req_scalar[k][i]);
     }
+  return ok;
+}
+
+// register copy of the FilterConsts fields every node needs (hoisted out of the node loop)
+struct HotConsts {
+  unsigned long long taint_bad0, prefer0, sel0, forbid0;
+  long long eq_cpu, eq_mem;
+  int32_t fit_pods, pods_need, n_pts, n_aff, n_anti;
+  uint32_t extras;
+};
+__device__ __forceinline__ HotConsts load_hot(const FilterConsts &fc) {
+  HotConsts h;
+  h.taint_bad0 = fc.taint_bad0; h.prefer0 = fc.prefer0; h.sel0 = fc.sel0; h.forbid0 = fc.forbid0;
+  h.eq_cpu = fc.eq_cpu; h.eq_mem = fc.eq_mem; h.fit_pods = fc.fit_pods; h.pods_need = fc.fit_pods ? 1 : INT32_MIN;
+  h.n_pts = fc.n_pts; h.n_aff = fc.n_aff; h.n_anti = fc.n_anti; h.extras = fc.extras;
+  return h;
+}
+
+// Hot path: the fused Filter pass for node i (shard-local index). One predicate-eval.
+// Plugin order does not matter for feasibility (the AND of all enabled plugins); the order only matters for the
+// FitError reasons, which the terminal diagnosis kernel reproduces.
+template <bool RESIDENT>
+__device__ __forceinline__ bool filter_node(const DevParams &p, const HotConsts &hc, const FilterConsts &fc,
+                                            const Tile &tl, int32_t i, int &raw) {
+  // NodeUnschedulable + TaintToleration (node_unschedulable.go:133-150, taint_toleration.go:111-122)
+  const unsigned long long taint0 = tl.taint0[i];
+  bool ok = (taint0 & hc.taint_bad0) == 0ull;
+  raw = __popcll(taint0 & hc.prefer0);
+  // NodeResourcesFit (fit.go:564-660)
+  if (RESIDENT) {
+    ok &= !(hc.pods_need > tl.free_pods[i]);
+    ok &= !(hc.eq_cpu > tl.free_cpu[i]);
+    ok &= !(hc.eq_mem > tl.free_mem[i]);
+  } else {
+    ok &= !(hc.fit_pods && tl.npods[i] + 1 > tl.alloc_pods[i]);
+    ok &= !(hc.eq_cpu > tl.alloc_cpu[i] - tl.req_cpu[i]);
+    ok &= !(hc.eq_mem > tl.alloc_mem[i] - tl.req_mem[i]);
+  }
+  // NodeAffinity nodeSelector, NodePorts, existing pods' anti-affinity: static bits
+  if (hc.sel0 | hc.forbid0) {
+    const unsigned long long sw = tl.static0[i];
+    ok &= ((~sw & hc.sel0) | (sw & hc.forbid0)) == 0ull;
   }
   // PodTopologySpread hard constraints (podtopologyspread/filtering.go:311-356)
-  if (t.filter_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) {
-    for (int c = 0; c < t.n_pts; c++) {
-      const ccsim_pts &pc = t.pts[c];
-      const DevCounter &dc = p.counters[pc.counter];
-      const int32_t dom = dc.topo_col < 0 ? i : p.topo[dc.topo_col][i];
-      if (dom < 0) { ok = false; break; }
-      const long long skew = (long long)counter_base(p, pc.counter, smem_cnt)[dom] + pc.self_match - (long long)ptsmin[c];
-      ok &= !(skew > pc.max_skew);
-    }
+  for (int c = 0; c < hc.n_pts; c++) {
+    const int32_t dom = fc.pts[c].col ? fc.pts[c].col[i] : i;
+    ok &= (dom >= 0) && !(fc.pts[c].cnt[dom < 0 ? 0 : dom] > fc.pts_lim[c]);
   }
   // InterPodAffinity required terms (interpodaffinity/filtering.go:367-432)
-  if (t.filter_enable & CCSIM_PL_INTER_POD_AFFINITY) {
-    if (t.n_aff > 0) {
-      bool pods_exist = true, missing = false;
-      for (int a = 0; a < t.n_aff; a++) {
-        const DevCounter &dc = p.counters[t.aff_counter[a]];
-        const int32_t dom = dc.topo_col < 0 ? i : p.topo[dc.topo_col][i];
-        if (dom < 0) { missing = true; break; }
-        if (counter_base(p, t.aff_counter[a], smem_cnt)[dom] <= 0) pods_exist = false;
-      }
-      ok &= !(missing || (!pods_exist && !(aff_total == 0 && (t.flags & CCSIM_TF_AFF_SELF_MATCH_ALL))));
+  if (hc.n_aff) {
+    bool pods_exist = true, missing = false;
+    for (int a = 0; a < hc.n_aff; a++) {
+      const int32_t dom = fc.aff[a].col ? fc.aff[a].col[i] : i;
+      missing |= (dom < 0);
+      pods_exist &= (dom >= 0) && (fc.aff[a].cnt[dom < 0 ? 0 : dom] > 0);
     }
-    for (int a = 0; a < t.n_anti; a++) {
-      const DevCounter &dc = p.counters[t.anti_counter[a]];
-      const int32_t dom = dc.topo_col < 0 ? i : p.topo[dc.topo_col][i];
-      if (dom >= 0) ok &= !(counter_base(p, t.anti_counter[a], smem_cnt)[dom] > 0);
-    }
+    ok &= !(missing || (!pods_exist && !fc.aff_bypass));
   }
-  if (!ok) return false;
-  // node-local score (framework.go:1137-1244: plugin score * weight, summed)
-  int64_t sc = 0;
-  if (t.score_enable & CCSIM_PL_FIT) sc += (int64_t)t.w_fit * score_least(a_cpu, a_mem, z_cpu, z_mem, t);
-  if ((t.score_enable & CCSIM_PL_BALANCED) && !(t.flags & CCSIM_TF_BALANCED_SKIP))
-    sc += (int64_t)t.w_balanced * score_balanced(a_cpu, a_mem, r_cpu, r_mem, t);
-  cls = raw;
-  score = sc;
-  return true;
+  for (int a = 0; a < hc.n_anti; a++) {
+    const int32_t dom = fc.anti[a].col ? fc.anti[a].col[i] : i;
+    ok &= !((dom >= 0) && (fc.anti[a].cnt[dom < 0 ? 0 : dom] > 0));
+  }
+  if (hc.extras && ok) ok = filter_extras(p.self, fc.tmpl_index, hc.extras, i);
+  return ok;
 }
+
+// node-local score of a feasible node (framework.go:1137-1244: plugin score * weight, summed); depends only on the
+// node's own NodeInfo and the template, so it is memoised per node until that node is committed again (the
+// reference's snapshot likewise only refreshes NodeInfos whose generation changed: backend/cache/cache.go:194-288).
+// lq_* = NonZeroRequested + pod non-zero request (LeastAllocated); bq_* = Requested + pod request (BalancedAllocation).
+__device__ __noinline__ int32_t score_node(int64_t a_cpu, int64_t a_mem, int64_t lq_cpu, int64_t lq_mem,
+                                           int64_t bq_cpu, int64_t bq_mem, ScoreWeights sw) {
+  int64_t sc = 0;
+  if (sw.w_fit) sc += (int64_t)sw.w_fit * score_least(a_cpu, a_mem, lq_cpu, lq_mem, sw.least_w_cpu, sw.least_w_mem);
+  if (sw.w_balanced) sc += (int64_t)sw.w_balanced * score_balanced(a_cpu, a_mem, bq_cpu, bq_mem);
+  return (int32_t)sc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// slot exchange primitives: relaxed 64-bit accesses that bypass L1 (the tag inside the word carries the ordering)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_slot(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_slot(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// warp-wide max of a packed 64-bit key with two REDUX.MAX.U32 (high word, then low word among the lanes that tie)
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+
+
+struct CommitInfo {
+  const int32_t *gtopo;   // global topology column (any node)
+  const int32_t *ltopo;   // this CTA's view of it (pre-offset tile column in resident mode)
+  int32_t inc;            // 0: this template does not touch the counter
+  int32_t pts_idx;        // PTS constraint tracking its minimum on this counter, or -1
+  int32_t n_present;
+  int32_t is_aff;
+  int32_t local;          // node-local counter
+  int32_t pad;
+};
+
 
 // TaintToleration NormalizeScore, reverse (helper/normalize_score.go:28-56)
 __device__ __forceinline__ int64_t taint_norm(int raw, int maxraw) {

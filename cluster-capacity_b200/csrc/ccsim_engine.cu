@@ -24,48 +24,46 @@
 #include <string>
 #include <vector>
 #include "ccsim_device.cuh"
+#ifdef CCSIM_PHASE_TIMERS
+#define PH_START() do { if (cta == 0 && tid == 0) tc0 = clock64(); } while (0)
+#define PH_MARK(i) do { if (cta == 0 && tid == 0) { tc1 = clock64(); ph[i] += tc1 - tc0; tc0 = tc1; } } while (0)
+#else
+#define PH_START() do {} while (0)
+#define PH_MARK(i) do {} while (0)
+#endif
+#include "ccsim_lean.cuh"
 
 #define BLOCK_THREADS 512
 #define MAX_WARPS (BLOCK_THREADS / 32)
 #define SMEM_CNT_MAX_INTS 16384      /* 64 KB of replicated counters in shared memory; above that: global replicas */
 #define WATCHDOG_SPINS (1u << 24)
 
-// ------------------------------------------------------------------------------------------------------------------
-// slot exchange primitives: relaxed 64-bit accesses that bypass L1 (the tag inside the word carries the ordering)
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_slot(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_slot(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-  #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-    v = other > v ? other : v;
-  }
-  return v;
-}
-
 struct __align__(16) WaveShared {
   ccsim_template tmpl;                              // current template
+  FilterConsts fc;                                  // folded per-wave constants of the Filter pass
   unsigned long long warp_best[MAX_WARPS][CCSIM_MAX_CLASSES];
+  const int32_t *topo_ptr[CCSIM_MAX_TOPO_COLS];     // topology columns as this CTA indexes them (pre-offset)
+  int32_t *cnt_ptr[CCSIM_MAX_COUNTERS];             // counter bases (shared replica / global replica / node-local column)
   int32_t ptsmin[CCSIM_MAX_PTS];
   int32_t ptsnum[CCSIM_MAX_PTS];
   long long aff_total;
   int32_t winner;        // global node index, -1 = none
   int32_t stop;          // 0 continue, 1 unschedulable, 2 limit, 3 error
+  int32_t dirty;         // FilterConsts must be rebuilt before the next scan
+  ScoreWeights sw;       // scalar copy of the template's score configuration (passed by value to score_node)
+  CommitInfo cinfo[CCSIM_MAX_COUNTERS];   // what a commit does to each counter under the current template
   int32_t scratch[MAX_WARPS];
 };
 
+// Statically allocated so that every access is a direct LDS/STS with a compile-time offset (a reference obtained by
+// casting the dynamic shared array makes nvcc re-derive the generic window base — S2UR SR_CgaCtaId — at each use).
+__shared__ WaveShared ws;
+
 // recount of a PTS constraint's minimum and its multiplicity over the present domains (all threads of the CTA)
-__device__ void pts_recount(const DevParams &p, WaveShared &ws, const int32_t *smem_cnt, int c) {
+__device__ void pts_recount(const DevParams &p, int c) {
   const ccsim_pts &pc = ws.tmpl.pts[c];
   const DevCounter &dc = p.counters[pc.counter];
-  const int32_t *cnt = counter_base(p, pc.counter, smem_cnt);
+  const int32_t *cnt = ws.cnt_ptr[pc.counter];
   int32_t m = INT32_MAX;
   for (int d = threadIdx.x; d < dc.n_present; d += blockDim.x) m = min(m, cnt[d]);
   for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -84,55 +82,164 @@ __device__ void pts_recount(const DevParams &p, WaveShared &ws, const int32_t *s
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += ws.scratch[w];
     ws.ptsmin[c] = pc.min_zero ? 0 : m;    // filtering.go:56-69: fewer domains than minDomains -> global minimum 0
     ws.ptsnum[c] = s;
+    ws.dirty = 1;
   }
   __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // The persistent wave kernel (sequential engine: one winner per wave; always a valid execution of the reference loop)
+//   RESIDENT: the CTA's node tile (every column the Filter/Score pass reads) is staged into shared memory once and
+//             stays there for all waves; commits write through to the global columns (read by the diagnosis pass).
+//   streaming: tiles too large for shared memory are re-read from global memory (L2) every wave.
 // ------------------------------------------------------------------------------------------------------------------
+template <bool RESIDENT>
 __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WaveShared &ws = *reinterpret_cast<WaveShared *>(smem_raw);
-  int32_t *smem_cnt = reinterpret_cast<int32_t *>(smem_raw + sizeof(WaveShared));
+  int32_t *smem_cnt = reinterpret_cast<int32_t *>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
   const int32_t lo = min(p.n, cta * p.chunk), hi = min(p.n, lo + p.chunk);
   const int ncls = p.n_classes;
+  const bool use_cache = (p.n_templates == 1);
 
-  // ---- prologue: template 0, replicated counters, PTS minima ----
+  // ---- tile: shared-memory columns (pre-offset by -lo) or the global columns themselves ----
+  Tile tl;
+  int32_t *tile_topo = nullptr, *tile_local = nullptr;
+  if (RESIDENT) {
+    const size_t cp = (size_t)p.chunk_pad;
+    unsigned char *base = smem_raw + (((size_t)p.smem_cnt_ints * 4 + 15) & ~(size_t)15);
+    unsigned long long *q8 = reinterpret_cast<unsigned long long *>(base);
+    unsigned long long *s_taint = q8;            q8 += cp;
+    unsigned long long *s_static = q8;           if (p.static_words > 0) q8 += cp;
+    long long *s_acpu = (long long *)q8;         q8 += cp;
+    long long *s_amem = (long long *)q8;         q8 += cp;
+    long long *s_rcpu = (long long *)q8;         q8 += cp;
+    long long *s_rmem = (long long *)q8;         q8 += cp;
+    long long *s_zcpu = (long long *)q8;         q8 += cp;
+    long long *s_zmem = (long long *)q8;         q8 += cp;
+    long long *s_fcpu = (long long *)q8;         q8 += cp;
+    long long *s_fmem = (long long *)q8;         q8 += cp;
+    int32_t *q4 = reinterpret_cast<int32_t *>(q8);
+    int32_t *s_fpods = q4;                       q4 += cp;
+    int32_t *s_apods = q4;                       q4 += cp;
+    int32_t *s_npods = q4;                       q4 += cp;
+    int32_t *s_score = q4;                       q4 += cp;
+    tile_topo = q4;                              q4 += cp * p.n_topo;
+    tile_local = q4;
+    for (int32_t i = lo + tid; i < hi; i += blockDim.x) {
+      const int32_t j = i - lo;
+      s_taint[j] = p.taint_mask[i];
+      if (p.static_words > 0) s_static[j] = p.static_mask[i];
+      s_acpu[j] = p.alloc_cpu[i]; s_amem[j] = p.alloc_mem[i];
+      s_rcpu[j] = p.req_cpu[i];   s_rmem[j] = p.req_mem[i];
+      s_zcpu[j] = p.nz_cpu[i];    s_zmem[j] = p.nz_mem[i];
+      s_apods[j] = p.alloc_pods[i]; s_npods[j] = p.npods[i];
+      s_fcpu[j] = s_acpu[j] - s_rcpu[j]; s_fmem[j] = s_amem[j] - s_rmem[j]; s_fpods[j] = s_apods[j] - s_npods[j];
+      s_score[j] = -1;
+      for (int c = 0; c < p.n_topo; c++) tile_topo[(size_t)c * cp + j] = p.topo[c][i];
+    }
+    tl.taint0 = s_taint - lo; tl.static0 = s_static - lo;
+    tl.alloc_cpu = s_acpu - lo; tl.alloc_mem = s_amem - lo; tl.req_cpu = s_rcpu - lo; tl.req_mem = s_rmem - lo;
+    tl.nz_cpu = s_zcpu - lo; tl.nz_mem = s_zmem - lo;
+    tl.alloc_pods = s_apods - lo; tl.npods = s_npods - lo; tl.score = s_score - lo;
+    tl.free_cpu = s_fcpu - lo; tl.free_mem = s_fmem - lo; tl.free_pods = s_fpods - lo;
+  } else {
+    tl.taint0 = (const unsigned long long *)p.taint_mask; tl.static0 = (const unsigned long long *)p.static_mask;
+    tl.alloc_cpu = (const long long *)p.alloc_cpu; tl.alloc_mem = (const long long *)p.alloc_mem;
+    tl.req_cpu = (long long *)p.req_cpu; tl.req_mem = (long long *)p.req_mem;
+    tl.nz_cpu = (long long *)p.nz_cpu; tl.nz_mem = (long long *)p.nz_mem;
+    tl.alloc_pods = p.alloc_pods; tl.npods = p.npods; tl.score = p.score_cache;
+    tl.free_cpu = nullptr; tl.free_mem = nullptr; tl.free_pods = nullptr;
+    for (int32_t i = lo + tid; i < hi; i += blockDim.x) p.score_cache[i] = -1;
+  }
+
+  // ---- prologue: template 0, replicated counters, pointer tables, PTS minima ----
   for (int k = tid; k < (int)(sizeof(ccsim_template) / 8); k += blockDim.x)
     reinterpret_cast<unsigned long long *>(&ws.tmpl)[k] = reinterpret_cast<const unsigned long long *>(&p.templates[0])[k];
-  for (int j = 0; j < p.n_counters; j++) {
-    const DevCounter &dc = p.counters[j];
-    if (dc.topo_col < 0) continue;   // node-local columns are restored by the host before the launch
-    int32_t *dst = dc.smem_off >= 0 ? smem_cnt + dc.smem_off : dc.work + (size_t)cta * dc.n_domains;
-    for (int d = tid; d < dc.n_domains; d += blockDim.x) dst[d] = dc.init[d];
+  {
+    int nl = 0;
+    for (int j = 0; j < p.n_counters; j++) {
+      const DevCounter &dc = p.counters[j];
+      if (dc.topo_col < 0) {   // node-local column (restored by the host before the launch)
+        int32_t *col = dc.work;
+        if (RESIDENT) {
+          int32_t *sc = tile_local + (size_t)nl * p.chunk_pad;
+          for (int32_t i = lo + tid; i < hi; i += blockDim.x) sc[i - lo] = dc.work[i];
+          col = sc - lo;
+        }
+        if (tid == 0) ws.cnt_ptr[j] = col;
+        nl++;
+        continue;
+      }
+      int32_t *dst = dc.smem_off >= 0 ? smem_cnt + dc.smem_off : dc.work + (size_t)cta * dc.n_domains;
+      for (int d = tid; d < dc.n_domains; d += blockDim.x) dst[d] = dc.init[d];
+      if (tid == 0) ws.cnt_ptr[j] = dst;
+    }
   }
-  if (tid == 0) { ws.aff_total = p.templates[0].aff_total_init; ws.winner = -1; ws.stop = 0; }
+  if (tid == 0) {
+    for (int c = 0; c < p.n_topo; c++) ws.topo_ptr[c] = RESIDENT ? (tile_topo + (size_t)c * p.chunk_pad - lo) : p.topo[c];
+    ws.aff_total = p.templates[0].aff_total_init; ws.winner = -1; ws.stop = 0; ws.dirty = 1;
+  }
   __syncthreads();
-  for (int c = 0; c < ws.tmpl.n_pts; c++) pts_recount(p, ws, smem_cnt, c);
+  for (int c = 0; c < ws.tmpl.n_pts; c++) pts_recount(p, c);
 
+#ifdef CCSIM_PHASE_TIMERS
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0;
+#endif
   long long k = 0;
+  uint32_t tag = 1;          // 1..4095; waves k and k+2 (same parity buffer) always differ
+  int32_t ti = 0;            // template of pod k = k % n_templates (report.go:160)
   for (;; k++) {
+    PH_START();
     // postBindHook limit (pkg/framework/simulator.go:300-305): checked after the k-th pod was bound
     if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ws.stop = 2; __syncthreads(); break; }
     if (p.n_templates > 1) {
-      const ccsim_template *src = &p.templates[k % p.n_templates];
+      const ccsim_template *src = &p.templates[ti];
       for (int q = tid; q < (int)(sizeof(ccsim_template) / 8); q += blockDim.x)
         reinterpret_cast<unsigned long long *>(&ws.tmpl)[q] = reinterpret_cast<const unsigned long long *>(src)[q];
+      if (tid == 0) ws.dirty = 1;
       __syncthreads();
     }
     const ccsim_template &t = ws.tmpl;
+    if (ws.dirty) {    // uniform: written before the last barrier
+      if (tid == 0) {
+        build_filter_consts(p, t, ti, ws.topo_ptr, ws.cnt_ptr, ws.ptsmin, ws.aff_total, ws.fc);
+        ws.sw.w_fit = (t.score_enable & CCSIM_PL_FIT) ? t.w_fit : 0;
+        ws.sw.w_balanced = ((t.score_enable & CCSIM_PL_BALANCED) && !(t.flags & CCSIM_TF_BALANCED_SKIP)) ? t.w_balanced : 0;
+        ws.sw.least_w_cpu = t.least_w_cpu; ws.sw.least_w_mem = t.least_w_mem;
+        for (int j = 0; j < p.n_counters; j++) {
+          const DevCounter &dc = p.counters[j];
+          CommitInfo &ci = ws.cinfo[j];
+          const bool skip = (dc.inc == 0) || (dc.is_aff && !(t.flags & CCSIM_TF_AFF_SELF_MATCH_ALL));
+          ci.inc = skip ? 0 : dc.inc;
+          ci.local = dc.topo_col < 0; ci.is_aff = dc.is_aff; ci.n_present = dc.n_present;
+          ci.gtopo = dc.topo_col < 0 ? nullptr : p.topo[dc.topo_col];
+          ci.ltopo = dc.topo_col < 0 ? nullptr : ws.topo_ptr[dc.topo_col];
+          ci.pts_idx = -1;
+          for (int c = 0; c < t.n_pts; c++) if (t.pts[c].counter == j && !t.pts[c].min_zero) ci.pts_idx = c;
+        }
+        ws.dirty = 0;
+      }
+      __syncthreads();
+    }
+    const FilterConsts &fc = ws.fc;
+    const HotConsts hc = load_hot(fc);
 
-    // ---- fused Filter + Score over this CTA's tile ----
+    // ---- fused Filter pass over this CTA's tile (+ memoised node-local score of the feasible nodes) ----
     unsigned long long best[CCSIM_MAX_CLASSES];
     #pragma unroll
     for (int c = 0; c < CCSIM_MAX_CLASSES; c++) best[c] = 0ull;
     for (int32_t i = lo + tid; i < hi; i += blockDim.x) {
-      int cls; int64_t sc;
-      if (eval_node(p, t, smem_cnt, ws.ptsmin, ws.aff_total, i, cls, sc)) {
+      int cls;
+      if (filter_node<RESIDENT>(p, hc, fc, tl, i, cls)) {
+        int32_t sc = use_cache ? tl.score[i] : -1;
+        if (sc < 0) {
+          sc = score_node(tl.alloc_cpu[i], tl.alloc_mem[i], tl.nz_cpu[i] + t.least_cpu, tl.nz_mem[i] + t.least_mem,
+                          tl.req_cpu[i] + t.bal_cpu, tl.req_mem[i] + t.bal_mem, ws.sw);
+          if (use_cache) tl.score[i] = sc;
+        }
         const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
         if (ncls == 1) best[0] = key > best[0] ? key : best[0];
         else {
@@ -148,96 +255,124 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
       v = warp_max_u64(v);
       if (lane == 0) ws.warp_best[warp][c] = v;
     }
+    PH_MARK(0);
     __syncthreads();                                                    // S1
+    PH_MARK(1);
 
     if (warp == 0) {
-      const unsigned long long tag = (unsigned long long)(k % 4095) + 1ull;   // 1..4095; waves k and k+2 (same parity buffer) differ
-      const unsigned long long tagbits = tag << KEY_TAG_SHIFT;
-      unsigned long long *myslots = p.slots + ((size_t)(k & 1) * p.grid + cta) * CCSIM_MAX_CLASSES;
+      const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
+      unsigned long long *myslots = p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
       // CTA arg-max per class, published as one tagged word each
       for (int c = 0; c < ncls; c++) {
         unsigned long long v = (lane < (int)(blockDim.x >> 5)) ? ws.warp_best[lane][c] : 0ull;
         v = warp_max_u64(v);
         if (lane == 0) st_slot(&myslots[c], v | tagbits);
       }
-      // gather every CTA's word (poll until its tag is this wave's)
-      const unsigned long long *all = p.slots + (size_t)(k & 1) * p.grid * CCSIM_MAX_CLASSES;
+      PH_MARK(2);
+      // gather every CTA's word: all of a lane's loads are in flight together; retry until every tag is this wave's
+      const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE;
       unsigned long long cbest[CCSIM_MAX_CLASSES];
       bool dead = false;
       for (int c = 0; c < ncls; c++) {
+        unsigned long long v[CCSIM_MAX_GRID / 32];
+        unsigned spins = 0;
+        bool pending;
+        do {
+          pending = false;
+          #pragma unroll
+          for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) {
+            const int b = lane + 32 * q;
+            v[q] = (b < p.grid) ? ld_slot(&all[(size_t)b * SLOT_STRIDE + c]) : tagbits;
+          }
+          #pragma unroll
+          for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) pending |= ((uint32_t)(v[q] >> KEY_TAG_SHIFT) != tag);
+          if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+        } while (__any_sync(0xffffffffu, pending));
         unsigned long long m = 0ull;
-        for (int b = lane; b < p.grid; b += 32) {
-          unsigned long long v;
-          unsigned spins = 0;
-          do {
-            v = ld_slot(&all[(size_t)b * CCSIM_MAX_CLASSES + c]);
-            if (++spins > WATCHDOG_SPINS) { dead = true; break; }
-          } while ((v >> KEY_TAG_SHIFT) != tag);
-          v &= KEY_BODY_MASK;
-          m = v > m ? v : m;
-        }
+        #pragma unroll
+        for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const unsigned long long b = v[q] & KEY_BODY_MASK; m = b > m ? b : m; }
         cbest[c] = warp_max_u64(m);
       }
       dead = __any_sync(0xffffffffu, dead);
+      PH_MARK(3);
       // prioritizeNodes + selectHost over the class winners (schedule_one.go:776-941)
-      int maxraw = 0;
-      for (int c = 0; c < ncls; c++) if (cbest[c] != 0ull) maxraw = c;
-      unsigned long long wkey = 0ull;
-      for (int c = 0; c < ncls; c++) {
-        if (cbest[c] == 0ull) continue;
-        int64_t total = key_score(cbest[c]);
-        if (t.score_enable & CCSIM_PL_TAINT_TOLERATION) total += (int64_t)t.w_taint * taint_norm(c, maxraw);
-        const unsigned long long kk = pack_key(total, key_index(cbest[c]));
-        wkey = kk > wkey ? kk : wkey;
+      unsigned long long wkey = cbest[0];
+      if (ncls > 1 || (t.score_enable & CCSIM_PL_TAINT_TOLERATION)) {
+        int maxraw = 0;
+        for (int c = 0; c < ncls; c++) if (cbest[c] != 0ull) maxraw = c;
+        wkey = 0ull;
+        for (int c = 0; c < ncls; c++) {
+          if (cbest[c] == 0ull) continue;
+          int64_t total = key_score(cbest[c]);
+          if (t.score_enable & CCSIM_PL_TAINT_TOLERATION) total += (int64_t)t.w_taint * taint_norm(c, maxraw);
+          const unsigned long long kk = pack_key(total, key_index(cbest[c]));
+          wkey = kk > wkey ? kk : wkey;
+        }
       }
       if (lane == 0) {
         if (dead) { ws.stop = 3; ws.winner = -1; }
         else if (wkey == 0ull) { ws.stop = 1; ws.winner = -1; }
         else ws.winner = (int32_t)key_index(wkey);
       }
-      __syncwarp();
       // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
       if (!dead && wkey != 0ull) {
         const int32_t g = (int32_t)key_index(wkey);
         const int32_t w = g - p.node_base;
         const bool mine = (w >= lo && w < hi);
-        if (mine && lane == 0) {
-          p.req_cpu[w] += t.req_cpu; p.req_mem[w] += t.req_mem; p.req_eph[w] += t.req_eph;
-          for (int q = 0; q < p.n_scalars; q++) p.req_scalar[q][w] += t.req_scalar[q];
-          p.nz_cpu[w] += t.nz_cpu; p.nz_mem[w] += t.nz_mem;
-          p.npods[w] += 1;
-          if (p.placed_mask) p.placed_mask[w] |= 1ull << (k % p.n_templates);
+        if (mine && lane == 31) {
+          const long long rc = tl.req_cpu[w] + t.req_cpu, rm = tl.req_mem[w] + t.req_mem;
+          const long long zc = tl.nz_cpu[w] + t.nz_cpu, zm = tl.nz_mem[w] + t.nz_mem;
+          const int32_t np = tl.npods[w] + 1;
+          tl.req_cpu[w] = rc; tl.req_mem[w] = rm; tl.nz_cpu[w] = zc; tl.nz_mem[w] = zm; tl.npods[w] = np;
+          tl.score[w] = -1;    // this node's NodeInfo generation changed
+          if (RESIDENT) {      // write through: the global columns stay the authoritative snapshot-after-run
+            tl.free_cpu[w] = tl.alloc_cpu[w] - rc; tl.free_mem[w] = tl.alloc_mem[w] - rm; tl.free_pods[w] = tl.alloc_pods[w] - np;
+            p.req_cpu[w] = rc; p.req_mem[w] = rm; p.nz_cpu[w] = zc; p.nz_mem[w] = zm; p.npods[w] = np;
+          }
+          if (t.req_eph != 0) p.req_eph[w] += t.req_eph;
+          for (int q = 0; q < p.n_scalars; q++) if (t.req_scalar[q] != 0) p.req_scalar[q][w] += t.req_scalar[q];
+          if (p.placed_mask) p.placed_mask[w] |= 1ull << ti;
           // ClusterCapacityBinder.Bind + postBindHook: record pod k -> node (plugin.go:34-53; simulator.go:297-312)
           if (k < p.pod_cap) p.pod_node[k] = g; else ws.stop = 3;
         }
-        // per-domain counters: every CTA applies the same update to its own replica
+        // per-domain counters: every CTA applies the same update to its own replica, one lane per counter
         // (the next cycle's PreFilter recount would see this clone: podtopologyspread/filtering.go:255-289,
         //  interpodaffinity/filtering.go:234-271)
-        if (lane == 0) {
-          for (int j = 0; j < p.n_counters; j++) {
-            const DevCounter &dc = p.counters[j];
-            if (dc.inc == 0) continue;
-            if (dc.is_aff && !(t.flags & CCSIM_TF_AFF_SELF_MATCH_ALL)) continue;
-            if (dc.topo_col < 0) { if (mine) dc.work[w] += dc.inc; if (dc.is_aff) ws.aff_total += dc.inc; continue; }
-            const int32_t dom = p.topo[dc.topo_col][w];   // single-GPU: the winner is always a local node
-            if (dom < 0) continue;
-            int32_t *cnt = dc.smem_off >= 0 ? smem_cnt + dc.smem_off : dc.work + (size_t)cta * dc.n_domains;
-            const int32_t old = cnt[dom];
-            cnt[dom] = old + dc.inc;
-            if (dc.is_aff) ws.aff_total += dc.inc;
-            for (int c = 0; c < t.n_pts; c++) {
-              if (t.pts[c].counter != j || t.pts[c].min_zero) continue;
-              if (dom < dc.n_present && old == ws.ptsmin[c]) ws.ptsnum[c] -= 1;   // left the minimum level
+        if (lane < p.n_counters) {
+          const int j = lane;
+          const CommitInfo ci = ws.cinfo[j];
+          if (ci.inc) {
+            if (ci.local) {
+              if (mine) {
+                const int32_t nv = ws.cnt_ptr[j][w] + ci.inc;
+                ws.cnt_ptr[j][w] = nv;
+                if (RESIDENT) p.counters[j].work[w] = nv;
+              }
+              if (ci.is_aff) { atomicAdd((unsigned long long *)&ws.aff_total, (unsigned long long)ci.inc); ws.dirty = 1; }
+            } else {
+              // the winner's domain id: from this CTA's tile if it owns the node, else from the global column (L2)
+              const int32_t dom = mine ? ci.ltopo[w] : ci.gtopo[w];
+              if (dom >= 0) {
+                int32_t *cnt = ws.cnt_ptr[j];
+                const int32_t old = cnt[dom];
+                cnt[dom] = old + ci.inc;
+                if (ci.is_aff) { atomicAdd((unsigned long long *)&ws.aff_total, (unsigned long long)ci.inc); ws.dirty = 1; }
+                if (ci.pts_idx >= 0 && dom < ci.n_present && old == ws.ptsmin[ci.pts_idx]) ws.ptsnum[ci.pts_idx] -= 1;
+              }
             }
           }
         }
       }
     }
+    PH_MARK(4);
     __syncthreads();                                                    // S2
+    PH_MARK(5);
     if (ws.stop) break;
     // a PTS minimum whose last domain moved up: recount (rare: once per n_present commits at that level)
     for (int c = 0; c < t.n_pts; c++)
-      if (!t.pts[c].min_zero && ws.ptsnum[c] <= 0 && p.counters[t.pts[c].counter].n_present > 0) pts_recount(p, ws, smem_cnt, c);
+      if (!t.pts[c].min_zero && ws.ptsnum[c] <= 0 && p.counters[t.pts[c].counter].n_present > 0) pts_recount(p, c);
+    tag = (tag == 4095u) ? 1u : tag + 1u;
+    ti = (ti + 1 == p.n_templates) ? 0 : ti + 1;
   }
 
   // ---- epilogue ----
@@ -245,7 +380,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
     for (int j = 0; j < p.n_counters; j++) {
       const DevCounter &dc = p.counters[j];
       if (dc.topo_col < 0) continue;
-      const int32_t *src = dc.smem_off >= 0 ? smem_cnt + dc.smem_off : dc.work;
+      const int32_t *src = ws.cnt_ptr[j];
       for (int d = tid; d < dc.n_domains; d += blockDim.x) p.final_cnt[p.final_off[j] + d] = src[d];
     }
     if (tid == 0) {
@@ -257,6 +392,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
       o->evals = o->waves * (long long)p.n;
       for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ws.ptsmin[c];
       o->aff_total = ws.aff_total;
+#ifdef CCSIM_PHASE_TIMERS
+      for (int q = 0; q < 8; q++) o->phase_cycles[q] = ph[q];
+#endif
     }
   }
 }
@@ -404,6 +542,9 @@ struct ccsim_handle {
   ccsim_config cfg;
   int sm_count = 0;
   size_t l2_bytes = 0;
+  size_t smem_optin = 0;
+  int last_resident = 0;
+  int last_lean = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -427,6 +568,7 @@ struct ccsim_handle {
   int32_t *w_npods = nullptr;
   int64_t *w_req_scalar[CCSIM_MAX_SCALARS] = {};
   uint64_t *w_placed = nullptr;
+  int32_t *w_score = nullptr;
   int32_t *d_taint_off = nullptr; uint8_t *d_taint_list = nullptr;
   int64_t pod_bound = 0;       // sum over nodes of max(0, alloc_pods - npods): no run can place more
   int max_prefer_pop = 0;      // max over nodes of popcount(taint & prefer): number of normalisation classes - 1
@@ -443,6 +585,7 @@ struct ccsim_handle {
   int32_t *d_pod_node = nullptr; int64_t pod_cap = 0;
   std::vector<int32_t> h_pod_node;
   DevOut *d_out = nullptr;
+  DevParams *d_params = nullptr;
   int64_t last_placed = 0;
   void *d_flush = nullptr; size_t flush_bytes = 0;
 };
@@ -501,9 +644,15 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
   cudaMalloc((void **)&h->d_out, sizeof(DevOut));
-  cudaMalloc((void **)&h->d_slots, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * CCSIM_MAX_CLASSES);
-  cudaFuncSetAttribute(ccsim_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(sizeof(WaveShared) + SMEM_CNT_MAX_INTS * sizeof(int32_t)));
+  cudaMalloc((void **)&h->d_params, sizeof(DevParams));
+  cudaMalloc((void **)&h->d_slots, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * SLOT_STRIDE);
+  h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  cudaFuncSetAttribute(ccsim_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(h->smem_optin - sizeof(WaveShared) - 1024));
+  cudaFuncSetAttribute(ccsim_wave_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(h->smem_optin - sizeof(LeanShared) - 1024));
+  cudaFuncSetAttribute(ccsim_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(SMEM_CNT_MAX_INTS * sizeof(int32_t) + 16));
   *out = h;
   return CCSIM_OK;
 }
@@ -513,7 +662,7 @@ extern "C" void ccsim_destroy(ccsim_handle *h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   free_pool(h->allocs); free_pool(h->tmpl_allocs);
-  cudaFree(h->d_out); cudaFree(h->d_slots); cudaFree(h->d_pod_node); cudaFree(h->d_flush);
+  cudaFree(h->d_out); cudaFree(h->d_params); cudaFree(h->d_slots); cudaFree(h->d_pod_node); cudaFree(h->d_flush);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -567,6 +716,7 @@ extern "C" int ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nd) {
   for (int k = 0; k < nd->n_scalars; k++) WK(w_req_scalar[k], int64_t);
   h->w_placed = nullptr;
   if (nd->has_placed_mask) WK(w_placed, uint64_t);
+  WK(w_score, int32_t);
 #undef WK
   h->d_taint_off = nullptr; h->d_taint_list = nullptr;
   if (nd->taint_list_off && nd->taint_list && n > 0) {
@@ -668,7 +818,7 @@ static void fill_params(ccsim_handle *h, DevParams &p, int64_t max_pods) {
   p.taint_mask = h->d_taint; p.static_mask = h->d_static;
   for (int k = 0; k < nd.n_topo_cols; k++) p.topo[k] = h->d_topo[k];
   p.req_cpu = h->w_req_cpu; p.req_mem = h->w_req_mem; p.req_eph = h->w_req_eph; p.nz_cpu = h->w_nz_cpu; p.nz_mem = h->w_nz_mem;
-  p.npods = h->w_npods; p.placed_mask = h->w_placed;
+  p.npods = h->w_npods; p.placed_mask = h->w_placed; p.score_cache = h->w_score;
   for (int w = 0; w < CCSIM_MAX_TAINT_WORDS; w++) { p.taint_nosched[w] = nd.taint_nosched[w]; p.taint_prefer[w] = nd.taint_prefer[w]; }
   p.templates = h->d_templates;
   for (int j = 0; j < h->n_counters; j++) { p.counters[j] = h->counters[j]; p.final_off[j] = h->final_off[j]; }
@@ -712,7 +862,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
         CK(cudaMemcpyAsync(h->counters[j].work, h->counters[j].init, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
   }
   CK(cudaMemsetAsync(h->d_out, 0, sizeof(DevOut), s));
-  CK(cudaMemsetAsync(h->d_slots, 0, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * CCSIM_MAX_CLASSES, s));
+  CK(cudaMemsetAsync(h->d_slots, 0, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * SLOT_STRIDE, s));
 
   if (n == 0) {   // ErrNoNodesAvailable (scheduler.go:68): nothing to evaluate; the host formats the message
     out->placed = 0; out->stop_code = CCSIM_STOP_UNSCHEDULABLE; out->pod_node = nullptr;
@@ -729,13 +879,76 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   fill_params(h, p, max_pods);
   p.grid = grid;
   p.chunk = (n + grid - 1) / grid;
-  const size_t smem = sizeof(WaveShared) + (size_t)h->smem_cnt_ints * sizeof(int32_t);
+  // resident mode: every column the Filter/Score pass reads is staged into shared memory once
+  int n_local = 0;
+  for (int j = 0; j < h->n_counters; j++) if (h->counters[j].topo_col < 0) n_local++;
+  p.n_local = n_local;
+  p.chunk_pad = (p.chunk + 3) & ~3;
+  p.smem_cnt_ints = h->smem_cnt_ints;
+  const size_t cnt_bytes = ((size_t)h->smem_cnt_ints * 4 + 15) & ~(size_t)15;
+  const size_t per_node = 8 * (9 + (h->meta.static_words > 0 ? 1 : 0)) + 4 * (4 + h->meta.n_topo_cols + n_local);
+  const size_t smem_res = cnt_bytes + per_node * (size_t)p.chunk_pad;
+  const size_t smem_str = cnt_bytes;
+  const bool resident = smem_res + sizeof(WaveShared) + 1024 <= h->smem_optin && !getenv("CCSIM_FORCE_STREAMING");
+  p.tile_resident = resident ? 1 : 0;
+  h->last_resident = p.tile_resident;
+  size_t smem = resident ? smem_res : smem_str;
+  const void *kern = resident ? (const void *)ccsim_wave_kernel<true> : (const void *)ccsim_wave_kernel<false>;
+  int block = BLOCK_THREADS;
+  // lean resident kernel: the common case (see ccsim_lean.cuh for the eligibility rules)
+  LeanParams lp; memset(&lp, 0, sizeof(lp));
+  // measured on B200 (profiles/r1_kernel_variants.md): the lean kernel wins when per-domain terms are present (C4),
+  // the generic resident kernel wins on purely node-local templates; CCSIM_FORCE_LEAN / CCSIM_FORCE_GENERIC override.
+  bool lean = resident && h->n_templates == 1 && h->meta.taint_words == 1 && h->meta.static_words <= 1 &&
+              (h->n_counters > 0 || getenv("CCSIM_FORCE_LEAN")) && !getenv("CCSIM_FORCE_GENERIC");
+  if (lean) {
+    const ccsim_template &T = h->h_templates[0];
+    const bool nzfit = (T.filter_enable & CCSIM_PL_FIT) && !(T.flags & CCSIM_TF_FIT_ALL_ZERO);
+    if (nzfit && T.req_eph > 0) lean = false;
+    if (nzfit) for (int k = 0; k < h->meta.n_scalars; k++) if (T.req_scalar[k] != 0) lean = false;
+    if ((T.filter_enable & CCSIM_PL_NODE_AFFINITY) && (T.flags & CCSIM_TF_HAS_AFFINITY_TERMS)) lean = false;
+    if ((T.filter_enable & CCSIM_PL_NODE_NAME) && T.nodename_idx >= 0) lean = false;
+    if (T.flags & CCSIM_TF_PREFILTER_NODES) lean = false;
+    if ((T.filter_enable & CCSIM_PL_NODE_PORTS) && (T.flags & CCSIM_TF_HAS_HOST_PORTS) && h->w_placed) lean = false;
+    if (T.n_pts + T.n_aff + T.n_anti > LEAN_MAX_TERMS) lean = false;
+    int ns = 0;
+    for (int j = 0; j < h->n_counters && lean; j++) {
+      const DevCounter &dc = h->counters[j];
+      if (dc.topo_col >= 0 && dc.smem_off < 0) { lean = false; break; }
+      int slot = -1;
+      if (dc.topo_col >= 0) for (int q = 0; q < ns; q++) if (lp.slot_topo[q] == dc.topo_col) slot = q;
+      if (slot < 0) {
+        if (ns >= LEAN_MAX_SLOTS) { lean = false; break; }
+        slot = ns++;
+        lp.slot_topo[slot] = dc.topo_col >= 0 ? dc.topo_col : -1;
+        lp.slot_counter[slot] = dc.topo_col >= 0 ? -1 : j;
+      }
+      lp.counter_slot[j] = slot;
+    }
+    if (lean) {
+      lp.n_slots = ns;
+      int units = (10 + ns + 3) / 4;
+      if ((units & 1) == 0) units++;
+      lp.stride_u = units;
+      const int want1024 = (n + LEAN_THREADS - 1) / LEAN_THREADS;
+      (void)want1024;
+      lp.rec_bytes_total = (uint32_t)((size_t)units * 16 * p.chunk_pad);
+      const size_t smem_lean = cnt_bytes + lp.rec_bytes_total + (size_t)p.chunk_pad * (6 * 8 + 2 * 4);
+      if (smem_lean + sizeof(LeanShared) + 1024 > h->smem_optin) lean = false;
+      else { smem = smem_lean; kern = (const void *)ccsim_wave_lean_kernel; block = LEAN_THREADS; }
+    }
+  }
+  h->last_lean = lean ? 1 : 0;
+  p.self = h->d_params;
+  CK(cudaMemcpyAsync(h->d_params, &p, sizeof(DevParams), cudaMemcpyHostToDevice, s));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel, BLOCK_THREADS, smem));
+  if (lean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel, block, smem));
+  else if (resident) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<true>, block, smem));
+  else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<false>, block, smem));
   if (occ < 1 || occ * h->sm_count < grid) return fail(h, CCSIM_ECUDA, "persistent grid %d does not fit (occupancy %d x %d SMs)", grid, occ, h->sm_count);
-  void *args[] = { (void *)&p };
+  void *args[] = { (void *)&p, (void *)&lp };
   CK(cudaEventRecord(h->ev0, s));
-  CK(cudaLaunchCooperativeKernel((const void *)ccsim_wave_kernel, dim3(grid), dim3(BLOCK_THREADS), args, smem, s));
+  CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));
   h->launches++;
   CK(cudaEventRecord(h->ev1, s));
   DevOut ho;
@@ -743,6 +956,13 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   CK(cudaStreamSynchronize(s));
   if (ho.error) return fail(h, CCSIM_ECUDA, "wave kernel aborted (error %d: %s)", ho.error, ho.error == 1 ? "exchange watchdog / output overflow" : "?");
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+#ifdef CCSIM_PHASE_TIMERS
+  fprintf(stderr, "[ccsim %s tile %zu B smem] ", lean ? "lean" : (resident ? "resident" : "streaming"), smem);
+  fprintf(stderr, "[ccsim phases, CTA0 cycles/wave] scan=%.0f S1=%.0f publish=%.0f gather=%.0f commit=%.0f S2=%.0f (waves=%lld, %.3f ms)\n",
+          (double)ho.phase_cycles[0] / ho.waves, (double)ho.phase_cycles[1] / ho.waves, (double)ho.phase_cycles[2] / ho.waves,
+          (double)ho.phase_cycles[3] / ho.waves, (double)ho.phase_cycles[4] / ho.waves, (double)ho.phase_cycles[5] / ho.waves,
+          (long long)ho.waves, ms);
+#endif
   out->placed = ho.placed; out->stop_code = ho.stop_code; out->waves = ho.waves; out->evals = ho.evals; out->run_ms = ms;
   h->last_placed = ho.placed;
   if (ho.stop_code == CCSIM_STOP_UNSCHEDULABLE) {

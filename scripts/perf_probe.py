@@ -1,0 +1,26 @@
+"""Quick device-time probe of the wave kernel on the BASELINE configs (not the bench contract; see bench.py)."""
+import importlib, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+abi = importlib.import_module("cluster-capacity_b200._abi")
+synth = importlib.import_module("cluster-capacity_b200.synth")
+engine = importlib.import_module("cluster-capacity_b200.engine")
+
+def probe(name, snap, tmpl, ctr, limit, bytes_per_eval):
+    with engine.Engine(device=0) as eng:
+        t0 = time.time(); eng.load_nodes(snap); eng.set_templates(tmpl, ctr); t1 = time.time()
+        r = eng.run(limit)
+        r = eng.run(limit)
+        info = eng.device_info()
+    us = r.run_ms * 1e3 / max(1, r.waves)
+    print("%-28s n=%-8d grid=%-4d placed=%-8d waves=%-8d run=%9.3f ms  %6.2f us/wave  %.3g evals/s  %.0f GB/s algorithmic  (load %.1f ms)" % (
+        name, snap.n, info["grid"], r.placed, r.waves, r.run_ms, us, r.evals / (r.run_ms * 1e-3),
+        r.evals * bytes_per_eval / (r.run_ms * 1e-3) / 1e9, (t1 - t0) * 1e3), flush=True)
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
+    if "c2" in which: probe("C2 10k fit-only", *synth.c2(), 20000, 72)
+    if "c2big" in which: probe("C2 100k fit-only", *synth.c2(n=100_000), 20000, 72)
+    if "c3" in which: probe("C3 50k full filters", *synth.c3(), 20000, 88)
+    if "c4" in which: probe("C4 100k PTS+IPA", *synth.c4(), 0, 96)
+    if "c5" in which: probe("C5 1M x 64 templates", *synth.c5(), 6400, 72)
