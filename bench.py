@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the cluster-capacity hot path.
+
+One "step" = one complete capacity analysis (ClusterCapacity.Run: place clones of the podspec until one does not fit)
+of the synthetic BASELINE config C4: 100 000 nodes, 3 DoNotSchedule topology-spread constraints (zone/rack/region) +
+required hostname anti-affinity, 200 000 pre-existing pods (cluster-capacity_b200/synth.py, seed 3).
+
+  value     predicate-evals/s with the snapshot already resident in HBM (ccsim_run only)
+  e2e       the same metric through the C-ABI with HOST buffers: ccsim_load_nodes (H2D from pinned memory) +
+            ccsim_set_templates + ccsim_run + result read-back inside the timed region
+  roofline  algorithmic bytes (96 B per predicate-eval for C4) / wave-kernel time vs the measured HBM peak
+  cpu_baseline / --impl reference: the CPU oracle (a port of the reference's loop; no Go toolchain exists to run the
+            reference itself) on the box's host cores, on a bounded prefix of the same workload.
+
+N > 1 (torchrun): every rank analyses its own replica of the workload on its own GPU (no collective on the data path;
+"replicas only" until the node-sharded multi-GPU run lands) — weak scaling, value = sum over ranks / max time.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+abi = importlib.import_module("cluster-capacity_b200._abi")
+synth = importlib.import_module("cluster-capacity_b200.synth")
+
+WORKLOAD = "C4: 100k nodes, 3x PodTopologySpread(DoNotSchedule zone/rack/region) + hostname anti-affinity, 200k existing pods"
+B_EVAL = 96  # algorithmic bytes per predicate-eval for C4
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def usable_cores():
+    """Host threads this process may really use: min(cpu_count, affinity mask, cgroup cpu quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_oracle_rate(snap, tmpl, ctr, budget_s=20.0):
+    """Times the CPU oracle on a bounded prefix of the workload. The OpenMP node-axis split is calibrated first (the
+    reference's own default is 16 goroutines, KS:apis/config/v1/defaults.go:108-110): the best of a few thread counts
+    up to the usable cores is used, so that the baseline is as strong as this host allows."""
+    from oracle import binding as oracle
+    cores = usable_cores()
+    cand = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores} | {min(cores, 16)})
+    best, best_rate = cand[0], 0.0
+    for c in cand:
+        oracle.run(snap, tmpl, ctr, max_pods=4, threads=c)
+        t0 = time.perf_counter()
+        r = oracle.run(snap, tmpl, ctr, max_pods=24, threads=c)
+        rate = r.evals / (time.perf_counter() - t0)
+        if rate > best_rate:
+            best, best_rate = c, rate
+    pods = int(max(50, min(20000, budget_s * best_rate / max(1, snap.n))))
+    t0 = time.perf_counter()
+    r = oracle.run(snap, tmpl, ctr, max_pods=pods, threads=best)
+    dt = time.perf_counter() - t0
+    return r, dt, best, cores, pods
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation is Go (no toolchain here), so this arm times the CPU
+    oracle port of the same loop with all host threads on a bounded prefix of the same workload. Rank 0 only."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    snap, tmpl, ctr = synth.c4()
+    steps = max(1, min(args.steps, 3))
+    evals = placed = 0
+    dt = 0.0
+    threads = cores = pods = 0
+    for _ in range(steps):
+        r, d, threads, cores, pods = cpu_oracle_rate(snap, tmpl, ctr, budget_s=15.0)
+        evals += r.evals
+        placed += r.placed
+        dt += d
+    val = evals / dt
+    line = {
+        "impl": "reference", "metric": "predicate-evals/sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "first %d placements of the run" % pods,
+                   "note": "no Go toolchain: the CPU oracle (C port of the reference loop, canonical mode) stands in for the reference"},
+        "placements_per_sec": placed / dt,
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port", "usable_cores": cores,
+                         "sample": "first %d placements (%d evals) per step, OpenMP over the node axis, thread count calibrated" % (pods, evals // steps)},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def pinned_snapshot(snap):
+    """Copy the snapshot's arrays into pinned host memory (torch) so that the e2e H2D copies are real DMA transfers."""
+    import torch
+    keep = []
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+
+    s2 = abi.Snapshot(snap.n, pin(snap.alloc_cpu), pin(snap.alloc_mem), pin(snap.alloc_pods), alloc_eph=pin(snap.alloc_eph),
+                      req_cpu=pin(snap.req_cpu), req_mem=pin(snap.req_mem), req_eph=pin(snap.req_eph), npods=pin(snap.npods),
+                      nz_cpu=pin(snap.nz_cpu), nz_mem=pin(snap.nz_mem), taint_mask=pin(snap.taint_mask),
+                      taint_nosched=snap.taint_nosched, taint_prefer=snap.taint_prefer,
+                      static_mask=pin(snap.static_mask) if snap.static_words else None, topo=[pin(t) for t in snap.topo])
+    s2._pins = keep
+    nbytes = sum(t.numel() * t.element_size() for t in keep)
+    return s2, nbytes
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    engine = importlib.import_module("cluster-capacity_b200.engine")
+
+    snap, tmpl, ctr = synth.c4()
+    psnap, h2d_bytes = pinned_snapshot(snap)
+    ctr_bytes = sum(c.n_domains * 4 for c in ctr)
+    warm = max(3, args.warmup)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = engine.Engine(device=local)
+    eng.load_nodes(psnap)
+    eng.set_templates(tmpl, ctr)
+    for _ in range(warm):
+        res = eng.run(0)
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- resident-input arm: K steps, L2 flushed (untimed) between steps, each step bracketed by a synchronize ----
+    launches0 = eng.kernel_launches()
+    step_wall = []
+    kernel_ms = 0.0
+    evals = placed = waves = 0
+    barrier()
+    for _ in range(args.steps):
+        eng.flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = eng.run(0)
+        torch.cuda.synchronize()
+        step_wall.append(time.perf_counter() - t0)
+        kernel_ms += res.run_ms
+        evals += res.evals
+        placed += res.placed
+        waves += res.waves
+    barrier()
+    flushes = args.steps
+    launches = eng.kernel_launches() - launches0 - flushes
+    t_total = sum(step_wall)
+    # ---- end-to-end arm: host buffers -> C-ABI -> results on the host, everything inside the timed region ----
+    e2e_wall = []
+    e2e_evals = 0
+    d2h = 0
+    for it in range(args.steps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.load_nodes(psnap)          # H2D of every column (pinned source)
+        eng.set_templates(tmpl, ctr)   # H2D of the template table + per-domain counters
+        r2 = eng.run(0)                # run + D2H of pod->node, histogram, counters
+        torch.cuda.synchronize()
+        if it > 0:                     # first iteration warms the allocator
+            e2e_wall.append(time.perf_counter() - t0)
+            e2e_evals += r2.evals
+            d2h = r2.placed * 4 + abi.C.sizeof(abi.Result)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    # max over ranks of the timed regions, sum of the work
+    vals = torch.tensor([t_total, sum(e2e_wall), kernel_ms], dtype=torch.float64, device="cuda")
+    work = torch.tensor([float(evals), float(placed), float(e2e_evals)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    t_total, t_e2e, kernel_ms_max = [float(x) for x in vals.tolist()]
+    evals_all, placed_all, e2e_evals_all = [float(x) for x in work.tolist()]
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        achieved = (evals * B_EVAL) / (kernel_ms * 1e-3) / 1e9     # this rank's kernel: GB/s of algorithmic bytes
+        line = {
+            "metric": "predicate-evals/sec", "value": evals_all / t_total, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "nodes": snap.n, "templates": 1, "mode": "canonical (percentageOfNodesToScore=100)",
+                       "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (2x L2 write, untimed); the 10 MB snapshot is re-read from HBM once per step and then lives in shared memory",
+                       "bytes_per_eval_algorithmic": B_EVAL, "placed_per_step": int(placed / args.steps),
+                       "waves_per_step": int(waves / args.steps)},
+            "placements_per_sec": placed_all / t_total,
+            "kernel_ms_per_step": kernel_ms / args.steps,
+            "e2e": {"value": e2e_evals_all / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_bytes + ctr_bytes + len(tmpl) * abi.C.sizeof(abi.Template)),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": peak_kind,
+                         "note": "algorithmic bytes = evals x 96 B (SURVEY.md §8d) over the wave kernel's CUDA-event time; the node tiles are shared-memory resident, so DRAM traffic is ~0 (see profiles/)"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            rc, dtc, threads, cores, pods = cpu_oracle_rate(snap, tmpl, ctr, budget_s=15.0)
+            line["cpu_baseline"] = {"value": rc.evals / dtc, "unit": "evals/s", "cores": threads, "kind": "port", "usable_cores": cores,
+                                    "sample": "first %d placements of the same run (%d evals, %.1f s), OpenMP thread count calibrated" % (pods, rc.evals, dtc)}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

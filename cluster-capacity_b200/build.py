@@ -10,13 +10,25 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-lcudart", "-ldl"]
 
 
+HOST_DIR = os.path.join(_HERE, "csrc", "host")
+HOST_SRC = [os.path.join(HOST_DIR, "cchost.cpp")]
+HOST_DEPS = HOST_SRC + [os.path.join(HOST_DIR, f) for f in ("json.hpp", "quantity.hpp", "objects.hpp", "encoder.hpp")] + [
+    os.path.join(_HERE, "..", "include", "cchost.h"), os.path.join(_HERE, "..", "include", "ccsim.h")]
+HOST_OUT = os.path.join(_HERE, "libcchost.so")
+
+
 def build(force=False, verbose=False):
+    """libccsim.so (CUDA, sm_100a) then libcchost.so (C++ host side, links libccsim via $ORIGIN rpath)."""
+    DEPS.append(os.path.join(_HERE, "csrc", "ccsim_lean.cuh"))
     newest = max(os.path.getmtime(p) for p in DEPS)
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
-        return OUT
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
-    subprocess.check_call(cmd)
+    if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+        subprocess.check_call(cmd)
+    newest = max([os.path.getmtime(p) for p in HOST_DEPS] + [os.path.getmtime(OUT)])
+    if force or not os.path.exists(HOST_OUT) or os.path.getmtime(HOST_OUT) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", HOST_OUT] + HOST_SRC +
+                              ["-L" + _HERE, "-lccsim", "-Wl,-rpath,$ORIGIN"])
     return OUT
 
 

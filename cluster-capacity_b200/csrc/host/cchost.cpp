@@ -1,0 +1,425 @@
+// cchost.cpp — libcchost.so: the host side of the hot path, mirroring the reference's pkg/framework surface
+// (ClusterCapacity New / SyncWithClient / Run / Report / Close and ClusterCapacityReviewPrint) on top of libccsim.
+// See include/cchost.h for the mapping to reference file:line.
+#include <chrono>
+#include <cstdarg>
+#include <ctime>
+#include <sstream>
+#include "../../../include/cchost.h"
+#include "encoder.hpp"
+
+using namespace cch;
+
+namespace {
+
+const char *kReasonText[CCSIM_R_FIXED_COUNT] = {
+    "node(s) were unschedulable",                                          // nodeunschedulable/node_unschedulable.go:49
+    "node(s) didn't match the requested node name",                        // nodename/node_name.go:43
+    "node(s) didn't match Pod's node affinity/selector",                   // nodeaffinity/node_affinity.go:64
+    "node(s) didn't have free ports for the requested pod ports",          // nodeports/node_ports.go:51
+    "Too many pods", "Insufficient cpu", "Insufficient memory", "Insufficient ephemeral-storage",   // noderesources/fit.go:567-616
+    "node(s) didn't match pod topology spread constraints (missing required label)",                 // podtopologyspread/filtering.go
+    "node(s) didn't match pod topology spread constraints",
+    "node(s) didn't match pod affinity rules",                             // interpodaffinity/filtering.go:36-42
+    "node(s) didn't match pod anti-affinity rules",
+    "node(s) didn't satisfy existing pods anti-affinity rules",
+    "node(s) didn't satisfy plugin(s) [NodeAffinity]",                     // schedule_one.go:533
+};
+
+// FitError.Error() (framework/types.go:787-838): "0/N nodes are available: <sorted 'count reason'>."
+std::string fit_error_body(int n, const std::vector<std::pair<std::string, int64_t>> &hist) {
+  std::string msg = "0/" + std::to_string(n) + " nodes are available:";
+  std::vector<std::string> strs;
+  for (auto &kv : hist) if (kv.second) strs.push_back(std::to_string(kv.second) + " " + kv.first);
+  std::sort(strs.begin(), strs.end());
+  if (!strs.empty()) {
+    msg += " ";
+    for (size_t i = 0; i < strs.size(); i++) { if (i) msg += ", "; msg += strs[i]; }
+    msg += ".";
+  }
+  return msg;
+}
+
+std::string rfc3339_now() {
+  using namespace std::chrono;
+  auto now = system_clock::now();
+  time_t t = system_clock::to_time_t(now);
+  long ns = (long)(duration_cast<nanoseconds>(now.time_since_epoch()).count() % 1000000000LL);
+  struct tm g; gmtime_r(&t, &g);
+  char buf[64]; strftime(buf, sizeof(buf), "%Y-%m-%dT%H:%M:%S", &g);
+  char frac[16]; snprintf(frac, sizeof(frac), "%09ld", ns);
+  std::string f(frac);
+  while (!f.empty() && f.back() == '0') f.pop_back();
+  return std::string(buf) + (f.empty() ? "" : "." + f) + "Z";
+}
+
+// ---- YAML emitter for the report (sigs.k8s.io/yaml: JSON -> map -> go-yaml, keys sorted) ----
+bool yaml_plain_ok(const std::string &s) {
+  if (s.empty()) return false;
+  static const char *special[] = {"null", "Null", "NULL", "~", "true", "True", "TRUE", "false", "False", "FALSE", "yes", "Yes", "no", "No", "on", "off", "y", "n"};
+  for (auto *w : special) if (s == w) return false;
+  char c0 = s[0];
+  if (strchr("-?:,[]{}#&*!|>'\"%@` ", c0)) return false;
+  if (isdigit((unsigned char)c0) || c0 == '.' || c0 == '+') {   // could parse as a number
+    char *e = nullptr; strtod(s.c_str(), &e);
+    if (e && *e == 0) return false;
+  }
+  if (s.back() == ' ' || s.back() == ':') return false;
+  for (size_t i = 0; i < s.size(); i++) {
+    unsigned char c = (unsigned char)s[i];
+    if (c < 0x20 || c == 0x7f) return false;
+    if (c == ':' && (i + 1 == s.size() || s[i + 1] == ' ')) return false;
+    if (c == '#' && i > 0 && s[i - 1] == ' ') return false;
+  }
+  return true;
+}
+std::string yaml_scalar(const Json &j) {
+  switch (j.type) {
+    case Json::Null: return "null";
+    case Json::Bool: return j.b ? "true" : "false";
+    case Json::Number: return j.s;
+    case Json::String: {
+      if (yaml_plain_ok(j.s)) return j.s;
+      bool simple = true;
+      for (unsigned char c : j.s) if (c < 0x20 || c == '\\' ) simple = false;
+      if (simple && j.s.find('\'') == std::string::npos) return "'" + j.s + "'";
+      std::string o; json_escape(j.s, o); return o;
+    }
+    default: return "";
+  }
+}
+void yaml_emit(const Json &j, int indent, std::string &out) {
+  std::string pad(indent, ' ');
+  if (j.type == Json::Object) {
+    std::vector<const std::pair<std::string, Json> *> kv;
+    for (auto &p : j.obj) kv.push_back(&p);
+    std::sort(kv.begin(), kv.end(), [](auto *a, auto *b) { return a->first < b->first; });
+    for (auto *p : kv) {
+      const Json &v = p->second;
+      std::string key = yaml_plain_ok(p->first) ? p->first : ("\"" + p->first + "\"");
+      if (v.type == Json::Object && !v.obj.empty()) { out += pad + key + ":\n"; yaml_emit(v, indent + 2, out); }
+      else if (v.type == Json::Array && !v.arr.empty()) { out += pad + key + ":\n"; yaml_emit(v, indent, out); }
+      else if (v.type == Json::Object) out += pad + key + ": {}\n";
+      else if (v.type == Json::Array) out += pad + key + ": []\n";
+      else out += pad + key + ": " + yaml_scalar(v) + "\n";
+    }
+  } else if (j.type == Json::Array) {
+    for (auto &v : j.arr) {
+      if ((v.type == Json::Object && !v.obj.empty()) || (v.type == Json::Array && !v.arr.empty())) {
+        std::string sub; yaml_emit(v, indent + 2, sub);
+        sub[indent] = '-';   // first line: replace the first pad character of the nested block by the dash
+        out += sub;
+      } else if (v.type == Json::Object) out += pad + "- {}\n";
+      else if (v.type == Json::Array) out += pad + "- []\n";
+      else out += pad + "- " + yaml_scalar(v) + "\n";
+    }
+  } else out += pad + yaml_scalar(j) + "\n";
+}
+
+}  // namespace
+
+struct cc_handle {
+  SchedConfig cfg;
+  Pod tmpl;
+  int64_t max_pods = 0;
+  std::set<std::string> exclude;
+  int device = 0;
+  std::vector<Node> nodes;
+  std::vector<Pod> pods;
+  std::map<std::string, Labels> ns_labels;
+  bool synced = false, ran = false, closed = false;
+  Encoded enc;
+  bool have_enc = false;
+  // Status{Pods, StopReason} (pkg/framework/simulator.go:90-93)
+  std::vector<int32_t> pod_node;
+  std::string stop_reason;
+  Json report;   // cached like c.report (simulator.go:161-169)
+  bool have_report = false;
+  std::string err, out;
+};
+
+static std::string g_new_err;
+static int fail(cc_handle *h, int code, const std::string &m) { if (h) h->err = m; else g_new_err = m; return code; }
+
+static void ensure_encoded(cc_handle *h) {
+  if (h->have_enc) return;
+  Encoder enc(h->cfg, h->tmpl, h->nodes, h->pods, h->ns_labels, h->exclude);
+  h->enc = enc.encode();
+  h->have_enc = true;
+}
+
+extern "C" const char *cc_last_error(const cc_handle *h) { return h ? h->err.c_str() : g_new_err.c_str(); }
+
+extern "C" int cc_new(const char *sched_config_json, const char *pod_json, int64_t max_pods, const char *exclude_nodes,
+                      int32_t device, cc_handle **out) {
+  if (!pod_json || !out) return fail(nullptr, CC_EINVAL, "null argument");
+  try {
+    cc_handle *h = new cc_handle();
+    h->cfg = SchedConfig::parse(sched_config_json ? sched_config_json : "");
+    h->tmpl = Pod::parse(parse_json(pod_json));
+    h->max_pods = max_pods;
+    h->device = device;
+    if (exclude_nodes) {
+      std::stringstream ss(exclude_nodes); std::string item;
+      while (std::getline(ss, item, ',')) if (!item.empty()) h->exclude.insert(item);
+    }
+    *out = h;
+    return CC_OK;
+  } catch (const std::exception &e) { return fail(nullptr, CC_EINVAL, e.what()); }
+}
+
+static std::vector<Json> items_of(const char *text) {
+  std::vector<Json> v;
+  if (!text || !*text) return v;
+  Json j = parse_json(text);
+  if (j.is_array()) v = j.arr;
+  else if (j.at("items").is_array()) v = j.at("items").arr;
+  else if (j.is_object()) v.push_back(j);
+  return v;
+}
+
+extern "C" int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const char *pods_json, const char *namespaces_json) {
+  if (!h) return CC_EINVAL;
+  if (h->closed) return fail(h, CC_ESTATE, "closed");
+  try {
+    h->nodes.clear(); h->pods.clear(); h->ns_labels.clear();
+    for (auto &j : items_of(nodes_json)) h->nodes.push_back(Node::parse(j));
+    for (auto &j : items_of(pods_json)) h->pods.push_back(Pod::parse(j));
+    for (auto &j : items_of(namespaces_json)) h->ns_labels[j.at("metadata").at("name").str()] = parse_labels(j.at("metadata").at("labels"));
+    h->synced = true; h->have_enc = false; h->ran = false; h->have_report = false;
+    return CC_OK;
+  } catch (const std::exception &e) { return fail(h, CC_EINVAL, e.what()); }
+}
+
+extern "C" int cc_run(cc_handle *h) {
+  if (!h) return CC_EINVAL;
+  if (h->closed) return fail(h, CC_ESTATE, "closed");
+  if (!h->synced) return fail(h, CC_ESTATE, "cc_sync_with_objects must come first");
+  try {
+    ensure_encoded(h);
+  } catch (const Unsupported &e) { return fail(h, CC_EUNSUPPORTED, std::string("unsupported on the GPU path: ") + e.what());
+  } catch (const std::exception &e) { return fail(h, CC_EINVAL, e.what()); }
+  const Encoded &E = h->enc;
+  h->pod_node.clear();
+  h->have_report = false;
+  if (E.n == 0) {   // ErrNoNodesAvailable (scheduler.go:68; schedule_one.go:165-168)
+    h->stop_reason = "Unschedulable: no nodes available to schedule pods";
+    h->ran = true;
+    return CC_OK;
+  }
+  if (!E.prefilter_msg.empty()) {   // PreFilter rejected the pod outright: FitError carries only the PreFilter message
+    h->stop_reason = "Unschedulable: 0/" + std::to_string(E.n) + " nodes are available: " + E.prefilter_msg + ". preemption: " +
+                     fit_error_body(E.n, {{"Preemption is not helpful for scheduling", E.n}});
+    h->ran = true;
+    return CC_OK;
+  }
+  ccsim_config cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.abi_version = CCSIM_ABI_VERSION; cfg.device = h->device; cfg.engine = CCSIM_ENGINE_AUTO; cfg.rank = 0; cfg.world = 1;
+  ccsim_handle *eng = nullptr;
+  int rc = ccsim_create(&cfg, &eng);
+  if (rc) return fail(h, CC_EENGINE, std::string("ccsim_create: ") + ccsim_last_error(nullptr));
+  ccsim_nodes nd; E.fill_nodes(nd);
+  ccsim_result res;
+  auto bail = [&](const char *what) { std::string m = std::string(what) + ": " + ccsim_last_error(eng); ccsim_destroy(eng); return fail(h, CC_EENGINE, m); };
+  if ((rc = ccsim_load_nodes(eng, &nd))) return bail("ccsim_load_nodes");
+  if ((rc = ccsim_set_templates(eng, 1, &E.tmpl, (int32_t)E.counters.size(), E.counters.data()))) return bail("ccsim_set_templates");
+  if ((rc = ccsim_run(eng, h->max_pods, &res))) return bail("ccsim_run");
+  h->pod_node.assign(res.pod_node, res.pod_node + res.placed);
+  if (res.stop_code == CCSIM_STOP_LIMIT_REACHED) {
+    h->stop_reason = "LimitReached: Maximum number of pods simulated: " + std::to_string(h->max_pods);   // simulator.go:301
+  } else {
+    std::vector<std::pair<std::string, int64_t>> hist;
+    for (int r = 0; r < CCSIM_R_FIXED_COUNT; r++) hist.push_back({kReasonText[r], res.reason_hist[r]});
+    for (size_t k = 0; k < E.scalar_names.size(); k++) hist.push_back({"Insufficient " + E.scalar_names[k], res.reason_hist[CCSIM_R_SCALAR0 + k]});
+    for (size_t t = 0; t < E.taint_dict.size(); t++)   // taint_toleration.go:120
+      hist.push_back({"node(s) had untolerated taint {" + E.taint_dict[t].key + ": " + E.taint_dict[t].value + "}", res.reason_hist[CCSIM_R_TAINT0 + t]});
+    std::string msg = fit_error_body(E.n, hist);
+    // DefaultPreemption PostFilter (default_preemption.go:132-143; preemption.go:234-279): no victims anywhere
+    std::string post;
+    if (h->tmpl.preemption_policy == "Never") post = "not eligible due to preemptionPolicy=Never.";
+    else post = fit_error_body(E.n, {{"No preemption victims found for incoming pod", res.preempt_no_victims},
+                                     {"Preemption is not helpful for scheduling", res.preempt_not_helpful}});
+    h->stop_reason = "Unschedulable: " + msg + " preemption: " + post;   // simulator.go:332
+  }
+  ccsim_destroy(eng);
+  h->ran = true;
+  return CC_OK;
+}
+
+// getResourceRequest (report.go:111-144): containers only, cpu/memory summed as quantities, scalars as Value()
+static Json requirements_json(const Pod &p) {
+  Quantity cpu = Quantity::parse("0"); cpu.format = Quantity::DecimalSI;
+  Quantity mem = Quantity::parse("0"); mem.format = Quantity::BinarySI;
+  std::map<std::string, int64_t> scalars; bool have_scalars = false;
+  for (auto &c : p.containers)
+    for (auto &kv : c.requests) {
+      if (kv.first == "memory") { Quantity q = kv.second; q.add(mem); mem = q; }
+      else if (kv.first == "cpu") { Quantity q = kv.second; q.add(cpu); cpu = q; }
+      else if (is_scalar_resource_name(kv.first)) { scalars[kv.first] += kv.second.value(); have_scalars = true; }
+    }
+  Json prim = Json::object();
+  prim.set("cpu", Json::string(cpu.str()));
+  prim.set("memory", Json::string(mem.str()));
+  prim.set("nvdia.com/gpu", Json::string("0"));   // [sic] report.go:35,116
+  Json res = Json::object();
+  res.set("primaryResources", prim);
+  if (have_scalars) { Json s = Json::object(); for (auto &kv : scalars) s.set(kv.first, Json::number(kv.second)); res.set("scalarResources", s); }
+  else res.set("scalarResources", Json::null());
+  Json req = Json::object();
+  req.set("podName", Json::string(p.name));
+  req.set("resources", res);
+  if (p.has_node_selector) { Json s = Json::object(); for (auto &kv : p.node_selector) s.set(kv.first, Json::string(kv.second)); req.set("nodeSelectors", s); }
+  else req.set("nodeSelectors", Json::null());
+  return req;
+}
+
+static int build_report(cc_handle *h) {
+  if (h->have_report) return CC_OK;
+  if (!h->ran) return fail(h, CC_ESTATE, "Report() before Run(): no stop reason yet (the reference panics here, report.go:102-106)");
+  Json spec = Json::object();
+  Json tmpls = Json::array(); tmpls.push(h->tmpl.raw);
+  spec.set("templates", tmpls);
+  spec.set("replicas", Json::number(h->max_pods));
+  Json reqs = Json::array(); reqs.push(requirements_json(h->tmpl));
+  spec.set("podRequirements", reqs);
+  Json status = Json::object();
+  status.set("creationTimestamp", Json::string(rfc3339_now()));
+  status.set("replicas", Json::number((long long)h->pod_node.size()));
+  // getMainFailReason (report.go:100-109): split at the first ':'
+  const std::string &sr = h->stop_reason;
+  size_t nl = sr.find('\n');
+  std::string first = nl == std::string::npos ? sr : sr.substr(0, nl);
+  size_t colon = first.find(':');
+  Json fr = Json::object();
+  fr.set("failType", Json::string(first.substr(0, colon)));
+  std::string m = colon == std::string::npos ? "" : first.substr(colon + 1);
+  while (!m.empty() && m.front() == ' ') m.erase(m.begin());
+  while (!m.empty() && m.back() == ' ') m.pop_back();
+  fr.set("failMessage", Json::string(m));
+  status.set("failReason", fr);
+  // parsePodsReview (report.go:146-180): ReplicasOnNodes in order of first placement
+  Json rons = Json::array();
+  {
+    std::vector<int64_t> count(h->enc.n, 0); std::vector<int32_t> order;
+    for (int32_t w : h->pod_node) { if (count[w]++ == 0) order.push_back(w); }
+    for (int32_t w : order) { Json r = Json::object(); r.set("nodeName", Json::string(h->enc.names[w])); r.set("replicas", Json::number(count[w])); rons.push(r); }
+  }
+  Json podres = Json::object();
+  podres.set("podName", Json::string(h->tmpl.name));
+  podres.set("replicasOnNodes", rons);
+  podres.set("failSummary", Json::null());   // never populated by the reference (report.go:174-179)
+  Json pods = Json::array(); pods.push(podres);
+  status.set("pods", pods);
+  h->report = Json::object();
+  h->report.set("spec", spec);
+  h->report.set("status", status);
+  h->have_report = true;
+  return CC_OK;
+}
+
+extern "C" const char *cc_report_json(cc_handle *h) {
+  if (!h || build_report(h)) return nullptr;
+  h->out = json_dump(h->report);
+  return h->out.c_str();
+}
+
+extern "C" const char *cc_report_print(cc_handle *h, int32_t verbose, const char *format) {
+  if (!h || build_report(h)) return nullptr;
+  std::string f = format ? format : "";
+  if (f == "json") { h->out = json_dump(h->report) + "\n"; return h->out.c_str(); }
+  if (f == "yaml") { h->out.clear(); yaml_emit(h->report, 0, h->out); return h->out.c_str(); }
+  if (!f.empty()) { fail(h, CC_EINVAL, "output format \"" + f + "\" not recognized"); return nullptr; }   // report.go:315
+  // clusterCapacityReviewPrettyPrint (report.go:235-285)
+  std::string o;
+  const Json &req = h->report.at("spec").at("podRequirements").arr[0];
+  const Json &st = h->report.at("status");
+  const Json &pod = st.at("pods").arr[0];
+  long long total = 0;
+  for (auto &r : pod.at("replicasOnNodes").arr) total += r.at("replicas").i64();
+  if (verbose) {
+    o += req.at("podName").str() + " pod requirements:\n";
+    o += "\t- CPU: " + req.at("resources").at("primaryResources").at("cpu").str() + "\n";
+    o += "\t- Memory: " + req.at("resources").at("primaryResources").at("memory").str() + "\n";
+    const Json &sc = req.at("resources").at("scalarResources");
+    if (sc.is_object()) { o += "\t- ScalarResources: map["; bool fst = true; for (auto &kv : sc.obj) { if (!fst) o += " "; o += kv.first + ":" + kv.second.s; fst = false; } o += "]\n"; }
+    const Json &ns = req.at("nodeSelectors");
+    if (ns.is_object()) {   // labels.SelectorFromSet(...).String(): sorted "k=v" joined by ","
+      std::vector<std::string> kv; for (auto &p : ns.obj) kv.push_back(p.first + "=" + p.second.str());
+      std::sort(kv.begin(), kv.end());
+      o += "\t- NodeSelector: "; for (size_t i = 0; i < kv.size(); i++) { if (i) o += ","; o += kv[i]; } o += "\n";
+    }
+    o += "\n";
+    o += "The cluster can schedule " + std::to_string(total) + " instance(s) of the pod " + pod.at("podName").str() + ".\n";
+    o += "\nTermination reason: " + st.at("failReason").at("failType").str() + ": " + st.at("failReason").at("failMessage").str() + "\n";
+    if (st.at("replicas").i64() > 0) {
+      o += "\nPod distribution among nodes:\n";
+      o += pod.at("podName").str() + "\n";
+      for (auto &r : pod.at("replicasOnNodes").arr) o += "\t- " + r.at("nodeName").str() + ": " + std::to_string(r.at("replicas").i64()) + " instance(s)\n";
+    }
+  } else o += std::to_string(total) + "\n";
+  h->out = o;
+  return h->out.c_str();
+}
+
+extern "C" const char *cc_stop_reason(cc_handle *h) { return h ? h->stop_reason.c_str() : nullptr; }
+extern "C" int64_t cc_scheduled_count(cc_handle *h) { return h ? (int64_t)h->pod_node.size() : 0; }
+extern "C" const char *cc_scheduled_node(cc_handle *h, int64_t k) {
+  if (!h || k < 0 || k >= (int64_t)h->pod_node.size()) return nullptr;
+  return h->enc.names[h->pod_node[k]].c_str();
+}
+extern "C" void cc_close(cc_handle *h) { if (h) { h->closed = true; delete h; } }
+
+extern "C" const char *cc_debug_encoded_snapshot(cc_handle *h) {
+  if (!h) return nullptr;
+  try { ensure_encoded(h); }
+  catch (const Unsupported &e) { fail(h, CC_EUNSUPPORTED, std::string("unsupported on the GPU path: ") + e.what()); return nullptr; }
+  catch (const std::exception &e) { fail(h, CC_EINVAL, e.what()); return nullptr; }
+  const Encoded &E = h->enc;
+  auto arr64 = [](const std::vector<int64_t> &v) { Json a = Json::array(); for (auto x : v) a.push(Json::number(x)); return a; };
+  auto arr32 = [](const std::vector<int32_t> &v) { Json a = Json::array(); for (auto x : v) a.push(Json::number(x)); return a; };
+  auto arru64 = [](const uint64_t *v, size_t n) { Json a = Json::array(); for (size_t i = 0; i < n; i++) a.push(Json::number_text(std::to_string((unsigned long long)v[i]))); return a; };
+  Json j = Json::object();
+  Json names = Json::array(); for (auto &s : E.names) names.push(Json::string(s));
+  j.set("names", names);
+  Json nd = Json::object();
+  nd.set("n", Json::number(E.n));
+  nd.set("alloc_cpu", arr64(E.alloc_cpu)); nd.set("alloc_mem", arr64(E.alloc_mem)); nd.set("alloc_eph", arr64(E.alloc_eph));
+  nd.set("alloc_pods", arr32(E.alloc_pods));
+  nd.set("req_cpu", arr64(E.req_cpu)); nd.set("req_mem", arr64(E.req_mem)); nd.set("req_eph", arr64(E.req_eph));
+  nd.set("npods", arr32(E.npods)); nd.set("nz_cpu", arr64(E.nz_cpu)); nd.set("nz_mem", arr64(E.nz_mem));
+  Json sn = Json::array(); for (auto &s : E.scalar_names) sn.push(Json::string(s));
+  nd.set("scalar_names", sn);
+  Json as = Json::array(), rs = Json::array();
+  for (auto &v : E.alloc_scalar) as.push(arr64(v));
+  for (auto &v : E.req_scalar) rs.push(arr64(v));
+  nd.set("alloc_scalar", as); nd.set("req_scalar", rs);
+  nd.set("taint_words", Json::number(E.taint_words)); nd.set("static_words", Json::number(E.static_words));
+  nd.set("taint_mask", arru64(E.taint_mask.data(), E.taint_mask.size()));
+  nd.set("static_mask", arru64(E.static_mask.data(), (size_t)E.static_words * E.n));
+  nd.set("taint_nosched", arru64(E.taint_nosched, CCSIM_MAX_TAINT_WORDS)); nd.set("taint_prefer", arru64(E.taint_prefer, CCSIM_MAX_TAINT_WORDS));
+  Json td = Json::array();
+  for (auto &t : E.taint_dict) { Json x = Json::object(); x.set("key", Json::string(t.key)); x.set("value", Json::string(t.value)); x.set("effect", Json::string(t.effect)); td.push(x); }
+  nd.set("taint_dict", td);
+  nd.set("taint_off", arr32(E.taint_off));
+  { Json tl = Json::array(); for (auto x : E.taint_list) tl.push(Json::number(x)); nd.set("taint_list", tl); }
+  Json topo = Json::array(); for (auto &c : E.topo) topo.push(arr32(c));
+  nd.set("topo", topo);
+  nd.set("has_placed_mask", Json::boolean(E.has_placed_mask));
+  j.set("nodes", nd);
+  // the template as raw bytes (hex) — the tests memcpy it into the ctypes struct
+  std::string hex; const unsigned char *tb = reinterpret_cast<const unsigned char *>(&E.tmpl);
+  static const char *d = "0123456789abcdef";
+  for (size_t i = 0; i < sizeof(ccsim_template); i++) { hex += d[tb[i] >> 4]; hex += d[tb[i] & 15]; }
+  j.set("template_hex", Json::string(hex));
+  Json ctr = Json::array();
+  for (size_t k = 0; k < E.counters.size(); k++) {
+    Json c = Json::object();
+    c.set("topo_col", Json::number(E.counters[k].topo_col)); c.set("n_present", Json::number(E.counters[k].n_present));
+    c.set("inc", Json::number(E.counters[k].inc)); c.set("init", arr32(E.counter_init[k]));
+    ctr.push(c);
+  }
+  j.set("counters", ctr);
+  j.set("prefilter_msg", Json::string(E.prefilter_msg));
+  h->out = json_dump(j);
+  return h->out.c_str();
+}

@@ -1,0 +1,515 @@
+// encoder.hpp — Node/Pod objects -> the flat snapshot of include/ccsim.h.
+//
+// What the reference builds incrementally through informer events, reproduced here in one pass:
+//   node order        nodeTree.addNode / list(): zones in first-seen order, round-robin across zones
+//                     (kubernetes/pkg/scheduler/backend/cache/node_tree.go:51-67,119-143); nodes enter in the order of the
+//                     source List() minus --exclude-nodes (pkg/framework/simulator.go:203-215)
+//   NodeInfo          SetNode: Allocatable (framework/types.go:461-465); AddPodInfo/update: Requested, NonZeroRequested,
+//                     len(Pods), UsedPorts, PodsWithRequiredAntiAffinity (types.go:333-343,409-427); pods whose node is
+//                     unknown/excluded are dropped (backend/cache/cache.go:439-443,223); terminal pods never enter
+//                     (simulator.go:196)
+//   PodInfo           CalculateResource (types.go:700-734)
+// and the per-template PreFilter/PreScore state is folded into ccsim_template / ccsim_counter (static bits, masks,
+// per-domain initial counts).
+#pragma once
+#include <cstring>
+#include <functional>
+#include "../../../include/ccsim.h"
+#include "objects.hpp"
+
+namespace cch {
+
+struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct SchedConfig {
+  int pct_nodes_to_score = 0;
+  uint32_t filter_enable = CCSIM_PL_ALL, score_enable = CCSIM_PL_ALL;
+  int w_taint = 3, w_node_affinity = 2, w_fit = 1, w_pts = 2, w_ipa = 2, w_balanced = 1, w_image = 1;
+  static uint32_t plugin_bit(const std::string &n) {
+    if (n == "NodeUnschedulable") return CCSIM_PL_NODE_UNSCHEDULABLE;
+    if (n == "NodeName") return CCSIM_PL_NODE_NAME;
+    if (n == "TaintToleration") return CCSIM_PL_TAINT_TOLERATION;
+    if (n == "NodeAffinity") return CCSIM_PL_NODE_AFFINITY;
+    if (n == "NodePorts") return CCSIM_PL_NODE_PORTS;
+    if (n == "NodeResourcesFit") return CCSIM_PL_FIT;
+    if (n == "PodTopologySpread") return CCSIM_PL_POD_TOPOLOGY_SPREAD;
+    if (n == "InterPodAffinity") return CCSIM_PL_INTER_POD_AFFINITY;
+    if (n == "NodeResourcesBalancedAllocation") return CCSIM_PL_BALANCED;
+    if (n == "ImageLocality") return CCSIM_PL_IMAGE_LOCALITY;
+    return 0;
+  }
+  static SchedConfig parse(const std::string &text) {
+    SchedConfig c;
+    if (text.empty()) return c;
+    Json j = parse_json(text);
+    c.pct_nodes_to_score = (int)j.at("percentageOfNodesToScore").i64(0);
+    for (auto &x : j.at("disabledFilters").arr) c.filter_enable &= ~plugin_bit(x.str());
+    for (auto &x : j.at("disabledScores").arr) c.score_enable &= ~plugin_bit(x.str());
+    const Json &w = j.at("weights");
+    if (w.is_object())
+      for (auto &kv : w.obj) {
+        int v = (int)kv.second.i64(1);
+        if (kv.first == "TaintToleration") c.w_taint = v; else if (kv.first == "NodeAffinity") c.w_node_affinity = v;
+        else if (kv.first == "NodeResourcesFit") c.w_fit = v; else if (kv.first == "PodTopologySpread") c.w_pts = v;
+        else if (kv.first == "InterPodAffinity") c.w_ipa = v; else if (kv.first == "NodeResourcesBalancedAllocation") c.w_balanced = v;
+        else if (kv.first == "ImageLocality") c.w_image = v;
+      }
+    return c;
+  }
+};
+
+struct PodResource { int64_t cpu = 0, mem = 0, eph = 0; std::map<std::string, int64_t> scalar; int64_t non0_cpu = 0, non0_mem = 0; };
+
+// Resource.Add over a ResourceList (framework/types.go:979-1001)
+inline void resource_add(PodResource &r, const ResourceList &rl) {
+  for (auto &kv : rl) {
+    if (kv.first == "cpu") r.cpu += kv.second.milli_value();
+    else if (kv.first == "memory") r.mem += kv.second.value();
+    else if (kv.first == "ephemeral-storage") r.eph += kv.second.value();
+    else if (kv.first == "pods") {}
+    else if (is_scalar_resource_name(kv.first)) r.scalar[kv.first] += kv.second.value();
+  }
+}
+
+inline ResourceList default_non_missing() {
+  ResourceList d;
+  d["cpu"] = Quantity::parse("100m");          // schedutil.DefaultMilliCPURequest
+  d["memory"] = Quantity::parse("209715200");  // schedutil.DefaultMemoryRequest = 200 * 1024 * 1024
+  return d;
+}
+
+// PodInfo.CalculateResource (framework/types.go:700-734)
+inline PodResource calculate_resource(const Pod &p) {
+  PodResource out;
+  ResourceList req = p.requests(/*use_status=*/true, /*skip_pod_level=*/false, nullptr);
+  ResourceList nm;
+  if (!p.has_pod_level_requests) nm = default_non_missing();
+  else {
+    ResourceList d = default_non_missing();
+    for (auto &kv : d) if (!req.count(kv.first)) nm[kv.first] = kv.second;
+  }
+  ResourceList non0 = req;
+  if (!nm.empty()) non0 = p.requests(true, false, &nm);
+  resource_add(out, req);
+  auto ic = non0.find("cpu"); auto im = non0.find("memory");
+  out.non0_cpu = ic == non0.end() ? 0 : ic->second.milli_value();
+  out.non0_mem = im == non0.end() ? 0 : im->second.value();
+  return out;
+}
+
+struct Encoded {
+  int32_t n = 0;
+  std::vector<std::string> names;
+  std::vector<int64_t> alloc_cpu, alloc_mem, alloc_eph, req_cpu, req_mem, req_eph, nz_cpu, nz_mem;
+  std::vector<int32_t> alloc_pods, npods;
+  std::vector<std::string> scalar_names;
+  std::vector<std::vector<int64_t>> alloc_scalar, req_scalar;
+  int taint_words = 1, static_words = 0;
+  std::vector<uint64_t> taint_mask, static_mask;   // word-major
+  std::vector<Taint> taint_dict;
+  uint64_t taint_nosched[CCSIM_MAX_TAINT_WORDS] = {0}, taint_prefer[CCSIM_MAX_TAINT_WORDS] = {0};
+  std::vector<int32_t> taint_off;
+  std::vector<uint8_t> taint_list;
+  std::vector<std::vector<int32_t>> topo;
+  std::vector<std::vector<int32_t>> counter_init;
+  std::vector<ccsim_counter> counters;
+  ccsim_template tmpl;
+  bool has_placed_mask = false;
+  std::string prefilter_msg;   // non-empty: PreFilter rejected the pod for every node (e.g. conflicting metadata.name affinity)
+
+  void fill_nodes(ccsim_nodes &nd) const {
+    memset(&nd, 0, sizeof(nd));
+    nd.n_nodes = n; nd.n_scalars = (int32_t)scalar_names.size(); nd.taint_words = taint_words; nd.static_words = static_words;
+    nd.n_topo_cols = (int32_t)topo.size(); nd.has_placed_mask = has_placed_mask ? 1 : 0;
+    nd.alloc_cpu = alloc_cpu.data(); nd.alloc_mem = alloc_mem.data(); nd.alloc_eph = alloc_eph.data(); nd.alloc_pods = alloc_pods.data();
+    nd.req_cpu = req_cpu.data(); nd.req_mem = req_mem.data(); nd.req_eph = req_eph.data(); nd.npods = npods.data();
+    nd.nz_cpu = nz_cpu.data(); nd.nz_mem = nz_mem.data();
+    for (size_t k = 0; k < scalar_names.size(); k++) { nd.alloc_scalar[k] = alloc_scalar[k].data(); nd.req_scalar[k] = req_scalar[k].data(); }
+    nd.taint_mask = taint_mask.data(); nd.static_mask = static_mask.data();
+    for (size_t k = 0; k < topo.size(); k++) nd.topo[k] = topo[k].data();
+    for (int w = 0; w < CCSIM_MAX_TAINT_WORDS; w++) { nd.taint_nosched[w] = taint_nosched[w]; nd.taint_prefer[w] = taint_prefer[w]; }
+    nd.taint_list_off = taint_off.data(); nd.taint_list = taint_list.data();
+  }
+};
+
+class Encoder {
+ public:
+  Encoder(const SchedConfig &cfg, const Pod &tmpl, const std::vector<Node> &nodes_in, const std::vector<Pod> &pods_in,
+          const std::map<std::string, Labels> &ns_labels, const std::set<std::string> &exclude)
+      : cfg_(cfg), t_(tmpl), ns_labels_(ns_labels) {
+    // ---- node order: nodeTree (zones in first-seen order, round-robin) ----
+    std::vector<const Node *> kept;
+    for (auto &n : nodes_in) if (!exclude.count(n.name)) kept.push_back(&n);
+    std::vector<std::string> zones;
+    std::map<std::string, std::vector<const Node *>> tree;
+    std::set<std::string> seen;
+    for (auto *n : kept) {
+      if (seen.count(n->name)) continue;   // "Did not add to the NodeTree because it already exists"
+      seen.insert(n->name);
+      std::string z = n->zone_key();
+      if (!tree.count(z)) zones.push_back(z);
+      tree[z].push_back(n);
+    }
+    size_t total = seen.size(), idx = 0;
+    while (nodes_.size() < total) {
+      for (auto &z : zones) { auto &v = tree[z]; if (idx < v.size()) nodes_.push_back(v[idx]); }
+      idx++;
+    }
+    for (size_t i = 0; i < nodes_.size(); i++) node_index_[nodes_[i]->name] = (int)i;
+    // ---- pods: non-terminal, bound to a known node ----
+    pods_on_.resize(nodes_.size());
+    for (auto &p : pods_in) {
+      if (p.phase == "Succeeded" || p.phase == "Failed") continue;
+      if (p.node_name.empty()) continue;   // pending pods are not replayed (documented deviation)
+      auto it = node_index_.find(p.node_name);
+      if (it == node_index_.end()) continue;
+      pods_on_[it->second].push_back(&p);
+    }
+  }
+
+  Encoded encode() {
+    Encoded e;
+    memset(&e.tmpl, 0, sizeof(e.tmpl));
+    const int n = (int)nodes_.size();
+    e.n = n;
+    guards();
+    // ---- template request vectors (A2) ----
+    ccsim_template &T = e.tmpl;
+    T.filter_enable = cfg_.filter_enable; T.score_enable = cfg_.score_enable;
+    T.w_taint = cfg_.w_taint; T.w_node_affinity = cfg_.w_node_affinity; T.w_fit = cfg_.w_fit; T.w_pts = cfg_.w_pts;
+    T.w_ipa = cfg_.w_ipa; T.w_balanced = cfg_.w_balanced; T.w_image = cfg_.w_image;
+    T.least_w_cpu = 1; T.least_w_mem = 1;
+    T.nodename_idx = -1; T.prefilter_bit = -1;
+    PodResource fit;     // computePodResourceRequest (fit.go:224-233): PodRequests with pod-level resources, SetMaxResource from zero
+    resource_add(fit, t_.requests(false, false, nullptr));
+    PodResource cr = calculate_resource(t_);   // what a committed clone adds (types.go:409-427)
+    T.req_cpu = cr.cpu; T.req_mem = cr.mem; T.req_eph = cr.eph;
+    T.nz_cpu = cr.non0_cpu; T.nz_mem = cr.non0_mem;
+    if (fit.cpu != cr.cpu || fit.mem != cr.mem || fit.eph != cr.eph) throw Unsupported("template requests differ between Filter and NodeInfo accounting");
+    for (auto &kv : fit.scalar) if (kv.second != 0) e.scalar_names.push_back(kv.first);
+    if (e.scalar_names.size() > CCSIM_MAX_SCALARS) throw Unsupported("more than 4 extended resources requested");
+    for (size_t k = 0; k < e.scalar_names.size(); k++) T.req_scalar[k] = fit.scalar[e.scalar_names[k]];
+    {   // LeastAllocated pod request: pod-level resources skipped, non-zero defaults (resource_allocation.go:118-140; fit.go:186)
+      ResourceList d = default_non_missing();
+      ResourceList lr = t_.requests(false, true, &d);
+      T.least_cpu = lr.count("cpu") ? lr["cpu"].milli_value() : 0;
+      T.least_mem = lr.count("memory") ? lr["memory"].value() : 0;
+      ResourceList br = t_.requests(true, false, nullptr);   // BalancedAllocation: useRequested, pod-level honoured
+      T.bal_cpu = br.count("cpu") ? br["cpu"].milli_value() : 0;
+      T.bal_mem = br.count("memory") ? br["memory"].value() : 0;
+    }
+    if (fit.cpu == 0 && fit.mem == 0 && fit.eph == 0 && fit.scalar.empty()) T.flags |= CCSIM_TF_FIT_ALL_ZERO;
+    if (T.bal_cpu == 0 && T.bal_mem == 0) T.flags |= CCSIM_TF_BALANCED_SKIP;
+
+    // ---- node columns (A1) ----
+    e.names.resize(n);
+    auto z64 = [&](std::vector<int64_t> &v) { v.assign(n, 0); };
+    z64(e.alloc_cpu); z64(e.alloc_mem); z64(e.alloc_eph); z64(e.req_cpu); z64(e.req_mem); z64(e.req_eph); z64(e.nz_cpu); z64(e.nz_mem);
+    e.alloc_pods.assign(n, 0); e.npods.assign(n, 0);
+    e.alloc_scalar.assign(e.scalar_names.size(), std::vector<int64_t>(n, 0));
+    e.req_scalar.assign(e.scalar_names.size(), std::vector<int64_t>(n, 0));
+    for (int i = 0; i < n; i++) {
+      const Node &nd = *nodes_[i];
+      e.names[i] = nd.name;
+      for (auto &kv : nd.allocatable) {   // NewResource(node.Status.Allocatable)
+        if (kv.first == "cpu") e.alloc_cpu[i] += kv.second.milli_value();
+        else if (kv.first == "memory") e.alloc_mem[i] += kv.second.value();
+        else if (kv.first == "ephemeral-storage") e.alloc_eph[i] += kv.second.value();
+        else if (kv.first == "pods") e.alloc_pods[i] += (int32_t)kv.second.value();
+        else for (size_t k = 0; k < e.scalar_names.size(); k++) if (kv.first == e.scalar_names[k]) e.alloc_scalar[k][i] += kv.second.value();
+      }
+      for (auto *p : pods_on_[i]) {
+        PodResource pr = calculate_resource(*p);
+        e.req_cpu[i] += pr.cpu; e.req_mem[i] += pr.mem; e.req_eph[i] += pr.eph;
+        e.nz_cpu[i] += pr.non0_cpu; e.nz_mem[i] += pr.non0_mem;
+        for (size_t k = 0; k < e.scalar_names.size(); k++) { auto it = pr.scalar.find(e.scalar_names[k]); if (it != pr.scalar.end()) e.req_scalar[k][i] += it->second; }
+        e.npods[i] += 1;
+      }
+    }
+    // ---- taints: dictionary in first-seen order ----
+    std::map<Taint, int> tid;
+    for (int i = 0; i < n; i++)
+      for (auto &t : nodes_[i]->taints)
+        if (!tid.count(t)) {
+          int id = (int)e.taint_dict.size();
+          if (id == CCSIM_TAINT_UNSCHEDULABLE_BIT) { e.taint_dict.push_back(Taint{"", "", "__reserved__"}); id++; }   // bit 63 of word 0 is reserved
+          tid[t] = id; e.taint_dict.push_back(t);
+        }
+    if (e.taint_dict.size() > 64 * CCSIM_MAX_TAINT_WORDS || e.taint_dict.size() > 255) throw Unsupported("more than 255 distinct taints in the cluster");
+    e.taint_words = std::max<int>(1, (int)(e.taint_dict.size() + 63) / 64);
+    e.taint_mask.assign((size_t)e.taint_words * n, 0);
+    e.taint_off.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+      for (auto &t : nodes_[i]->taints) { int id = tid[t]; e.taint_mask[(size_t)(id >> 6) * n + i] |= 1ull << (id & 63); e.taint_list.push_back((uint8_t)id); }
+      e.taint_off[i + 1] = (int32_t)e.taint_list.size();
+      if (nodes_[i]->unschedulable) e.taint_mask[i] |= 1ull << CCSIM_TAINT_UNSCHEDULABLE_BIT;
+    }
+    if (e.taint_list.empty()) e.taint_list.push_back(0);
+    std::vector<Toleration> prefer_tols;   // getAllTolerationPreferNoSchedule (taint_toleration.go:129-137)
+    for (auto &tl : t_.tolerations) if (tl.effect.empty() || tl.effect == "PreferNoSchedule") prefer_tols.push_back(tl);
+    for (size_t id = 0; id < e.taint_dict.size(); id++) {
+      const Taint &t = e.taint_dict[id];
+      const int w = (int)id >> 6; const uint64_t b = 1ull << (id & 63);
+      if (t.effect == "NoSchedule" || t.effect == "NoExecute") { e.taint_nosched[w] |= b; if (tolerations_tolerate(t_.tolerations, t)) T.tol_nosched[w] |= b; }
+      if (t.effect == "PreferNoSchedule") { e.taint_prefer[w] |= b; if (tolerations_tolerate(prefer_tols, t)) T.tol_prefer[w] |= b; }
+    }
+    if (tolerations_tolerate(t_.tolerations, Taint{"node.kubernetes.io/unschedulable", "", "NoSchedule"})) T.flags |= CCSIM_TF_TOLERATES_UNSCHEDULABLE;
+
+    // ---- static bits ----
+    std::vector<std::vector<char>> bits;   // bits[b][i]
+    auto new_bit = [&](const std::function<bool(int)> &f) { std::vector<char> v(n); for (int i = 0; i < n; i++) v[i] = f(i) ? 1 : 0; bits.push_back(v); return (int)bits.size() - 1; };
+    auto set_mask = [&](uint64_t *m, int b) { m[b >> 6] |= 1ull << (b & 63); };
+    // NodeAffinity (nodeaffinity.go:306-332; node_affinity.go:147-227)
+    const bool no_affinity = !t_.has_required_node_affinity;
+    if (!(no_affinity && !t_.has_node_selector)) {
+      T.flags |= CCSIM_TF_HAS_NODE_SELECTOR;   // the Filter is not skipped
+      if (!t_.node_selector.empty()) {
+        Selector s = Selector::from_set(t_.node_selector);
+        set_mask(T.sel_mask, new_bit([&](int i) { return s.matches(nodes_[i]->labels); }));
+      }
+      if (t_.has_required_node_affinity) {
+        T.flags |= CCSIM_TF_HAS_AFFINITY_TERMS;
+        if (t_.node_affinity_terms.size() > CCSIM_MAX_AFF_TERMS) throw Unsupported("more than 8 nodeSelectorTerms");
+        T.n_aff_terms = (int32_t)t_.node_affinity_terms.size();
+        for (size_t k = 0; k < t_.node_affinity_terms.size(); k++) {
+          const NodeSelectorTerm &nt = t_.node_affinity_terms[k];
+          set_mask(T.aff_term_mask[k], new_bit([&](int i) { return nt.matches(nodes_[i]->labels, nodes_[i]->name); }));
+        }
+        // PreFilterResult.NodeNames (node_affinity.go:164-194): every term pins metadata.name In [...]
+        std::set<std::string> names; bool all_terms_pin = !t_.node_affinity_terms.empty();
+        for (auto &nt : t_.node_affinity_terms) {
+          bool pinned = false; std::set<std::string> term_names;
+          for (auto &r : nt.match_fields)
+            if (r.key == "metadata.name" && r.op == "In") {
+              std::set<std::string> s(r.values.begin(), r.values.end());
+              if (!pinned) { term_names = s; pinned = true; }
+              else { std::set<std::string> x; for (auto &v : term_names) if (s.count(v)) x.insert(v); term_names = x; }
+            }
+          if (!pinned) { all_terms_pin = false; break; }
+          names.insert(term_names.begin(), term_names.end());
+        }
+        if (all_terms_pin) {
+          if (names.empty()) e.prefilter_msg = "node(s) didn't match Pod's node affinity/selector";   // errReasonConflict path is host-formatted
+          else { T.flags |= CCSIM_TF_PREFILTER_NODES; T.prefilter_bit = new_bit([&](int i) { return names.count(nodes_[i]->name) > 0; }); }
+        }
+      }
+    }
+    // NodePorts (node_ports.go:68-76,157-185)
+    std::vector<ContainerPort> want = t_.host_ports();
+    if (!want.empty()) {
+      T.flags |= CCSIM_TF_HAS_HOST_PORTS;
+      e.has_placed_mask = true;
+      T.port_tmpl_conflict = 1;   // a clone always conflicts with another clone of the same template
+      auto norm = [](const ContainerPort &p, std::string &ip, std::string &proto) { ip = p.host_ip.empty() ? "0.0.0.0" : p.host_ip; proto = p.protocol.empty() ? "TCP" : p.protocol; };
+      set_mask(T.port_static_mask, new_bit([&](int i) {
+        for (auto *p : pods_on_[i])
+          for (auto &u : p->host_ports()) {
+            std::string uip, uproto; norm(u, uip, uproto);
+            for (auto &w : want) {
+              std::string wip, wproto; norm(w, wip, wproto);
+              if (w.host_port != u.host_port || wproto != uproto) continue;
+              if (wip == "0.0.0.0" || uip == "0.0.0.0" || wip == uip) return true;
+            }
+          }
+        return false;
+      }));
+    }
+    // ---- PodTopologySpread hard constraints (plugin.go:257-278; common.go:86-127; filtering.go:235-308) ----
+    const Labels *t_ns_labels = ns_labels_.count(t_.ns) ? &ns_labels_.at(t_.ns) : nullptr;
+    std::vector<const TopologySpreadConstraint *> hard;
+    for (auto &c : t_.spread) if (c.when_unsatisfiable == "DoNotSchedule" || c.when_unsatisfiable.empty()) hard.push_back(&c);
+    if (hard.size() > CCSIM_MAX_PTS) throw Unsupported("more than 8 hard topology spread constraints");
+    std::vector<Selector> hard_sel;
+    for (auto *c : hard) {
+      Selector s = Selector::from_label_selector(c->label_selector);
+      if (!c->match_label_keys.empty()) {   // mergeLabelSetWithSelector
+        Labels ml;
+        for (auto &k : c->match_label_keys) { auto it = t_.labels.find(k); if (it != t_.labels.end()) ml[k] = it->second; }
+        if (!ml.empty()) { Selector m = Selector::from_set(ml); if (!s.nothing) for (auto &r : s.reqs) m.reqs.push_back(r); else m = s; s = m; }
+      }
+      hard_sel.push_back(s);
+    }
+    auto required_affinity_match = [&](int i) {   // RequiredNodeAffinity.Match
+      if (!t_.node_selector.empty() && !Selector::from_set(t_.node_selector).matches(nodes_[i]->labels)) return false;
+      if (t_.has_required_node_affinity) {
+        for (auto &nt : t_.node_affinity_terms) if (nt.matches(nodes_[i]->labels, nodes_[i]->name)) return true;
+        return false;
+      }
+      return true;
+    };
+    auto untolerated = [&](int i) {
+      for (auto &t : nodes_[i]->taints) if ((t.effect == "NoSchedule" || t.effect == "NoExecute") && !tolerations_tolerate(t_.tolerations, t)) return true;
+      return false;
+    };
+    for (size_t c = 0; c < hard.size(); c++) {
+      const TopologySpreadConstraint &tc = *hard[c];
+      // domains: eligible nodes (all constraint keys present + inclusion policies) define TpValueToMatchNum; they get ids [0,n_present)
+      std::map<std::string, int> dom_id; std::vector<int64_t> counts;
+      std::vector<char> eligible(n, 0);
+      for (int i = 0; i < n; i++) {
+        bool all_keys = true;
+        for (auto *h : hard) if (!nodes_[i]->labels.count(h->topology_key)) all_keys = false;
+        if (!all_keys) continue;
+        if (tc.node_affinity_policy == "Honor" && !required_affinity_match(i)) continue;
+        if (tc.node_taints_policy == "Honor" && untolerated(i)) continue;
+        eligible[i] = 1;
+        const std::string &v = nodes_[i]->labels.at(tc.topology_key);
+        if (!dom_id.count(v)) { int id = (int)dom_id.size(); dom_id[v] = id; counts.push_back(0); }
+        int64_t cnt = 0;   // countPodsMatchSelector (common.go:144-158)
+        if (!hard_sel[c].empty())
+          for (auto *p : pods_on_[i]) if (!p->terminating && p->ns == t_.ns && hard_sel[c].matches(p->labels)) cnt++;
+        counts[dom_id[v]] += cnt;
+      }
+      const int n_present = (int)dom_id.size();
+      std::vector<int32_t> col(n, -1);
+      for (int i = 0; i < n; i++) {
+        auto it = nodes_[i]->labels.find(tc.topology_key);
+        if (it == nodes_[i]->labels.end()) continue;
+        if (!dom_id.count(it->second)) { int id = (int)dom_id.size(); dom_id[it->second] = id; counts.push_back(0); }   // value only on ineligible nodes: matchNum 0, never in the min
+        col[i] = dom_id[it->second];
+      }
+      int colidx = (int)e.topo.size();
+      e.topo.push_back(col);
+      std::vector<int32_t> init(counts.begin(), counts.end());
+      const bool self = hard_sel[c].matches(t_.labels);
+      add_counter(e, colidx, init, n_present, self ? 1 : 0);
+      T.pts[c].counter = (int32_t)e.counters.size() - 1;
+      T.pts[c].max_skew = tc.max_skew;
+      T.pts[c].self_match = self ? 1 : 0;
+      T.pts[c].min_zero = n_present < tc.min_domains ? 1 : 0;
+    }
+    T.n_pts = (int32_t)hard.size();
+    // ---- InterPodAffinity required terms (interpodaffinity/filtering.go:204-309) ----
+    auto term_matches_pod = [&](const AffinityTerm &t, const Pod &p, const Labels *nsl) { return t.matches(p.ns, p.labels, nsl); };
+    // incoming pod's terms: namespaceSelector is resolved against the namespace list and merged into Namespaces
+    // (mergeAffinityTermNamespacesIfNotEmpty), after which matching uses nil namespace labels
+    auto merged = [&](const std::vector<AffinityTerm> &in) {
+      std::vector<AffinityTerm> out = in;
+      for (auto &t : out) {
+        if (!t.ns_selector.nothing && !t.ns_selector.empty())
+          for (auto &kv : ns_labels_) if (t.ns_selector.matches(kv.second)) t.namespaces.insert(kv.first);
+      }
+      return out;
+    };
+    std::vector<AffinityTerm> aff = merged(t_.aff_required), anti = merged(t_.anti_required);
+    auto ipa_counter = [&](const std::string &key, const std::function<int(const Pod &)> &weight, int inc, int32_t &out_idx) {
+      // one counter per topology key; node-local when every node has the key with a unique value
+      std::map<std::string, int> dom_id; std::vector<int32_t> col(n, -1); std::vector<int64_t> counts;
+      bool unique = true;
+      for (int i = 0; i < n; i++) {
+        auto it = nodes_[i]->labels.find(key);
+        if (it == nodes_[i]->labels.end()) { unique = false; continue; }
+        if (dom_id.count(it->second)) unique = false; else { int id = (int)dom_id.size(); dom_id[it->second] = id; counts.push_back(0); }
+        col[i] = dom_id[it->second];
+      }
+      std::vector<int64_t> per_node(n, 0);
+      for (int i = 0; i < n; i++) { if (col[i] < 0) continue; for (auto *p : pods_on_[i]) per_node[i] += weight(*p); counts[col[i]] += per_node[i]; }
+      if (unique && n > 0) {
+        std::vector<int32_t> init(per_node.begin(), per_node.end());
+        add_counter(e, -1, init, n, inc);
+      } else {
+        int colidx = (int)e.topo.size();
+        e.topo.push_back(col);
+        std::vector<int32_t> init(counts.begin(), counts.end());
+        add_counter(e, colidx, init, (int)init.size(), inc);
+      }
+      out_idx = (int32_t)e.counters.size() - 1;
+    };
+    if (!aff.empty()) {
+      bool self_all = true;
+      for (auto &t : aff) if (!term_matches_pod(t, t_, nullptr)) self_all = false;
+      if (self_all) T.flags |= CCSIM_TF_AFF_SELF_MATCH_ALL;
+      std::vector<std::string> keys;
+      for (auto &t : aff) if (std::find(keys.begin(), keys.end(), t.topology_key) == keys.end()) keys.push_back(t.topology_key);
+      if (keys.size() > CCSIM_MAX_IPA) throw Unsupported("more than 8 pod-affinity topology keys");
+      int64_t total = 0;
+      for (size_t k = 0; k < keys.size(); k++) {
+        int nterms = 0; for (auto &t : aff) if (t.topology_key == keys[k]) nterms++;
+        auto w = [&](const Pod &p) { for (auto &t : aff) if (!term_matches_pod(t, p, nullptr)) return 0; return nterms; };   // podMatchesAllAffinityTerms
+        ipa_counter(keys[k], w, nterms, T.aff_counter[k]);
+        const ccsim_counter &cc = e.counters.back();
+        for (int d = 0; d < cc.n_domains; d++) total += e.counter_init.back()[d];
+      }
+      T.n_aff = (int32_t)keys.size();
+      T.aff_total_init = total;
+    }
+    if (!anti.empty()) {
+      std::vector<std::string> keys;
+      for (auto &t : anti) if (std::find(keys.begin(), keys.end(), t.topology_key) == keys.end()) keys.push_back(t.topology_key);
+      if (keys.size() > CCSIM_MAX_IPA) throw Unsupported("more than 8 pod-anti-affinity topology keys");
+      for (size_t k = 0; k < keys.size(); k++) {
+        auto w = [&](const Pod &p) { int c = 0; for (auto &t : anti) if (t.topology_key == keys[k] && term_matches_pod(t, p, nullptr)) c++; return c; };
+        int inc = w(t_);
+        ipa_counter(keys[k], w, inc, T.anti_counter[k]);
+      }
+      T.n_anti = (int32_t)keys.size();
+    }
+    // existing pods' required anti-affinity against the incoming pod (getExistingAntiAffinityCounts): static bit
+    {
+      std::set<std::pair<std::string, std::string>> blocked;
+      for (int i = 0; i < n; i++)
+        for (auto *p : pods_on_[i])
+          for (auto &t : p->anti_required)
+            if (t.matches(t_.ns, t_.labels, t_ns_labels)) {
+              auto it = nodes_[i]->labels.find(t.topology_key);
+              if (it != nodes_[i]->labels.end()) blocked.insert({t.topology_key, it->second});
+            }
+      if (!blocked.empty())
+        set_mask(T.existing_anti_mask, new_bit([&](int i) {
+          for (auto &kv : nodes_[i]->labels) if (blocked.count({kv.first, kv.second})) return true;
+          return false;
+        }));
+    }
+    if (e.topo.size() > CCSIM_MAX_TOPO_COLS || e.counters.size() > CCSIM_MAX_COUNTERS) throw Unsupported("too many topology columns");
+    // ---- pack static bits ----
+    if (bits.size() > 64 * CCSIM_MAX_STATIC_WORDS) throw Unsupported("too many static predicate bits");
+    e.static_words = (int)(bits.size() + 63) / 64;
+    e.static_mask.assign((size_t)std::max(1, e.static_words) * n, 0);
+    for (size_t b = 0; b < bits.size(); b++)
+      for (int i = 0; i < n; i++) if (bits[b][i]) e.static_mask[(size_t)(b >> 6) * n + i] |= 1ull << (b & 63);
+    for (size_t j = 0; j < e.counters.size(); j++) e.counters[j].init = e.counter_init[j].data();
+    return e;
+  }
+
+  const std::vector<const Node *> &nodes() const { return nodes_; }
+
+ private:
+  SchedConfig cfg_;
+  const Pod &t_;
+  const std::map<std::string, Labels> &ns_labels_;
+  std::vector<const Node *> nodes_;
+  std::map<std::string, int> node_index_;
+  std::vector<std::vector<const Pod *>> pods_on_;
+
+  static void add_counter(Encoded &e, int topo_col, const std::vector<int32_t> &init, int n_present, int inc) {
+    ccsim_counter c; memset(&c, 0, sizeof(c));
+    c.topo_col = topo_col; c.n_domains = (int32_t)init.size(); c.n_present = n_present; c.inc = inc;
+    e.counter_init.push_back(init);
+    e.counters.push_back(c);
+  }
+
+  // what the GPU path does not implement is refused, naming the plugin
+  void guards() const {
+    if (t_.has_pvc_volume) throw Unsupported("pod uses PersistentVolumeClaim/ephemeral volumes (VolumeBinding/VolumeZone/NodeVolumeLimits/VolumeRestrictions)");
+    if (t_.has_resource_claims) throw Unsupported("pod uses resourceClaims (DynamicResources)");
+    if (t_.has_scheduling_gates) throw Unsupported("pod has schedulingGates");
+    if (t_.has_preferred_node_affinity) throw Unsupported("preferred nodeAffinity (NodeAffinity score)");
+    if (!t_.aff_preferred.empty() || !t_.anti_preferred.empty()) throw Unsupported("preferred pod (anti-)affinity (InterPodAffinity score)");
+    for (auto &c : t_.spread) if (c.when_unsatisfiable == "ScheduleAnyway") throw Unsupported("ScheduleAnyway topology spread constraints (PodTopologySpread score)");
+    for (auto &c : t_.init_containers) (void)c;
+    const Labels *tl = ns_labels_.count(t_.ns) ? &ns_labels_.at(t_.ns) : nullptr;
+    for (size_t i = 0; i < nodes_.size(); i++) {
+      for (auto *p : pods_on_[i]) {
+        if (p->priority < t_.priority) throw Unsupported("an existing pod has lower priority than the simulated pod (DefaultPreemption would evict it)");
+        // InterPodAffinity scoring is skipped only if no existing pod's affinity term matches the incoming pod (scoring.go:128-221)
+        for (auto &t : p->aff_required) if (t.matches(t_.ns, t_.labels, tl)) throw Unsupported("an existing pod's required pod affinity matches the simulated pod (InterPodAffinity score)");
+        for (auto &t : p->aff_preferred) if (t.matches(t_.ns, t_.labels, tl)) throw Unsupported("an existing pod's preferred pod affinity matches the simulated pod (InterPodAffinity score)");
+        for (auto &t : p->anti_preferred) if (t.matches(t_.ns, t_.labels, tl)) throw Unsupported("an existing pod's preferred pod anti-affinity matches the simulated pod (InterPodAffinity score)");
+      }
+      for (auto &im : nodes_[i]->image_names)
+        for (auto &c : t_.containers) if (!c.image.empty() && im.find(c.image) != std::string::npos) throw Unsupported("a node already holds the pod's image (ImageLocality score)");
+    }
+  }
+};
+
+}  // namespace cch

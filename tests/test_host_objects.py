@@ -1,0 +1,88 @@
+"""CPU: the C++ host encoder (libcchost) + the flat C oracle against the object-level Python oracle (oracle/objref.py)
+on random small clusters and every supported podspec feature. No GPU: the encoded snapshot is run by the C oracle."""
+import importlib
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import binding as oracle
+from oracle import objref
+
+fw = importlib.import_module("cluster-capacity_b200.framework")
+abi = importlib.import_module("cluster-capacity_b200._abi")
+
+
+def run_both(nodes, pods, tmpl, max_pods=0, exclude=()):
+    ref = objref.Simulator(tmpl, max_pods, exclude)
+    ref.sync(nodes, pods)
+    ref.run()
+    cc = fw.New(None, None, tmpl, max_pods, list(exclude))
+    cc.SyncWithClient(fw.ListClient(nodes, pods))
+    enc = cc.EncodedSnapshot()
+    snap, T, ctr, tdict, snames, names = helpers.from_encoded(enc)
+    got = oracle.run(snap, T, ctr, max_pods=max_pods)
+    seq = [names[i] for i in got.pod_node.tolist()]
+    sr = helpers.stop_reason_from_result(got, snap.n, max_pods, tdict, snames, preemption_never=tmpl["spec"].get("preemptionPolicy") == "Never")
+    cc.Close()
+    return ref, seq, sr
+
+
+@pytest.mark.parametrize("variant", helpers.TEMPLATE_VARIANTS)
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_encoder_matches_object_oracle(built, variant, seed):
+    nodes, pods = helpers.random_cluster(seed, n_nodes=30, n_pods=50)
+    tmpl = helpers.template(variant, seed)
+    ref, seq, sr = run_both(nodes, pods, tmpl)
+    assert seq == ref.pods_status
+    assert sr == ref.stop_reason
+
+
+def test_limit_and_exclude(built):
+    nodes, pods = helpers.random_cluster(7, n_nodes=25, n_pods=30)
+    tmpl = helpers.template("plain")
+    ref, seq, sr = run_both(nodes, pods, tmpl, max_pods=17, exclude=("node-03", "node-11"))
+    assert seq == ref.pods_status and sr == ref.stop_reason == "LimitReached: Maximum number of pods simulated: 17"
+    assert "node-03" not in seq and "node-11" not in seq
+
+
+def test_readme_demo_objects(built):
+    # README.md:44-66 — 4 nodes x 2 CPU / 4 GiB, examples/pod.yaml: 52 instances, 13 per node
+    nodes = [helpers.make_node("kube-node-%d" % i, cpu="2", mem="4Gi", pods="110") for i in range(1, 5)]
+    tmpl = helpers.make_pod("small-pod", cpu="150m", mem="100Mi")
+    ref, seq, sr = run_both(nodes, [], tmpl)
+    assert len(seq) == 52 and seq == ref.pods_status
+    assert sr == ("Unschedulable: 0/4 nodes are available: 4 Insufficient cpu. preemption: 0/4 nodes are available: "
+                  "4 No preemption victims found for incoming pod.")
+
+
+def test_zone_round_robin_node_order(built):
+    # node_tree.go:119-143: zones in first-seen order, round-robin; equal scores -> first node in that order wins
+    zs = ["a", "a", "a", "b", "b", "c"]
+    nodes = [helpers.make_node("n%d" % i, labels={"topology.kubernetes.io/zone": z}) for i, z in enumerate(zs)]
+    ref, seq, _ = run_both(nodes, [], helpers.make_pod("p", cpu="1", mem="1Gi"), max_pods=6)
+    assert seq == ref.pods_status == ["n0", "n3", "n5", "n1", "n4", "n2"]
+
+
+def test_unsupported_features_are_refused(built):
+    nodes, pods = helpers.random_cluster(1, n_nodes=5, n_pods=0)
+    t = helpers.make_pod("p", cpu="100m")
+    t["spec"]["topologySpreadConstraints"] = [{"maxSkew": 1, "topologyKey": "x", "whenUnsatisfiable": "ScheduleAnyway", "labelSelector": {}}]
+    cc = fw.New(None, None, t, 0, [])
+    cc.SyncWithClient(fw.ListClient(nodes, pods))
+    with pytest.raises(fw.UnsupportedError, match="PodTopologySpread score"):
+        cc.EncodedSnapshot()
+    t2 = helpers.make_pod("p", cpu="100m")
+    t2["spec"]["volumes"] = [{"name": "v", "persistentVolumeClaim": {"claimName": "c"}}]
+    cc2 = fw.New(None, None, t2, 0, [])
+    cc2.SyncWithClient(fw.ListClient(nodes, pods))
+    with pytest.raises(fw.UnsupportedError, match="VolumeBinding"):
+        cc2.EncodedSnapshot()
+
+
+def test_quantities_round_up(built):
+    # Quantity.MilliValue()/Value() are ceilings (quantity.go:812-834): 0.1m cpu -> 1 milli, 1.5 bytes -> 2
+    nodes = [helpers.make_node("n0", cpu="10m", mem="10", pods="100")]
+    t = helpers.make_pod("p", cpu="0.1m", mem="1.5")
+    ref, seq, sr = run_both(nodes, [], t)
+    assert len(seq) == 5 and seq == ref.pods_status   # memory: floor(10 / 2)
