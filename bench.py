@@ -12,8 +12,10 @@ required hostname anti-affinity, 200 000 pre-existing pods (cluster-capacity_b20
   cpu_baseline / --impl reference: the CPU oracle (a port of the reference's loop; no Go toolchain exists to run the
             reference itself) on the box's host cores, on a bounded prefix of the same workload.
 
-N > 1 (torchrun): every rank analyses its own replica of the workload on its own GPU (no collective on the data path;
-"replicas only" until the node-sharded multi-GPU run lands) — weak scaling, value = sum over ranks / max time.
+N > 1 (torchrun): node-sharded run, weak scaling: the cluster grows to N x 100k nodes (racks x N), rank r owns
+a contiguous block of the node axis, the per-wave exchange of shard winners happens inside the persistent kernel over peer
+memory (NVLink), torch.distributed (NCCL) only carries the IPC handles and the final small reductions. value = evals of the
+whole job / max-over-ranks time. `--mode replicas` runs N independent single-GPU analyses instead (no data-path collective).
 """
 import argparse
 import importlib
@@ -34,6 +36,15 @@ synth = importlib.import_module("cluster-capacity_b200.synth")
 
 WORKLOAD = "C4: 100k nodes, 3x PodTopologySpread(DoNotSchedule zone/rack/region) + hostname anti-affinity, 200k existing pods"
 B_EVAL = 96  # algorithmic bytes per predicate-eval for C4
+
+
+def profiled_traffic():
+    """dram__bytes_read+write per launch of the wave kernel from the committed ncu --set full capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_wave_c4_traffic.json")) as f:
+            return float(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -178,6 +189,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"], help="N>1: node-sharded run or independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -191,7 +203,12 @@ def main():
     torch.cuda.set_device(local)
     engine = importlib.import_module("cluster-capacity_b200.engine")
 
-    snap, tmpl, ctr = synth.c4()
+    sharded_run = world > 1 and args.mode == "sharded"
+    sharded = importlib.import_module("cluster-capacity_b200.sharded")
+    if sharded_run:   # weak scaling: world x 100k nodes, hierarchy kept (racks scale with the node count)
+        snap, tmpl, ctr = synth.c4(n=100_000 * world, n_existing=200_000 * world, racks=1024 * world)
+    else:
+        snap, tmpl, ctr = synth.c4()
     psnap, h2d_bytes = pinned_snapshot(snap)
     ctr_bytes = sum(c.n_domains * 4 for c in ctr)
     warm = max(3, args.warmup)
@@ -202,9 +219,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng = engine.Engine(device=local)
+    eng = engine.Engine(device=local, rank=rank if sharded_run else 0, world=world if sharded_run else 1)
     eng.load_nodes(psnap)
     eng.set_templates(tmpl, ctr)
+    if sharded_run:
+        eng.connect_peers(dist)
+        lo_, hi_ = sharded.shard_bounds(snap.n, world, rank)
+        h2d_bytes = int(h2d_bytes * (hi_ - lo_) / snap.n)
     for _ in range(warm):
         res = eng.run(0)
     sampler = ClockSampler(local)
@@ -218,6 +239,8 @@ def main():
     for _ in range(args.steps):
         eng.flush_l2()
         torch.cuda.synchronize()
+        if sharded_run:
+            dist.barrier()
         t0 = time.perf_counter()
         res = eng.run(0)
         torch.cuda.synchronize()
@@ -236,8 +259,10 @@ def main():
     d2h = 0
     for it in range(args.steps + 1):
         torch.cuda.synchronize()
+        if sharded_run:
+            dist.barrier()
         t0 = time.perf_counter()
-        eng.load_nodes(psnap)          # H2D of every column (pinned source)
+        eng.load_nodes(psnap)          # H2D of every column of this rank's shard (pinned source)
         eng.set_templates(tmpl, ctr)   # H2D of the template table + per-domain counters
         r2 = eng.run(0)                # run + D2H of pod->node, histogram, counters
         torch.cuda.synchronize()
@@ -252,6 +277,8 @@ def main():
     # max over ranks of the timed regions, sum of the work
     vals = torch.tensor([t_total, sum(e2e_wall), kernel_ms], dtype=torch.float64, device="cuda")
     work = torch.tensor([float(evals), float(placed), float(e2e_evals)], dtype=torch.float64, device="cuda")
+    if sharded_run:
+        work[1] = work[1] / world      # placements are replicated on every rank of a sharded run; evals are per shard
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
@@ -260,13 +287,13 @@ def main():
 
     if rank == 0:
         peak, peak_kind = measured_peak()
-        achieved = (evals * B_EVAL) / (kernel_ms * 1e-3) / 1e9     # this rank's kernel: GB/s of algorithmic bytes
+        achieved = (evals * B_EVAL) / (kernel_ms * 1e-3) / 1e9     # this rank's kernel (its shard): GB/s of algorithmic bytes
         line = {
             "metric": "predicate-evals/sec", "value": evals_all / t_total, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "nodes": snap.n, "templates": 1, "mode": "canonical (percentageOfNodesToScore=100)",
-                       "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
+                       "parallelism": ("node-sharded x%d (in-kernel peer-memory exchange per wave)" % world if sharded_run else "replicas x%d" % world) if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (2x L2 write, untimed); the 10 MB snapshot is re-read from HBM once per step and then lives in shared memory",
                        "bytes_per_eval_algorithmic": B_EVAL, "placed_per_step": int(placed / args.steps),
                        "waves_per_step": int(waves / args.steps)},
@@ -277,7 +304,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind,
+                         "traffic": profiled_traffic() if world == 1 else None, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": evals * B_EVAL / args.steps,
                          "note": "algorithmic bytes = evals x 96 B (SURVEY.md §8d) over the wave kernel's CUDA-event time; the node tiles are shared-memory resident, so DRAM traffic is ~0 (see profiles/)"},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -48,6 +48,7 @@ struct DevParams {
   int32_t grid;         // CTAs of the persistent kernel
   int32_t chunk;        // nodes per CTA (contiguous ownership)
   int32_t rank, world;
+  uint32_t epoch;       // run counter (1..255), folded into every exchanged word
   // immutable columns
   const int64_t *alloc_cpu, *alloc_mem, *alloc_eph;
   const int32_t *alloc_pods;
@@ -71,8 +72,10 @@ struct DevParams {
   int32_t final_off[CCSIM_MAX_COUNTERS];
   // exchange: slots[parity][cta][class]
   unsigned long long *slots;
-  // cross-GPU exchange (multi-GPU persistent mode): xslots[parity][rank][class] in every peer's memory
-  unsigned long long *xslots_peer[8];
+  // cross-GPU exchange (node-sharded run): xslots[parity][rank][SLOT_STRIDE] lives in every rank's memory;
+  // xslots_peer[r] is rank r's copy as mapped into this process (CUDA IPC over NVLink), xslots_peer[rank] the local one
+  unsigned long long *xslots_peer[CCSIM_MAX_WORLD];
+  const int32_t *topo_full[CCSIM_MAX_TOPO_COLS];   // whole-cluster topology columns (sharded runs: winners of other shards)
   int32_t *pod_node;
   int64_t pod_cap;
   int64_t max_pods;
@@ -83,9 +86,11 @@ struct DevParams {
 };
 
 // ---- key packing ----------------------------------------------------------------------------------------------
-// [63:52] tag (wave+1, 12 bit, never 0)  [51:32] score+1 (0 = no feasible node)  [31:0] 0xFFFFFFFF - global node index
+// [63:56] run epoch  [55:44] wave tag (1..4095)  [43:32] score+1 (0 = no feasible node)  [31:0] 0xFFFFFFFF - global node index
 // max over keys = highest score, ties -> lowest node index = "first max in scan order" (selectHost, schedule_one.go:894-941).
-#define KEY_TAG_SHIFT 52
+// The epoch makes words left over from an earlier Run (in particular in the cross-GPU buffers, which cannot be cleared
+// without a host barrier) never validate. Scores are < 4095 (checked on the host: sum of weights * 100).
+#define KEY_TAG_SHIFT 44
 #define KEY_BODY_MASK ((1ull << KEY_TAG_SHIFT) - 1)
 __device__ __forceinline__ unsigned long long pack_key(int64_t score, uint32_t gidx) {
   return ((unsigned long long)(score + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - gidx);
@@ -398,6 +403,15 @@ __device__ __forceinline__ unsigned long long ld_slot(const unsigned long long *
   return v;
 }
 // warp-wide max of a packed 64-bit key with two REDUX.MAX.U32 (high word, then low word among the lanes that tie)
+// system-scope variants for words that cross NVLink (peer memory)
+__device__ __forceinline__ void st_slot_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_slot_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
   const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
   const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
@@ -417,6 +431,35 @@ struct CommitInfo {
   int32_t pad;
 };
 
+
+#ifndef WATCHDOG_SPINS
+#define WATCHDOG_SPINS (1u << 24)
+#endif
+// Second level of the per-wave exchange for node-sharded multi-GPU runs (warp 0 of every CTA, after the intra-GPU gather):
+// CTA 0 stores this GPU's class winners, tagged, into EVERY rank's exchange buffer (P2P stores over NVLink; 8-byte stores
+// are single transactions, the tag inside the word validates it), then every CTA polls its LOCAL copy for all ranks.
+// This is the whole collective: an all-gather of one word per rank fused into the kernel, no NCCL call per wave.
+__device__ __forceinline__ bool cross_gpu_exchange(const DevParams &p, long long k, uint32_t tag, int ncls,
+                                                   unsigned long long *cbest, int lane, int cta) {
+  const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
+  const size_t base = (size_t)(k & 1) * CCSIM_MAX_WORLD * SLOT_STRIDE;
+  if (cta == 0 && lane < p.world)
+    for (int c = 0; c < ncls; c++) st_slot_sys(&p.xslots_peer[lane][base + (size_t)p.rank * SLOT_STRIDE + c], cbest[c] | tagbits);
+  const unsigned long long *local = p.xslots_peer[p.rank] + base;
+  bool dead = false;
+  for (int c = 0; c < ncls; c++) {
+    unsigned long long v = tagbits;
+    unsigned spins = 0;
+    bool pending;
+    do {
+      if (lane < p.world) v = ld_slot_sys(&local[(size_t)lane * SLOT_STRIDE + c]);
+      pending = ((uint32_t)(v >> KEY_TAG_SHIFT) != tag);
+      if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+    } while (__any_sync(0xffffffffu, pending));
+    cbest[c] = warp_max_u64(lane < p.world ? (v & KEY_BODY_MASK) : 0ull);
+  }
+  return __any_sync(0xffffffffu, dead);
+}
 
 // TaintToleration NormalizeScore, reverse (helper/normalize_score.go:28-56)
 __device__ __forceinline__ int64_t taint_norm(int raw, int maxraw) {

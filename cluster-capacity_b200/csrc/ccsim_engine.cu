@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0;
 #endif
   long long k = 0;
-  uint32_t tag = 1;          // 1..4095; waves k and k+2 (same parity buffer) always differ
+  uint32_t wtag = 1;         // 1..4095; waves k and k+2 (same parity buffer) always differ
+  uint32_t tag = (p.epoch << 12) | wtag;
   int32_t ti = 0;            // template of pod k = k % n_templates (report.go:160)
   for (;; k++) {
     PH_START();
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
           const bool skip = (dc.inc == 0) || (dc.is_aff && !(t.flags & CCSIM_TF_AFF_SELF_MATCH_ALL));
           ci.inc = skip ? 0 : dc.inc;
           ci.local = dc.topo_col < 0; ci.is_aff = dc.is_aff; ci.n_present = dc.n_present;
-          ci.gtopo = dc.topo_col < 0 ? nullptr : p.topo[dc.topo_col];
+          ci.gtopo = dc.topo_col < 0 ? nullptr : p.topo_full[dc.topo_col];
           ci.ltopo = dc.topo_col < 0 ? nullptr : ws.topo_ptr[dc.topo_col];
           ci.pts_idx = -1;
           for (int c = 0; c < t.n_pts; c++) if (t.pts[c].counter == j && !t.pts[c].min_zero) ci.pts_idx = c;
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
         cbest[c] = warp_max_u64(m);
       }
       dead = __any_sync(0xffffffffu, dead);
+      if (p.world > 1 && !dead) dead = cross_gpu_exchange(p, k, tag, ncls, cbest, lane, cta);
       PH_MARK(3);
       // prioritizeNodes + selectHost over the class winners (schedule_one.go:776-941)
       unsigned long long wkey = cbest[0];
@@ -335,6 +337,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
           // ClusterCapacityBinder.Bind + postBindHook: record pod k -> node (plugin.go:34-53; simulator.go:297-312)
           if (k < p.pod_cap) p.pod_node[k] = g; else ws.stop = 3;
         }
+        if (p.world > 1 && !mine && cta == 0 && lane == 31) {   // sharded run: every rank keeps the whole pod -> node sequence
+          const bool local = (w >= 0 && w < p.n);
+          if (!local) { if (k < p.pod_cap) p.pod_node[k] = g; else ws.stop = 3; }
+        }
         // per-domain counters: every CTA applies the same update to its own replica, one lane per counter
         // (the next cycle's PreFilter recount would see this clone: podtopologyspread/filtering.go:255-289,
         //  interpodaffinity/filtering.go:234-271)
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
               if (ci.is_aff) { atomicAdd((unsigned long long *)&ws.aff_total, (unsigned long long)ci.inc); ws.dirty = 1; }
             } else {
               // the winner's domain id: from this CTA's tile if it owns the node, else from the global column (L2)
-              const int32_t dom = mine ? ci.ltopo[w] : ci.gtopo[w];
+              const int32_t dom = mine ? ci.ltopo[w] : ci.gtopo[g];   // gtopo: whole-cluster column, global index
               if (dom >= 0) {
                 int32_t *cnt = ws.cnt_ptr[j];
                 const int32_t old = cnt[dom];
@@ -371,7 +377,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
     // a PTS minimum whose last domain moved up: recount (rare: once per n_present commits at that level)
     for (int c = 0; c < t.n_pts; c++)
       if (!t.pts[c].min_zero && ws.ptsnum[c] <= 0 && p.counters[t.pts[c].counter].n_present > 0) pts_recount(p, c);
-    tag = (tag == 4095u) ? 1u : tag + 1u;
+    wtag = (wtag == 4095u) ? 1u : wtag + 1u;
+    tag = (p.epoch << 12) | wtag;
     ti = (ti + 1 == p.n_templates) ? 0 : ti + 1;
   }
 
@@ -582,6 +589,11 @@ struct ccsim_handle {
   // run state
   int grid = 0;
   unsigned long long *d_slots = nullptr;
+  unsigned long long *d_xslots = nullptr;                 // cross-GPU exchange buffer (exported over CUDA IPC)
+  unsigned long long *x_peer[CCSIM_MAX_WORLD] = {};       // every rank's buffer as mapped here
+  bool peers_ready = false;
+  uint32_t epoch = 0;
+  int32_t *d_topo_full[CCSIM_MAX_TOPO_COLS] = {};
   int32_t *d_pod_node = nullptr; int64_t pod_cap = 0;
   std::vector<int32_t> h_pod_node;
   DevOut *d_out = nullptr;
@@ -625,7 +637,7 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
   ccsim_handle *h = nullptr;
   if (!cfg || !out) return fail(h, CCSIM_EINVAL, "null argument");
   if (cfg->abi_version != CCSIM_ABI_VERSION) return fail(h, CCSIM_EINVAL, "abi_version %d != %d", cfg->abi_version, CCSIM_ABI_VERSION);
-  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(h, CCSIM_EINVAL, "bad rank/world");
+  if (cfg->world < 1 || cfg->world > CCSIM_MAX_WORLD || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(h, CCSIM_EINVAL, "bad rank/world");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -646,6 +658,9 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
   cudaMalloc((void **)&h->d_out, sizeof(DevOut));
   cudaMalloc((void **)&h->d_params, sizeof(DevParams));
   cudaMalloc((void **)&h->d_slots, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * SLOT_STRIDE);
+  cudaMalloc((void **)&h->d_xslots, sizeof(unsigned long long) * 2 * CCSIM_MAX_WORLD * SLOT_STRIDE);
+  cudaMemset(h->d_xslots, 0, sizeof(unsigned long long) * 2 * CCSIM_MAX_WORLD * SLOT_STRIDE);
+  h->x_peer[cfg->rank] = h->d_xslots;
   h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   cudaFuncSetAttribute(ccsim_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(WaveShared) - 1024));
@@ -662,6 +677,8 @@ extern "C" void ccsim_destroy(ccsim_handle *h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   free_pool(h->allocs); free_pool(h->tmpl_allocs);
+  for (int r = 0; r < CCSIM_MAX_WORLD; r++) if (h->x_peer[r] && r != h->cfg.rank) cudaIpcCloseMemHandle(h->x_peer[r]);
+  cudaFree(h->d_xslots);
   cudaFree(h->d_out); cudaFree(h->d_params); cudaFree(h->d_slots); cudaFree(h->d_pod_node); cudaFree(h->d_flush);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -709,6 +726,9 @@ extern "C" int ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nd) {
   for (int k = 0; k < nd->n_topo_cols; k++) {
     if (!nd->topo[k] && N > 0) return fail(h, CCSIM_EINVAL, "null topo column %d", k);
     if ((rc = dev_upload<int32_t>(h, h->allocs, &h->d_topo[k], nd->topo[k] ? nd->topo[k] + lo : nullptr, (size_t)n))) return rc;
+    h->d_topo_full[k] = h->d_topo[k];
+    if (h->cfg.world > 1)   // winners of other shards: their domain ids are looked up in the whole-cluster column
+      if ((rc = dev_upload<int32_t>(h, h->allocs, &h->d_topo_full[k], nd->topo[k], (size_t)N))) return rc;
   }
   // working copies
 #define WK(dst, T) if ((rc = dev_alloc<T>(h, h->allocs, &h->dst, (size_t)n))) return rc
@@ -769,6 +789,11 @@ extern "C" int ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const c
     if ((T.flags & CCSIM_TF_PREFILTER_NODES) && (T.prefilter_bit < 0 || T.prefilter_bit >= 64 * nd.static_words))
       return fail(h, CCSIM_EINVAL, "template %d: prefilter_bit", t);
   }
+  for (int t = 0; t < n_templates; t++) {
+    const ccsim_template &T = templates[t];
+    const long long wsum = (long long)abs(T.w_taint) + abs(T.w_node_affinity) + abs(T.w_fit) + abs(T.w_pts) + abs(T.w_ipa) + abs(T.w_balanced) + abs(T.w_image);
+    if (wsum * 100 >= 4095) return fail(h, CCSIM_EUNSUPPORTED, "template %d: sum of score weights %lld too large for the packed key", t, wsum);
+  }
   if (h->max_prefer_pop + 1 > CCSIM_MAX_CLASSES)
     return fail(h, CCSIM_EUNSUPPORTED, "a node carries %d PreferNoSchedule taints (max %d)", h->max_prefer_pop, CCSIM_MAX_CLASSES - 1);
   h->h_templates.assign(templates, templates + n_templates);
@@ -816,7 +841,8 @@ static void fill_params(ccsim_handle *h, DevParams &p, int64_t max_pods) {
   p.alloc_cpu = h->d_alloc_cpu; p.alloc_mem = h->d_alloc_mem; p.alloc_eph = h->d_alloc_eph; p.alloc_pods = h->d_alloc_pods;
   for (int k = 0; k < nd.n_scalars; k++) { p.alloc_scalar[k] = h->d_alloc_scalar[k]; p.req_scalar[k] = h->w_req_scalar[k]; }
   p.taint_mask = h->d_taint; p.static_mask = h->d_static;
-  for (int k = 0; k < nd.n_topo_cols; k++) p.topo[k] = h->d_topo[k];
+  for (int k = 0; k < nd.n_topo_cols; k++) { p.topo[k] = h->d_topo[k]; p.topo_full[k] = h->d_topo_full[k]; }
+  for (int r = 0; r < CCSIM_MAX_WORLD; r++) p.xslots_peer[r] = h->x_peer[r];
   p.req_cpu = h->w_req_cpu; p.req_mem = h->w_req_mem; p.req_eph = h->w_req_eph; p.nz_cpu = h->w_nz_cpu; p.nz_mem = h->w_nz_mem;
   p.npods = h->w_npods; p.placed_mask = h->w_placed; p.score_cache = h->w_score;
   for (int w = 0; w < CCSIM_MAX_TAINT_WORDS; w++) { p.taint_nosched[w] = nd.taint_nosched[w]; p.taint_prefer[w] = nd.taint_prefer[w]; }
@@ -832,7 +858,7 @@ static void fill_params(ccsim_handle *h, DevParams &p, int64_t max_pods) {
 extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   if (!h || !out) return fail(h, CCSIM_EINVAL, "null argument");
   if (!h->have_nodes || !h->have_templates) return fail(h, CCSIM_ESTATE, "load_nodes and set_templates must come first");
-  if (h->cfg.world > 1) return fail(h, CCSIM_EUNSUPPORTED, "multi-GPU run: use ccsim_comm_init + sharded run (not in this build)");
+  if (h->cfg.world > 1 && !h->peers_ready) return fail(h, CCSIM_ESTATE, "sharded run: ccsim_peer_import must come first");
   CK(cudaSetDevice(h->cfg.device));
   memset(out, 0, sizeof(*out));
   out->n_nodes = h->n_global;
@@ -863,6 +889,8 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   }
   CK(cudaMemsetAsync(h->d_out, 0, sizeof(DevOut), s));
   CK(cudaMemsetAsync(h->d_slots, 0, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * SLOT_STRIDE, s));
+  // (the cross-GPU buffer is NOT cleared here: peers may already be writing wave 0 of this run; stale words are
+  //  harmless because runs advance a per-handle epoch that is folded into the tag)
 
   if (n == 0) {   // ErrNoNodesAvailable (scheduler.go:68): nothing to evaluate; the host formats the message
     out->placed = 0; out->stop_code = CCSIM_STOP_UNSCHEDULABLE; out->pod_node = nullptr;
@@ -879,6 +907,8 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   fill_params(h, p, max_pods);
   p.grid = grid;
   p.chunk = (n + grid - 1) / grid;
+  h->epoch = (h->epoch % 255u) + 1u;     // every rank of a sharded run calls ccsim_run the same number of times
+  p.epoch = h->epoch;
   // resident mode: every column the Filter/Score pass reads is staged into shared memory once
   int n_local = 0;
   for (int j = 0; j < h->n_counters; j++) if (h->counters[j].topo_col < 0) n_local++;
@@ -1032,5 +1062,28 @@ extern "C" int ccsim_flush_l2(ccsim_handle *h) {
   return CCSIM_OK;
 }
 
-extern "C" int ccsim_nccl_unique_id(uint8_t id_out[128]) { (void)id_out; return CCSIM_EUNSUPPORTED; }
-extern "C" int ccsim_comm_init(ccsim_handle *h, const uint8_t id[128]) { (void)id; return fail(h, CCSIM_EUNSUPPORTED, "multi-GPU not built yet"); }
+extern "C" int ccsim_peer_export(ccsim_handle *h, uint8_t handle_out[CCSIM_IPC_HANDLE_BYTES]) {
+  if (!h || !handle_out) return fail(h, CCSIM_EINVAL, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaIpcMemHandle_t mh;
+  CK(cudaIpcGetMemHandle(&mh, h->d_xslots));
+  static_assert(sizeof(mh) == CCSIM_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  memcpy(handle_out, &mh, sizeof(mh));
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_peer_import(ccsim_handle *h, int32_t world, const uint8_t *handles) {
+  if (!h || !handles) return fail(h, CCSIM_EINVAL, "null argument");
+  if (world != h->cfg.world) return fail(h, CCSIM_EINVAL, "world %d != configured %d", world, h->cfg.world);
+  CK(cudaSetDevice(h->cfg.device));
+  for (int r = 0; r < world; r++) {
+    if (r == h->cfg.rank) { h->x_peer[r] = h->d_xslots; continue; }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, handles + (size_t)r * CCSIM_IPC_HANDLE_BYTES, sizeof(mh));
+    void *ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->x_peer[r] = (unsigned long long *)ptr;
+  }
+  h->peers_ready = true;
+  return CCSIM_OK;
+}

@@ -127,7 +127,7 @@ __device__ void lean_build_consts(const DevParams &p, const LeanParams &lp) {
     const bool skip = (dc.inc == 0) || (dc.is_aff && !(fl & CCSIM_TF_AFF_SELF_MATCH_ALL));
     ci.inc = skip ? 0 : dc.inc;
     ci.local = dc.topo_col < 0; ci.is_aff = dc.is_aff; ci.n_present = dc.n_present;
-    ci.gtopo = dc.topo_col < 0 ? nullptr : p.topo[dc.topo_col];
+    ci.gtopo = dc.topo_col < 0 ? nullptr : p.topo_full[dc.topo_col];
     ci.ltopo = nullptr;
     ci.pts_idx = -1;
     for (int c = 0; c < t.n_pts; c++) if (t.pts[c].counter == j && !t.pts[c].min_zero) ci.pts_idx = c;
@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0;
 #endif
   long long k = 0;
-  uint32_t tag = 1;
+  uint32_t wtag = 1;
+  uint32_t tag = (p.epoch << 12) | wtag;
   for (;; k++) {
     PH_START();
     if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ls.stop = 2; __syncthreads(); break; }
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
         cbest[c] = warp_max_u64(m);
       }
       dead = __any_sync(0xffffffffu, dead);
+      if (p.world > 1 && !dead) dead = cross_gpu_exchange(p, k, tag, ncls, cbest, lane, cta);
       PH_MARK(3);
       unsigned long long wkey = cbest[0];
       if (ncls > 1 || (t.score_enable & CCSIM_PL_TAINT_TOLERATION)) {
@@ -358,6 +360,10 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
           p.req_cpu[w] = rc; p.req_mem[w] = rm; p.nz_cpu[w] = zc; p.nz_mem[w] = zm; p.npods[w] = np;   // write through
           if (k < p.pod_cap) p.pod_node[k] = g; else ls.stop = 3;
         }
+        if (p.world > 1 && !mine && cta == 0 && lane == 31) {   // sharded run: every rank keeps the whole pod -> node sequence
+          const bool local = (w >= 0 && w < p.n);
+          if (!local) { if (k < p.pod_cap) p.pod_node[k] = g; else ls.stop = 3; }
+        }
         if (lane < p.n_counters) {
           const int j = lane;
           const CommitInfo ci = ls.cinfo[j];
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
               }
               if (ci.is_aff) { atomicAdd((unsigned long long *)&ls.aff_total, (unsigned long long)ci.inc); ls.dirty = 1; }
             } else {
-              const int32_t dom = mine ? reinterpret_cast<const int32_t *>(rec + (size_t)jw * su)[10 + lp.counter_slot[j]] : ci.gtopo[w];
+              const int32_t dom = mine ? reinterpret_cast<const int32_t *>(rec + (size_t)jw * su)[10 + lp.counter_slot[j]] : ci.gtopo[g];
               if (dom >= 0) {
                 int32_t *cnt = smem_cnt + p.counters[j].smem_off;
                 const int32_t old = cnt[dom];
@@ -390,7 +396,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
     if (ls.stop) break;
     for (int c = 0; c < ls.tmpl.n_pts; c++)
       if (!ls.tmpl.pts[c].min_zero && ls.ptsnum[c] <= 0 && p.counters[ls.tmpl.pts[c].counter].n_present > 0) lean_pts_recount(p, smem_cnt, c);
-    tag = (tag == 4095u) ? 1u : tag + 1u;
+    wtag = (wtag == 4095u) ? 1u : wtag + 1u;
+    tag = (p.epoch << 12) | wtag;
   }
 
   if (cta == 0) {

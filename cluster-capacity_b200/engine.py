@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, "libccsim.so")
 _lib = None
 
 EXPORTS = ["ccsim_create", "ccsim_destroy", "ccsim_last_error", "ccsim_abi_version", "ccsim_load_nodes",
-           "ccsim_set_templates", "ccsim_run", "ccsim_node_counts", "ccsim_nccl_unique_id", "ccsim_comm_init",
+           "ccsim_set_templates", "ccsim_run", "ccsim_node_counts", "ccsim_peer_export", "ccsim_peer_import",
            "ccsim_device_info", "ccsim_kernel_launches", "ccsim_flush_l2"]
 
 
@@ -50,10 +50,10 @@ def lib():
         L.ccsim_kernel_launches.argtypes = [C.c_void_p]
         L.ccsim_flush_l2.restype = C.c_int
         L.ccsim_flush_l2.argtypes = [C.c_void_p]
-        L.ccsim_nccl_unique_id.restype = C.c_int
-        L.ccsim_nccl_unique_id.argtypes = [abi.PU8]
-        L.ccsim_comm_init.restype = C.c_int
-        L.ccsim_comm_init.argtypes = [C.c_void_p, abi.PU8]
+        L.ccsim_peer_export.restype = C.c_int
+        L.ccsim_peer_export.argtypes = [C.c_void_p, abi.PU8]
+        L.ccsim_peer_import.restype = C.c_int
+        L.ccsim_peer_import.argtypes = [C.c_void_p, C.c_int32, abi.PU8]
         _lib = L
     return _lib
 
@@ -106,6 +106,20 @@ class Engine:
         res = abi.Result()
         self._check(lib().ccsim_run(self._h, max_pods, C.byref(res)), "ccsim_run")
         return RunResult(res)
+
+    def connect_peers(self, dist):
+        """Node-sharded multi-GPU run: all-gather the CUDA IPC handles of the exchange buffers over torch.distributed
+        and map every peer's buffer (the per-wave exchange itself then happens inside the persistent kernel)."""
+        import torch
+        mine = np.zeros(64, np.uint8)
+        self._check(lib().ccsim_peer_export(self._h, mine.ctypes.data_as(abi.PU8)), "ccsim_peer_export")
+        world = dist.get_world_size()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(mine).to(dev)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        allh = np.concatenate([o.cpu().numpy() for o in out]).astype(np.uint8)
+        self._check(lib().ccsim_peer_import(self._h, world, allh.ctypes.data_as(abi.PU8)), "ccsim_peer_import")
 
     def node_counts(self, t=0):
         counts = np.zeros(max(1, self._n), np.int32)

@@ -248,9 +248,15 @@ int  ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out);
  * and the index of the first pod placed on each node (-1 none): ReplicasOnNodes is ordered by first placement. */
 int  ccsim_node_counts(ccsim_handle *h, int32_t t, int32_t *counts /*[n_nodes]*/, int64_t *first_pod /*[n_nodes]*/);
 
-/* multi-GPU (node-axis shards): NCCL unique id exchange is done by the caller (torch.distributed) */
-int  ccsim_nccl_unique_id(uint8_t id_out[128]);
-int  ccsim_comm_init(ccsim_handle *h, const uint8_t id[128]);
+/* multi-GPU (node-axis shards): one process per GPU, rank r owns nodes [r*ceil(N/W), ...).
+ * The per-wave exchange of the shard winners happens INSIDE the persistent kernel through peer memory (NVLink/NVSwitch):
+ * every rank exports the CUDA IPC handle of its exchange buffer, the caller all-gathers the handles (torch.distributed)
+ * and every rank imports its peers' buffers. Results: placed / stop_code / pod_node are identical on every rank;
+ * reason_hist, preempt_* and evals are per shard and must be summed by the caller (one small all-reduce). */
+#define CCSIM_IPC_HANDLE_BYTES 64
+#define CCSIM_MAX_WORLD 8
+int  ccsim_peer_export(ccsim_handle *h, uint8_t handle_out[CCSIM_IPC_HANDLE_BYTES]);
+int  ccsim_peer_import(ccsim_handle *h, int32_t world, const uint8_t *handles /* world x CCSIM_IPC_HANDLE_BYTES, rank order */);
 
 /* introspection for tests / bench */
 int  ccsim_device_info(ccsim_handle *h, int32_t *sm_count, int32_t *grid, int32_t *block, int64_t *l2_bytes);
