@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
     PH_START();
     // postBindHook limit (pkg/framework/simulator.go:300-305): checked after the k-th pod was bound
     if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ws.stop = 2; __syncthreads(); break; }
+    if (k > p.pod_cap) { if (tid == 0) ws.stop = 3; __syncthreads(); break; }   // cannot happen (pod_cap bounds every run): never spin forever
     if (p.n_templates > 1) {
       const ccsim_template *src = &p.templates[ti];
       for (int q = tid; q < (int)(sizeof(ccsim_template) / 8); q += blockDim.x)
@@ -927,10 +928,9 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   int block = BLOCK_THREADS;
   // lean resident kernel: the common case (see ccsim_lean.cuh for the eligibility rules)
   LeanParams lp; memset(&lp, 0, sizeof(lp));
-  // measured on B200 (profiles/r1_kernel_variants.md): the lean kernel wins when per-domain terms are present (C4),
-  // the generic resident kernel wins on purely node-local templates; CCSIM_FORCE_LEAN / CCSIM_FORCE_GENERIC override.
-  bool lean = resident && h->n_templates == 1 && h->meta.taint_words == 1 && h->meta.static_words <= 1 &&
-              (h->n_counters > 0 || getenv("CCSIM_FORCE_LEAN")) && !getenv("CCSIM_FORCE_GENERIC");
+  // measured on B200 (profiles/r1_kernel_variants.md): at 768 threads the lean kernel beats the generic resident kernel on
+  // every eligible workload (C2 2.50 vs 2.67, C3 2.64 vs 2.84, C4 4.27 vs 4.95 us/wave); CCSIM_FORCE_GENERIC overrides.
+  bool lean = resident && h->n_templates == 1 && h->meta.taint_words == 1 && h->meta.static_words <= 1 && !getenv("CCSIM_FORCE_GENERIC");
   if (lean) {
     const ccsim_template &T = h->h_templates[0];
     const bool nzfit = (T.filter_enable & CCSIM_PL_FIT) && !(T.flags & CCSIM_TF_FIT_ALL_ZERO);

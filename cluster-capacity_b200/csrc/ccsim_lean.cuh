@@ -15,7 +15,7 @@
 #pragma once
 #include "ccsim_device.cuh"
 
-#define LEAN_THREADS 1024
+#define LEAN_THREADS 768
 #define LEAN_WARPS (LEAN_THREADS / 32)
 #define LEAN_MAX_TERMS 16
 #define LEAN_MAX_SLOTS 10   /* extra int32 slots per record: domain ids and node-local counters */
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
   for (;; k++) {
     PH_START();
     if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ls.stop = 2; __syncthreads(); break; }
+    if (k > p.pod_cap) { if (tid == 0) ls.stop = 3; __syncthreads(); break; }   // cannot happen (pod_cap bounds every run): never spin forever
     if (ls.dirty) {
       if (tid == 0) { lean_build_consts(p, lp); ls.dirty = 0; }
       __syncthreads();
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
       const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
       unsigned long long *myslots = p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
       for (int c = 0; c < ncls; c++) {
-        const unsigned long long v = warp_max_u64(ls.warp_best[lane][c]);
+        const unsigned long long v = warp_max_u64(lane < LEAN_WARPS ? ls.warp_best[lane][c] : 0ull);
         if (lane == 0) st_slot(&myslots[c], v | tagbits);
       }
       PH_MARK(2);

@@ -11,7 +11,7 @@ import numpy as np
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libccsim.so")
+SO_PATH = os.environ.get("CCSIM_SO") or os.path.join(_HERE, "libccsim.so")   # CCSIM_SO: kernel-variant experiments only
 _lib = None
 
 EXPORTS = ["ccsim_create", "ccsim_destroy", "ccsim_last_error", "ccsim_abi_version", "ccsim_load_nodes",
