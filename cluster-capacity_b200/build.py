@@ -20,6 +20,7 @@ HOST_OUT = os.path.join(_HERE, "libcchost.so")
 def build(force=False, verbose=False):
     """libccsim.so (CUDA, sm_100a) then libcchost.so (C++ host side, links libccsim via $ORIGIN rpath)."""
     DEPS.append(os.path.join(_HERE, "csrc", "ccsim_lean.cuh"))
+    DEPS.append(os.path.join(_HERE, "csrc", "ccsim_batched.cuh"))
     newest = max(os.path.getmtime(p) for p in DEPS)
     if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -32,6 +32,7 @@
 #define PH_MARK(i) do {} while (0)
 #endif
 #include "ccsim_lean.cuh"
+#include "ccsim_batched.cuh"
 
 #define BLOCK_THREADS 512
 #define MAX_WARPS (BLOCK_THREADS / 32)
@@ -553,6 +554,7 @@ struct ccsim_handle {
   size_t smem_optin = 0;
   int last_resident = 0;
   int last_lean = 0;
+  int last_batched = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -667,6 +669,8 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
                        (int)(h->smem_optin - sizeof(WaveShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(LeanShared) - 1024));
+  cudaFuncSetAttribute(ccsim_wave_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(h->smem_optin - sizeof(LeanShared) - sizeof(BatchShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(SMEM_CNT_MAX_INTS * sizeof(int32_t) + 16));
   *out = h;
@@ -969,10 +973,22 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
     }
   }
   h->last_lean = lean ? 1 : 0;
+  // batched tie-run engine (ccsim_batched.cuh): one template, node-local predicates and scorers only
+  bool batched = lean && h->n_counters == 0 && h->max_prefer_pop == 0 && h->cfg.world == 1 &&
+                 h->cfg.engine != CCSIM_ENGINE_SEQUENTIAL && !getenv("CCSIM_FORCE_SEQUENTIAL");
+  if (batched) {
+    const size_t smem_b = smem + (size_t)p.chunk_pad * 12;
+    if (smem_b + sizeof(LeanShared) + sizeof(BatchShared) + 1024 > h->smem_optin) batched = false;
+    else { smem = smem_b; kern = (const void *)ccsim_wave_batched_kernel; }
+  }
+  if (h->cfg.engine == CCSIM_ENGINE_BATCHED && !batched)
+    return fail(h, CCSIM_EUNSUPPORTED, "batched engine needs one template with node-local predicates only, no PreferNoSchedule taints, a resident tile and a single GPU");
+  h->last_batched = batched ? 1 : 0;
   p.self = h->d_params;
   CK(cudaMemcpyAsync(h->d_params, &p, sizeof(DevParams), cudaMemcpyHostToDevice, s));
   int occ = 0;
-  if (lean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel, block, smem));
+  if (batched) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_batched_kernel, block, smem));
+  else if (lean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel, block, smem));
   else if (resident) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<true>, block, smem));
   else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<false>, block, smem));
   if (occ < 1 || occ * h->sm_count < grid) return fail(h, CCSIM_ECUDA, "persistent grid %d does not fit (occupancy %d x %d SMs)", grid, occ, h->sm_count);
@@ -987,7 +1003,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   if (ho.error) return fail(h, CCSIM_ECUDA, "wave kernel aborted (error %d: %s)", ho.error, ho.error == 1 ? "exchange watchdog / output overflow" : "?");
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 #ifdef CCSIM_PHASE_TIMERS
-  fprintf(stderr, "[ccsim %s tile %zu B smem] ", lean ? "lean" : (resident ? "resident" : "streaming"), smem);
+  fprintf(stderr, "[ccsim %s tile %zu B smem] ", batched ? "batched" : (lean ? "lean" : (resident ? "resident" : "streaming")), smem);
   fprintf(stderr, "[ccsim phases, CTA0 cycles/wave] scan=%.0f S1=%.0f publish=%.0f gather=%.0f commit=%.0f S2=%.0f (waves=%lld, %.3f ms)\n",
           (double)ho.phase_cycles[0] / ho.waves, (double)ho.phase_cycles[1] / ho.waves, (double)ho.phase_cycles[2] / ho.waves,
           (double)ho.phase_cycles[3] / ho.waves, (double)ho.phase_cycles[4] / ho.waves, (double)ho.phase_cycles[5] / ho.waves,

@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 GiB, MiB = 1 << 30, 1 << 20
 
 
-def gpu_run(snap, tmpl, ctr=(), max_pods=0):
+def gpu_run(snap, tmpl, ctr=(), max_pods=0, engine_kind=abi.ENGINE_SEQUENTIAL):
     engine = importlib.import_module("cluster-capacity_b200.engine")
-    with engine.Engine(device=0) as eng:
+    with engine.Engine(device=0, engine=engine_kind) as eng:
         eng.load_nodes(snap)
         eng.set_templates(tmpl, ctr)
         res = eng.run(max_pods)
@@ -24,8 +24,16 @@ def gpu_run(snap, tmpl, ctr=(), max_pods=0):
 
 
 def check(snap, tmpl, ctr=(), max_pods=0, threads=4):
-    got, counts, first = gpu_run(snap, tmpl, ctr, max_pods)
+    """Sequential engine (one winner per wave: evals/waves equal the reference-equivalent count) AND the default engine
+    (AUTO: batched tie-run waves when the template is node-local) against the oracle."""
     want = oracle.run(snap, tmpl, ctr, max_pods=max_pods, threads=threads)
+    auto, acounts, _ = gpu_run(snap, tmpl, ctr, max_pods, abi.ENGINE_AUTO)
+    assert auto.placed == want.placed and auto.stop_code == want.stop_code
+    assert np.array_equal(auto.pod_node, want.pod_node), "AUTO engine: placement sequence differs from the oracle"
+    assert np.array_equal(auto.reason_hist, want.reason_hist)
+    assert (auto.preempt_no_victims, auto.preempt_not_helpful) == (want.preempt_no_victims, want.preempt_not_helpful)
+    assert auto.waves <= want.waves
+    got, counts, first = gpu_run(snap, tmpl, ctr, max_pods, abi.ENGINE_SEQUENTIAL)
     assert got.placed == want.placed
     assert got.stop_code == want.stop_code
     assert np.array_equal(got.pod_node, want.pod_node)
@@ -136,9 +144,39 @@ def test_host_ports_one_clone_per_node(built):
 
 
 def test_full_size_c2_properties(built):
-    """BASELINE config C2 at full size (10k nodes): closed-form count and per-node distribution (KA5), no oracle run."""
+    """BASELINE config C2 at full size (10k nodes): closed-form count and per-node distribution (KA5), no oracle run;
+    the batched engine and the sequential engine must produce the same pod -> node sequence."""
     snap, tmpl, ctr = synth.c2()
     got, counts, _ = gpu_run(snap, tmpl, ctr)
     cap = synth.closed_form_capacity(snap, tmpl[0])
     assert got.placed == int(cap.sum()) and np.array_equal(counts, cap)
     assert got.evals == (got.placed + 1) * snap.n
+    bat, bcounts, _ = gpu_run(snap, tmpl, ctr, 0, abi.ENGINE_BATCHED)
+    assert np.array_equal(bat.pod_node, got.pod_node) and np.array_equal(bcounts, cap)
+    assert bat.waves < got.waves // 50
+
+
+@pytest.mark.parametrize("limit", [1, 2, 7, 63, 64, 65, 500, 4093, 4096, 10007])
+def test_batched_limit_truncates_mid_wave(built, limit):
+    snap, tmpl, ctr = synth.c2(n=3000, seed=11)
+    want = oracle.run(snap, tmpl, ctr, max_pods=limit, threads=4)
+    bat, _, _ = gpu_run(snap, tmpl, ctr, limit, abi.ENGINE_BATCHED)
+    assert bat.stop_code == want.stop_code == abi.STOP_LIMIT_REACHED and bat.placed == limit
+    assert np.array_equal(bat.pod_node, want.pod_node)
+
+
+def test_batched_refuses_coupled_templates(built):
+    engine = importlib.import_module("cluster-capacity_b200.engine")
+    snap, tmpl, ctr = synth.c4(n=2000, n_existing=4000, zones=4, racks=16, regions=2)
+    with engine.Engine(device=0, engine=abi.ENGINE_BATCHED) as eng:
+        eng.load_nodes(snap)
+        eng.set_templates(tmpl, ctr)
+        with pytest.raises(engine.EngineError, match="batched engine needs"):
+            eng.run(0)
+
+
+def test_identical_nodes_all_tied(built):
+    # 500 identical nodes: every wave ties all feasible nodes (worst case for the tie-run ordering)
+    n = 500
+    snap = abi.Snapshot(n, np.full(n, 4000), np.full(n, 8 * GiB), np.full(n, 30))
+    check(snap, [abi.default_template(150, 100 * MiB)])
