@@ -69,6 +69,7 @@ REASON_TEXT = {
 
 STOP_UNSCHEDULABLE, STOP_LIMIT_REACHED = 0, 1
 ENGINE_AUTO, ENGINE_SEQUENTIAL, ENGINE_BATCHED = 0, 1, 2
+SAMPLING_CANONICAL, SAMPLING_REFERENCE = 0, 1
 
 P64 = C.POINTER(C.c_int64)
 P32 = C.POINTER(C.c_int32)
@@ -78,7 +79,8 @@ PU8 = C.POINTER(C.c_uint8)
 
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("engine", C.c_int32),
-                ("rank", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("rank", C.c_int32), ("world", C.c_int32), ("sampling", C.c_int32), ("pct_nodes_to_score", C.c_int32),
+                ("reserved", C.c_int32 * 1)]
 
 
 class Nodes(C.Structure):
@@ -134,7 +136,7 @@ class Template(C.Structure):
 class Result(C.Structure):
     _fields_ = [
         ("placed", C.c_int64), ("stop_code", C.c_int32), ("n_nodes", C.c_int32),
-        ("waves", C.c_int64), ("evals", C.c_int64),
+        ("waves", C.c_int64), ("evals", C.c_int64), ("examined", C.c_int64),
         ("reason_hist", C.c_int64 * R_TOTAL),
         ("preempt_no_victims", C.c_int64), ("preempt_not_helpful", C.c_int64),
         ("run_ms", C.c_double), ("pod_node", P32),

@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_batched_kernel(con
     o->error = (ls.stop == 3) ? 1 : 0;
     o->waves = waves;
     o->evals = waves * (long long)p.n + extra_evals;
+    o->examined = o->evals;
     for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = 0;
     o->aff_total = 0;
     (void)taint_const;

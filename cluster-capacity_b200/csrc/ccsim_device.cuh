@@ -32,6 +32,7 @@ struct DevOut {
   int32_t error;      // 0 ok, 1 watchdog (a CTA never saw its peers' slots), 2 pod_node overflow
   int64_t waves;
   int64_t evals;
+  int64_t examined;                // reference-equivalent nodes examined (== evals unless sampling)
   int32_t ptsmin[CCSIM_MAX_PTS];   // global minima at the terminal cycle (for the diagnosis pass)
   int64_t aff_total;
   unsigned long long reason_hist[CCSIM_R_TOTAL];
@@ -49,6 +50,7 @@ struct DevParams {
   int32_t chunk;        // nodes per CTA (contiguous ownership)
   int32_t rank, world;
   uint32_t epoch;       // run counter (1..255), folded into every exchanged word
+  long long sample_k;   // numFeasibleNodesToFind (reference sampling mode)
   // immutable columns
   const int64_t *alloc_cpu, *alloc_mem, *alloc_eph;
   const int32_t *alloc_pods;

@@ -667,7 +667,9 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
   h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   cudaFuncSetAttribute(ccsim_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(WaveShared) - 1024));
-  cudaFuncSetAttribute(ccsim_wave_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(ccsim_wave_lean_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(h->smem_optin - sizeof(LeanShared) - 1024));
+  cudaFuncSetAttribute(ccsim_wave_lean_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(LeanShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(LeanShared) - sizeof(BatchShared) - 1024));
@@ -931,6 +933,18 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   const void *kern = resident ? (const void *)ccsim_wave_kernel<true> : (const void *)ccsim_wave_kernel<false>;
   int block = BLOCK_THREADS;
   // lean resident kernel: the common case (see ccsim_lean.cuh for the eligibility rules)
+  // reference sampling mode (ccsim_config.sampling): numFeasibleNodesToFind (schedule_one.go:697-723)
+  const bool faithful = h->cfg.sampling == CCSIM_SAMPLING_REFERENCE;
+  {
+    const long long N = h->n_global;
+    long long pct = h->cfg.pct_nodes_to_score, kf = N;
+    if (N >= 100) {
+      if (pct == 0) { pct = 50 - N / 125; if (pct < 5) pct = 5; }
+      kf = N * pct / 100;
+      if (kf < 100) kf = 100;
+    }
+    p.sample_k = kf;
+  }
   LeanParams lp; memset(&lp, 0, sizeof(lp));
   // measured on B200 (profiles/r1_kernel_variants.md): at 768 threads the lean kernel beats the generic resident kernel on
   // every eligible workload (C2 2.50 vs 2.67, C3 2.64 vs 2.84, C4 4.27 vs 4.95 us/wave); CCSIM_FORCE_GENERIC overrides.
@@ -967,14 +981,16 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
       const int want1024 = (n + LEAN_THREADS - 1) / LEAN_THREADS;
       (void)want1024;
       lp.rec_bytes_total = (uint32_t)((size_t)units * 16 * p.chunk_pad);
-      const size_t smem_lean = cnt_bytes + lp.rec_bytes_total + (size_t)p.chunk_pad * (6 * 8 + 2 * 4);
+      const size_t smem_lean = cnt_bytes + lp.rec_bytes_total + (size_t)p.chunk_pad * (6 * 8 + 2 * 4 + (faithful ? 8 : 0));
       if (smem_lean + sizeof(LeanShared) + 1024 > h->smem_optin) lean = false;
-      else { smem = smem_lean; kern = (const void *)ccsim_wave_lean_kernel; block = LEAN_THREADS; }
+      else { smem = smem_lean; kern = faithful ? (const void *)ccsim_wave_lean_kernel<true> : (const void *)ccsim_wave_lean_kernel<false>; block = LEAN_THREADS; }
     }
   }
   h->last_lean = lean ? 1 : 0;
+  if (faithful && (!lean || h->cfg.world > 1))
+    return fail(h, CCSIM_EUNSUPPORTED, "reference sampling mode needs the lean resident kernel on a single GPU (one template, <=1 taint/static word, no extras)");
   // batched tie-run engine (ccsim_batched.cuh): one template, node-local predicates and scorers only
-  bool batched = lean && h->n_counters == 0 && h->max_prefer_pop == 0 && h->cfg.world == 1 &&
+  bool batched = lean && !faithful && h->n_counters == 0 && h->max_prefer_pop == 0 && h->cfg.world == 1 &&
                  h->cfg.engine != CCSIM_ENGINE_SEQUENTIAL && !getenv("CCSIM_FORCE_SEQUENTIAL");
   if (batched) {
     const size_t smem_b = smem + (size_t)p.chunk_pad * 12;
@@ -988,7 +1004,8 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   CK(cudaMemcpyAsync(h->d_params, &p, sizeof(DevParams), cudaMemcpyHostToDevice, s));
   int occ = 0;
   if (batched) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_batched_kernel, block, smem));
-  else if (lean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel, block, smem));
+  else if (lean && faithful) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel<true>, block, smem));
+  else if (lean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel<false>, block, smem));
   else if (resident) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<true>, block, smem));
   else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<false>, block, smem));
   if (occ < 1 || occ * h->sm_count < grid) return fail(h, CCSIM_ECUDA, "persistent grid %d does not fit (occupancy %d x %d SMs)", grid, occ, h->sm_count);
@@ -1010,6 +1027,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
           (long long)ho.waves, ms);
 #endif
   out->placed = ho.placed; out->stop_code = ho.stop_code; out->waves = ho.waves; out->evals = ho.evals; out->run_ms = ms;
+  out->examined = ho.examined ? ho.examined : ho.evals;
   h->last_placed = ho.placed;
   if (ho.stop_code == CCSIM_STOP_UNSCHEDULABLE) {
     const int ti = (int)(ho.placed % h->n_templates);

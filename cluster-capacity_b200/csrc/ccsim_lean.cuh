@@ -58,6 +58,9 @@ struct __align__(16) LeanShared {
   ScoreWeights sw;
   int32_t winner, stop, dirty, pad0;
   int32_t scratch[LEAN_WARPS];
+  // FAITHFUL sampling state
+  long long f_preA, f_preB, f_total, examined, examined_total;
+  unsigned long long warp_kth[LEAN_WARPS];
 };
 
 #ifndef WATCHDOG_SPINS
@@ -162,6 +165,47 @@ __device__ void lean_pts_recount(const DevParams &p, const int32_t *smem_cnt, in
   __syncthreads();
 }
 
+// tagged exchange of two 22-bit counts per CTA through word `word` of the slot line; returns for each of the two
+// counts the sum over lower CTAs and the total over all CTAs
+__device__ __forceinline__ bool exchange_pair(const DevParams &p, long long k, uint32_t tag, int word, unsigned long long a, unsigned long long b,
+                                              int lane, int cta, unsigned long long &preA, unsigned long long &totA,
+                                              unsigned long long &preB, unsigned long long &totB) {
+  const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
+  unsigned long long *myslot = p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE + word;
+  if (lane == 0) st_slot(myslot, ((a << 22) | b) | tagbits);
+  const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE + word;
+  unsigned long long v[CCSIM_MAX_GRID / 32];
+  unsigned spins = 0;
+  bool pending, dead = false;
+  do {
+    pending = false;
+    #pragma unroll
+    for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const int bb = lane + 32 * q; v[q] = (bb < p.grid) ? ld_slot(&all[(size_t)bb * SLOT_STRIDE]) : tagbits; }
+    #pragma unroll
+    for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) pending |= ((uint32_t)(v[q] >> KEY_TAG_SHIFT) != tag);
+    if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+  } while (__any_sync(0xffffffffu, pending));
+  unsigned long long pa = 0, ta = 0, pb = 0, tb = 0;
+  #pragma unroll
+  for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) {
+    const int bb = lane + 32 * q;
+    const unsigned long long x = (bb < p.grid) ? (v[q] & KEY_BODY_MASK) : 0ull;
+    const unsigned long long xa = x >> 22, xb = x & ((1ull << 22) - 1);
+    ta += xa; tb += xb;
+    if (bb < cta) { pa += xa; pb += xb; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    pa += __shfl_xor_sync(0xffffffffu, pa, o); ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    pb += __shfl_xor_sync(0xffffffffu, pb, o); tb += __shfl_xor_sync(0xffffffffu, tb, o);
+  }
+  preA = pa; totA = ta; preB = pb; totB = tb;
+  return __any_sync(0xffffffffu, dead);
+}
+
+// FAITHFUL: the reference's default sampling (adaptive numFeasibleNodesToFind + rotating start index,
+// schedule_one.go:538-539,644-723) as a deterministic sequential scan: only the first K feasible nodes in rotated order
+// compete, ties -> first maximum in rotated order, and the start index advances by the number of nodes examined.
+template <bool FAITHFUL>
 __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const DevParams p, const LeanParams lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t *smem_cnt = reinterpret_cast<int32_t *>(smem_raw);
@@ -172,6 +216,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
   long long *c_amem = c_acpu + cp, *c_rcpu = c_amem + cp, *c_rmem = c_rcpu + cp, *c_zcpu = c_rmem + cp, *c_zmem = c_zcpu + cp;
   int32_t *c_apods = reinterpret_cast<int32_t *>(c_zmem + cp);
   int32_t *c_npods = c_apods + cp;
+  int32_t *feas = c_npods + cp;     // FAITHFUL only: feasibility flag and exclusive feasible-rank of every tile node
+  int32_t *pre = feas + cp;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
@@ -179,6 +225,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
   const int32_t cnt_nodes = hi - lo;
   const int ncls = p.n_classes;
   const int su = lp.stride_u;
+  uint32_t start = 0;               // sched.nextStartNodeIndex (FAITHFUL)
 
   // ---- stage the tile (once): hot AoS records + cold SoA columns ----
   for (int32_t j = tid; j < cnt_nodes; j += LEAN_THREADS) {
@@ -206,7 +253,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
     if (dc.topo_col < 0) continue;
     for (int d = tid; d < dc.n_domains; d += LEAN_THREADS) smem_cnt[dc.smem_off + d] = dc.init[d];
   }
-  if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; }
+  if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; ls.examined = 0; ls.examined_total = 0; }
   __syncthreads();
   for (int c = 0; c < ls.tmpl.n_pts; c++) lean_pts_recount(p, smem_cnt, c);
 
@@ -261,12 +308,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
         }
         if (ls.has_aff) ok &= !(aff_missing | (!aff_exist & !ls.aff_bypass));
       }
+      if (FAITHFUL) feas[j] = ok ? 1 : 0;
       if (ok) {
         if (sc < 0) {   // stale memo: this node was committed since its score was last computed
           sc = score_node(c_acpu[j], c_amem[j], c_zcpu[j] + ls.tmpl.least_cpu, c_zmem[j] + ls.tmpl.least_mem,
                           c_rcpu[j] + ls.tmpl.bal_cpu, c_rmem[j] + ls.tmpl.bal_mem, ls.sw);
           reinterpret_cast<int32_t *>(rec + (size_t)j * su)[9] = sc;
         }
+        if (FAITHFUL) continue;     // keys are built after the sampling cut is known
         const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + lo + j));
         if (ncls == 1) best = key > best ? key : best;
         else {
@@ -275,6 +324,55 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
           for (int c = 0; c < CCSIM_MAX_CLASSES; c++) if (c == cls) bestc[c] = key > bestc[c] ? key : bestc[c];
         }
       }
+    }
+    unsigned long long kth = 0ull;    // FAITHFUL: rotated position + 1 of the K-th feasible node, if it is in this thread's nodes
+    if (FAITHFUL) {
+      __syncthreads();
+      // exclusive feasible-rank in node order (each thread owns a contiguous segment), tile total
+      const int seg = (cnt_nodes + LEAN_THREADS - 1) / LEAN_THREADS;
+      const int b0 = min(cnt_nodes, tid * seg), b1 = min(cnt_nodes, b0 + seg);
+      int32_t sfe = 0;
+      for (int j = b0; j < b1; j++) sfe += feas[j];
+      int32_t incl = sfe;
+      for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      if (lane == 31) ls.scratch[warp] = incl;
+      __syncthreads();
+      int32_t wbase = 0, ctot = 0;
+      for (int w = 0; w < LEAN_WARPS; w++) { if (w < warp) wbase += ls.scratch[w]; ctot += ls.scratch[w]; }
+      int32_t base = wbase + incl - sfe;
+      for (int j = b0; j < b1; j++) { pre[j] = base; base += feas[j]; }
+      __syncthreads();
+      // boundary of the rotation inside this tile: nodes with global index >= start come first ("part A")
+      const long long jb_ll = (long long)start - (long long)(p.node_base + lo);
+      const int32_t jb = jb_ll < 0 ? 0 : (jb_ll > cnt_nodes ? cnt_nodes : (int32_t)jb_ll);
+      const int32_t cB = jb >= cnt_nodes ? ctot : pre[jb];
+      const int32_t cA = ctot - cB;
+      if (warp == 0) {   // exchange 1: (cA, cB) of every tile -> feasible-rank offsets of this tile's two parts
+        unsigned long long preA, totA, preB, totB;
+        bool dead = exchange_pair(p, k, tag, CCSIM_MAX_CLASSES + 1, (unsigned long long)cA, (unsigned long long)cB, lane, cta, preA, totA, preB, totB);
+        if (lane == 0) { ls.f_preA = (long long)preA; ls.f_preB = (long long)(totA + preB); ls.f_total = (long long)(totA + totB); if (dead) ls.stop = 3; }
+      }
+      __syncthreads();
+      const long long preA = ls.f_preA, preB = ls.f_preB, K = p.sample_k;
+      for (int32_t j = tid; j < cnt_nodes; j += LEAN_THREADS) {
+        if (!feas[j]) continue;
+        const long long gr = (j >= jb) ? preA + (pre[j] - cB) : preB + pre[j];
+        if (gr >= K) continue;                       // beyond numFeasibleNodesToFind: never examined
+        const uint32_t gidx = (uint32_t)(p.node_base + lo + j);
+        const uint32_t rot = gidx >= start ? gidx - start : gidx + (uint32_t)p.n_global - start;
+        if (gr == K - 1) kth = (unsigned long long)rot + 1ull;
+        const int32_t sc = reinterpret_cast<const int32_t *>(rec + (size_t)j * su)[9];
+        const unsigned long long key = pack_key(sc, rot);     // ties -> first in rotated order
+        if (ncls == 1) best = key > best ? key : best;
+        else {
+          const unsigned long long taint0 = reinterpret_cast<const unsigned long long *>(rec + (size_t)j * su)[0];
+          const int cls = __popcll(taint0 & prefer0);
+          #pragma unroll
+          for (int c = 0; c < CCSIM_MAX_CLASSES; c++) if (c == cls) bestc[c] = key > bestc[c] ? key : bestc[c];
+        }
+      }
+      const unsigned long long kv = warp_max_u64(kth);
+      if (lane == 0) ls.warp_kth[warp] = kv;
     }
     if (ncls == 1) {
       const unsigned long long v = warp_max_u64(best);
@@ -296,10 +394,32 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
         const unsigned long long v = warp_max_u64(lane < LEAN_WARPS ? ls.warp_best[lane][c] : 0ull);
         if (lane == 0) st_slot(&myslots[c], v | tagbits);
       }
+      if (FAITHFUL) {
+        const unsigned long long kv = warp_max_u64(lane < LEAN_WARPS ? ls.warp_kth[lane] : 0ull);
+        if (lane == 0) st_slot(&myslots[CCSIM_MAX_CLASSES], kv | tagbits);
+      }
       PH_MARK(2);
       const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE;
       unsigned long long cbest[CCSIM_MAX_CLASSES];
       bool dead = false;
+      unsigned long long kth_all = 0ull;
+      if (FAITHFUL) {
+        unsigned long long v[CCSIM_MAX_GRID / 32];
+        unsigned spins = 0;
+        bool pending;
+        do {
+          pending = false;
+          #pragma unroll
+          for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const int b = lane + 32 * q; v[q] = (b < p.grid) ? ld_slot(&all[(size_t)b * SLOT_STRIDE + CCSIM_MAX_CLASSES]) : tagbits; }
+          #pragma unroll
+          for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) pending |= ((uint32_t)(v[q] >> KEY_TAG_SHIFT) != tag);
+          if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+        } while (__any_sync(0xffffffffu, pending));
+        unsigned long long m = 0ull;
+        #pragma unroll
+        for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const unsigned long long b = v[q] & KEY_BODY_MASK; m = b > m ? b : m; }
+        kth_all = warp_max_u64(m);
+      }
       for (int c = 0; c < ncls; c++) {
         unsigned long long v[CCSIM_MAX_GRID / 32];
         unsigned spins = 0;
@@ -340,10 +460,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
         if (dead) { ls.stop = 3; ls.winner = -1; }
         else if (wkey == 0ull) { ls.stop = 1; ls.winner = -1; }
         else ls.winner = (int32_t)key_index(wkey);
+        if (FAITHFUL) {   // processedNodes of this cycle (schedule_one.go:538-539): up to and including the K-th feasible node
+          ls.examined = (ls.f_total >= p.sample_k && kth_all > 0ull) ? (long long)kth_all : (long long)p.n_global;
+          if (cta == 0) ls.examined_total += ls.examined;
+        }
       }
       // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
       if (!dead && wkey != 0ull) {
-        const int32_t g = (int32_t)key_index(wkey);
+        const int32_t g = FAITHFUL ? (int32_t)(((unsigned long long)start + key_index(wkey)) % (unsigned long long)p.n_global) : (int32_t)key_index(wkey);
         const int32_t w = g - p.node_base;
         const bool mine = (w >= lo && w < hi);
         const int32_t jw = w - lo;
@@ -399,6 +523,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
       if (!ls.tmpl.pts[c].min_zero && ls.ptsnum[c] <= 0 && p.counters[ls.tmpl.pts[c].counter].n_present > 0) lean_pts_recount(p, smem_cnt, c);
     wtag = (wtag == 4095u) ? 1u : wtag + 1u;
     tag = (p.epoch << 12) | wtag;
+    if (FAITHFUL) start = (uint32_t)(((unsigned long long)start + (unsigned long long)ls.examined) % (unsigned long long)p.n_global);
   }
 
   if (cta == 0) {
@@ -414,6 +539,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
       o->error = (ls.stop == 3) ? 1 : 0;
       o->waves = (ls.stop == 2) ? k : k + 1;
       o->evals = o->waves * (long long)p.n;
+      o->examined = FAITHFUL ? ls.examined_total : o->evals;
       for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ls.ptsmin[c];
       o->aff_total = ls.aff_total;
 #ifdef CCSIM_PHASE_TIMERS

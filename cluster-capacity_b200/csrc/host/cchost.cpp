@@ -215,6 +215,7 @@ extern "C" int cc_run(cc_handle *h) {
   }
   ccsim_config cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.abi_version = CCSIM_ABI_VERSION; cfg.device = h->device; cfg.engine = CCSIM_ENGINE_AUTO; cfg.rank = 0; cfg.world = 1;
+  if (h->cfg.reference_sampling && h->cfg.pct_nodes_to_score != 100) { cfg.sampling = CCSIM_SAMPLING_REFERENCE; cfg.pct_nodes_to_score = h->cfg.pct_nodes_to_score; }
   ccsim_handle *eng = nullptr;
   int rc = ccsim_create(&cfg, &eng);
   if (rc) return fail(h, CC_EENGINE, std::string("ccsim_create: ") + ccsim_last_error(nullptr));

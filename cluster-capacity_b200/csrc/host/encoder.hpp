@@ -22,7 +22,8 @@ namespace cch {
 struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
 
 struct SchedConfig {
-  int pct_nodes_to_score = 0;
+  int pct_nodes_to_score = 100;   // canonical contract unless "sampling":"reference" asks for the reference's adaptive sampling
+  bool reference_sampling = false;
   uint32_t filter_enable = CCSIM_PL_ALL, score_enable = CCSIM_PL_ALL;
   int w_taint = 3, w_node_affinity = 2, w_fit = 1, w_pts = 2, w_ipa = 2, w_balanced = 1, w_image = 1;
   static uint32_t plugin_bit(const std::string &n) {
@@ -42,7 +43,8 @@ struct SchedConfig {
     SchedConfig c;
     if (text.empty()) return c;
     Json j = parse_json(text);
-    c.pct_nodes_to_score = (int)j.at("percentageOfNodesToScore").i64(0);
+    c.reference_sampling = j.at("sampling").str() == "reference";
+    c.pct_nodes_to_score = (int)j.at("percentageOfNodesToScore").i64(c.reference_sampling ? 0 : 100);
     for (auto &x : j.at("disabledFilters").arr) c.filter_enable &= ~plugin_bit(x.str());
     for (auto &x : j.at("disabledScores").arr) c.score_enable &= ~plugin_bit(x.str());
     const Json &w = j.at("weights");

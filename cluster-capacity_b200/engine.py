@@ -65,6 +65,7 @@ class RunResult:
         self.n_nodes = int(res.n_nodes)
         self.waves = int(res.waves)
         self.evals = int(res.evals)
+        self.examined = int(res.examined)
         self.run_ms = float(res.run_ms)
         self.reason_hist = np.array(res.reason_hist[:], dtype=np.int64)
         self.preempt_no_victims = int(res.preempt_no_victims)
@@ -78,10 +79,11 @@ class RunResult:
 class Engine:
     """One ccsim handle (one GPU / one node-axis shard)."""
 
-    def __init__(self, device=0, engine=abi.ENGINE_AUTO, rank=0, world=1):
+    def __init__(self, device=0, engine=abi.ENGINE_AUTO, rank=0, world=1, sampling=abi.SAMPLING_CANONICAL, pct_nodes_to_score=0):
         cfg = abi.Config()
         cfg.abi_version = abi.ABI_VERSION
         cfg.device, cfg.engine, cfg.rank, cfg.world = device, engine, rank, world
+        cfg.sampling, cfg.pct_nodes_to_score = sampling, pct_nodes_to_score
         self._h = C.c_void_p()
         rc = lib().ccsim_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:

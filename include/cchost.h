@@ -34,7 +34,8 @@ typedef struct cc_handle cc_handle;
 #define CC_EENGINE      -7   /* libccsim failed (no GPU, CUDA error) */
 
 /* pod_json: the simulated pod (v1.Pod as JSON, already defaulted/validated by the CLI like ParseAPISpec does).
- * sched_config_json: NULL/"" for the default profile, or a small JSON {"percentageOfNodesToScore":100,
+ * sched_config_json: NULL/"" for the default profile in canonical mode, or a small JSON {"sampling":"reference",
+ *   "percentageOfNodesToScore":0,   (reference sampling: adaptive numFeasibleNodesToFind + rotating start index)
  *   "disabledFilters":["NodeResourcesFit",...], "disabledScores":[...], "weights":{"NodeResourcesFit":1,...}}.
  * exclude_nodes: comma-separated node names (--exclude-nodes), may be NULL. device: CUDA ordinal. */
 int cc_new(const char *sched_config_json, const char *pod_json, int64_t max_pods, const char *exclude_nodes,

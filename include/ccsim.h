@@ -112,6 +112,13 @@ enum {
 #define CCSIM_STOP_UNSCHEDULABLE 0
 #define CCSIM_STOP_LIMIT_REACHED 1
 
+/* sampling: CANONICAL = percentageOfNodesToScore 100 (every node filtered every cycle, start index fixed);
+ * REFERENCE = the default profile's sampling as a deterministic sequential scan: stop at the numFeasibleNodesToFind-th
+ * feasible node in rotated order, nextStartNodeIndex advances by the nodes examined (schedule_one.go:538-539,610-723).
+ * Ties -> first maximum in (rotated) scan order in both. */
+#define CCSIM_SAMPLING_CANONICAL 0
+#define CCSIM_SAMPLING_REFERENCE 1
+
 /* engine selection */
 #define CCSIM_ENGINE_AUTO        0  /* batched tie-run waves when provably order-equivalent, else sequential */
 #define CCSIM_ENGINE_SEQUENTIAL  1  /* one winner per wave (always valid; evals = (placed+1)*N)               */
@@ -122,7 +129,9 @@ typedef struct ccsim_config {
   int32_t device;           /* CUDA device ordinal */
   int32_t engine;           /* CCSIM_ENGINE_* */
   int32_t rank, world;      /* node-axis shard of a multi-GPU run; world=1 for a single GPU */
-  int32_t reserved[3];
+  int32_t sampling;         /* CCSIM_SAMPLING_*: which valid execution of the (non-deterministic) reference loop is reproduced */
+  int32_t pct_nodes_to_score; /* percentageOfNodesToScore for CCSIM_SAMPLING_REFERENCE (0 = adaptive, schedule_one.go:697-723) */
+  int32_t reserved[1];
 } ccsim_config;
 
 /*
@@ -220,6 +229,7 @@ typedef struct ccsim_result {
   int32_t n_nodes;
   int64_t waves;                  /* grid-wide waves executed */
   int64_t evals;                  /* (pod attempt, node) pairs pushed through the fused Filter pass on the device */
+  int64_t examined;               /* nodes the reference would have examined (== evals unless CCSIM_SAMPLING_REFERENCE) */
   int64_t reason_hist[CCSIM_R_TOTAL]; /* terminal FitError histogram (zero when stop_code == LIMIT_REACHED) */
   int64_t preempt_no_victims;     /* nodes whose terminal status code is Unschedulable ("No preemption victims found for incoming pod") */
   int64_t preempt_not_helpful;    /* the rest ("Preemption is not helpful for scheduling") */

@@ -45,6 +45,7 @@ class OracleResult:
         self.stop_code = int(res.stop_code)
         self.waves = int(res.waves)
         self.evals = int(res.evals)
+        self.examined = int(res.examined)
         self.reason_hist = np.array(res.reason_hist[:], dtype=np.int64)
         self.preempt_no_victims = int(res.preempt_no_victims)
         self.preempt_not_helpful = int(res.preempt_not_helpful)

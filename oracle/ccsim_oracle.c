@@ -428,7 +428,7 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
     if (max_pods > 0 && placed >= max_pods) { stop = CCSIM_STOP_LIMIT_REACHED; break; }
   }
 
-  out->placed = placed; out->stop_code = stop; out->waves = waves; out->evals = evals;
+  out->placed = placed; out->stop_code = stop; out->waves = waves; out->evals = evals; out->examined = evals;
   if (stop == CCSIM_STOP_UNSCHEDULABLE && n > 0) {
     /* FitError histogram: KS:framework/types.go:787-838; preemption suffix: KS:framework/preemption/preemption.go:234-331,
        PL:defaultpreemption/default_preemption.go:218-258 (no lower-priority victims on any node) */

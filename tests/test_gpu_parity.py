@@ -180,3 +180,26 @@ def test_identical_nodes_all_tied(built):
     n = 500
     snap = abi.Snapshot(n, np.full(n, 4000), np.full(n, 8 * GiB), np.full(n, 30))
     check(snap, [abi.default_template(150, 100 * MiB)])
+
+
+@pytest.mark.parametrize("gen,kw,pct", [("c2", dict(n=1500), 0), ("c2", dict(n=1500), 10), ("c2", dict(n=99), 0),
+                                        ("c3", dict(n=4000, prefer_taints=True), 0), ("c3", dict(n=4000), 30),
+                                        ("c4", dict(n=4000, n_existing=8000, zones=8, racks=64, regions=4), 0), ("c2", dict(n=700), 100)])
+def test_reference_sampling_mode(built, gen, kw, pct):
+    """A4: adaptive numFeasibleNodesToFind + rotating start index (schedule_one.go:538-539,697-723), as the deterministic
+    sequential scan the oracle's mode=1 restates: same pod -> node sequence, same number of nodes examined."""
+    engine = importlib.import_module("cluster-capacity_b200.engine")
+    snap, tmpl, ctr = getattr(synth, gen)(**kw)
+    limit = 3000
+    want = oracle.run(snap, tmpl, ctr, max_pods=limit, mode=1, pct=pct)
+    with engine.Engine(device=0, sampling=abi.SAMPLING_REFERENCE, pct_nodes_to_score=pct) as eng:
+        eng.load_nodes(snap)
+        eng.set_templates(tmpl, ctr)
+        got = eng.run(limit)
+    assert got.placed == want.placed and got.stop_code == want.stop_code
+    assert np.array_equal(got.pod_node, want.pod_node)
+    assert np.array_equal(got.reason_hist, want.reason_hist)
+    assert got.examined == want.evals
+    if pct == 100 or snap.n < 100:
+        canon = oracle.run(snap, tmpl, ctr, max_pods=limit)
+        assert np.array_equal(got.pod_node, canon.pod_node)
