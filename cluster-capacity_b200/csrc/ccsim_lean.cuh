@@ -24,14 +24,16 @@
 #define LT_ANTI 1
 #define LT_AFF 2
 
-struct LeanTerm {
-  int32_t kind;      // LT_*
+// One per-domain term of the Filter pass, 16 bytes (one LDS.128). PodTopologySpread and anti-affinity share one form:
+//   reject  <=>  (node has the topology key) ? count(domain) > lim : miss_rejects
+// (PTS: lim = maxSkew - selfMatch + globalMin, missing key rejects; anti-affinity: lim = 0, missing key passes).
+// Required pod-affinity terms (LT_AFF) need the all-terms "pods exist" logic and are evaluated in a second loop.
+struct __align__(16) LeanTerm {
+  int16_t kind;      // LT_*
+  int16_t miss_rejects;
   int32_t slot;      // record int index (10 + s) holding the node's domain id, or the node-local count itself
   int32_t cnt_off;   // offset of the counter in the shared replicated-counter area, -1: node-local (the slot IS the count)
-  int32_t lim;       // PTS: reject when count > lim
-  int32_t counter;   // index into DevParams.counters
-  int32_t pts_idx;   // PTS constraint index
-  int32_t pad[2];
+  int32_t lim;
 };
 
 struct LeanParams {
@@ -40,6 +42,9 @@ struct LeanParams {
   int32_t slot_topo[LEAN_MAX_SLOTS];     // slot s mirrors topology column slot_topo[s] (>=0) ...
   int32_t slot_counter[LEAN_MAX_SLOTS];  // ... or node-local counter slot_counter[s] (>=0)
   int32_t counter_slot[CCSIM_MAX_COUNTERS]; // counter j -> slot holding its domain id (topo) or its count (node-local)
+  int32_t n_payload;                        // topology slots whose domain id travels with the exchanged key (0: look it up in L2)
+  int32_t payload_slot[4];                  // payload position -> slot
+  int32_t counter_payload[CCSIM_MAX_COUNTERS]; // counter j -> payload position, -1: not carried
   uint32_t rec_bytes_total; // stride * chunk_pad
   uint32_t cold_off;        // byte offset of the cold SoA columns (alloc/req/nz) in dynamic shared memory
   uint32_t cnt_off_bytes;   // byte offset of the replicated counters (0)
@@ -49,7 +54,7 @@ struct __align__(16) LeanShared {
   ccsim_template tmpl;
   unsigned long long taint_bad0, prefer0, sel0, forbid0;
   long long eq_cpu, eq_mem;
-  int32_t pods_need, n_terms, aff_bypass, has_aff;
+  int32_t pods_need, n_terms, aff_bypass, has_aff, n_cmp_terms, pad1[3];   // terms[0..n_cmp_terms) are PTS/anti, the rest LT_AFF
   LeanTerm terms[LEAN_MAX_TERMS];
   CommitInfo cinfo[CCSIM_MAX_COUNTERS];
   unsigned long long warp_best[LEAN_WARPS][CCSIM_MAX_CLASSES];
@@ -95,30 +100,31 @@ __device__ void lean_build_consts(const DevParams &p, const LeanParams &lp) {
     for (int c = 0; c < t.n_pts; c++) {
       LeanTerm &lt = ls.terms[nt++];
       const int j = t.pts[c].counter;
-      lt.kind = LT_PTS; lt.counter = j; lt.pts_idx = c;
+      lt.kind = LT_PTS; lt.miss_rejects = 1;
       lt.slot = 10 + lp.counter_slot[j];
       lt.cnt_off = p.counters[j].topo_col < 0 ? -1 : p.counters[j].smem_off;
       const long long lim = (long long)t.pts[c].max_skew - t.pts[c].self_match + (long long)ls.ptsmin[c];
       lt.lim = lim > INT32_MAX ? INT32_MAX : (lim < INT32_MIN ? INT32_MIN : (int32_t)lim);
     }
   ls.has_aff = 0;
-  if (fe & CCSIM_PL_INTER_POD_AFFINITY) {
+  if (fe & CCSIM_PL_INTER_POD_AFFINITY)
+    for (int a = 0; a < t.n_anti; a++) {
+      LeanTerm &lt = ls.terms[nt++];
+      const int j = t.anti_counter[a];
+      lt.kind = LT_ANTI; lt.miss_rejects = 0; lt.lim = 0;
+      lt.slot = 10 + lp.counter_slot[j];
+      lt.cnt_off = p.counters[j].topo_col < 0 ? -1 : p.counters[j].smem_off;
+    }
+  ls.n_cmp_terms = nt;
+  if (fe & CCSIM_PL_INTER_POD_AFFINITY)
     for (int a = 0; a < t.n_aff; a++) {
       LeanTerm &lt = ls.terms[nt++];
       const int j = t.aff_counter[a];
-      lt.kind = LT_AFF; lt.counter = j; lt.pts_idx = -1; lt.lim = 0;
+      lt.kind = LT_AFF; lt.miss_rejects = 1; lt.lim = 0;
       lt.slot = 10 + lp.counter_slot[j];
       lt.cnt_off = p.counters[j].topo_col < 0 ? -1 : p.counters[j].smem_off;
       ls.has_aff = 1;
     }
-    for (int a = 0; a < t.n_anti; a++) {
-      LeanTerm &lt = ls.terms[nt++];
-      const int j = t.anti_counter[a];
-      lt.kind = LT_ANTI; lt.counter = j; lt.pts_idx = -1; lt.lim = 0;
-      lt.slot = 10 + lp.counter_slot[j];
-      lt.cnt_off = p.counters[j].topo_col < 0 ? -1 : p.counters[j].smem_off;
-    }
-  }
   ls.n_terms = nt;
   ls.aff_bypass = (ls.aff_total == 0 && (fl & CCSIM_TF_AFF_SELF_MATCH_ALL)) ? 1 : 0;
   ls.sw.w_fit = (t.score_enable & CCSIM_PL_FIT) ? t.w_fit : 0;
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
     // ---- fused Filter pass: one predicate-eval per node of the tile ----
     const unsigned long long taint_bad0 = ls.taint_bad0, prefer0 = ls.prefer0, sel0 = ls.sel0, forbid0 = ls.forbid0;
     const long long eq_cpu = ls.eq_cpu, eq_mem = ls.eq_mem;
-    const int32_t pods_need = ls.pods_need, n_terms = ls.n_terms;
+    const int32_t pods_need = ls.pods_need, n_terms = ls.n_terms, n_cmp = ls.n_cmp_terms;
     unsigned long long best = 0ull;      // single class
     unsigned long long bestc[CCSIM_MAX_CLASSES];
     if (ncls > 1) {
@@ -293,20 +299,31 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
       // NodeUnschedulable, TaintToleration, NodeAffinity(nodeSelector), NodePorts, existing anti-affinity, NodeResourcesFit
       bool ok = ((taint0 & taint_bad0) | (~static0 & sel0) | (static0 & forbid0)) == 0ull;
       ok &= (free_cpu >= eq_cpu) & (free_mem >= eq_mem) & (free_pods >= pods_need);
-      // PodTopologySpread / InterPodAffinity terms
-      if (n_terms) {
+      // PodTopologySpread + anti-affinity terms: reject <=> has ? count > lim : miss_rejects
+      if (n_cmp) {
         const int32_t *r4 = reinterpret_cast<const int32_t *>(r);
-        bool aff_exist = true, aff_missing = false;
-        for (int q = 0; q < n_terms; q++) {
+        #pragma unroll 4
+        for (int q = 0; q < n_cmp; q++) {
           const LeanTerm lt = ls.terms[q];
           const int32_t v = r4[lt.slot];                                  // domain id, or the node-local count
-          const int32_t c = lt.cnt_off < 0 ? v : smem_cnt[lt.cnt_off + (v < 0 ? 0 : v)];
-          const bool has = (lt.cnt_off < 0) || (v >= 0);
-          if (lt.kind == LT_PTS) ok &= has & (c <= lt.lim);
-          else if (lt.kind == LT_ANTI) ok &= !(has & (c > 0));
-          else { aff_missing |= !has; aff_exist &= has & (c > 0); }
+          const bool local = lt.cnt_off < 0;
+          const int32_t c = local ? v : smem_cnt[lt.cnt_off + (v < 0 ? 0 : v)];
+          const bool has = local | (v >= 0);
+          ok &= has ? (c <= lt.lim) : (lt.miss_rejects == 0);
         }
-        if (ls.has_aff) ok &= !(aff_missing | (!aff_exist & !ls.aff_bypass));
+      }
+      if (n_terms > n_cmp) {   // required pod affinity (interpodaffinity/filtering.go:382-408)
+        const int32_t *r4 = reinterpret_cast<const int32_t *>(r);
+        bool aff_exist = true, aff_missing = false;
+        for (int q = n_cmp; q < n_terms; q++) {
+          const LeanTerm lt = ls.terms[q];
+          const int32_t v = r4[lt.slot];
+          const bool local = lt.cnt_off < 0;
+          const int32_t c = local ? v : smem_cnt[lt.cnt_off + (v < 0 ? 0 : v)];
+          const bool has = local | (v >= 0);
+          aff_missing |= !has; aff_exist &= has & (c > 0);
+        }
+        ok &= !(aff_missing | (!aff_exist & !ls.aff_bypass));
       }
       if (FAITHFUL) feas[j] = ok ? 1 : 0;
       if (ok) {
@@ -398,6 +415,23 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
         const unsigned long long kv = warp_max_u64(lane < LEAN_WARPS ? ls.warp_kth[lane] : 0ull);
         if (lane == 0) st_slot(&myslots[CCSIM_MAX_CLASSES], kv | tagbits);
       }
+      // payload: the domain ids of this CTA's candidate ride along (two 22-bit ids per word), so that the CTAs that do
+      // not own the winner need no L2 lookup before updating their counter replicas
+      const bool use_payload = !FAITHFUL && lp.n_payload > 0 && ncls == 1 && p.world == 1;
+      if (use_payload) {
+        const unsigned long long vb0 = warp_max_u64(lane < LEAN_WARPS ? ls.warp_best[lane][0] : 0ull);
+        if (lane < 2 && 2 * lane < lp.n_payload) {
+          unsigned long long w = 0ull;
+          if (vb0 != 0ull) {
+            const int32_t jb = (int32_t)key_index(vb0) - p.node_base - lo;
+            const int32_t *r4 = reinterpret_cast<const int32_t *>(rec + (size_t)jb * su);
+            const unsigned long long d0 = (unsigned long long)(r4[10 + lp.payload_slot[2 * lane]] + 1);
+            const unsigned long long d1 = (2 * lane + 1 < lp.n_payload) ? (unsigned long long)(r4[10 + lp.payload_slot[2 * lane + 1]] + 1) : 0ull;
+            w = (d0 << 22) | d1;
+          }
+          st_slot(&myslots[CCSIM_MAX_CLASSES + 2 + lane], w | tagbits);
+        }
+      }
       PH_MARK(2);
       const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE;
       unsigned long long cbest[CCSIM_MAX_CLASSES];
@@ -442,6 +476,24 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
       }
       dead = __any_sync(0xffffffffu, dead);
       if (p.world > 1 && !dead) dead = cross_gpu_exchange(p, k, tag, ncls, cbest, lane, cta);
+      unsigned long long pw0 = 0ull, pw1 = 0ull;
+      if (use_payload && !dead && cbest[0] != 0ull) {
+        // the winner's CTA: the tile that contains its node index; its payload words were published before its key
+        const int32_t wcta = ((int32_t)key_index(cbest[0]) - p.node_base) / p.chunk;
+        const unsigned long long *pl = all + (size_t)wcta * SLOT_STRIDE + CCSIM_MAX_CLASSES + 2;
+        unsigned spins = 0;
+        unsigned long long a = tagbits, b = tagbits;
+        bool pending;
+        do {
+          if (lane == 0) a = ld_slot(&pl[0]);
+          if (lane == 1 && lp.n_payload > 2) b = ld_slot(&pl[1]);
+          pending = ((uint32_t)(a >> KEY_TAG_SHIFT) != tag) | ((uint32_t)(b >> KEY_TAG_SHIFT) != tag);
+          if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+        } while (__any_sync(0xffffffffu, pending));
+        pw0 = __shfl_sync(0xffffffffu, a, 0) & KEY_BODY_MASK;
+        pw1 = __shfl_sync(0xffffffffu, b, 1) & KEY_BODY_MASK;
+        dead = __any_sync(0xffffffffu, dead);
+      }
       PH_MARK(3);
       unsigned long long wkey = cbest[0];
       if (ncls > 1 || (t.score_enable & CCSIM_PL_TAINT_TOLERATION)) {
@@ -502,7 +554,11 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
               }
               if (ci.is_aff) { atomicAdd((unsigned long long *)&ls.aff_total, (unsigned long long)ci.inc); ls.dirty = 1; }
             } else {
-              const int32_t dom = mine ? reinterpret_cast<const int32_t *>(rec + (size_t)jw * su)[10 + lp.counter_slot[j]] : ci.gtopo[g];
+              int32_t dom;
+              const int pp = lp.counter_payload[j];
+              if (mine) dom = reinterpret_cast<const int32_t *>(rec + (size_t)jw * su)[10 + lp.counter_slot[j]];
+              else if (use_payload && pp >= 0) dom = (int32_t)(((pp < 2 ? pw0 : pw1) >> ((pp & 1) ? 0 : 22)) & ((1ull << 22) - 1)) - 1;
+              else dom = ci.gtopo[g];
               if (dom >= 0) {
                 int32_t *cnt = smem_cnt + p.counters[j].smem_off;
                 const int32_t old = cnt[dom];
