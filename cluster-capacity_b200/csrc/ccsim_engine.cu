@@ -974,20 +974,6 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
       lp.counter_slot[j] = slot;
     }
     if (lean) {
-      // payload: topology slots of counters that a commit updates (domain ids < 2^22 - 1), at most 4
-      lp.n_payload = 0;
-      for (int j = 0; j < CCSIM_MAX_COUNTERS; j++) lp.counter_payload[j] = -1;
-      bool payload_ok = true;
-      for (int j = 0; j < h->n_counters; j++) {
-        const DevCounter &dc = h->counters[j];
-        if (dc.topo_col < 0 || dc.inc == 0) continue;
-        if (dc.n_domains >= (1 << 22) - 1) { payload_ok = false; break; }
-        int pos = -1;
-        for (int q = 0; q < lp.n_payload; q++) if (lp.payload_slot[q] == lp.counter_slot[j]) pos = q;
-        if (pos < 0) { if (lp.n_payload >= 4) { payload_ok = false; break; } pos = lp.n_payload++; lp.payload_slot[pos] = lp.counter_slot[j]; }
-        lp.counter_payload[j] = pos;
-      }
-      if (!payload_ok || getenv("CCSIM_NO_PAYLOAD")) { lp.n_payload = 0; for (int j = 0; j < CCSIM_MAX_COUNTERS; j++) lp.counter_payload[j] = -1; }
       lp.n_slots = ns;
       int units = (10 + ns + 3) / 4;
       if ((units & 1) == 0) units++;

@@ -42,9 +42,6 @@ struct LeanParams {
   int32_t slot_topo[LEAN_MAX_SLOTS];     // slot s mirrors topology column slot_topo[s] (>=0) ...
   int32_t slot_counter[LEAN_MAX_SLOTS];  // ... or node-local counter slot_counter[s] (>=0)
   int32_t counter_slot[CCSIM_MAX_COUNTERS]; // counter j -> slot holding its domain id (topo) or its count (node-local)
-  int32_t n_payload;                        // topology slots whose domain id travels with the exchanged key (0: look it up in L2)
-  int32_t payload_slot[4];                  // payload position -> slot
-  int32_t counter_payload[CCSIM_MAX_COUNTERS]; // counter j -> payload position, -1: not carried
   uint32_t rec_bytes_total; // stride * chunk_pad
   uint32_t cold_off;        // byte offset of the cold SoA columns (alloc/req/nz) in dynamic shared memory
   uint32_t cnt_off_bytes;   // byte offset of the replicated counters (0)
@@ -415,23 +412,6 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
         const unsigned long long kv = warp_max_u64(lane < LEAN_WARPS ? ls.warp_kth[lane] : 0ull);
         if (lane == 0) st_slot(&myslots[CCSIM_MAX_CLASSES], kv | tagbits);
       }
-      // payload: the domain ids of this CTA's candidate ride along (two 22-bit ids per word), so that the CTAs that do
-      // not own the winner need no L2 lookup before updating their counter replicas
-      const bool use_payload = !FAITHFUL && lp.n_payload > 0 && ncls == 1 && p.world == 1;
-      if (use_payload) {
-        const unsigned long long vb0 = warp_max_u64(lane < LEAN_WARPS ? ls.warp_best[lane][0] : 0ull);
-        if (lane < 2 && 2 * lane < lp.n_payload) {
-          unsigned long long w = 0ull;
-          if (vb0 != 0ull) {
-            const int32_t jb = (int32_t)key_index(vb0) - p.node_base - lo;
-            const int32_t *r4 = reinterpret_cast<const int32_t *>(rec + (size_t)jb * su);
-            const unsigned long long d0 = (unsigned long long)(r4[10 + lp.payload_slot[2 * lane]] + 1);
-            const unsigned long long d1 = (2 * lane + 1 < lp.n_payload) ? (unsigned long long)(r4[10 + lp.payload_slot[2 * lane + 1]] + 1) : 0ull;
-            w = (d0 << 22) | d1;
-          }
-          st_slot(&myslots[CCSIM_MAX_CLASSES + 2 + lane], w | tagbits);
-        }
-      }
       PH_MARK(2);
       const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE;
       unsigned long long cbest[CCSIM_MAX_CLASSES];
@@ -476,24 +456,6 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
       }
       dead = __any_sync(0xffffffffu, dead);
       if (p.world > 1 && !dead) dead = cross_gpu_exchange(p, k, tag, ncls, cbest, lane, cta);
-      unsigned long long pw0 = 0ull, pw1 = 0ull;
-      if (use_payload && !dead && cbest[0] != 0ull) {
-        // the winner's CTA: the tile that contains its node index; its payload words were published before its key
-        const int32_t wcta = ((int32_t)key_index(cbest[0]) - p.node_base) / p.chunk;
-        const unsigned long long *pl = all + (size_t)wcta * SLOT_STRIDE + CCSIM_MAX_CLASSES + 2;
-        unsigned spins = 0;
-        unsigned long long a = tagbits, b = tagbits;
-        bool pending;
-        do {
-          if (lane == 0) a = ld_slot(&pl[0]);
-          if (lane == 1 && lp.n_payload > 2) b = ld_slot(&pl[1]);
-          pending = ((uint32_t)(a >> KEY_TAG_SHIFT) != tag) | ((uint32_t)(b >> KEY_TAG_SHIFT) != tag);
-          if (++spins > WATCHDOG_SPINS) { dead = true; break; }
-        } while (__any_sync(0xffffffffu, pending));
-        pw0 = __shfl_sync(0xffffffffu, a, 0) & KEY_BODY_MASK;
-        pw1 = __shfl_sync(0xffffffffu, b, 1) & KEY_BODY_MASK;
-        dead = __any_sync(0xffffffffu, dead);
-      }
       PH_MARK(3);
       unsigned long long wkey = cbest[0];
       if (ncls > 1 || (t.score_enable & CCSIM_PL_TAINT_TOLERATION)) {
@@ -554,11 +516,10 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
               }
               if (ci.is_aff) { atomicAdd((unsigned long long *)&ls.aff_total, (unsigned long long)ci.inc); ls.dirty = 1; }
             } else {
-              int32_t dom;
-              const int pp = lp.counter_payload[j];
-              if (mine) dom = reinterpret_cast<const int32_t *>(rec + (size_t)jw * su)[10 + lp.counter_slot[j]];
-              else if (use_payload && pp >= 0) dom = (int32_t)(((pp < 2 ? pw0 : pw1) >> ((pp & 1) ? 0 : 22)) & ((1ull << 22) - 1)) - 1;
-              else dom = ci.gtopo[g];
+              // the winner's domain id: from this CTA's tile if it owns the node, else from the whole-cluster column (L2).
+              // (Carrying the ids with the exchanged key — as extra words or packed into the key's low bits — was measured and is
+              //  not faster: profiles/r1_kernel_variants.md.)
+              const int32_t dom = mine ? reinterpret_cast<const int32_t *>(rec + (size_t)jw * su)[10 + lp.counter_slot[j]] : ci.gtopo[g];
               if (dom >= 0) {
                 int32_t *cnt = smem_cnt + p.counters[j].smem_off;
                 const int32_t old = cnt[dom];
