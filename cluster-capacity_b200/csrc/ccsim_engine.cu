@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
           ci.pts_idx = -1;
           for (int c = 0; c < t.n_pts; c++) if (t.pts[c].counter == j && !t.pts[c].min_zero) ci.pts_idx = c;
         }
-        ws.dirty = 0;
       }
       __syncthreads();
+      if (tid == 0) ws.dirty = 0;    // cleared only after every thread has read it
     }
     const FilterConsts &fc = ws.fc;
     const HotConsts hc = load_hot(fc);

@@ -270,9 +270,10 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
     PH_START();
     if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ls.stop = 2; __syncthreads(); break; }
     if (k > p.pod_cap) { if (tid == 0) ls.stop = 3; __syncthreads(); break; }   // cannot happen (pod_cap bounds every run): never spin forever
-    if (ls.dirty) {
-      if (tid == 0) { lean_build_consts(p, lp); ls.dirty = 0; }
+    if (ls.dirty) {   // uniform: set before the last barrier, cleared only after the barrier below (no thread can miss it)
+      if (tid == 0) lean_build_consts(p, lp);
       __syncthreads();
+      if (tid == 0) ls.dirty = 0;
     }
     // ---- fused Filter pass: one predicate-eval per node of the tile ----
     const unsigned long long taint_bad0 = ls.taint_bad0, prefer0 = ls.prefer0, sel0 = ls.sel0, forbid0 = ls.forbid0;
