@@ -6,7 +6,7 @@ CPU oracle. Field order and limits must match include/ccsim.h exactly; tests/tes
 import ctypes as C
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_TAINT_WORDS = 4
 MAX_STATIC_WORDS = 4
 MAX_SCALARS = 4
@@ -130,6 +130,8 @@ class Template(C.Structure):
         ("n_aff", C.c_int32), ("aff_counter", C.c_int32 * MAX_IPA),
         ("n_anti", C.c_int32), ("anti_counter", C.c_int32 * MAX_IPA),
         ("aff_total_init", C.c_int64),
+        ("n_pref_terms", C.c_int32), ("pref_weight", C.c_int32 * MAX_AFF_TERMS), ("pad_pref", C.c_int32),
+        ("pref_mask", (C.c_uint64 * MAX_STATIC_WORDS) * MAX_AFF_TERMS),
     ]
 
 

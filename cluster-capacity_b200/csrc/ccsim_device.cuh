@@ -62,6 +62,7 @@ struct DevParams {
   int32_t *npods;
   int64_t *req_scalar[CCSIM_MAX_SCALARS];
   uint64_t *placed_mask;   // nullptr unless a template has hostPorts
+  uint8_t *feas;           // per-node feasibility flag of the current wave (two-phase scoring: NodeAffinity preferred terms)
   int32_t *score_cache;    // memoised node-local score per node, -1 = stale (streaming mode; resident mode keeps it in the tile)
   int32_t tile_resident;   // 1: the CTA's node tile is staged into shared memory once and stays there for the whole run
   int32_t chunk_pad;       // chunk rounded up to a multiple of 4 (tile column stride)
@@ -461,6 +462,41 @@ __device__ __forceinline__ bool cross_gpu_exchange(const DevParams &p, long long
     cbest[c] = warp_max_u64(lane < p.world ? (v & KEY_BODY_MASK) : 0ull);
   }
   return __any_sync(0xffffffffu, dead);
+}
+
+// grid-wide max of one value (< 2^44) per CTA through word `word` of the slot lines (same tagged-word protocol as the keys)
+__device__ __forceinline__ unsigned long long exchange_max(const DevParams &p, long long k, uint32_t tag, int word,
+                                                           unsigned long long mine, int lane, int cta, bool &dead) {
+  const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
+  if (lane == 0) st_slot(p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE + word, (mine & KEY_BODY_MASK) | tagbits);
+  const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE + word;
+  unsigned long long v[CCSIM_MAX_GRID / 32];
+  unsigned spins = 0;
+  bool pending;
+  do {
+    pending = false;
+    #pragma unroll
+    for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const int b = lane + 32 * q; v[q] = (b < p.grid) ? ld_slot(&all[(size_t)b * SLOT_STRIDE]) : tagbits; }
+    #pragma unroll
+    for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) pending |= ((uint32_t)(v[q] >> KEY_TAG_SHIFT) != tag);
+    if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+  } while (__any_sync(0xffffffffu, pending));
+  unsigned long long m = 0ull;
+  #pragma unroll
+  for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const unsigned long long b = v[q] & KEY_BODY_MASK; m = b > m ? b : m; }
+  dead = __any_sync(0xffffffffu, dead);
+  return warp_max_u64(m);
+}
+
+// raw NodeAffinity score of a node: sum of the weights of the matching preferred terms (node_affinity.go:265-290)
+__device__ __forceinline__ int32_t node_affinity_raw(const DevParams &p, const ccsim_template &t, int32_t i) {
+  int32_t raw = 0;
+  for (int k = 0; k < t.n_pref_terms; k++) {
+    bool m = true;
+    for (int w = 0; w < p.static_words; w++) m &= ((p.static_mask[(size_t)w * p.n + i] & t.pref_mask[k][w]) == t.pref_mask[k][w]);
+    if (m) raw += t.pref_weight[k];
+  }
+  return raw;
 }
 
 // TaintToleration NormalizeScore, reverse (helper/normalize_score.go:28-56)

@@ -51,6 +51,7 @@ struct __align__(16) WaveShared {
   int32_t winner;        // global node index, -1 = none
   int32_t stop;          // 0 continue, 1 unschedulable, 2 limit, 3 error
   int32_t dirty;         // FilterConsts must be rebuilt before the next scan
+  long long na_max;      // two-phase scoring: max raw NodeAffinity score over the feasible nodes of this wave
   ScoreWeights sw;       // scalar copy of the template's score configuration (passed by value to score_node)
   CommitInfo cinfo[CCSIM_MAX_COUNTERS];   // what a commit does to each counter under the current template
   int32_t scratch[MAX_WARPS];
@@ -234,18 +235,51 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
     unsigned long long best[CCSIM_MAX_CLASSES];
     #pragma unroll
     for (int c = 0; c < CCSIM_MAX_CLASSES; c++) best[c] = 0ull;
+    // NodeAffinity preferred terms need the maximum raw score over the FEASIBLE nodes of this cycle before any node's total
+    // is known (helper/normalize_score.go:28-56): such templates take two passes over the tile with one extra exchange
+    const bool two_phase = (t.n_pref_terms > 0) && (t.score_enable & CCSIM_PL_NODE_AFFINITY);
+    int32_t na_local = 0;
     for (int32_t i = lo + tid; i < hi; i += blockDim.x) {
       int cls;
-      if (filter_node<RESIDENT>(p, hc, fc, tl, i, cls)) {
+      const bool ok = filter_node<RESIDENT>(p, hc, fc, tl, i, cls);
+      if (two_phase) p.feas[i] = ok ? 1 : 0;
+      if (ok) {
         int32_t sc = use_cache ? tl.score[i] : -1;
         if (sc < 0) {
           sc = score_node(tl.alloc_cpu[i], tl.alloc_mem[i], tl.nz_cpu[i] + t.least_cpu, tl.nz_mem[i] + t.least_mem,
                           tl.req_cpu[i] + t.bal_cpu, tl.req_mem[i] + t.bal_mem, ws.sw);
-          if (use_cache) tl.score[i] = sc;
+          if (use_cache || two_phase) tl.score[i] = sc;
         }
+        if (two_phase) { na_local = max(na_local, node_affinity_raw(p, t, i)); continue; }
         const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
         if (ncls == 1) best[0] = key > best[0] ? key : best[0];
         else {
+          #pragma unroll
+          for (int c = 0; c < CCSIM_MAX_CLASSES; c++) if (c == cls) best[c] = key > best[c] ? key : best[c];
+        }
+      }
+    }
+    if (two_phase) {
+      na_local = __reduce_max_sync(0xffffffffu, na_local);
+      if (lane == 0) ws.scratch[warp] = na_local;
+      __syncthreads();
+      if (warp == 0) {
+        int32_t m = (lane < (int)(blockDim.x >> 5)) ? ws.scratch[lane] : 0;
+        m = __reduce_max_sync(0xffffffffu, m);
+        bool dead = false;
+        const unsigned long long g = exchange_max(p, k, tag, CCSIM_MAX_CLASSES + 1, (unsigned long long)m, lane, cta, dead);
+        if (lane == 0) { ws.na_max = (long long)g; if (dead) ws.stop = 3; }
+      }
+      __syncthreads();
+      const long long na_max = ws.na_max;
+      for (int32_t i = lo + tid; i < hi; i += blockDim.x) {
+        if (!p.feas[i]) continue;
+        const long long raw = node_affinity_raw(p, t, i);
+        const long long na = na_max == 0 ? raw : 100 * raw / na_max;
+        const unsigned long long key = pack_key((long long)tl.score[i] + (long long)t.w_node_affinity * na, (uint32_t)(p.node_base + i));
+        if (ncls == 1) best[0] = key > best[0] ? key : best[0];
+        else {
+          const int cls = __popcll(tl.taint0[i] & hc.prefer0);
           #pragma unroll
           for (int c = 0; c < CCSIM_MAX_CLASSES; c++) if (c == cls) best[c] = key > best[c] ? key : best[c];
         }
@@ -579,6 +613,7 @@ struct ccsim_handle {
   int64_t *w_req_scalar[CCSIM_MAX_SCALARS] = {};
   uint64_t *w_placed = nullptr;
   int32_t *w_score = nullptr;
+  uint8_t *w_feas = nullptr;
   int32_t *d_taint_off = nullptr; uint8_t *d_taint_list = nullptr;
   int64_t pod_bound = 0;       // sum over nodes of max(0, alloc_pods - npods): no run can place more
   int max_prefer_pop = 0;      // max over nodes of popcount(taint & prefer): number of normalisation classes - 1
@@ -744,6 +779,7 @@ extern "C" int ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nd) {
   h->w_placed = nullptr;
   if (nd->has_placed_mask) WK(w_placed, uint64_t);
   WK(w_score, int32_t);
+  WK(w_feas, uint8_t);
 #undef WK
   h->d_taint_off = nullptr; h->d_taint_list = nullptr;
   if (nd->taint_list_off && nd->taint_list && n > 0) {
@@ -783,6 +819,7 @@ extern "C" int ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const c
   const ccsim_nodes &nd = h->meta;
   for (int t = 0; t < n_templates; t++) {
     const ccsim_template &T = templates[t];
+    if (T.n_pref_terms < 0 || T.n_pref_terms > CCSIM_MAX_AFF_TERMS) return fail(h, CCSIM_EINVAL, "template %d: n_pref_terms", t);
     if (T.n_pts < 0 || T.n_pts > CCSIM_MAX_PTS || T.n_aff < 0 || T.n_aff > CCSIM_MAX_IPA || T.n_anti < 0 || T.n_anti > CCSIM_MAX_IPA ||
         T.n_aff_terms < 0 || T.n_aff_terms > CCSIM_MAX_AFF_TERMS)
       return fail(h, CCSIM_EINVAL, "template %d: term counts out of range", t);
@@ -851,7 +888,7 @@ static void fill_params(ccsim_handle *h, DevParams &p, int64_t max_pods) {
   for (int k = 0; k < nd.n_topo_cols; k++) { p.topo[k] = h->d_topo[k]; p.topo_full[k] = h->d_topo_full[k]; }
   for (int r = 0; r < CCSIM_MAX_WORLD; r++) p.xslots_peer[r] = h->x_peer[r];
   p.req_cpu = h->w_req_cpu; p.req_mem = h->w_req_mem; p.req_eph = h->w_req_eph; p.nz_cpu = h->w_nz_cpu; p.nz_mem = h->w_nz_mem;
-  p.npods = h->w_npods; p.placed_mask = h->w_placed; p.score_cache = h->w_score;
+  p.npods = h->w_npods; p.placed_mask = h->w_placed; p.score_cache = h->w_score; p.feas = h->w_feas;
   for (int w = 0; w < CCSIM_MAX_TAINT_WORDS; w++) { p.taint_nosched[w] = nd.taint_nosched[w]; p.taint_prefer[w] = nd.taint_prefer[w]; }
   p.templates = h->d_templates;
   for (int j = 0; j < h->n_counters; j++) { p.counters[j] = h->counters[j]; p.final_off[j] = h->final_off[j]; }
@@ -948,7 +985,11 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   LeanParams lp; memset(&lp, 0, sizeof(lp));
   // measured on B200 (profiles/r1_kernel_variants.md): at 768 threads the lean kernel beats the generic resident kernel on
   // every eligible workload (C2 2.50 vs 2.67, C3 2.64 vs 2.84, C4 4.27 vs 4.95 us/wave); CCSIM_FORCE_GENERIC overrides.
-  bool lean = resident && h->n_templates == 1 && h->meta.taint_words == 1 && h->meta.static_words <= 1 && !getenv("CCSIM_FORCE_GENERIC");
+  bool has_pref = false;
+  for (auto &T : h->h_templates) if (T.n_pref_terms > 0 && (T.score_enable & CCSIM_PL_NODE_AFFINITY)) has_pref = true;
+  if (has_pref && (h->cfg.world > 1 || h->n_templates > 1))
+    return fail(h, CCSIM_EUNSUPPORTED, "preferred nodeAffinity terms: single template, single GPU only");
+  bool lean = resident && !has_pref && h->n_templates == 1 && h->meta.taint_words == 1 && h->meta.static_words <= 1 && !getenv("CCSIM_FORCE_GENERIC");
   if (lean) {
     const ccsim_template &T = h->h_templates[0];
     const bool nzfit = (T.filter_enable & CCSIM_PL_FIT) && !(T.flags & CCSIM_TF_FIT_ALL_ZERO);

@@ -296,6 +296,14 @@ class Encoder {
         }
       }
     }
+    // NodeAffinity preferred terms -> one static bit each (node_affinity.go:241-290)
+    if (t_.node_affinity_preferred.size() > CCSIM_MAX_AFF_TERMS) throw Unsupported("more than 8 preferred nodeAffinity terms");
+    T.n_pref_terms = (int32_t)t_.node_affinity_preferred.size();
+    for (size_t k = 0; k < t_.node_affinity_preferred.size(); k++) {
+      const NodeSelectorTerm &nt = t_.node_affinity_preferred[k].second;
+      T.pref_weight[k] = t_.node_affinity_preferred[k].first;
+      set_mask(T.pref_mask[k], new_bit([&](int i) { return nt.matches(nodes_[i]->labels, nodes_[i]->name); }));
+    }
     // NodePorts (node_ports.go:68-76,157-185)
     std::vector<ContainerPort> want = t_.host_ports();
     if (!want.empty()) {
@@ -495,7 +503,6 @@ class Encoder {
     if (t_.has_pvc_volume) throw Unsupported("pod uses PersistentVolumeClaim/ephemeral volumes (VolumeBinding/VolumeZone/NodeVolumeLimits/VolumeRestrictions)");
     if (t_.has_resource_claims) throw Unsupported("pod uses resourceClaims (DynamicResources)");
     if (t_.has_scheduling_gates) throw Unsupported("pod has schedulingGates");
-    if (t_.has_preferred_node_affinity) throw Unsupported("preferred nodeAffinity (NodeAffinity score)");
     if (!t_.aff_preferred.empty() || !t_.anti_preferred.empty()) throw Unsupported("preferred pod (anti-)affinity (InterPodAffinity score)");
     for (auto &c : t_.spread) if (c.when_unsatisfiable == "ScheduleAnyway") throw Unsupported("ScheduleAnyway topology spread constraints (PodTopologySpread score)");
     for (auto &c : t_.init_containers) (void)c;

@@ -184,6 +184,7 @@ struct Pod {
   bool has_required_node_affinity = false;
   std::vector<NodeSelectorTerm> node_affinity_terms;   // empty terms already dropped
   bool has_preferred_node_affinity = false;
+  std::vector<std::pair<int, NodeSelectorTerm>> node_affinity_preferred;   // (weight, preference); weight 0 / empty terms dropped
   std::vector<Toleration> tolerations;
   std::vector<AffinityTerm> aff_required, anti_required, aff_preferred, anti_preferred;
   std::vector<TopologySpreadConstraint> spread;
@@ -272,6 +273,25 @@ struct Pod {
     }
     const Json &pref = na.at("preferredDuringSchedulingIgnoredDuringExecution");
     p.has_preferred_node_affinity = pref.is_array() && !pref.arr.empty();
+    if (pref.is_array())
+      for (auto &pt : pref.arr) {   // NewPreferredSchedulingTerms (nodeaffinity.go:118-139)
+        NodeSelectorTerm nt;
+        const Json &t = pt.at("preference");
+        if (t.at("matchExpressions").is_array())
+          for (auto &e : t.at("matchExpressions").arr) {
+            Requirement r{e.at("key").str(), e.at("operator").str(), {}};
+            for (auto &v : e.at("values").arr) r.values.push_back(v.str());
+            nt.match_expressions.push_back(r);
+          }
+        if (t.at("matchFields").is_array())
+          for (auto &e : t.at("matchFields").arr) {
+            Requirement r{e.at("key").str(), e.at("operator").str(), {}};
+            for (auto &v : e.at("values").arr) r.values.push_back(v.str());
+            nt.match_fields.push_back(r);
+          }
+        const int w = (int)pt.at("weight").i64(0);
+        if (w != 0 && !nt.empty()) p.node_affinity_preferred.push_back({w, nt});
+      }
     if (sp.at("tolerations").is_array())
       for (auto &t : sp.at("tolerations").arr)
         p.tolerations.push_back(Toleration{t.at("key").str(), t.at("operator").str(), t.at("value").str(), t.at("effect").str()});

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CCSIM_ABI_VERSION 1
+#define CCSIM_ABI_VERSION 2
 
 /* ---- limits (compile-time, shared by host encoder, oracle and kernels) ---- */
 #define CCSIM_MAX_TAINT_WORDS   4   /* 64-bit words of the taint dictionary mask per node  */
@@ -221,6 +221,12 @@ typedef struct ccsim_template {
   int32_t n_anti;                 /* anti-affinity keys */
   int32_t anti_counter[CCSIM_MAX_IPA];
   int64_t aff_total_init;         /* sum of all affinity counts (len(affinityCounts)==0 test, filtering.go:396-405) */
+  /* NodeAffinity preferredDuringScheduling terms (node_affinity.go:241-290): raw score = sum of the weights of the
+   * matching terms (static bits), normalised per cycle to 100*raw/max over the feasible nodes (normalize_score.go:28-56) */
+  int32_t n_pref_terms;
+  int32_t pref_weight[CCSIM_MAX_AFF_TERMS];
+  int32_t pad_pref;
+  uint64_t pref_mask[CCSIM_MAX_AFF_TERMS][CCSIM_MAX_STATIC_WORDS];
 } ccsim_template;
 
 typedef struct ccsim_result {

@@ -288,6 +288,18 @@ static int taint_raw(const ccsim_nodes *nd, const ccsim_template *t, int32_t i) 
   return c;
 }
 
+/* raw NodeAffinity score: PL:nodeaffinity/node_affinity.go:265-290 (sum of the weights of the matching preferred terms) */
+static int64_t node_affinity_raw(const ccsim_nodes *nd, const ccsim_template *t, int32_t i) {
+  int64_t c = 0;
+  for (int k = 0; k < t->n_pref_terms; k++) {
+    int m = 1;
+    for (int w = 0; w < nd->static_words; w++)
+      if ((word(nd->static_mask, nd->n_nodes, w, i) & t->pref_mask[k][w]) != t->pref_mask[k][w]) m = 0;
+    if (m) c += t->pref_weight[k];
+  }
+  return c;
+}
+
 /* KS:schedule_one.go:697-723 */
 static int32_t num_feasible_nodes_to_find(int32_t n, int32_t pct) {
   if (n < 100) return n;
@@ -389,6 +401,12 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
     int32_t maxraw = 0;
     if (t->score_enable & CCSIM_PL_TAINT_TOLERATION)
       for (int32_t i = 0; i < n; i++) if (key[i] >= 0 && raw[i] > maxraw) maxraw = raw[i];
+    /* NodeAffinity preferred terms: PreScore Skip when the pod has none (node_affinity.go:246-249); else
+       DefaultNormalizeScore(100, reverse=false) over the feasible nodes (PL:helper/normalize_score.go:28-56) */
+    const int na_on = (t->score_enable & CCSIM_PL_NODE_AFFINITY) && t->n_pref_terms > 0;
+    int64_t na_max = 0;
+    if (na_on)
+      for (int32_t i = 0; i < n; i++) if (key[i] >= 0) { int64_t r = node_affinity_raw(nd, t, i); if (r > na_max) na_max = r; }
     int64_t best = -1; int32_t besti = -1;
     for (int32_t q = 0; q < n; q++) {
       int32_t i = (mode == 0) ? q : (start + q) % n;
@@ -397,6 +415,10 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
       if (t->score_enable & CCSIM_PL_TAINT_TOLERATION) {
         int64_t tt = (maxraw == 0) ? 100 : 100 - (100 * (int64_t)raw[i] / maxraw);
         total += (int64_t)t->w_taint * tt;
+      }
+      if (na_on) {
+        int64_t r = node_affinity_raw(nd, t, i);
+        total += (int64_t)t->w_node_affinity * (na_max == 0 ? r : 100 * r / na_max);
       }
       if (total > best) { best = total; besti = i; }
     }

@@ -594,14 +594,21 @@ class Simulator:
                 self.stop_reason = "Unschedulable: " + body(hist) + " preemption: " + post
                 return
             # prioritizeNodes + selectHost (KS:schedule_one.go:776-941): first max in node order
+            pref = [(t.get("weight", 0), t.get("preference") or {}) for t in
+                    (((pod["spec"].get("affinity") or {}).get("nodeAffinity") or {}).get("preferredDuringSchedulingIgnoredDuringExecution") or [])]
+            pref = [(w, pr) for w, pr in pref if w != 0 and (pr.get("matchExpressions") or pr.get("matchFields"))]   # nodeaffinity.go:118-139
+            na_raw = [sum(w for w, pr in pref if node_term_matches(pr, ni.node)) for ni in feasible]
+            na_max = max(na_raw) if na_raw else 0
             raws = [sum(1 for t in (ni.node.get("spec") or {}).get("taints") or []
                         if t.get("effect") == "PreferNoSchedule" and not tolerations_tolerate(tols_prefer, t)) for ni in feasible]
             mx = max(raws)
             best, best_ni = None, None
-            for ni, raw in zip(feasible, raws):
+            for idx, (ni, raw) in enumerate(zip(feasible, raws)):
                 least, bal = self._score(pod, ni)
                 tt = 100 if mx == 0 else 100 - (100 * raw // mx)
                 total = 3 * tt + least + (bal if bal is not None else 0)
+                if pref:      # NodeAffinity score, weight 2 (node_affinity.go:241-290; helper/normalize_score.go:28-56)
+                    total += 2 * (na_raw[idx] if na_max == 0 else 100 * na_raw[idx] // na_max)
                 if best is None or total > best:
                     best, best_ni = total, ni
             clone = {"metadata": dict(pod["metadata"]), "spec": dict(pod["spec"]), "status": {}}

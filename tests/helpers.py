@@ -124,7 +124,7 @@ def random_cluster(seed, n_nodes=40, n_pods=60, zones=3):
 
 
 TEMPLATE_VARIANTS = ["plain", "selector", "tolerations", "affinity_terms", "hostports", "spread_zone", "spread_two", "anti_hostname",
-                     "anti_zone", "affinity_zone", "extended", "best_effort", "init_overhead", "never_preempt", "gt_lt", "name_in"]
+                     "anti_zone", "affinity_zone", "extended", "best_effort", "init_overhead", "never_preempt", "gt_lt", "name_in", "pref_affinity", "pref_and_required"]
 
 
 def template(variant, seed=0):
@@ -147,6 +147,19 @@ def template(variant, seed=0):
         s["affinity"] = {"nodeAffinity": {"requiredDuringSchedulingIgnoredDuringExecution": {"nodeSelectorTerms": [
             {"matchFields": [{"key": "metadata.name", "operator": "In", "values": ["node-03"]}]},
             {"matchFields": [{"key": "metadata.name", "operator": "In", "values": ["node-07"]}]}]}}}
+    elif variant == "pref_affinity":
+        s["affinity"] = {"nodeAffinity": {"preferredDuringSchedulingIgnoredDuringExecution": [
+            {"weight": 50, "preference": {"matchExpressions": [{"key": "disk", "operator": "In", "values": ["ssd"]}]}},
+            {"weight": 20, "preference": {"matchExpressions": [{"key": "topology.kubernetes.io/zone", "operator": "In", "values": ["z1", "z2"]}]}},
+            {"weight": 0, "preference": {"matchExpressions": [{"key": "rank", "operator": "Exists"}]}},
+            {"weight": 7, "preference": {"matchExpressions": [{"key": "rank", "operator": "Gt", "values": ["4"]}]}}]}}
+        s["tolerations"] = [{"key": "dedicated", "operator": "Exists"}]
+    elif variant == "pref_and_required":
+        s["affinity"] = {"nodeAffinity": {
+            "requiredDuringSchedulingIgnoredDuringExecution": {"nodeSelectorTerms": [{"matchExpressions": [{"key": "disk", "operator": "Exists"}]}]},
+            "preferredDuringSchedulingIgnoredDuringExecution": [
+                {"weight": 100, "preference": {"matchExpressions": [{"key": "disk", "operator": "In", "values": ["hdd"]}]}},
+                {"weight": 1, "preference": {"matchFields": [{"key": "metadata.name", "operator": "In", "values": ["node-05"]}]}}]}}
     elif variant == "hostports":
         s["containers"][0]["ports"] = [{"containerPort": 80, "hostPort": 8080}]
     elif variant == "spread_zone":

@@ -203,3 +203,21 @@ def test_reference_sampling_mode(built, gen, kw, pct):
     if pct == 100 or snap.n < 100:
         canon = oracle.run(snap, tmpl, ctr, max_pods=limit)
         assert np.array_equal(got.pod_node, canon.pod_node)
+
+
+def test_preferred_node_affinity_two_phase(built):
+    """NodeAffinity preferred terms (A18): raw = sum of matching weights, normalised by the max over the feasible nodes of
+    each cycle — as the best nodes fill up the maximum (and with it every node's score) changes."""
+    rng = np.random.default_rng(17)
+    n = 2500
+    a_cpu = rng.choice([2000, 4000, 8000], n)
+    static = (rng.random(n) < 0.2).astype(np.uint64) | ((rng.random(n) < 0.5).astype(np.uint64) << np.uint64(1)) | ((rng.random(n) < 0.1).astype(np.uint64) << np.uint64(2))
+    taint = ((rng.random(n) < 0.3).astype(np.uint64) << np.uint64(0))
+    snap = abi.Snapshot(n, a_cpu, np.full(n, 16 * GiB), np.full(n, 12), static_mask=static.reshape(1, n),
+                        taint_mask=taint.reshape(1, n), taint_prefer=[1], taint_lists=[[0] if int(x) else [] for x in taint])
+    t = abi.default_template(500, 512 * MiB)
+    t.n_pref_terms = 3
+    for k, (bit, w) in enumerate([(0, 60), (1, 25), (2, 9)]):
+        t.pref_weight[k] = w
+        t.pref_mask[k][0] = 1 << bit
+    check(snap, [t], max_pods=6000)
