@@ -6,7 +6,7 @@ CPU oracle. Field order and limits must match include/ccsim.h exactly; tests/tes
 import ctypes as C
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_TAINT_WORDS = 4
 MAX_STATIC_WORDS = 4
 MAX_SCALARS = 4
@@ -100,12 +100,17 @@ class Nodes(C.Structure):
 
 class Counter(C.Structure):
     _fields_ = [("topo_col", C.c_int32), ("n_domains", C.c_int32), ("n_present", C.c_int32),
-                ("inc", C.c_int32), ("init", P32)]
+                ("inc", C.c_int32), ("elig_bit", C.c_int32), ("pad", C.c_int32), ("init", P32)]
 
 
 class Pts(C.Structure):
     _fields_ = [("counter", C.c_int32), ("max_skew", C.c_int32), ("self_match", C.c_int32),
                 ("min_zero", C.c_int32)]
+
+
+class Spts(C.Structure):
+    _fields_ = [("counter", C.c_int32), ("max_skew", C.c_int32), ("hostname", C.c_int32),
+                ("has_key_bit", C.c_int32)]
 
 
 class Template(C.Structure):
@@ -132,6 +137,9 @@ class Template(C.Structure):
         ("aff_total_init", C.c_int64),
         ("n_pref_terms", C.c_int32), ("pref_weight", C.c_int32 * MAX_AFF_TERMS), ("pad_pref", C.c_int32),
         ("pref_mask", (C.c_uint64 * MAX_STATIC_WORDS) * MAX_AFF_TERMS),
+        ("n_spts", C.c_int32), ("spts_ignored_bit", C.c_int32), ("spts", Spts * MAX_PTS),
+        ("n_ipa_score", C.c_int32), ("ipa_score_counter", C.c_int32 * MAX_IPA), ("pad_soft", C.c_int32),
+        ("image_score", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -247,18 +255,20 @@ def default_template(cpu_milli=0, mem=0, eph=0, nz_cpu=None, nz_mem=None, fit_on
     t.score_enable = (PL_FIT | PL_BALANCED) if fit_only else PL_ALL
     t.nodename_idx = -1
     t.prefilter_bit = -1
+    t.spts_ignored_bit = -1
     t.w_taint, t.w_node_affinity, t.w_fit, t.w_pts, t.w_ipa, t.w_balanced, t.w_image = 3, 2, 1, 2, 2, 1, 1
     t.least_w_cpu, t.least_w_mem = 1, 1
     return t
 
 
-def make_counter(topo_col, init, n_present=None, inc=0):
+def make_counter(topo_col, init, n_present=None, inc=0, elig_bit=-1):
     init = np.ascontiguousarray(init, dtype=np.int32)
     c = Counter()
     c.topo_col = topo_col
     c.n_domains = len(init)
     c.n_present = len(init) if n_present is None else n_present
     c.inc = inc
+    c.elig_bit = elig_bit
     c.init = _ptr(init, P32)
     c._keep = init
     return c

@@ -22,6 +22,8 @@ struct DevCounter {
   int32_t inc;
   int32_t smem_off;   // offset (in int32) into the CTA's shared counter area, or -1: per-CTA replica in global memory
   int32_t is_aff;     // counter belongs to a required pod-affinity key
+  int32_t elig_bit;   // static bit a node needs for its commits to count, -1 = every node
+  int32_t pad;
   int32_t *init;      // [n_domains] device copy of the initial counts (node-local: snapshot column)
   int32_t *work;      // node-local: working column [n]; replicated-global: base of grid*n_domains replicas
 };
@@ -62,7 +64,8 @@ struct DevParams {
   int32_t *npods;
   int64_t *req_scalar[CCSIM_MAX_SCALARS];
   uint64_t *placed_mask;   // nullptr unless a template has hostPorts
-  uint8_t *feas;           // per-node feasibility flag of the current wave (two-phase scoring: NodeAffinity preferred terms)
+  uint8_t *feas;           // per-node feasibility flag of the current wave (multi-phase scoring: normalised soft scorers)
+  uint32_t *stamp[CCSIM_MAX_PTS];   // soft PTS constraint c (non-hostname): [n_domains + 1] "a scored node of wave k+1 is in this domain"
   int32_t *score_cache;    // memoised node-local score per node, -1 = stale (streaming mode; resident mode keeps it in the tile)
   int32_t tile_resident;   // 1: the CTA's node tile is staged into shared memory once and stays there for the whole run
   int32_t chunk_pad;       // chunk rounded up to a multiple of 4 (tile column stride)
@@ -431,7 +434,7 @@ struct CommitInfo {
   int32_t n_present;
   int32_t is_aff;
   int32_t local;          // node-local counter
-  int32_t pad;
+  int32_t elig_bit;       // static bit the winner must carry, -1 none
 };
 
 
@@ -486,6 +489,92 @@ __device__ __forceinline__ unsigned long long exchange_max(const DevParams &p, l
   for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const unsigned long long b = v[q] & KEY_BODY_MASK; m = b > m ? b : m; }
   dead = __any_sync(0xffffffffu, dead);
   return warp_max_u64(m);
+}
+
+// Several grid-wide maxima at once: lane q < NV publishes vals[q] (< 2^44, 0 = "nothing") in word word0+q of this CTA's
+// slot line; every CTA then gathers all lines. One wait for the slowest CTA, the remaining words are already there.
+template <int NV>
+__device__ __forceinline__ void exchange_max_n(const DevParams &p, long long k, uint32_t tag, int word0,
+                                               unsigned long long (&vals)[NV], int lane, int cta, bool &dead) {
+  const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
+  unsigned long long mine = 0ull;
+  #pragma unroll
+  for (int q = 0; q < NV; q++) if (lane == q) mine = vals[q];
+  if (lane < NV) st_slot(p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE + word0 + lane, (mine & KEY_BODY_MASK) | tagbits);
+  #pragma unroll
+  for (int w = 0; w < NV; w++) {
+    const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE + word0 + w;
+    unsigned long long v[CCSIM_MAX_GRID / 32];
+    unsigned spins = 0;
+    bool pending;
+    do {
+      pending = false;
+      #pragma unroll
+      for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const int b = lane + 32 * q; v[q] = (b < p.grid) ? ld_slot(&all[(size_t)b * SLOT_STRIDE]) : tagbits; }
+      #pragma unroll
+      for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) pending |= ((uint32_t)(v[q] >> KEY_TAG_SHIFT) != tag);
+      if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+    } while (__any_sync(0xffffffffu, pending));
+    unsigned long long m = 0ull;
+    #pragma unroll
+    for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const unsigned long long b = v[q] & KEY_BODY_MASK; m = b > m ? b : m; }
+    vals[w] = warp_max_u64(m);
+  }
+  dead = __any_sync(0xffffffffu, dead);
+}
+
+// grid-wide sum of one count per CTA (< 2^44 in total), with release/acquire fences around it: global stores made by the
+// CTA before the call (after a __syncthreads) are visible to every CTA's threads after it (and their next __syncthreads)
+__device__ __forceinline__ unsigned long long exchange_sum_fenced(const DevParams &p, long long k, uint32_t tag, int word,
+                                                                  unsigned long long mine, int lane, int cta, bool &dead) {
+  const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
+  __threadfence();
+  if (lane == 0) st_slot(p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE + word, (mine & KEY_BODY_MASK) | tagbits);
+  const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE + word;
+  unsigned long long v[CCSIM_MAX_GRID / 32];
+  unsigned spins = 0;
+  bool pending;
+  do {
+    pending = false;
+    #pragma unroll
+    for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const int b = lane + 32 * q; v[q] = (b < p.grid) ? ld_slot(&all[(size_t)b * SLOT_STRIDE]) : tagbits; }
+    #pragma unroll
+    for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) pending |= ((uint32_t)(v[q] >> KEY_TAG_SHIFT) != tag);
+    if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+  } while (__any_sync(0xffffffffu, pending));
+  __threadfence();
+  unsigned long long s = 0ull;
+  #pragma unroll
+  for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) s += v[q] & KEY_BODY_MASK;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  dead = __any_sync(0xffffffffu, dead);
+  return s;
+}
+
+__device__ __forceinline__ bool static_bit(const DevParams &p, int32_t i, int b) {
+  return (p.static_mask[(size_t)(b >> 6) * p.n + i] >> (b & 63)) & 1ull;
+}
+
+// Go's math.Log on amd64 = the pure-Go port of FreeBSD's e_log.c (go/src/math/log.go:80-129), every operation rounded on
+// its own (no FMA contraction: GOAMD64=v1). x must be a positive normal number (here: an integer >= 2).
+__device__ __noinline__ double go_log(double x) {
+  const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10;
+  const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01, L3 = 2.857142874366239149e-01,
+               L4 = 2.222219843214978396e-01, L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
+               L7 = 1.479819860511658591e-01;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+  int ki = (int)((bits >> 52) & 0x7ffull) - 1022;                                   // Frexp: x = f1 * 2^ki, f1 in [0.5, 1)
+  double f1 = __longlong_as_double((long long)((bits & 0x800fffffffffffffull) | (1022ull << 52)));
+  if (f1 < 0.70710678118654752440) { f1 = __dmul_rn(f1, 2.0); ki--; }
+  const double f = __dsub_rn(f1, 1.0), k = (double)ki;
+  const double s = __ddiv_rn(f, __dadd_rn(2.0, f)), s2 = __dmul_rn(s, s), s4 = __dmul_rn(s2, s2);
+  const double t1 = __dmul_rn(s2, __dadd_rn(L1, __dmul_rn(s4, __dadd_rn(L3, __dmul_rn(s4, __dadd_rn(L5, __dmul_rn(s4, L7)))))));
+  const double t2 = __dmul_rn(s4, __dadd_rn(L2, __dmul_rn(s4, __dadd_rn(L4, __dmul_rn(s4, L6)))));
+  const double R = __dadd_rn(t1, t2), hfsq = __dmul_rn(__dmul_rn(0.5, f), f);
+  // k*Ln2Hi - ((hfsq - (s*(hfsq+R) + k*Ln2Lo)) - f)
+  const double inner = __dadd_rn(__dmul_rn(s, __dadd_rn(hfsq, R)), __dmul_rn(k, Ln2Lo));
+  return __dsub_rn(__dmul_rn(k, Ln2Hi), __dsub_rn(__dsub_rn(hfsq, inner), f));
 }
 
 // raw NodeAffinity score of a node: sum of the weights of the matching preferred terms (node_affinity.go:265-290)

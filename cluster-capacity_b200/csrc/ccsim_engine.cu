@@ -16,6 +16,7 @@
 // inter-CTA ordering is needed beyond the key exchange.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <climits>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -51,7 +52,11 @@ struct __align__(16) WaveShared {
   int32_t winner;        // global node index, -1 = none
   int32_t stop;          // 0 continue, 1 unschedulable, 2 limit, 3 error
   int32_t dirty;         // FilterConsts must be rebuilt before the next scan
-  long long na_max;      // two-phase scoring: max raw NodeAffinity score over the feasible nodes of this wave
+  // normalised soft scorers (multi-phase waves): extrema of the raw scores over the feasible nodes of this wave
+  long long na_max, spts_min, spts_max, ipa_min, ipa_max;
+  long long spts_scored;                 // feasible nodes that are not in IgnoredNodes
+  double spts_w[CCSIM_MAX_PTS];          // topologyNormalizingWeight per soft constraint
+  long long red[MAX_WARPS][6];           // block reductions of the above
   ScoreWeights sw;       // scalar copy of the template's score configuration (passed by value to score_node)
   CommitInfo cinfo[CCSIM_MAX_COUNTERS];   // what a commit does to each counter under the current template
   int32_t scratch[MAX_WARPS];
@@ -87,6 +92,37 @@ __device__ void pts_recount(const DevParams &p, int c) {
     ws.dirty = 1;
   }
   __syncthreads();
+}
+
+// PodTopologySpread.Score of a node that is not in IgnoredNodes, with this wave's weights (scoring.go:192-224,302-304)
+__device__ __forceinline__ long long spts_raw(const DevParams &p, const ccsim_template &t, int32_t i) {
+  double score = 0.0;
+  for (int c = 0; c < t.n_spts; c++) {
+    const ccsim_spts sc = t.spts[c];
+    long long cnt;
+    if (sc.hostname) {
+      if (sc.has_key_bit >= 0 && !static_bit(p, i, sc.has_key_bit)) continue;
+      cnt = ws.cnt_ptr[sc.counter][i];
+    } else {
+      const int32_t dom = ws.topo_ptr[p.counters[sc.counter].topo_col][i];
+      if (dom < 0) continue;
+      cnt = ws.cnt_ptr[sc.counter][dom];
+    }
+    score = __dadd_rn(score, __dadd_rn(__dmul_rn((double)cnt, ws.spts_w[c]), (double)(sc.max_skew - 1)));
+  }
+  return __double2ll_rn(round(score)) ;   // math.Round: half away from zero (round() already yields an integer value)
+}
+
+// InterPodAffinity.Score (interpodaffinity/scoring.go:236-256)
+__device__ __forceinline__ long long ipa_raw(const DevParams &p, const ccsim_template &t, int32_t i) {
+  long long sc = 0;
+  for (int k = 0; k < t.n_ipa_score; k++) {
+    const int j = t.ipa_score_counter[k];
+    const int32_t tc = p.counters[j].topo_col;
+    const int32_t dom = tc < 0 ? i : ws.topo_ptr[tc][i];
+    if (dom >= 0) sc += ws.cnt_ptr[j][dom];
+  }
+  return sc;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -218,7 +254,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
           CommitInfo &ci = ws.cinfo[j];
           const bool skip = (dc.inc == 0) || (dc.is_aff && !(t.flags & CCSIM_TF_AFF_SELF_MATCH_ALL));
           ci.inc = skip ? 0 : dc.inc;
-          ci.local = dc.topo_col < 0; ci.is_aff = dc.is_aff; ci.n_present = dc.n_present;
+          ci.local = dc.topo_col < 0; ci.is_aff = dc.is_aff; ci.n_present = dc.n_present; ci.elig_bit = dc.elig_bit;
           ci.gtopo = dc.topo_col < 0 ? nullptr : p.topo_full[dc.topo_col];
           ci.ltopo = dc.topo_col < 0 ? nullptr : ws.topo_ptr[dc.topo_col];
           ci.pts_idx = -1;
@@ -235,22 +271,43 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
     unsigned long long best[CCSIM_MAX_CLASSES];
     #pragma unroll
     for (int c = 0; c < CCSIM_MAX_CLASSES; c++) best[c] = 0ull;
-    // NodeAffinity preferred terms need the maximum raw score over the FEASIBLE nodes of this cycle before any node's total
-    // is known (helper/normalize_score.go:28-56): such templates take two passes over the tile with one extra exchange
-    const bool two_phase = (t.n_pref_terms > 0) && (t.score_enable & CCSIM_PL_NODE_AFFINITY);
-    int32_t na_local = 0;
+    // Normalised soft scorers (NodeAffinity preferred terms, PodTopologySpread ScheduleAnyway/system defaults, InterPodAffinity
+    // score) need extrema of their raw scores over the FEASIBLE nodes of this cycle before any node's total is known
+    // (helper/normalize_score.go:28-56; podtopologyspread/scoring.go:226-265; interpodaffinity/scoring.go:258-290): such
+    // templates take up to three passes over the tile with one or two extra grid-wide exchanges per wave.
+    const bool na_on = (t.n_pref_terms > 0) && (t.score_enable & CCSIM_PL_NODE_AFFINITY);
+    const bool spts_on = (t.n_spts > 0) && (t.score_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD);
+    const bool ipa_on = (t.n_ipa_score > 0) && (t.score_enable & CCSIM_PL_INTER_POD_AFFINITY);
+    const bool soft = na_on || spts_on || ipa_on;
+    const int32_t w_image = ((t.score_enable & CCSIM_PL_IMAGE_LOCALITY) && t.image_score) ? t.w_image : 0;
+    const uint32_t stamp_now = (uint32_t)(k + 1);
+    long long na_local = 0, ipa_lo = LLONG_MAX, ipa_hi = LLONG_MIN, scored_local = 0;
     for (int32_t i = lo + tid; i < hi; i += blockDim.x) {
       int cls;
       const bool ok = filter_node<RESIDENT>(p, hc, fc, tl, i, cls);
-      if (two_phase) p.feas[i] = ok ? 1 : 0;
+      if (soft) p.feas[i] = ok ? 1 : 0;
       if (ok) {
         int32_t sc = use_cache ? tl.score[i] : -1;
         if (sc < 0) {
           sc = score_node(tl.alloc_cpu[i], tl.alloc_mem[i], tl.nz_cpu[i] + t.least_cpu, tl.nz_mem[i] + t.least_mem,
                           tl.req_cpu[i] + t.bal_cpu, tl.req_mem[i] + t.bal_mem, ws.sw);
-          if (use_cache || two_phase) tl.score[i] = sc;
+          if (w_image) sc += w_image * (int32_t)t.image_score[i];
+          if (use_cache || soft) tl.score[i] = sc;
         }
-        if (two_phase) { na_local = max(na_local, node_affinity_raw(p, t, i)); continue; }
+        if (soft) {
+          if (na_on) na_local = max(na_local, (long long)node_affinity_raw(p, t, i));
+          if (ipa_on) { const long long r = ipa_raw(p, t, i); ipa_lo = min(ipa_lo, r); ipa_hi = max(ipa_hi, r); }
+          if (spts_on && !(t.spts_ignored_bit >= 0 && static_bit(p, i, t.spts_ignored_bit))) {
+            scored_local++;
+            for (int c = 0; c < t.n_spts; c++) {
+              if (t.spts[c].hostname) continue;
+              const DevCounter &dc = p.counters[t.spts[c].counter];
+              const int32_t dom = ws.topo_ptr[dc.topo_col][i];
+              __stcg(&p.stamp[c][dom < 0 ? dc.n_domains : dom], stamp_now);   // a missing key reads as the value ""
+            }
+          }
+          continue;
+        }
         const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
         if (ncls == 1) best[0] = key > best[0] ? key : best[0];
         else {
@@ -259,24 +316,99 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
         }
       }
     }
-    if (two_phase) {
-      na_local = __reduce_max_sync(0xffffffffu, na_local);
-      if (lane == 0) ws.scratch[warp] = na_local;
-      __syncthreads();
-      if (warp == 0) {
-        int32_t m = (lane < (int)(blockDim.x >> 5)) ? ws.scratch[lane] : 0;
-        m = __reduce_max_sync(0xffffffffu, m);
-        bool dead = false;
-        const unsigned long long g = exchange_max(p, k, tag, CCSIM_MAX_CLASSES + 1, (unsigned long long)m, lane, cta, dead);
-        if (lane == 0) { ws.na_max = (long long)g; if (dead) ws.stop = 3; }
+    if (soft) {
+      long long spts_lo = LLONG_MAX, spts_hi = 0;
+      if (spts_on) {
+        // ---- PreScore: sizes of the topologies among the scored nodes -> weights (scoring.go:60-116,294-296) ----
+        for (int o = 16; o > 0; o >>= 1) scored_local += __shfl_xor_sync(0xffffffffu, scored_local, o);
+        if (lane == 0) ws.red[warp][0] = scored_local;
+        __syncthreads();
+        if (warp == 0) {
+          long long m = (lane < (int)(blockDim.x >> 5)) ? ws.red[lane][0] : 0;
+          for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+          bool dead = false;
+          const unsigned long long g = exchange_sum_fenced(p, k, tag, CCSIM_MAX_CLASSES, (unsigned long long)m, lane, cta, dead);
+          if (lane == 0) { ws.spts_scored = (long long)g; if (dead) ws.stop = 3; }
+        }
+        __syncthreads();
+        for (int c = 0; c < t.n_spts; c++) {
+          long long size = ws.spts_scored;
+          if (!t.spts[c].hostname) {
+            const int nd1 = p.counters[t.spts[c].counter].n_domains + 1;
+            int32_t cnt = 0;
+            for (int d = tid; d < nd1; d += blockDim.x) cnt += (__ldcg(&p.stamp[c][d]) == stamp_now);
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane == 0) ws.scratch[warp] = cnt;
+            __syncthreads();
+            size = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) size += ws.scratch[w];
+          }
+          if (tid == 0) ws.spts_w[c] = go_log((double)(size + 2));
+          __syncthreads();
+        }
+        for (int32_t i = lo + tid; i < hi; i += blockDim.x) {
+          if (!p.feas[i] || (t.spts_ignored_bit >= 0 && static_bit(p, i, t.spts_ignored_bit))) continue;
+          const long long r = spts_raw(p, t, i);
+          spts_lo = min(spts_lo, r); spts_hi = max(spts_hi, r);
+        }
+      }
+      // ---- extrema over the feasible nodes: block reduction, then one grid-wide exchange of five words ----
+      {
+        long long v[5] = {na_local, spts_hi, spts_lo == LLONG_MAX ? LLONG_MIN : -spts_lo, ipa_hi, ipa_lo == LLONG_MAX ? LLONG_MIN : -ipa_lo};
+        #pragma unroll
+        for (int q = 0; q < 5; q++) {
+          for (int o = 16; o > 0; o >>= 1) { const long long u = __shfl_xor_sync(0xffffffffu, v[q], o); v[q] = u > v[q] ? u : v[q]; }
+          if (lane == 0) ws.red[warp][q] = v[q];
+        }
       }
       __syncthreads();
-      const long long na_max = ws.na_max;
+      if (warp == 0) {
+        const long long IPA_BIAS = 1ll << 40;
+        long long v[5];
+        #pragma unroll
+        for (int q = 0; q < 5; q++) {
+          long long m = (q == 0 || q == 1) ? 0 : LLONG_MIN;
+          if (lane < (int)(blockDim.x >> 5)) m = ws.red[lane][q];
+          for (int o = 16; o > 0; o >>= 1) { const long long u = __shfl_xor_sync(0xffffffffu, m, o); m = u > m ? u : m; }
+          v[q] = m;
+        }
+        // encode as non-zero unsigned maxima (0 = this CTA has no feasible node)
+        unsigned long long e[5];
+        e[0] = (unsigned long long)(v[0] + 1);
+        e[1] = (v[2] == LLONG_MIN) ? 0ull : (unsigned long long)(v[1] + 1);
+        e[2] = (v[2] == LLONG_MIN) ? 0ull : (unsigned long long)((1ll << 43) + v[2]);       // 2^43 - min
+        e[3] = (v[4] == LLONG_MIN) ? 0ull : (unsigned long long)(v[3] + IPA_BIAS);
+        e[4] = (v[4] == LLONG_MIN) ? 0ull : (unsigned long long)(v[4] + IPA_BIAS);          // bias - min
+        bool dead = false;
+        exchange_max_n<5>(p, k, tag, CCSIM_MAX_CLASSES + 1, e, lane, cta, dead);
+        if (lane == 0) {
+          ws.na_max = e[0] ? (long long)e[0] - 1 : 0;
+          ws.spts_max = e[1] ? (long long)e[1] - 1 : 0;
+          ws.spts_min = e[2] ? (1ll << 43) - (long long)e[2] : LLONG_MAX;
+          ws.ipa_max = e[3] ? (long long)e[3] - IPA_BIAS : LLONG_MIN;
+          ws.ipa_min = e[4] ? IPA_BIAS - (long long)e[4] : LLONG_MAX;
+          if (dead) ws.stop = 3;
+        }
+      }
+      __syncthreads();
+      const long long na_max = ws.na_max, pmin = ws.spts_min, pmax = ws.spts_max, imin = ws.ipa_min, imax = ws.ipa_max;
       for (int32_t i = lo + tid; i < hi; i += blockDim.x) {
         if (!p.feas[i]) continue;
-        const long long raw = node_affinity_raw(p, t, i);
-        const long long na = na_max == 0 ? raw : 100 * raw / na_max;
-        const unsigned long long key = pack_key((long long)tl.score[i] + (long long)t.w_node_affinity * na, (uint32_t)(p.node_base + i));
+        long long total = tl.score[i];
+        if (na_on) {
+          const long long raw = node_affinity_raw(p, t, i);
+          total += (long long)t.w_node_affinity * (na_max == 0 ? raw : 100 * raw / na_max);
+        }
+        if (spts_on && !(t.spts_ignored_bit >= 0 && static_bit(p, i, t.spts_ignored_bit))) {
+          const long long r = spts_raw(p, t, i);
+          total += (long long)t.w_pts * (pmax == 0 ? 100 : 100 * (pmax + pmin - r) / pmax);
+        }
+        if (ipa_on && imax > imin) {
+          const long long r = ipa_raw(p, t, i);
+          const double f = __dmul_rn(100.0, __ddiv_rn((double)(r - imin), (double)(imax - imin)));
+          total += (long long)t.w_ipa * __double2ll_rz(f);
+        }
+        const unsigned long long key = pack_key(total, (uint32_t)(p.node_base + i));
         if (ncls == 1) best[0] = key > best[0] ? key : best[0];
         else {
           const int cls = __popcll(tl.taint0[i] & hc.prefer0);
@@ -383,7 +515,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
         if (lane < p.n_counters) {
           const int j = lane;
           const CommitInfo ci = ws.cinfo[j];
-          if (ci.inc) {
+          if (ci.inc && !(ci.elig_bit >= 0 && !static_bit(p, w, ci.elig_bit))) {   // elig_bit only exists on single-GPU runs: w is a local index
             if (ci.local) {
               if (mine) {
                 const int32_t nv = ws.cnt_ptr[j][w] + ci.inc;
@@ -614,6 +746,8 @@ struct ccsim_handle {
   uint64_t *w_placed = nullptr;
   int32_t *w_score = nullptr;
   uint8_t *w_feas = nullptr;
+  uint32_t *d_stamp[CCSIM_MAX_PTS] = {nullptr};
+  size_t stamp_len[CCSIM_MAX_PTS] = {0};
   int32_t *d_taint_off = nullptr; uint8_t *d_taint_list = nullptr;
   int64_t pod_bound = 0;       // sum over nodes of max(0, alloc_pods - npods): no run can place more
   int max_prefer_pop = 0;      // max over nodes of popcount(taint & prefer): number of normalisation classes - 1
@@ -832,7 +966,18 @@ extern "C" int ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const c
     for (int a = 0; a < T.n_anti; a++) if (T.anti_counter[a] < 0 || T.anti_counter[a] >= n_counters) return fail(h, CCSIM_EINVAL, "anti counter index");
     if ((T.flags & CCSIM_TF_PREFILTER_NODES) && (T.prefilter_bit < 0 || T.prefilter_bit >= 64 * nd.static_words))
       return fail(h, CCSIM_EINVAL, "template %d: prefilter_bit", t);
+    if (T.n_spts < 0 || T.n_spts > CCSIM_MAX_PTS || T.n_ipa_score < 0 || T.n_ipa_score > CCSIM_MAX_IPA)
+      return fail(h, CCSIM_EINVAL, "template %d: soft term counts out of range", t);
+    if (T.spts_ignored_bit >= 64 * nd.static_words) return fail(h, CCSIM_EINVAL, "template %d: spts_ignored_bit", t);
+    for (int c = 0; c < T.n_spts; c++) {
+      const ccsim_spts &sc = T.spts[c];
+      if (sc.counter < 0 || sc.counter >= n_counters) return fail(h, CCSIM_EINVAL, "template %d: spts counter index", t);
+      if ((sc.hostname != 0) != (counters[sc.counter].topo_col < 0)) return fail(h, CCSIM_EINVAL, "template %d: spts %d: hostname constraints use node-local counters (and only they)", t, c);
+      if (sc.has_key_bit >= 64 * nd.static_words) return fail(h, CCSIM_EINVAL, "template %d: spts has_key_bit", t);
+    }
+    for (int a = 0; a < T.n_ipa_score; a++) if (T.ipa_score_counter[a] < 0 || T.ipa_score_counter[a] >= n_counters) return fail(h, CCSIM_EINVAL, "ipa score counter index");
   }
+  for (int j = 0; j < n_counters; j++) if (counters[j].elig_bit >= 64 * nd.static_words) return fail(h, CCSIM_EINVAL, "counter %d: elig_bit", j);
   for (int t = 0; t < n_templates; t++) {
     const ccsim_template &T = templates[t];
     const long long wsum = (long long)abs(T.w_taint) + abs(T.w_node_affinity) + abs(T.w_fit) + abs(T.w_pts) + abs(T.w_ipa) + abs(T.w_balanced) + abs(T.w_image);
@@ -842,14 +987,31 @@ extern "C" int ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const c
     return fail(h, CCSIM_EUNSUPPORTED, "a node carries %d PreferNoSchedule taints (max %d)", h->max_prefer_pop, CCSIM_MAX_CLASSES - 1);
   h->h_templates.assign(templates, templates + n_templates);
   int rc;
-  if ((rc = dev_upload<ccsim_template>(h, h->tmpl_allocs, &h->d_templates, templates, (size_t)n_templates))) return rc;
+  {
+    // ImageLocality columns: this shard's slice goes to the device, the device copy of the template points at it
+    std::vector<ccsim_template> dev_t(templates, templates + n_templates);
+    for (int t = 0; t < n_templates; t++)
+      if (templates[t].image_score) {
+        uint8_t *d = nullptr;
+        if ((rc = dev_upload<uint8_t>(h, h->tmpl_allocs, &d, templates[t].image_score + h->node_base, (size_t)h->n))) return rc;
+        dev_t[t].image_score = d;
+      }
+    if ((rc = dev_upload<ccsim_template>(h, h->tmpl_allocs, &h->d_templates, dev_t.data(), (size_t)n_templates))) return rc;
+    CK(cudaStreamSynchronize(h->stream));   // dev_t is about to go out of scope
+  }
+  for (int c = 0; c < CCSIM_MAX_PTS; c++) { h->d_stamp[c] = nullptr; h->stamp_len[c] = 0; }
+  for (int c = 0; c < templates[0].n_spts; c++)
+    if (!templates[0].spts[c].hostname) {
+      h->stamp_len[c] = (size_t)counters[templates[0].spts[c].counter].n_domains + 1;
+      if ((rc = dev_alloc<uint32_t>(h, h->tmpl_allocs, &h->d_stamp[c], h->stamp_len[c]))) return rc;
+    }
   // counters: small domain sets live replicated in shared memory, large ones as per-CTA replicas in global memory
   h->smem_cnt_ints = 0; h->final_total = 0;
   const int grid_max = std::min(h->sm_count, CCSIM_MAX_GRID);
   for (int j = 0; j < n_counters; j++) {
     const ccsim_counter &c = counters[j];
     DevCounter &d = h->counters[j];
-    d.topo_col = c.topo_col; d.inc = c.inc; d.n_present = c.n_present; d.is_aff = 0; d.smem_off = -1; d.work = nullptr;
+    d.topo_col = c.topo_col; d.inc = c.inc; d.n_present = c.n_present; d.is_aff = 0; d.smem_off = -1; d.work = nullptr; d.elig_bit = c.elig_bit; d.pad = 0;
     for (int a = 0; a < templates[0].n_aff; a++) if (templates[0].aff_counter[a] == j) d.is_aff = 1;
     if (c.topo_col >= nd.n_topo_cols) return fail(h, CCSIM_EINVAL, "counter %d: topo_col", j);
     if (c.topo_col < 0) {
@@ -889,6 +1051,7 @@ static void fill_params(ccsim_handle *h, DevParams &p, int64_t max_pods) {
   for (int r = 0; r < CCSIM_MAX_WORLD; r++) p.xslots_peer[r] = h->x_peer[r];
   p.req_cpu = h->w_req_cpu; p.req_mem = h->w_req_mem; p.req_eph = h->w_req_eph; p.nz_cpu = h->w_nz_cpu; p.nz_mem = h->w_nz_mem;
   p.npods = h->w_npods; p.placed_mask = h->w_placed; p.score_cache = h->w_score; p.feas = h->w_feas;
+  for (int c = 0; c < CCSIM_MAX_PTS; c++) p.stamp[c] = h->d_stamp[c];
   for (int w = 0; w < CCSIM_MAX_TAINT_WORDS; w++) { p.taint_nosched[w] = nd.taint_nosched[w]; p.taint_prefer[w] = nd.taint_prefer[w]; }
   p.templates = h->d_templates;
   for (int j = 0; j < h->n_counters; j++) { p.counters[j] = h->counters[j]; p.final_off[j] = h->final_off[j]; }
@@ -931,6 +1094,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
       if (h->counters[j].topo_col < 0)
         CK(cudaMemcpyAsync(h->counters[j].work, h->counters[j].init, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
   }
+  for (int c = 0; c < CCSIM_MAX_PTS; c++) if (h->d_stamp[c]) CK(cudaMemsetAsync(h->d_stamp[c], 0, h->stamp_len[c] * 4, s));
   CK(cudaMemsetAsync(h->d_out, 0, sizeof(DevOut), s));
   CK(cudaMemsetAsync(h->d_slots, 0, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * SLOT_STRIDE, s));
   // (the cross-GPU buffer is NOT cleared here: peers may already be writing wave 0 of this run; stale words are
@@ -985,10 +1149,18 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   LeanParams lp; memset(&lp, 0, sizeof(lp));
   // measured on B200 (profiles/r1_kernel_variants.md): at 768 threads the lean kernel beats the generic resident kernel on
   // every eligible workload (C2 2.50 vs 2.67, C3 2.64 vs 2.84, C4 4.27 vs 4.95 us/wave); CCSIM_FORCE_GENERIC overrides.
-  bool has_pref = false;
-  for (auto &T : h->h_templates) if (T.n_pref_terms > 0 && (T.score_enable & CCSIM_PL_NODE_AFFINITY)) has_pref = true;
-  if (has_pref && (h->cfg.world > 1 || h->n_templates > 1))
-    return fail(h, CCSIM_EUNSUPPORTED, "preferred nodeAffinity terms: single template, single GPU only");
+  // normalised soft scorers / ImageLocality columns run in the generic kernel only (multi-phase waves)
+  bool has_pref = false, has_soft = false;
+  for (auto &T : h->h_templates) {
+    if (T.n_pref_terms > 0 && (T.score_enable & CCSIM_PL_NODE_AFFINITY)) has_soft = true;
+    if (T.n_spts > 0 && (T.score_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD)) has_soft = true;
+    if (T.n_ipa_score > 0 && (T.score_enable & CCSIM_PL_INTER_POD_AFFINITY)) has_soft = true;
+    if (T.image_score && (T.score_enable & CCSIM_PL_IMAGE_LOCALITY)) has_pref = true;
+  }
+  for (int j = 0; j < h->n_counters; j++) if (h->counters[j].elig_bit >= 0) has_soft = true;
+  if (has_soft && (h->cfg.world > 1 || h->n_templates > 1))
+    return fail(h, CCSIM_EUNSUPPORTED, "normalised soft scorers (preferred nodeAffinity, ScheduleAnyway spreading, pod-affinity scoring): single template, single GPU only");
+  has_pref = has_pref || has_soft;
   bool lean = resident && !has_pref && h->n_templates == 1 && h->meta.taint_words == 1 && h->meta.static_words <= 1 && !getenv("CCSIM_FORCE_GENERIC");
   if (lean) {
     const ccsim_template &T = h->h_templates[0];

@@ -127,6 +127,7 @@ struct cc_handle {
   std::vector<Node> nodes;
   std::vector<Pod> pods;
   std::map<std::string, Labels> ns_labels;
+  std::vector<WorkloadSelector> workloads;   // Services / RCs / ReplicaSets / StatefulSets (system-default topology spreading)
   bool synced = false, ran = false, closed = false;
   Encoded enc;
   bool have_enc = false;
@@ -144,6 +145,7 @@ static int fail(cc_handle *h, int code, const std::string &m) { if (h) h->err = 
 static void ensure_encoded(cc_handle *h) {
   if (h->have_enc) return;
   Encoder enc(h->cfg, h->tmpl, h->nodes, h->pods, h->ns_labels, h->exclude);
+  enc.set_workloads(&h->workloads);
   h->enc = enc.encode();
   h->have_enc = true;
 }
@@ -182,11 +184,27 @@ extern "C" int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const 
   if (!h) return CC_EINVAL;
   if (h->closed) return fail(h, CC_ESTATE, "closed");
   try {
-    h->nodes.clear(); h->pods.clear(); h->ns_labels.clear();
+    h->nodes.clear(); h->pods.clear(); h->ns_labels.clear(); h->workloads.clear();
     for (auto &j : items_of(nodes_json)) h->nodes.push_back(Node::parse(j));
     for (auto &j : items_of(pods_json)) h->pods.push_back(Pod::parse(j));
     for (auto &j : items_of(namespaces_json)) h->ns_labels[j.at("metadata").at("name").str()] = parse_labels(j.at("metadata").at("labels"));
     h->synced = true; h->have_enc = false; h->ran = false; h->have_report = false;
+    return CC_OK;
+  } catch (const std::exception &e) { return fail(h, CC_EINVAL, e.what()); }
+}
+
+extern "C" int cc_sync_workloads(cc_handle *h, const char *services_json, const char *rcs_json, const char *replicasets_json,
+                                 const char *statefulsets_json) {
+  if (!h) return CC_EINVAL;
+  if (h->closed) return fail(h, CC_ESTATE, "closed");
+  if (!h->synced) return fail(h, CC_ESTATE, "cc_sync_with_objects must come first");
+  try {
+    h->workloads.clear();
+    for (auto &j : items_of(services_json)) h->workloads.push_back(WorkloadSelector::parse(j, "Service"));
+    for (auto &j : items_of(rcs_json)) h->workloads.push_back(WorkloadSelector::parse(j, "ReplicationController"));
+    for (auto &j : items_of(replicasets_json)) h->workloads.push_back(WorkloadSelector::parse(j, "ReplicaSet"));
+    for (auto &j : items_of(statefulsets_json)) h->workloads.push_back(WorkloadSelector::parse(j, "StatefulSet"));
+    h->have_enc = false; h->ran = false; h->have_report = false;
     return CC_OK;
   } catch (const std::exception &e) { return fail(h, CC_EINVAL, e.what()); }
 }
@@ -416,10 +434,11 @@ extern "C" const char *cc_debug_encoded_snapshot(cc_handle *h) {
   for (size_t k = 0; k < E.counters.size(); k++) {
     Json c = Json::object();
     c.set("topo_col", Json::number(E.counters[k].topo_col)); c.set("n_present", Json::number(E.counters[k].n_present));
-    c.set("inc", Json::number(E.counters[k].inc)); c.set("init", arr32(E.counter_init[k]));
+    c.set("inc", Json::number(E.counters[k].inc)); c.set("elig_bit", Json::number(E.counters[k].elig_bit)); c.set("init", arr32(E.counter_init[k]));
     ctr.push(c);
   }
   j.set("counters", ctr);
+  { Json is = Json::array(); for (auto x : E.image_score) is.push(Json::number(x)); j.set("image_score", is); }   // template_hex holds a process-local pointer
   j.set("prefilter_msg", Json::string(E.prefilter_msg));
   h->out = json_dump(j);
   return h->out.c_str();

@@ -26,6 +26,7 @@ struct SchedConfig {
   bool reference_sampling = false;
   uint32_t filter_enable = CCSIM_PL_ALL, score_enable = CCSIM_PL_ALL;
   int w_taint = 3, w_node_affinity = 2, w_fit = 1, w_pts = 2, w_ipa = 2, w_balanced = 1, w_image = 1;
+  int hard_pod_affinity_weight = 1;   // InterPodAffinityArgs.HardPodAffinityWeight (apis/config/v1/defaults.go:206-209)
   static uint32_t plugin_bit(const std::string &n) {
     if (n == "NodeUnschedulable") return CCSIM_PL_NODE_UNSCHEDULABLE;
     if (n == "NodeName") return CCSIM_PL_NODE_NAME;
@@ -47,6 +48,7 @@ struct SchedConfig {
     c.pct_nodes_to_score = (int)j.at("percentageOfNodesToScore").i64(c.reference_sampling ? 0 : 100);
     for (auto &x : j.at("disabledFilters").arr) c.filter_enable &= ~plugin_bit(x.str());
     for (auto &x : j.at("disabledScores").arr) c.score_enable &= ~plugin_bit(x.str());
+    if (!j.at("hardPodAffinityWeight").is_null()) c.hard_pod_affinity_weight = (int)j.at("hardPodAffinityWeight").i64(1);
     const Json &w = j.at("weights");
     if (w.is_object())
       for (auto &kv : w.obj) {
@@ -116,6 +118,7 @@ struct Encoded {
   std::vector<std::vector<int32_t>> counter_init;
   std::vector<ccsim_counter> counters;
   ccsim_template tmpl;
+  std::vector<uint8_t> image_score;   // ImageLocality per node (empty: all zero)
   bool has_placed_mask = false;
   std::string prefilter_msg;   // non-empty: PreFilter rejected the pod for every node (e.g. conflicting metadata.name affinity)
 
@@ -169,6 +172,9 @@ class Encoder {
     }
   }
 
+  // Services / RCs / ReplicaSets / StatefulSets of the snapshot: only helper.DefaultSelector reads them (system-default spreading)
+  void set_workloads(const std::vector<WorkloadSelector> *w) { workloads_ = w; }
+
   Encoded encode() {
     Encoded e;
     memset(&e.tmpl, 0, sizeof(e.tmpl));
@@ -181,7 +187,7 @@ class Encoder {
     T.w_taint = cfg_.w_taint; T.w_node_affinity = cfg_.w_node_affinity; T.w_fit = cfg_.w_fit; T.w_pts = cfg_.w_pts;
     T.w_ipa = cfg_.w_ipa; T.w_balanced = cfg_.w_balanced; T.w_image = cfg_.w_image;
     T.least_w_cpu = 1; T.least_w_mem = 1;
-    T.nodename_idx = -1; T.prefilter_bit = -1;
+    T.nodename_idx = -1; T.prefilter_bit = -1; T.spts_ignored_bit = -1;
     PodResource fit;     // computePodResourceRequest (fit.go:224-233): PodRequests with pod-level resources, SetMaxResource from zero
     resource_add(fit, t_.requests(false, false, nullptr));
     PodResource cr = calculate_resource(t_);   // what a committed clone adds (types.go:409-427)
@@ -329,16 +335,17 @@ class Encoder {
     std::vector<const TopologySpreadConstraint *> hard;
     for (auto &c : t_.spread) if (c.when_unsatisfiable == "DoNotSchedule" || c.when_unsatisfiable.empty()) hard.push_back(&c);
     if (hard.size() > CCSIM_MAX_PTS) throw Unsupported("more than 8 hard topology spread constraints");
-    std::vector<Selector> hard_sel;
-    for (auto *c : hard) {
-      Selector s = Selector::from_label_selector(c->label_selector);
-      if (!c->match_label_keys.empty()) {   // mergeLabelSetWithSelector
+    auto constraint_selector = [&](const TopologySpreadConstraint &c) {   // filterTopologySpreadConstraints (common.go:86-127)
+      Selector s = Selector::from_label_selector(c.label_selector);
+      if (!c.match_label_keys.empty()) {   // mergeLabelSetWithSelector
         Labels ml;
-        for (auto &k : c->match_label_keys) { auto it = t_.labels.find(k); if (it != t_.labels.end()) ml[k] = it->second; }
+        for (auto &k : c.match_label_keys) { auto it = t_.labels.find(k); if (it != t_.labels.end()) ml[k] = it->second; }
         if (!ml.empty()) { Selector m = Selector::from_set(ml); if (!s.nothing) for (auto &r : s.reqs) m.reqs.push_back(r); else m = s; s = m; }
       }
-      hard_sel.push_back(s);
-    }
+      return s;
+    };
+    std::vector<Selector> hard_sel;
+    for (auto *c : hard) hard_sel.push_back(constraint_selector(*c));
     auto required_affinity_match = [&](int i) {   // RequiredNodeAffinity.Match
       if (!t_.node_selector.empty() && !Selector::from_set(t_.node_selector).matches(nodes_[i]->labels)) return false;
       if (t_.has_required_node_affinity) {
@@ -470,6 +477,143 @@ class Encoder {
           return false;
         }));
     }
+    // ---- PodTopologySpread score: ScheduleAnyway constraints, or the system defaults when a Service / owning controller
+    //      selects the pod (scoring.go:60-186; plugin.go:48-59; common.go:64-81) ----
+    if (cfg_.score_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) {
+      struct SoftC { int max_skew; std::string key; Selector sel; std::string nap, ntp; };
+      std::vector<SoftC> soft;
+      const bool require_all = !t_.spread.empty();   // requireAllTopologies (scoring.go:140)
+      if (!t_.spread.empty()) {
+        for (auto &c : t_.spread)
+          if (c.when_unsatisfiable == "ScheduleAnyway") soft.push_back({c.max_skew, c.topology_key, constraint_selector(c), c.node_affinity_policy, c.node_taints_policy});
+      } else {
+        Selector ds = default_selector();
+        if (!ds.empty()) {
+          soft.push_back({3, "kubernetes.io/hostname", ds, "Honor", "Ignore"});
+          soft.push_back({5, "topology.kubernetes.io/zone", ds, "Honor", "Ignore"});
+        }
+      }
+      if (soft.size() > CCSIM_MAX_PTS) throw Unsupported("more than 8 ScheduleAnyway topology spread constraints");
+      if (!soft.empty()) {
+        std::vector<char> all_keys(n, 1);
+        bool any_missing = false;
+        for (int i = 0; i < n; i++)
+          for (auto &c : soft) if (!nodes_[i]->labels.count(c.key)) { all_keys[i] = 0; any_missing = true; }
+        T.spts_ignored_bit = (require_all && any_missing) ? new_bit([&](int i) { return !all_keys[i]; }) : -1;
+        auto matching_pods = [&](int i, const Selector &sel) {   // countPodsMatchSelector (common.go:144-158)
+          int64_t cnt = 0;
+          if (!sel.empty()) for (auto *p : pods_on_[i]) if (!p->terminating && p->ns == t_.ns && sel.matches(p->labels)) cnt++;
+          return cnt;
+        };
+        for (size_t c = 0; c < soft.size(); c++) {
+          const SoftC &sc = soft[c];
+          const int inc = (!sc.sel.empty() && sc.sel.matches(t_.labels)) ? 1 : 0;
+          ccsim_spts &S = T.spts[c];
+          S.max_skew = sc.max_skew; S.has_key_bit = -1;
+          if (sc.key == "kubernetes.io/hostname") {   // per-node counts, read at Score (scoring.go:211-212)
+            S.hostname = 1;
+            std::vector<int32_t> init(n);
+            bool everyone = true;
+            for (int i = 0; i < n; i++) { init[i] = (int32_t)matching_pods(i, sc.sel); if (!nodes_[i]->labels.count(sc.key)) everyone = false; }
+            if (!everyone) S.has_key_bit = new_bit([&](int i) { return nodes_[i]->labels.count(sc.key) > 0; });
+            add_counter(e, -1, init, n, inc);
+          } else {
+            S.hostname = 0;
+            std::map<std::string, int> dom_id; std::vector<int64_t> counts; std::vector<int32_t> col(n, -1);
+            std::vector<char> counted(n, 0);
+            bool everyone = true, explicit_empty = false, missing = false;
+            for (int i = 0; i < n; i++) {
+              auto it = nodes_[i]->labels.find(sc.key);
+              if (it == nodes_[i]->labels.end()) { missing = true; everyone = false; continue; }
+              if (it->second.empty()) explicit_empty = true;
+              if (!dom_id.count(it->second)) { int id = (int)dom_id.size(); dom_id[it->second] = id; counts.push_back(0); }
+              col[i] = dom_id[it->second];
+              // processAllNode (scoring.go:157-186)
+              if (require_all && !all_keys[i]) { everyone = false; continue; }
+              if (sc.nap == "Honor" && !required_affinity_match(i)) { everyone = false; continue; }
+              if (sc.ntp == "Honor" && untolerated(i)) { everyone = false; continue; }
+              counted[i] = 1;
+              counts[col[i]] += matching_pods(i, sc.sel);
+            }
+            if (!require_all && missing && explicit_empty) throw Unsupported("a topology label with an empty value next to nodes without the label (PodTopologySpread score)");
+            int colidx = (int)e.topo.size();
+            e.topo.push_back(col);
+            std::vector<int32_t> init(counts.begin(), counts.end());
+            add_counter(e, colidx, init, (int)init.size(), inc);
+            if (!everyone && inc) e.counters.back().elig_bit = new_bit([&, counted](int i) { return counted[i] != 0; });
+          }
+          S.counter = (int32_t)e.counters.size() - 1;
+        }
+        T.n_spts = (int32_t)soft.size();
+      }
+    }
+    // ---- InterPodAffinity score (scoring.go:51-234): signed weights per (topologyKey, value) ----
+    if (cfg_.score_enable & CCSIM_PL_INTER_POD_AFFINITY) {
+      std::vector<AffinityTerm> paff = merged(t_.aff_preferred), panti = merged(t_.anti_preferred);
+      const int hw = cfg_.hard_pod_affinity_weight;
+      // what existing pod `p` contributes to key -> weight (processExistingPod, scoring.go:81-125)
+      auto contributions = [&](const Pod &p, std::map<std::string, int64_t> &out) {
+        for (auto &t : paff) if (t.matches(p.ns, p.labels, nullptr)) out[t.topology_key] += t.weight;
+        for (auto &t : panti) if (t.matches(p.ns, p.labels, nullptr)) out[t.topology_key] -= t.weight;
+        if (hw > 0) for (auto &t : p.aff_required) if (t.matches(t_.ns, t_.labels, t_ns_labels)) out[t.topology_key] += hw;
+        for (auto &t : p.aff_preferred) if (t.matches(t_.ns, t_.labels, t_ns_labels)) out[t.topology_key] += t.weight;
+        for (auto &t : p.anti_preferred) if (t.matches(t_.ns, t_.labels, t_ns_labels)) out[t.topology_key] -= t.weight;
+      };
+      std::vector<std::string> keys;
+      auto note = [&](const std::map<std::string, int64_t> &m) { for (auto &kv : m) if (std::find(keys.begin(), keys.end(), kv.first) == keys.end()) keys.push_back(kv.first); };
+      std::map<std::string, int64_t> clone;   // a placed clone is an existing pod of the next cycle
+      contributions(t_, clone);
+      note(clone);
+      std::map<const Pod *, std::map<std::string, int64_t>> per_pod;
+      for (int i = 0; i < n; i++)
+        for (auto *p : pods_on_[i]) {
+          if (p->aff_required.empty() && p->aff_preferred.empty() && p->anti_preferred.empty() && paff.empty() && panti.empty()) continue;
+          std::map<std::string, int64_t> m; contributions(*p, m);
+          if (!m.empty()) { note(m); per_pod[p] = m; }
+        }
+      if (keys.size() > CCSIM_MAX_IPA) throw Unsupported("more than 8 topology keys in pod (anti-)affinity scoring terms");
+      for (size_t k = 0; k < keys.size(); k++) {
+        auto w = [&](const Pod &p) { auto it = per_pod.find(&p); if (it == per_pod.end()) return 0; auto jt = it->second.find(keys[k]); return jt == it->second.end() ? 0 : (int)jt->second; };
+        ipa_counter(keys[k], w, clone.count(keys[k]) ? (int)clone[keys[k]] : 0, T.ipa_score_counter[k]);
+      }
+      T.n_ipa_score = (int32_t)keys.size();
+    }
+    // ---- ImageLocality (image_locality.go:54-131; backend/cache/cache.go:680-703): static per node ----
+    if (cfg_.score_enable & CCSIM_PL_IMAGE_LOCALITY) {
+      std::map<std::string, std::pair<int64_t, std::set<int>>> states;   // name -> (size as first registered, nodes)
+      for (int i = 0; i < n; i++)
+        for (auto &im : nodes_[i]->images) {
+          auto it = states.find(im.first);
+          if (it == states.end()) states[im.first] = {im.second, {i}}; else it->second.second.insert(i);
+        }
+      auto normalized = [](std::string name) {
+        const auto colon = name.rfind(':'), slash = name.rfind('/');
+        const long long c = colon == std::string::npos ? -1 : (long long)colon, s = slash == std::string::npos ? -1 : (long long)slash;
+        if (c <= s) name += ":latest";
+        return name;
+      };
+      std::vector<std::string> want;
+      for (auto &c : t_.init_containers) want.push_back(normalized(c.image));
+      for (auto &c : t_.containers) want.push_back(normalized(c.image));
+      const int64_t mb = 1024 * 1024, min_thr = 23 * mb, max_thr = 1000 * mb * (int64_t)want.size();
+      bool any = false;
+      std::vector<uint8_t> col(n, 0);
+      for (int i = 0; i < n; i++) {
+        int64_t sum = 0;
+        std::set<std::string> here; for (auto &im : nodes_[i]->images) here.insert(im.first);
+        for (auto &wname : want)
+          if (here.count(wname)) {
+            const auto &st = states[wname];
+            const double spread = (double)st.second.size() / (double)n;
+            sum += (int64_t)((double)st.first * spread);
+          }
+        if (sum < min_thr) sum = min_thr; else if (sum > max_thr) sum = max_thr;
+        const int64_t sc = max_thr > min_thr ? 100 * (sum - min_thr) / (max_thr - min_thr) : 0;
+        col[i] = (uint8_t)sc;
+        if (sc) any = true;
+      }
+      if (any) e.image_score = col;
+    }
     if (e.topo.size() > CCSIM_MAX_TOPO_COLS || e.counters.size() > CCSIM_MAX_COUNTERS) throw Unsupported("too many topology columns");
     // ---- pack static bits ----
     if (bits.size() > 64 * CCSIM_MAX_STATIC_WORDS) throw Unsupported("too many static predicate bits");
@@ -478,6 +622,7 @@ class Encoder {
     for (size_t b = 0; b < bits.size(); b++)
       for (int i = 0; i < n; i++) if (bits[b][i]) e.static_mask[(size_t)(b >> 6) * n + i] |= 1ull << (b & 63);
     for (size_t j = 0; j < e.counters.size(); j++) e.counters[j].init = e.counter_init[j].data();
+    T.image_score = e.image_score.empty() ? nullptr : e.image_score.data();
     return e;
   }
 
@@ -490,10 +635,35 @@ class Encoder {
   std::vector<const Node *> nodes_;
   std::map<std::string, int> node_index_;
   std::vector<std::vector<const Pod *>> pods_on_;
+  const std::vector<WorkloadSelector> *workloads_ = nullptr;
+
+  // helper.DefaultSelector (plugins/helper/spread.go:40-93)
+  Selector default_selector() const {
+    Labels set;
+    Selector sel; sel.nothing = false;
+    if (!workloads_) return sel;
+    for (auto &w : *workloads_)   // GetPodServices (spread.go:96-113): nil selectors match nothing
+      if (w.kind == "Service" && w.ns == t_.ns && w.has_map && Selector::from_set(w.map).matches(t_.labels))
+        for (auto &kv : w.map) set[kv.first] = kv.second;
+    sel = Selector::from_set(set);
+    if (t_.owner_kind.empty()) return sel;
+    for (auto &w : *workloads_) {
+      if (w.ns != t_.ns || w.name != t_.owner_name || w.kind != t_.owner_kind) continue;
+      if (w.kind == "ReplicationController" && t_.owner_api_version == "v1") {
+        for (auto &kv : w.map) set[kv.first] = kv.second;
+        sel = Selector::from_set(set);
+      } else if ((w.kind == "ReplicaSet" || w.kind == "StatefulSet") && t_.owner_api_version == "apps/v1") {
+        Selector other = Selector::from_label_selector(w.label_selector);
+        if (!other.nothing) for (auto &r : other.reqs) sel.reqs.push_back(r);
+      }
+      break;
+    }
+    return sel;
+  }
 
   static void add_counter(Encoded &e, int topo_col, const std::vector<int32_t> &init, int n_present, int inc) {
     ccsim_counter c; memset(&c, 0, sizeof(c));
-    c.topo_col = topo_col; c.n_domains = (int32_t)init.size(); c.n_present = n_present; c.inc = inc;
+    c.topo_col = topo_col; c.n_domains = (int32_t)init.size(); c.n_present = n_present; c.inc = inc; c.elig_bit = -1;
     e.counter_init.push_back(init);
     e.counters.push_back(c);
   }
@@ -503,21 +673,9 @@ class Encoder {
     if (t_.has_pvc_volume) throw Unsupported("pod uses PersistentVolumeClaim/ephemeral volumes (VolumeBinding/VolumeZone/NodeVolumeLimits/VolumeRestrictions)");
     if (t_.has_resource_claims) throw Unsupported("pod uses resourceClaims (DynamicResources)");
     if (t_.has_scheduling_gates) throw Unsupported("pod has schedulingGates");
-    if (!t_.aff_preferred.empty() || !t_.anti_preferred.empty()) throw Unsupported("preferred pod (anti-)affinity (InterPodAffinity score)");
-    for (auto &c : t_.spread) if (c.when_unsatisfiable == "ScheduleAnyway") throw Unsupported("ScheduleAnyway topology spread constraints (PodTopologySpread score)");
-    for (auto &c : t_.init_containers) (void)c;
-    const Labels *tl = ns_labels_.count(t_.ns) ? &ns_labels_.at(t_.ns) : nullptr;
-    for (size_t i = 0; i < nodes_.size(); i++) {
-      for (auto *p : pods_on_[i]) {
+    for (size_t i = 0; i < nodes_.size(); i++)
+      for (auto *p : pods_on_[i])
         if (p->priority < t_.priority) throw Unsupported("an existing pod has lower priority than the simulated pod (DefaultPreemption would evict it)");
-        // InterPodAffinity scoring is skipped only if no existing pod's affinity term matches the incoming pod (scoring.go:128-221)
-        for (auto &t : p->aff_required) if (t.matches(t_.ns, t_.labels, tl)) throw Unsupported("an existing pod's required pod affinity matches the simulated pod (InterPodAffinity score)");
-        for (auto &t : p->aff_preferred) if (t.matches(t_.ns, t_.labels, tl)) throw Unsupported("an existing pod's preferred pod affinity matches the simulated pod (InterPodAffinity score)");
-        for (auto &t : p->anti_preferred) if (t.matches(t_.ns, t_.labels, tl)) throw Unsupported("an existing pod's preferred pod anti-affinity matches the simulated pod (InterPodAffinity score)");
-      }
-      for (auto &im : nodes_[i]->image_names)
-        for (auto &c : t_.containers) if (!c.image.empty() && im.find(c.image) != std::string::npos) throw Unsupported("a node already holds the pod's image (ImageLocality score)");
-    }
   }
 };
 

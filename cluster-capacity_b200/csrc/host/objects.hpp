@@ -145,6 +145,7 @@ struct AffinityTerm {
   Selector selector;
   Selector ns_selector;     // nil -> Nothing
   std::string topology_key;
+  int weight = 0;           // preferred terms only (WeightedPodAffinityTerm.weight)
   bool matches(const std::string &pod_ns, const Labels &pod_labels, const Labels *ns_labels) const {
     static const Labels none;
     if (namespaces.count(pod_ns) || ns_selector.matches(ns_labels ? *ns_labels : none)) return selector.matches(pod_labels);
@@ -175,6 +176,7 @@ struct Pod {
   std::string name, ns, node_name, phase, scheduler_name, preemption_policy;
   Labels labels;
   bool terminating = false;      // metadata.deletionTimestamp set
+  std::string owner_api_version, owner_kind, owner_name;   // metav1.GetControllerOf: the ownerReference with controller=true
   int priority = 0;
   std::vector<Container> containers, init_containers;
   ResourceList overhead, pod_level_requests;
@@ -205,6 +207,7 @@ struct Pod {
       if ((!nss.is_array() || nss.arr.empty()) && !nsel.is_object()) t.namespaces.insert(pod_ns);
       else if (nss.is_array()) for (auto &x : nss.arr) t.namespaces.insert(x.str());
       t.ns_selector = Selector::from_label_selector(nsel);
+      if (weighted) t.weight = (int)e0.at("weight").i64(0);
       out.push_back(t);
     }
     return out;
@@ -236,6 +239,9 @@ struct Pod {
     if (p.ns.empty()) p.ns = "default";
     p.labels = parse_labels(md.at("labels"));
     p.terminating = !md.at("deletionTimestamp").is_null();
+    if (md.at("ownerReferences").is_array())
+      for (auto &o : md.at("ownerReferences").arr)
+        if (o.at("controller").truthy()) { p.owner_api_version = o.at("apiVersion").str(); p.owner_kind = o.at("kind").str(); p.owner_name = o.at("name").str(); break; }
     p.node_name = sp.at("nodeName").str();
     p.phase = st.at("phase").str();
     p.scheduler_name = sp.at("schedulerName").str();
@@ -389,6 +395,7 @@ struct Node {
   std::vector<Taint> taints;
   ResourceList allocatable;
   std::vector<std::string> image_names;
+  std::vector<std::pair<std::string, int64_t>> images;   // (name, sizeBytes) for every name of every status.images entry
 
   static Node parse(const Json &j) {
     Node n;
@@ -401,7 +408,10 @@ struct Node {
     n.allocatable = parse_resources(j.at("status").at("allocatable"));
     if (j.at("status").at("images").is_array())
       for (auto &im : j.at("status").at("images").arr)
-        if (im.at("names").is_array()) for (auto &nm : im.at("names").arr) n.image_names.push_back(nm.str());
+        if (im.at("names").is_array()) for (auto &nm : im.at("names").arr) {
+          n.image_names.push_back(nm.str());
+          n.images.push_back({nm.str(), im.at("sizeBytes").i64(0)});
+        }
     return n;
   }
   // utilnode.GetZoneKey (component-helpers/node/topology/helpers.go:31-58)
@@ -412,6 +422,26 @@ struct Node {
     if (!get("failure-domain.beta.kubernetes.io/region", region)) get("topology.kubernetes.io/region", region);
     if (region.empty() && zone.empty()) return "";
     return region + ":" + std::string(1, '\0') + ":" + zone;
+  }
+};
+
+// The objects helper.DefaultSelector reads (plugins/helper/spread.go:40-113): Services select by a label map, RCs too,
+// ReplicaSets / StatefulSets by a LabelSelector.
+struct WorkloadSelector {
+  std::string kind, ns, name;
+  bool has_map = false;      // Service/RC: spec.selector != nil
+  Labels map;
+  Json label_selector;       // RS/StatefulSet: spec.selector
+  static WorkloadSelector parse(const Json &j, const std::string &kind) {
+    WorkloadSelector w;
+    w.kind = kind;
+    w.ns = j.at("metadata").at("namespace").str();
+    if (w.ns.empty()) w.ns = "default";
+    w.name = j.at("metadata").at("name").str();
+    const Json &sel = j.at("spec").at("selector");
+    if (kind == "Service" || kind == "ReplicationController") { w.has_map = sel.is_object(); w.map = parse_labels(sel); }
+    else w.label_selector = sel;
+    return w;
   }
 };
 

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libcchost.so")
 _lib = None
 
-EXPORTS = ["cc_new", "cc_sync_with_objects", "cc_run", "cc_report_json", "cc_report_print", "cc_stop_reason",
+EXPORTS = ["cc_new", "cc_sync_with_objects", "cc_sync_workloads", "cc_run", "cc_report_json", "cc_report_print", "cc_stop_reason",
            "cc_scheduled_count", "cc_scheduled_node", "cc_close", "cc_last_error", "cc_debug_encoded_snapshot"]
 
 
@@ -39,6 +39,8 @@ def lib():
         L.cc_new.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.cc_sync_with_objects.restype = C.c_int
         L.cc_sync_with_objects.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.cc_sync_workloads.restype = C.c_int
+        L.cc_sync_workloads.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
         L.cc_run.restype = C.c_int
         L.cc_run.argtypes = [C.c_void_p]
         for f in ("cc_report_json", "cc_stop_reason", "cc_last_error", "cc_debug_encoded_snapshot"):
@@ -59,8 +61,11 @@ def lib():
 class ListClient:
     """Stand-in for the clientset SyncWithClient LISTs from: plain lists of object dicts."""
 
-    def __init__(self, nodes=(), pods=(), namespaces=()):
+    def __init__(self, nodes=(), pods=(), namespaces=(), services=(), replication_controllers=(), replica_sets=(), stateful_sets=()):
         self.nodes, self.pods, self.namespaces = list(nodes), list(pods), list(namespaces)
+        # simulator.go:217-281 copies these too; the scheduler reads them only for system-default topology spreading
+        self.services, self.replication_controllers = list(services), list(replication_controllers)
+        self.replica_sets, self.stateful_sets = list(replica_sets), list(stateful_sets)
 
 
 class ClusterCapacity:
@@ -79,6 +84,11 @@ class ClusterCapacity:
                                         json.dumps(getattr(client, "namespaces", [])).encode())
         if rc:
             self._err(rc, "SyncWithClient")
+        wl = [getattr(client, a, None) or [] for a in ("services", "replication_controllers", "replica_sets", "stateful_sets")]
+        if any(wl):
+            rc = lib().cc_sync_workloads(self._h, *[json.dumps(x).encode() for x in wl])
+            if rc:
+                self._err(rc, "SyncWithClient(workloads)")
         self._report = None
 
     def Run(self):

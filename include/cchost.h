@@ -36,11 +36,19 @@ typedef struct cc_handle cc_handle;
 /* pod_json: the simulated pod (v1.Pod as JSON, already defaulted/validated by the CLI like ParseAPISpec does).
  * sched_config_json: NULL/"" for the default profile in canonical mode, or a small JSON {"sampling":"reference",
  *   "percentageOfNodesToScore":0,   (reference sampling: adaptive numFeasibleNodesToFind + rotating start index)
- *   "disabledFilters":["NodeResourcesFit",...], "disabledScores":[...], "weights":{"NodeResourcesFit":1,...}}.
+ *   "disabledFilters":["NodeResourcesFit",...], "disabledScores":[...], "weights":{"NodeResourcesFit":1,...},
+ *   "hardPodAffinityWeight":1}.
  * exclude_nodes: comma-separated node names (--exclude-nodes), may be NULL. device: CUDA ordinal. */
 int cc_new(const char *sched_config_json, const char *pod_json, int64_t max_pods, const char *exclude_nodes,
            int32_t device, cc_handle **out);
 int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const char *pods_json, const char *namespaces_json);
+/* Optional, between cc_sync_with_objects and cc_run: the Services / ReplicationControllers / ReplicaSets / StatefulSets
+ * SyncWithClient copies (simulator.go:217-281). The scheduler reads them in one place only: helper.DefaultSelector
+ * (plugins/helper/spread.go:40-93), which gives a pod WITHOUT topologySpreadConstraints the two system-default soft
+ * constraints when a Service (or its owning controller) selects it (podtopologyspread/plugin.go:48-59). Lists or bare
+ * arrays as JSON; any may be NULL. */
+int cc_sync_workloads(cc_handle *h, const char *services_json, const char *rcs_json, const char *replicasets_json,
+                      const char *statefulsets_json);
 int cc_run(cc_handle *h);
 const char *cc_report_json(cc_handle *h);
 const char *cc_report_print(cc_handle *h, int32_t verbose, const char *format /* "", "json", "yaml" */);

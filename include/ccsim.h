@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CCSIM_ABI_VERSION 2
+#define CCSIM_ABI_VERSION 3
 
 /* ---- limits (compile-time, shared by host encoder, oracle and kernels) ---- */
 #define CCSIM_MAX_TAINT_WORDS   4   /* 64-bit words of the taint dictionary mask per node  */
@@ -174,9 +174,21 @@ typedef struct ccsim_counter {
   int32_t topo_col;      /* index into ccsim_nodes.topo, or -1: node-local (every node its own domain, e.g. unique hostnames) */
   int32_t n_domains;     /* D; for node-local counters = n_nodes */
   int32_t n_present;     /* PTS only: domains [0,n_present) are in TpValueToMatchNum (take part in the global min) */
-  int32_t inc;           /* added to the winner's domain at every commit (self-match count) */
+  int32_t inc;           /* added to the winner's domain at every commit (self-match count; signed for score counters) */
+  int32_t elig_bit;      /* static bit a node must carry for its commits to count (soft PTS: "has every constraint key and
+                            passes the node-inclusion policies", scoring.go:157-186); -1 = every node */
+  int32_t pad;
   const int32_t *init;   /* [n_domains] counts from pre-existing pods */
 } ccsim_counter;
+
+/* One ScheduleAnyway / system-default topology-spread constraint (PL:podtopologyspread/scoring.go:60-265). */
+typedef struct ccsim_spts {
+  int32_t counter;       /* matching pods per domain (node-local column when hostname != 0) */
+  int32_t max_skew;
+  int32_t hostname;      /* 1: topologyKey == kubernetes.io/hostname: per-node count, weight from the number of scored nodes */
+  int32_t has_key_bit;   /* hostname constraints: static bit "node carries the key", -1 = every node does.
+                            Other keys: the topology column says -1 where the key is missing */
+} ccsim_spts;
 
 typedef struct ccsim_pts {
   int32_t counter;       /* index into counters */
@@ -227,6 +239,23 @@ typedef struct ccsim_template {
   int32_t pref_weight[CCSIM_MAX_AFF_TERMS];
   int32_t pad_pref;
   uint64_t pref_mask[CCSIM_MAX_AFF_TERMS][CCSIM_MAX_STATIC_WORDS];
+  /* PodTopologySpread score (scoring.go:60-265): soft constraints in spec order (or the two system defaults when a
+   * Service/RC/RS/StatefulSet selects the pod, plugin.go:48-59, helper/spread.go:40-93). Per cycle: weight_c =
+   * log(size_c + 2) with size_c = distinct domains (hostname: nodes) among the feasible non-ignored nodes; node raw =
+   * Round(sum_c cnt_c(node) * weight_c + (maxSkew_c - 1)); normalised 100*(max+min-raw)/max over the same nodes. */
+  int32_t n_spts;
+  int32_t spts_ignored_bit;       /* static bit "node misses one of the constraint keys" (IgnoredNodes, only when the
+                                     constraints come from the podspec); -1: no node is ignored */
+  ccsim_spts spts[CCSIM_MAX_PTS];
+  /* InterPodAffinity score (interpodaffinity/scoring.go:51-295): per topology key a counter of signed weights
+   * (preferred terms of the pod vs existing pods, existing pods' required*hardPodAffinityWeight / preferred terms vs the
+   * pod); node raw = sum over keys the node carries; normalised int64(100 * float64(raw-min)/float64(max-min)). */
+  int32_t n_ipa_score;
+  int32_t ipa_score_counter[CCSIM_MAX_IPA];
+  int32_t pad_soft;
+  /* ImageLocality (imagelocality/image_locality.go:54-131): the score is static per node and template (image states do
+   * not change when pods are assumed); [n_nodes] values 0..100 or NULL (all 0). Host memory at ccsim_set_templates. */
+  const uint8_t *image_score;
 } ccsim_template;
 
 typedef struct ccsim_result {

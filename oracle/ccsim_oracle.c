@@ -300,6 +300,59 @@ static int64_t node_affinity_raw(const ccsim_nodes *nd, const ccsim_template *t,
   return c;
 }
 
+static inline int static_bit(const ccsim_nodes *nd, int32_t i, int b) {
+  return (int)((word(nd->static_mask, nd->n_nodes, b >> 6, i) >> (b & 63)) & 1ull);
+}
+
+/* Go's math.Log on amd64: the pure-Go port of FreeBSD's e_log.c (go/src/math/log.go:80-129; only s390x has an
+ * assembly version). No fused multiply-add (GOAMD64=v1), hence -ffp-contract=off. Finite x > 0 only. */
+static double go_log(double x) {
+  const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10;
+  const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01, L3 = 2.857142874366239149e-01,
+               L4 = 2.222219843214978396e-01, L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
+               L7 = 1.479819860511658591e-01;
+  int ki; double f1 = frexp(x, &ki);
+  if (f1 < 0.70710678118654752440 /* Sqrt2/2 */) { f1 *= 2; ki--; }
+  const double f = f1 - 1, k = (double)ki;
+  const double s = f / (2 + f), s2 = s * s, s4 = s2 * s2;
+  const double t1 = s2 * (L1 + s4 * (L3 + s4 * (L5 + s4 * L7)));
+  const double t2 = s4 * (L2 + s4 * (L4 + s4 * L6));
+  const double R = t1 + t2, hfsq = 0.5 * f * f;
+  return k * Ln2Hi - ((hfsq - (s * (hfsq + R) + k * Ln2Lo)) - f);
+}
+
+/* PodTopologySpread.Score for one node given the cycle's weights (PL:podtopologyspread/scoring.go:192-224,302-304);
+ * the caller has already excluded IgnoredNodes */
+static int64_t spts_raw(const ccsim_nodes *nd, const ostate *s, const ccsim_template *t, const ccsim_counter *ctr,
+                        const double *weight, int32_t i) {
+  double score = 0;
+  for (int c = 0; c < t->n_spts; c++) {
+    const ccsim_spts *sc = &t->spts[c];
+    int64_t cnt;
+    if (sc->hostname) {
+      if (sc->has_key_bit >= 0 && !static_bit(nd, i, sc->has_key_bit)) continue;
+      cnt = s->cnt[sc->counter][i];
+    } else {
+      const int32_t dom = nd->topo[ctr[sc->counter].topo_col][i];
+      if (dom < 0) continue;
+      cnt = s->cnt[sc->counter][dom];
+    }
+    score += (double)cnt * weight[c] + (double)(sc->max_skew - 1);
+  }
+  return (int64_t)round(score);   /* math.Round: half away from zero */
+}
+
+/* InterPodAffinity.Score (PL:interpodaffinity/scoring.go:236-256) */
+static int64_t ipa_raw(const ccsim_nodes *nd, const ostate *s, const ccsim_template *t, const ccsim_counter *ctr, int32_t i) {
+  int64_t sc = 0;
+  for (int k = 0; k < t->n_ipa_score; k++) {
+    const int j = t->ipa_score_counter[k];
+    const int32_t dom = ctr[j].topo_col < 0 ? i : nd->topo[ctr[j].topo_col][i];
+    if (dom >= 0) sc += s->cnt[j][dom];
+  }
+  return sc;
+}
+
 /* KS:schedule_one.go:697-723 */
 static int32_t num_feasible_nodes_to_find(int32_t n, int32_t pct) {
   if (n < 100) return n;
@@ -315,8 +368,8 @@ static inline int64_t score_rest(const ccsim_nodes *nd, const ostate *s, const c
   if (t->score_enable & CCSIM_PL_FIT) sc += (int64_t)t->w_fit * score_least(nd, s, t, i);
   if ((t->score_enable & CCSIM_PL_BALANCED) && !(t->flags & CCSIM_TF_BALANCED_SKIP))
     sc += (int64_t)t->w_balanced * score_balanced(nd, s, t, i);
-  /* ImageLocality: weight * 0 on snapshots whose nodes list no images (PL:imagelocality/image_locality.go:54-115).
-     NodeAffinity preferred / PodTopologySpread soft / InterPodAffinity preferred: PreScore Skip for the supported podspecs. */
+  /* ImageLocality: static per node (PL:imagelocality/image_locality.go:54-131); NULL = no node holds an image of the pod */
+  if ((t->score_enable & CCSIM_PL_IMAGE_LOCALITY) && t->image_score) sc += (int64_t)t->w_image * t->image_score[i];
   return sc;
 }
 
@@ -407,6 +460,45 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
     int64_t na_max = 0;
     if (na_on)
       for (int32_t i = 0; i < n; i++) if (key[i] >= 0) { int64_t r = node_affinity_raw(nd, t, i); if (r > na_max) na_max = r; }
+    /* PodTopologySpread PreScore/Score/NormalizeScore over the feasible nodes (PL:podtopologyspread/scoring.go:60-265) */
+    const int spts_on = (t->score_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) && t->n_spts > 0;
+    double spts_w[CCSIM_MAX_PTS]; int64_t spts_min = INT64_MAX, spts_max = 0;
+    if (spts_on) {
+      int64_t scored = 0;
+      for (int32_t i = 0; i < n; i++)
+        if (key[i] >= 0 && !(t->spts_ignored_bit >= 0 && static_bit(nd, i, t->spts_ignored_bit))) scored++;
+      for (int c = 0; c < t->n_spts; c++) {
+        int64_t size = scored;
+        if (!t->spts[c].hostname) {   /* distinct values among the scored nodes; a missing key reads as the value "" */
+          const ccsim_counter *cc = &ctr[t->spts[c].counter];
+          uint8_t *seen = (uint8_t*)calloc((size_t)cc->n_domains + 1, 1);
+          size = 0;
+          for (int32_t i = 0; i < n; i++) {
+            if (key[i] < 0 || (t->spts_ignored_bit >= 0 && static_bit(nd, i, t->spts_ignored_bit))) continue;
+            int32_t dom = nd->topo[cc->topo_col][i];
+            if (dom < 0) dom = cc->n_domains;
+            if (!seen[dom]) { seen[dom] = 1; size++; }
+          }
+          free(seen);
+        }
+        spts_w[c] = go_log((double)(size + 2));
+      }
+      for (int32_t i = 0; i < n; i++) {
+        if (key[i] < 0 || (t->spts_ignored_bit >= 0 && static_bit(nd, i, t->spts_ignored_bit))) continue;
+        const int64_t r = spts_raw(nd, &s, t, ctr, spts_w, i);
+        if (r < spts_min) spts_min = r;
+        if (r > spts_max) spts_max = r;
+      }
+    }
+    /* InterPodAffinity NormalizeScore (PL:interpodaffinity/scoring.go:258-290) */
+    const int ipa_on = (t->score_enable & CCSIM_PL_INTER_POD_AFFINITY) && t->n_ipa_score > 0;
+    int64_t ipa_min = INT64_MAX, ipa_max = INT64_MIN;
+    if (ipa_on)
+      for (int32_t i = 0; i < n; i++) if (key[i] >= 0) {
+        const int64_t r = ipa_raw(nd, &s, t, ctr, i);
+        if (r < ipa_min) ipa_min = r;
+        if (r > ipa_max) ipa_max = r;
+      }
     int64_t best = -1; int32_t besti = -1;
     for (int32_t q = 0; q < n; q++) {
       int32_t i = (mode == 0) ? q : (start + q) % n;
@@ -419,6 +511,15 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
       if (na_on) {
         int64_t r = node_affinity_raw(nd, t, i);
         total += (int64_t)t->w_node_affinity * (na_max == 0 ? r : 100 * r / na_max);
+      }
+      if (spts_on && !(t->spts_ignored_bit >= 0 && static_bit(nd, i, t->spts_ignored_bit))) {
+        const int64_t r = spts_raw(nd, &s, t, ctr, spts_w, i);
+        total += (int64_t)t->w_pts * (spts_max == 0 ? 100 : 100 * (spts_max + spts_min - r) / spts_max);
+      }
+      if (ipa_on && ipa_max > ipa_min) {
+        const int64_t r = ipa_raw(nd, &s, t, ctr, i);
+        const double f = 100.0 * ((double)(r - ipa_min) / (double)(ipa_max - ipa_min));
+        total += (int64_t)t->w_ipa * (int64_t)f;
       }
       if (total > best) { best = total; besti = i; }
     }
@@ -438,6 +539,7 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
       int is_aff = 0;
       for (int a = 0; a < t->n_aff; a++) if (t->aff_counter[a] == j) is_aff = 1;
       if (is_aff && !(t->flags & CCSIM_TF_AFF_SELF_MATCH_ALL)) continue;
+      if (ctr[j].elig_bit >= 0 && !static_bit(nd, w, ctr[j].elig_bit)) continue;
       int32_t dom = ctr[j].topo_col < 0 ? w : nd->topo[ctr[j].topo_col][w];
       if (dom < 0) continue;
       s.cnt[j][dom] += ctr[j].inc;

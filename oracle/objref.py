@@ -256,7 +256,45 @@ def affinity_terms(pod, kind, required=True):
             names = {ns}
         out.append({"namespaces": names, "selector": t.get("labelSelector"), "nsSelector": t.get("namespaceSelector"),
                     "topologyKey": t.get("topologyKey", "")})
+    if not required:
+        for o, wt in zip(out, aff.get("preferredDuringSchedulingIgnoredDuringExecution") or []):
+            o["weight"] = wt.get("weight", 0)
     return out
+
+
+def go_log(x):
+    """Go's math.Log on amd64 (go/src/math/log.go:80-129, the FreeBSD e_log.c port; no FMA)."""
+    Ln2Hi, Ln2Lo = 6.93147180369123816490e-01, 1.90821492927058770002e-10
+    L1, L2, L3, L4 = 6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01
+    L5, L6, L7 = 1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01
+    f1, ki = math.frexp(x)
+    if f1 < math.sqrt(2) / 2:
+        f1 *= 2
+        ki -= 1
+    f = f1 - 1
+    k = float(ki)
+    s = f / (2 + f)
+    s2 = s * s
+    s4 = s2 * s2
+    t1 = s2 * (L1 + s4 * (L3 + s4 * (L5 + s4 * L7)))
+    t2 = s4 * (L2 + s4 * (L4 + s4 * L6))
+    R = t1 + t2
+    hfsq = 0.5 * f * f
+    return k * Ln2Hi - ((hfsq - (s * (hfsq + R) + k * Ln2Lo)) - f)
+
+
+def go_round(x):
+    """math.Round: half away from zero."""
+    t = math.trunc(x)
+    if abs(x - t) >= 0.5:
+        t += math.copysign(1.0, x)
+    return int(t)
+
+
+def normalized_image_name(name):          # PL:imagelocality/image_locality.go:124-131
+    if name.rfind(":") <= name.rfind("/"):
+        name += ":latest"
+    return name
 
 
 def term_matches(term, pod, ns_labels):  # AffinityTerm.Matches (KF:types.go:379-384)
@@ -333,7 +371,7 @@ class Simulator:
         self.pods_status = []      # node name per scheduled pod
         self.stop_reason = None
 
-    def sync(self, nodes, pods, namespaces=()):
+    def sync(self, nodes, pods, namespaces=(), services=(), rcs=(), replicasets=(), statefulsets=()):
         """SyncWithClient (simulator.go:176-295) + the informer-driven cache build (KS:backend/cache/node_tree.go:51-143)."""
         zones, tree, seen = [], {}, set()
         for n in nodes:
@@ -361,6 +399,202 @@ class Simulator:
             if nn and nn in by_name:
                 by_name[nn].add_pod(p)
         self.ns_labels = {ns["metadata"]["name"]: (ns["metadata"].get("labels") or {}) for ns in namespaces}
+        self.services, self.rcs, self.replicasets, self.statefulsets = list(services), list(rcs), list(replicasets), list(statefulsets)
+        # image states (KS:backend/cache/cache.go:680-703): size as first registered, number of nodes holding the name
+        self.image_states = {}
+        for ni in self.infos:
+            for im in (ni.node.get("status") or {}).get("images") or []:
+                for name in im.get("names") or []:
+                    stt = self.image_states.setdefault(name, [im.get("sizeBytes", 0), set()])
+                    stt[1].add(ni.name)
+
+    def _default_selector(self, pod):
+        """helper.DefaultSelector (PL:helper/spread.go:40-113) as a list of requirements (None = selects nothing... never here)."""
+        ns = pod["metadata"].get("namespace") or "default"
+        labels = pod["metadata"].get("labels") or {}
+        lset = {}
+        for svc in self.services:
+            if (svc["metadata"].get("namespace") or "default") != ns:
+                continue
+            sel = (svc.get("spec") or {}).get("selector")
+            if sel is None:
+                continue
+            if all(labels.get(k) == v for k, v in sel.items()):
+                lset.update(sel)
+        reqs = {"matchLabels": dict(lset), "matchExpressions": []}
+        owner = next((o for o in pod["metadata"].get("ownerReferences") or [] if o.get("controller")), None)
+        if owner is None:
+            return reqs
+        def find(lst):
+            return next((o for o in lst if (o["metadata"].get("namespace") or "default") == ns and o["metadata"]["name"] == owner.get("name")), None)
+        if owner.get("kind") == "ReplicationController" and owner.get("apiVersion") == "v1":
+            rc = find(self.rcs)
+            if rc is not None:
+                reqs["matchLabels"].update((rc.get("spec") or {}).get("selector") or {})
+        elif owner.get("kind") in ("ReplicaSet", "StatefulSet") and owner.get("apiVersion") == "apps/v1":
+            o = find(self.replicasets if owner["kind"] == "ReplicaSet" else self.statefulsets)
+            if o is not None and (o.get("spec") or {}).get("selector") is not None:
+                sel = o["spec"]["selector"]
+                extra = [{"key": k, "operator": "In", "values": [v]} for k, v in (sel.get("matchLabels") or {}).items()]
+                reqs["matchExpressions"] = extra + list(sel.get("matchExpressions") or [])
+        return reqs
+
+    def _soft_constraints(self, pod):
+        """initPreScoreState's constraint list (PL:podtopologyspread/scoring.go:60-82; plugin.go:48-59; common.go:64-127)."""
+        spec = pod["spec"]
+        labels = pod["metadata"].get("labels") or {}
+        out = []
+        if spec.get("topologySpreadConstraints"):
+            for c in spec["topologySpreadConstraints"]:
+                if c.get("whenUnsatisfiable") != "ScheduleAnyway":
+                    continue
+                out.append({"key": c["topologyKey"], "maxSkew": c.get("maxSkew", 1), "selector": c.get("labelSelector"),
+                            "mlk": {k: labels[k] for k in c.get("matchLabelKeys") or [] if k in labels},
+                            "affPolicy": c.get("nodeAffinityPolicy") or "Honor", "taintPolicy": c.get("nodeTaintsPolicy") or "Ignore"})
+            return out, True
+        sel = self._default_selector(pod)
+        if not sel["matchLabels"] and not sel["matchExpressions"]:
+            return [], False
+        for key, skew in (("kubernetes.io/hostname", 3), ("topology.kubernetes.io/zone", 5)):
+            out.append({"key": key, "maxSkew": skew, "selector": sel, "mlk": {}, "affPolicy": "Honor", "taintPolicy": "Ignore"})
+        return out, False
+
+    @staticmethod
+    def _csel_matches(c, lbls):
+        if c["selector"] is None:
+            return False
+        for k, v in c["mlk"].items():
+            if lbls.get(k) != v:
+                return False
+        return label_selector_matches(c["selector"], lbls)
+
+    def _count_matching(self, c, ni, ns):          # countPodsMatchSelector (common.go:144-158)
+        if label_selector_empty(c["selector"]) and not c["mlk"]:
+            return 0
+        return sum(1 for p in ni.pods if p["metadata"].get("deletionTimestamp") is None and
+                   (p["metadata"].get("namespace") or "default") == ns and self._csel_matches(c, p["metadata"].get("labels") or {}))
+
+    def _pts_scores(self, pod, feasible):
+        """PodTopologySpread PreScore + Score + NormalizeScore (PL:podtopologyspread/scoring.go:60-265). None = Skip."""
+        cons, require_all = self._soft_constraints(pod)
+        if not cons:
+            return None
+        spec = pod["spec"]
+        ns = pod["metadata"].get("namespace") or "default"
+        ignored, pair_counts, topo_size = set(), [dict() for _ in cons], [0] * len(cons)
+        for ni in feasible:
+            if require_all and any(c["key"] not in ni.labels for c in cons):
+                ignored.add(ni.name)
+                continue
+            for i, c in enumerate(cons):
+                if c["key"] == "kubernetes.io/hostname":
+                    continue
+                v = ni.labels.get(c["key"], "")
+                if v not in pair_counts[i]:
+                    pair_counts[i][v] = 0
+                    topo_size[i] += 1
+        weights = []
+        for i, c in enumerate(cons):
+            sz = topo_size[i]
+            if c["key"] == "kubernetes.io/hostname":
+                sz = len(feasible) - len(ignored)
+            weights.append(go_log(float(sz + 2)))
+        for ni in self.infos:
+            if require_all and any(c["key"] not in ni.labels for c in cons):
+                continue
+            for i, c in enumerate(cons):
+                if c["affPolicy"] == "Honor" and not required_node_affinity_match(pod, ni.node):
+                    continue
+                if c["taintPolicy"] == "Honor" and any(t.get("effect") in ("NoSchedule", "NoExecute") and not tolerations_tolerate(spec.get("tolerations"), t)
+                                                        for t in (ni.node.get("spec") or {}).get("taints") or []):
+                    continue
+                v = ni.labels.get(c["key"], "")
+                if v not in pair_counts[i]:
+                    continue
+                pair_counts[i][v] += self._count_matching(c, ni, ns)
+        raw = []
+        for ni in feasible:
+            if ni.name in ignored:
+                raw.append(None)
+                continue
+            sc = 0.0
+            for i, c in enumerate(cons):
+                if c["key"] in ni.labels:
+                    if c["key"] == "kubernetes.io/hostname":
+                        cnt = self._count_matching(c, ni, ns)
+                    else:
+                        cnt = pair_counts[i][ni.labels[c["key"]]]
+                    sc += float(cnt) * weights[i] + float(c["maxSkew"] - 1)
+            raw.append(go_round(sc))
+        vals = [r for r in raw if r is not None]
+        mn = min(vals) if vals else (1 << 63) - 1
+        mx = max(vals + [0])
+        out = []
+        for r in raw:
+            if r is None:
+                out.append(0)
+            elif mx == 0:
+                out.append(100)
+            else:
+                out.append(100 * (mx + mn - r) // mx)
+        return out
+
+    def _ipa_scores(self, pod, feasible, hard_weight=1):
+        """InterPodAffinity PreScore + Score + NormalizeScore (PL:interpodaffinity/scoring.go:51-295). None = Skip."""
+        ns = pod["metadata"].get("namespace") or "default"
+        nsl = self.ns_labels.get(ns, {})
+        paff = affinity_terms(pod, "podAffinity", required=False)
+        panti = affinity_terms(pod, "podAntiAffinity", required=False)
+        for t in paff + panti:       # mergeAffinityTermNamespacesIfNotEmpty
+            if t["nsSelector"] is not None and not label_selector_empty(t["nsSelector"]):
+                for name, nl in self.ns_labels.items():
+                    if label_selector_matches(t["nsSelector"], nl):
+                        t["namespaces"].add(name)
+        topo = {}
+
+        def process(term, weight, target, nslabels, node_labels, mult):
+            if term_matches(term, target, nslabels) and term["topologyKey"] in node_labels:
+                d = topo.setdefault(term["topologyKey"], {})
+                v = node_labels[term["topologyKey"]]
+                d[v] = d.get(v, 0) + weight * mult
+        for ni in self.infos:
+            if not ni.labels:
+                continue
+            for p in ni.pods:
+                for t in paff:
+                    process(t, t["weight"], p, None, ni.labels, 1)
+                for t in panti:
+                    process(t, t["weight"], p, None, ni.labels, -1)
+                if hard_weight > 0:
+                    for t in affinity_terms(p, "podAffinity"):
+                        process(t, hard_weight, pod, nsl, ni.labels, 1)
+                for t in affinity_terms(p, "podAffinity", required=False):
+                    process(t, t["weight"], pod, nsl, ni.labels, 1)
+                for t in affinity_terms(p, "podAntiAffinity", required=False):
+                    process(t, t["weight"], pod, nsl, ni.labels, -1)
+        if not topo:
+            return None
+        raw = [sum(vals.get(ni.labels[k], 0) for k, vals in topo.items() if k in ni.labels) for ni in feasible]
+        mn, mx = min(raw), max(raw)
+        return [int(100.0 * (float(r - mn) / float(mx - mn))) if mx > mn else 0 for r in raw]
+
+    def _image_score(self, pod, ni):
+        """ImageLocality.Score (PL:imagelocality/image_locality.go:54-122)."""
+        spec = pod["spec"]
+        conts = list(spec.get("initContainers") or []) + list(spec.get("containers") or [])
+        here = set()
+        for im in (ni.node.get("status") or {}).get("images") or []:
+            here.update(im.get("names") or [])
+        total = 0
+        for c in conts:
+            name = normalized_image_name(c.get("image", ""))
+            if name in here:
+                size, nodes = self.image_states[name]
+                total += int(float(size) * (float(len(nodes)) / float(len(self.infos))))
+        mb = 1024 * 1024
+        lo, hi = 23 * mb, 1000 * mb * len(conts)
+        total = min(max(total, lo), hi)
+        return 100 * (total - lo) // (hi - lo)
 
     # ---- one scheduling cycle -----------------------------------------------------------------------------------
     def _prefilter(self, pod):
@@ -602,6 +836,8 @@ class Simulator:
             raws = [sum(1 for t in (ni.node.get("spec") or {}).get("taints") or []
                         if t.get("effect") == "PreferNoSchedule" and not tolerations_tolerate(tols_prefer, t)) for ni in feasible]
             mx = max(raws)
+            pts = self._pts_scores(pod, feasible)
+            ipa = self._ipa_scores(pod, feasible)
             best, best_ni = None, None
             for idx, (ni, raw) in enumerate(zip(feasible, raws)):
                 least, bal = self._score(pod, ni)
@@ -609,6 +845,11 @@ class Simulator:
                 total = 3 * tt + least + (bal if bal is not None else 0)
                 if pref:      # NodeAffinity score, weight 2 (node_affinity.go:241-290; helper/normalize_score.go:28-56)
                     total += 2 * (na_raw[idx] if na_max == 0 else 100 * na_raw[idx] // na_max)
+                if pts is not None:      # weight 2
+                    total += 2 * pts[idx]
+                if ipa is not None:      # weight 2
+                    total += 2 * ipa[idx]
+                total += self._image_score(pod, ni)     # weight 1
                 if best is None or total > best:
                     best, best_ni = total, ni
             clone = {"metadata": dict(pod["metadata"]), "spec": dict(pod["spec"]), "status": {}}

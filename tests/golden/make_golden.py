@@ -45,7 +45,7 @@ def main():
         for variant in helpers.TEMPLATE_VARIANTS:
             tmpl = helpers.template(variant, seed)
             sim = objref.Simulator(tmpl, 0, ())
-            sim.sync(nodes, pods)
+            helpers.objref_sync(sim, nodes, pods, variant)
             sim.run()
             gen["cases"].append({"name": "%s_seed%d" % (variant, seed), "cluster_seed": seed, "variant": variant,
                                  "scheduled": sim.pods_status, "stop_reason": sim.stop_reason})

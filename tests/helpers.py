@@ -28,7 +28,11 @@ def from_encoded(enc):
     raw = bytes.fromhex(enc["template_hex"])
     assert len(raw) == C.sizeof(abi.Template)
     C.memmove(C.byref(t), raw, len(raw))
-    ctr = [abi.make_counter(c["topo_col"], np.array(c["init"], np.int32), n_present=c["n_present"], inc=c["inc"]) for c in enc["counters"]]
+    ctr = [abi.make_counter(c["topo_col"], np.array(c["init"], np.int32), n_present=c["n_present"], inc=c["inc"], elig_bit=c.get("elig_bit", -1))
+           for c in enc["counters"]]
+    img = np.array(enc.get("image_score") or [], np.uint8)   # template_hex carries a pointer of the encoding process: replace it
+    t._keep_img = img
+    t.image_score = img.ctypes.data_as(C.POINTER(C.c_uint8)) if len(img) else None
     return snap, [t], ctr, nd["taint_dict"], nd["scalar_names"], enc["names"]
 
 
@@ -102,6 +106,13 @@ def random_cluster(seed, n_nodes=40, n_pods=60, zones=3):
         nodes.append(make_node("node-%02d" % i, cpu=rng.choice(["2", "4", "8", "3500m"]), mem=rng.choice(["4Gi", "8Gi", "16Gi", "6000Mi"]),
                                pods=str(rng.choice([5, 8, 12, 110])), labels=labels, taints=taints,
                                unschedulable=rng.random() < 0.05, extra_alloc=extra))
+        images = []
+        if rng.random() < 0.3:
+            images.append({"names": ["img:latest", "registry.local/img@sha256:0123"], "sizeBytes": rng.choice([120, 300, 700]) * 1024 * 1024})
+        if rng.random() < 0.2:
+            images.append({"names": ["y:latest"], "sizeBytes": 900 * 1024 * 1024})
+        if images:
+            nodes[-1]["status"]["images"] = images
     for j in range(n_pods):
         node = "node-%02d" % rng.randrange(n_nodes) if rng.random() < 0.92 else None
         labels = {"app": rng.choice(["web", "db", "sim"])}
@@ -109,6 +120,18 @@ def random_cluster(seed, n_nodes=40, n_pods=60, zones=3):
         if rng.random() < 0.15:
             extra["affinity"] = {"podAntiAffinity": {"requiredDuringSchedulingIgnoredDuringExecution": [
                 {"labelSelector": {"matchLabels": {"app": rng.choice(["sim", "db"])}}, "topologyKey": rng.choice(["kubernetes.io/hostname", "topology.kubernetes.io/zone"])}]}}
+        r = rng.random()
+        if r < 0.08:      # scored through hardPodAffinityWeight when it matches the incoming pod
+            extra.setdefault("affinity", {})["podAffinity"] = {"requiredDuringSchedulingIgnoredDuringExecution": [
+                {"labelSelector": {"matchLabels": {"app": rng.choice(["sim", "web"])}}, "topologyKey": "topology.kubernetes.io/zone"}]}
+        elif r < 0.16:
+            extra.setdefault("affinity", {})["podAffinity"] = {"preferredDuringSchedulingIgnoredDuringExecution": [
+                {"weight": rng.choice([10, 35]), "podAffinityTerm": {"labelSelector": {"matchExpressions": [{"key": "app", "operator": "In", "values": ["sim", "web"]}]},
+                                                                    "topologyKey": rng.choice(["topology.kubernetes.io/zone", "disk"])}}]}
+        elif r < 0.24:
+            aa = extra.setdefault("affinity", {}).setdefault("podAntiAffinity", {})
+            aa["preferredDuringSchedulingIgnoredDuringExecution"] = [
+                {"weight": rng.choice([5, 60]), "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "sim"}}, "topologyKey": "kubernetes.io/hostname"}}]
         p = make_pod("pod-%03d" % j, cpu=rng.choice([None, "100m", "250m", "1"]), mem=rng.choice([None, "64Mi", "256Mi", "1Gi"]),
                      node=node, labels=labels, phase=rng.choice(["Running"] * 8 + ["Succeeded", "Pending"]), **extra)
         if rng.random() < 0.2:
@@ -124,7 +147,31 @@ def random_cluster(seed, n_nodes=40, n_pods=60, zones=3):
 
 
 TEMPLATE_VARIANTS = ["plain", "selector", "tolerations", "affinity_terms", "hostports", "spread_zone", "spread_two", "anti_hostname",
-                     "anti_zone", "affinity_zone", "extended", "best_effort", "init_overhead", "never_preempt", "gt_lt", "name_in", "pref_affinity", "pref_and_required"]
+                     "anti_zone", "affinity_zone", "extended", "best_effort", "init_overhead", "never_preempt", "gt_lt", "name_in", "pref_affinity", "pref_and_required",
+                     "soft_spread", "soft_and_hard", "pref_pod_affinity", "svc_default_spread", "owner_default_spread"]
+
+
+def workloads_for(variant):
+    """Services / controllers synced next to the nodes and pods (only the *_default_spread variants need them)."""
+    svc = lambda name, sel, ns="default": {"apiVersion": "v1", "kind": "Service", "metadata": {"name": name, "namespace": ns}, "spec": {"selector": sel}}
+    if variant == "svc_default_spread":
+        return {"services": [svc("sim", {"app": "sim"}), svc("other-ns", {"app": "sim", "x": "y"}, ns="kube-system"), svc("web", {"app": "web"}),
+                             {"apiVersion": "v1", "kind": "Service", "metadata": {"name": "headless", "namespace": "default"}, "spec": {}}]}
+    if variant == "owner_default_spread":
+        return {"services": [svc("web", {"app": "web"})],
+                "replica_sets": [{"apiVersion": "apps/v1", "kind": "ReplicaSet", "metadata": {"name": "sim-rs", "namespace": "default"},
+                                  "spec": {"selector": {"matchExpressions": [{"key": "app", "operator": "In", "values": ["sim", "db"]}]}}}]}
+    return {}
+
+
+def list_client(fw, nodes, pods, variant=None, namespaces=()):
+    return fw.ListClient(nodes, pods, namespaces, **workloads_for(variant))
+
+
+def objref_sync(sim, nodes, pods, variant=None, namespaces=()):
+    w = workloads_for(variant)
+    sim.sync(nodes, pods, namespaces, services=w.get("services", ()), rcs=w.get("replication_controllers", ()),
+             replicasets=w.get("replica_sets", ()), statefulsets=w.get("stateful_sets", ()))
 
 
 def template(variant, seed=0):
@@ -160,6 +207,25 @@ def template(variant, seed=0):
             "preferredDuringSchedulingIgnoredDuringExecution": [
                 {"weight": 100, "preference": {"matchExpressions": [{"key": "disk", "operator": "In", "values": ["hdd"]}]}},
                 {"weight": 1, "preference": {"matchFields": [{"key": "metadata.name", "operator": "In", "values": ["node-05"]}]}}]}}
+    elif variant == "soft_spread":
+        s["topologySpreadConstraints"] = [
+            {"maxSkew": 2, "topologyKey": "topology.kubernetes.io/zone", "whenUnsatisfiable": "ScheduleAnyway", "labelSelector": {"matchLabels": {"app": "sim"}}},
+            {"maxSkew": 1, "topologyKey": "kubernetes.io/hostname", "whenUnsatisfiable": "ScheduleAnyway",
+             "labelSelector": {"matchExpressions": [{"key": "app", "operator": "In", "values": ["sim", "web"]}]}}]
+    elif variant == "soft_and_hard":
+        s["topologySpreadConstraints"] = [
+            {"maxSkew": 3, "topologyKey": "topology.kubernetes.io/zone", "whenUnsatisfiable": "DoNotSchedule", "labelSelector": {"matchLabels": {"app": "sim"}}},
+            {"maxSkew": 1, "topologyKey": "topology.kubernetes.io/region", "whenUnsatisfiable": "ScheduleAnyway", "labelSelector": {"matchLabels": {"app": "sim"}},
+             "nodeTaintsPolicy": "Honor"},
+            {"maxSkew": 4, "topologyKey": "disk", "whenUnsatisfiable": "ScheduleAnyway", "labelSelector": {"matchLabels": {"app": "db"}}, "nodeAffinityPolicy": "Ignore"}]
+    elif variant == "pref_pod_affinity":
+        s["affinity"] = {"podAffinity": {"preferredDuringSchedulingIgnoredDuringExecution": [
+            {"weight": 40, "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "db"}}, "topologyKey": "topology.kubernetes.io/zone"}},
+            {"weight": 15, "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "sim"}}, "topologyKey": "disk"}}]},
+            "podAntiAffinity": {"preferredDuringSchedulingIgnoredDuringExecution": [
+                {"weight": 25, "podAffinityTerm": {"labelSelector": {"matchLabels": {"app": "sim"}}, "topologyKey": "kubernetes.io/hostname"}}]}}
+    elif variant == "owner_default_spread":
+        p["metadata"]["ownerReferences"] = [{"apiVersion": "apps/v1", "kind": "ReplicaSet", "name": "sim-rs", "controller": True, "uid": "u"}]
     elif variant == "hostports":
         s["containers"][0]["ports"] = [{"containerPort": 80, "hostPort": 8080}]
     elif variant == "spread_zone":

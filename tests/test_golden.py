@@ -16,9 +16,9 @@ ASSERTED = json.load(open(os.path.join(GOLD, "reference_asserted.json")))["cases
 SEQS = json.load(open(os.path.join(GOLD, "objref_sequences.json")))["cases"]
 
 
-def cpu_path(nodes, pods, tmpl, max_pods):
+def cpu_path(nodes, pods, tmpl, max_pods, variant=None):
     cc = fw.New(None, None, tmpl, max_pods, [])
-    cc.SyncWithClient(fw.ListClient(nodes, pods))
+    cc.SyncWithClient(helpers.list_client(fw, nodes, pods, variant))
     snap, T, ctr, tdict, snames, names = helpers.from_encoded(cc.EncodedSnapshot())
     got = oracle.run(snap, T, ctr, max_pods=max_pods)
     sr = helpers.stop_reason_from_result(got, snap.n, max_pods, tdict, snames, tmpl["spec"].get("preemptionPolicy") == "Never")
@@ -41,7 +41,7 @@ def test_reference_asserted_outcomes_cpu(built, case):
 @pytest.mark.parametrize("case", SEQS, ids=[c["name"] for c in SEQS])
 def test_frozen_sequences_cpu(built, case):
     nodes, pods = helpers.random_cluster(case["cluster_seed"], n_nodes=24, n_pods=40)
-    seq, sr = cpu_path(nodes, pods, helpers.template(case["variant"], case["cluster_seed"]), 0)
+    seq, sr = cpu_path(nodes, pods, helpers.template(case["variant"], case["cluster_seed"]), 0, case["variant"])
     assert seq == case["scheduled"] and sr == case["stop_reason"]
 
 
@@ -54,7 +54,7 @@ def test_golden_gpu(built, case):
         nodes, pods = helpers.random_cluster(case["cluster_seed"], n_nodes=24, n_pods=40)
         tmpl, limit = helpers.template(case["variant"], case["cluster_seed"]), 0
     cc = fw.New(None, None, tmpl, limit, [])
-    cc.SyncWithClient(fw.ListClient(nodes, pods))
+    cc.SyncWithClient(helpers.list_client(fw, nodes, pods, case.get("variant")))
     cc.Run()
     if "expect" in case:
         assert len(cc.ScheduledPods()) == case["expect"]["replicas"] and cc.StopReason().split(":")[0] == case["expect"]["failType"]

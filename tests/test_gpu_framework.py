@@ -13,12 +13,12 @@ fw = importlib.import_module("cluster-capacity_b200.framework")
 pytestmark = pytest.mark.gpu
 
 
-def analyse(nodes, pods, tmpl, max_pods=0, exclude=()):
+def analyse(nodes, pods, tmpl, max_pods=0, exclude=(), variant=None):
     cc = fw.New(None, None, tmpl, max_pods, list(exclude))
-    cc.SyncWithClient(fw.ListClient(nodes, pods))
+    cc.SyncWithClient(helpers.list_client(fw, nodes, pods, variant))
     cc.Run()
     ref = objref.Simulator(tmpl, max_pods, exclude)
-    ref.sync(nodes, pods)
+    helpers.objref_sync(ref, nodes, pods, variant)
     ref.run()
     return cc, ref
 
@@ -38,7 +38,7 @@ def check(cc, ref):
 @pytest.mark.parametrize("variant", helpers.TEMPLATE_VARIANTS)
 def test_framework_matches_object_oracle(built, variant):
     nodes, pods = helpers.random_cluster(11, n_nodes=40, n_pods=70)
-    cc, ref = analyse(nodes, pods, helpers.template(variant))
+    cc, ref = analyse(nodes, pods, helpers.template(variant), variant=variant)
     check(cc, ref)
 
 

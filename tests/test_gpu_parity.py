@@ -221,3 +221,61 @@ def test_preferred_node_affinity_two_phase(built):
         t.pref_weight[k] = w
         t.pref_mask[k][0] = 1 << bit
     check(snap, [t], max_pods=6000)
+
+
+def _soft_cluster(seed, n=3000, system_default=False):
+    rng = np.random.default_rng(seed)
+    zone = rng.integers(0, 20, n).astype(np.int32)
+    zone[rng.random(n) < 0.07] = -1                        # nodes without the zone label
+    rack = rng.integers(0, 200, n).astype(np.int32)
+    bit = lambda a, b: a.astype(np.uint64) << np.uint64(b)
+    static = bit(zone < 0, 0) | bit(rng.random(n) < 0.9, 1) | bit(rng.random(n) < 0.8, 2)
+    taint = bit(rng.random(n) < 0.25, 0)
+    snap = abi.Snapshot(n, rng.choice([2000, 4000, 8000], n), np.full(n, 16 * GiB), rng.choice([6, 10, 14], n),
+                        static_mask=static.reshape(1, n), topo=[zone, rack], taint_mask=taint.reshape(1, n), taint_prefer=[1],
+                        taint_lists=[[0] if int(x) else [] for x in taint])
+    ctr = [abi.make_counter(0, rng.integers(0, 40, 20), inc=1, elig_bit=2),           # soft zone constraint, inclusion policies
+           abi.make_counter(-1, rng.integers(0, 3, n), inc=1),                        # soft hostname constraint
+           abi.make_counter(1, rng.integers(-50, 50, 200), inc=-3),                   # pod (anti-)affinity weights per rack
+           abi.make_counter(-1, rng.integers(-5, 20, n), inc=7)]                      # ... and per node
+    t = abi.default_template(300, 256 * MiB)
+    t.n_spts = 2
+    t.spts_ignored_bit = -1 if system_default else 0
+    t.spts[0].counter, t.spts[0].max_skew, t.spts[0].hostname, t.spts[0].has_key_bit = 0, 5, 0, -1
+    t.spts[1].counter, t.spts[1].max_skew, t.spts[1].hostname, t.spts[1].has_key_bit = 1, 3, 1, 1
+    t.n_ipa_score = 2
+    t.ipa_score_counter[0], t.ipa_score_counter[1] = 2, 3
+    img = np.where(rng.random(n) < 0.3, rng.integers(1, 101, n), 0).astype(np.uint8)
+    t._keep_img = img
+    t.image_score = img.ctypes.data_as(abi.C.POINTER(abi.C.c_uint8))
+    return snap, [t], ctr
+
+
+@pytest.mark.parametrize("system_default", [False, True])
+def test_soft_scorers_three_phase(built, system_default):
+    """PodTopologySpread score (log weights from the feasible set, min/max normalisation), InterPodAffinity score (float
+    normalisation), ImageLocality column and PreferNoSchedule classes together: every wave runs the three-pass pipeline."""
+    snap, tmpl, ctr = _soft_cluster(5 if system_default else 4, system_default=system_default)
+    got = check(snap, tmpl, ctr, max_pods=5000)
+    assert got.placed > 1000
+
+
+def test_soft_scorers_until_full(built):
+    snap, tmpl, ctr = _soft_cluster(6, n=700)
+    got = check(snap, tmpl, ctr)
+    assert got.stop_code == abi.STOP_UNSCHEDULABLE
+
+
+def test_image_locality_only_multi_template(built):
+    """ImageLocality is a static per-node, per-template column: no extra pass, also with several templates."""
+    rng = np.random.default_rng(8)
+    n = 2000
+    snap = abi.Snapshot(n, rng.choice([2000, 4000], n), np.full(n, 8 * GiB), np.full(n, 10))
+    tm = []
+    for k in range(3):
+        t = abi.default_template(200 + 100 * k, 128 * MiB)
+        img = np.where(rng.random(n) < 0.4, rng.integers(1, 101, n), 0).astype(np.uint8)
+        t._keep_img = img
+        t.image_score = img.ctypes.data_as(abi.C.POINTER(abi.C.c_uint8))
+        tm.append(t)
+    check(snap, tm, max_pods=3000)

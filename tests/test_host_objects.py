@@ -13,12 +13,12 @@ fw = importlib.import_module("cluster-capacity_b200.framework")
 abi = importlib.import_module("cluster-capacity_b200._abi")
 
 
-def run_both(nodes, pods, tmpl, max_pods=0, exclude=()):
+def run_both(nodes, pods, tmpl, max_pods=0, exclude=(), variant=None):
     ref = objref.Simulator(tmpl, max_pods, exclude)
-    ref.sync(nodes, pods)
+    helpers.objref_sync(ref, nodes, pods, variant)
     ref.run()
     cc = fw.New(None, None, tmpl, max_pods, list(exclude))
-    cc.SyncWithClient(fw.ListClient(nodes, pods))
+    cc.SyncWithClient(helpers.list_client(fw, nodes, pods, variant))
     enc = cc.EncodedSnapshot()
     snap, T, ctr, tdict, snames, names = helpers.from_encoded(enc)
     got = oracle.run(snap, T, ctr, max_pods=max_pods)
@@ -33,7 +33,7 @@ def run_both(nodes, pods, tmpl, max_pods=0, exclude=()):
 def test_encoder_matches_object_oracle(built, variant, seed):
     nodes, pods = helpers.random_cluster(seed, n_nodes=30, n_pods=50)
     tmpl = helpers.template(variant, seed)
-    ref, seq, sr = run_both(nodes, pods, tmpl)
+    ref, seq, sr = run_both(nodes, pods, tmpl, variant=variant)
     assert seq == ref.pods_status
     assert sr == ref.stop_reason
 
@@ -67,10 +67,10 @@ def test_zone_round_robin_node_order(built):
 def test_unsupported_features_are_refused(built):
     nodes, pods = helpers.random_cluster(1, n_nodes=5, n_pods=0)
     t = helpers.make_pod("p", cpu="100m")
-    t["spec"]["topologySpreadConstraints"] = [{"maxSkew": 1, "topologyKey": "x", "whenUnsatisfiable": "ScheduleAnyway", "labelSelector": {}}]
+    t["spec"]["resourceClaims"] = [{"name": "gpu", "resourceClaimName": "claim"}]
     cc = fw.New(None, None, t, 0, [])
     cc.SyncWithClient(fw.ListClient(nodes, pods))
-    with pytest.raises(fw.UnsupportedError, match="PodTopologySpread score"):
+    with pytest.raises(fw.UnsupportedError, match="DynamicResources"):
         cc.EncodedSnapshot()
     t2 = helpers.make_pod("p", cpu="100m")
     t2["spec"]["volumes"] = [{"name": "v", "persistentVolumeClaim": {"claimName": "c"}}]
@@ -86,3 +86,30 @@ def test_quantities_round_up(built):
     t = helpers.make_pod("p", cpu="0.1m", mem="1.5")
     ref, seq, sr = run_both(nodes, [], t)
     assert len(seq) == 5 and seq == ref.pods_status   # memory: floor(10 / 2)
+
+
+def test_system_default_spreading_needs_a_selecting_service(built):
+    """plugin.go:48-59 + helper/spread.go:40-113: a pod without topologySpreadConstraints gets the two system-default soft
+    constraints only when a Service of its namespace (or its owning controller) selects it; a Service in another namespace,
+    one selecting other labels and one with a nil selector change nothing."""
+    nodes, pods = helpers.random_cluster(9, n_nodes=30, n_pods=60)
+    tmpl = helpers.template("plain")
+    plain, seq_plain, _ = run_both(nodes, pods, tmpl)
+    ref, seq, sr = run_both(nodes, pods, tmpl, variant="svc_default_spread")
+    assert seq == ref.pods_status and sr == ref.stop_reason
+    assert seq != seq_plain                       # spreading changed the placement order
+    assert sorted(seq) == sorted(seq_plain)       # ... but not the capacity (scores never change feasibility)
+    irrelevant = {"services": helpers.workloads_for("svc_default_spread")["services"][1:]}
+    cc = fw.New(None, None, tmpl, 0, [])
+    cc.SyncWithClient(fw.ListClient(nodes, pods, **irrelevant))
+    enc = cc.EncodedSnapshot()
+    assert helpers.from_encoded(enc)[1][0].n_spts == 0
+    cc.Close()
+
+
+def test_go_log_matches_libm_to_an_ulp():
+    """The restated math.Log (FreeBSD e_log.c port) agrees with libm within 1 ulp on the sizes the scorer feeds it."""
+    import math
+    for n in list(range(2, 2000)) + [5000, 100002, 1000002]:
+        a, b = objref.go_log(float(n)), math.log(float(n))
+        assert abs(a - b) <= math.ulp(b), n
