@@ -74,6 +74,11 @@ def load_scheduler_config(path):
     return out
 
 
+# what SyncWithClient LISTs and the scheduler plugins of the hot path read (simulator.go:176-281); PVCs, PDBs and
+# StorageClasses are copied by the reference too, but only the out-of-scope volume / preemption plugins look at them
+KINDS = ("nodes", "pods", "namespaces", "services", "replicationcontrollers", "replicasets", "statefulsets")
+
+
 def load_snapshot(path):
     def items(obj):
         if obj is None:
@@ -83,19 +88,21 @@ def load_snapshot(path):
         return obj
     if os.path.isdir(path):
         out = {}
-        for k in ("nodes", "pods", "namespaces"):
+        for k in KINDS:
             fn = os.path.join(path, k + ".json")
             out[k] = items(json.load(open(fn))) if os.path.exists(fn) else []
         return out
     with open(path) as f:
         d = yaml.safe_load(f)
-    return {k: items(d.get(k)) for k in ("nodes", "pods", "namespaces")}
+    return {k: items(d.get(k)) for k in KINDS}
 
 
 def list_from_cluster(kubeconfig):
     base = ["kubectl"] + (["--kubeconfig", kubeconfig] if kubeconfig else [])
     out = {}
-    for k, args in (("nodes", ["get", "nodes"]), ("pods", ["get", "pods", "-A"]), ("namespaces", ["get", "namespaces"])):
+    for k, args in (("nodes", ["get", "nodes"]), ("pods", ["get", "pods", "-A"]), ("namespaces", ["get", "namespaces"]),
+                    ("services", ["get", "services", "-A"]), ("replicationcontrollers", ["get", "replicationcontrollers", "-A"]),
+                    ("replicasets", ["get", "replicasets.apps", "-A"]), ("statefulsets", ["get", "statefulsets.apps", "-A"])):
         out[k] = json.loads(subprocess.check_output(base + args + ["-o", "json"]))["items"]
     return out
 
@@ -122,7 +129,8 @@ def main(argv=None):
         pod = parse_api_spec(a.podspec)
         objs = load_snapshot(a.snapshot) if a.snapshot else list_from_cluster(a.kubeconfig)
         cc = fw.New(load_scheduler_config(a.default_config), None, pod, a.max_limit, [x for x in a.exclude_nodes.split(",") if x], device=a.device)
-        cc.SyncWithClient(fw.ListClient(objs["nodes"], objs["pods"], objs["namespaces"]))
+        cc.SyncWithClient(fw.ListClient(objs["nodes"], objs["pods"], objs["namespaces"], objs["services"], objs["replicationcontrollers"],
+                                        objs["replicasets"], objs["statefulsets"]))
         cc.Run()
         fw.ClusterCapacityReviewPrint(cc, a.verbose, a.output)
     except (fw.FrameworkError, OSError, subprocess.CalledProcessError) as e:   # the reference prints the error and exits 0 (server.go:68-71)
