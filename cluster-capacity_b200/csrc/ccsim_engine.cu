@@ -34,6 +34,7 @@
 #endif
 #include "ccsim_lean.cuh"
 #include "ccsim_batched.cuh"
+#include "ccsim_multi.cuh"
 
 #define BLOCK_THREADS 512
 #define MAX_WARPS (BLOCK_THREADS / 32)
@@ -721,6 +722,7 @@ struct ccsim_handle {
   int last_resident = 0;
   int last_lean = 0;
   int last_batched = 0;
+  int last_multi = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -842,6 +844,8 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
                        (int)(h->smem_optin - sizeof(LeanShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(LeanShared) - sizeof(BatchShared) - 1024));
+  cudaFuncSetAttribute(ccsim_wave_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(h->smem_optin - sizeof(LeanShared) - sizeof(MultiShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(SMEM_CNT_MAX_INTS * sizeof(int32_t) + 16));
   *out = h;
@@ -1213,16 +1217,37 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   if (h->cfg.engine == CCSIM_ENGINE_BATCHED && !batched)
     return fail(h, CCSIM_EUNSUPPORTED, "batched engine needs one template with node-local predicates only, no PreferNoSchedule taints, a resident tile and a single GPU");
   h->last_batched = batched ? 1 : 0;
+  // multi-commit waves (ccsim_multi.cuh): one template coupled through per-domain counters, one node per thread
+  MultiParams mp; memset(&mp, 0, sizeof(mp));
+  bool multi = lean && !faithful && !batched && h->n_counters > 0 && h->max_prefer_pop == 0 && h->cfg.world == 1 &&
+               h->cfg.engine == CCSIM_ENGINE_AUTO && !getenv("CCSIM_FORCE_SEQUENTIAL") && h->h_templates[0].n_aff == 0 &&
+               p.chunk <= LEAN_THREADS;
+  if (multi) {
+    for (int j = 0; j < h->n_counters; j++) if (h->counters[j].inc < 0) multi = false;   // feasibility must be monotone within a wave
+    uint32_t shift = 0;
+    for (int sl = 0; sl < lp.n_slots && multi; sl++) {
+      if (lp.slot_topo[sl] < 0) continue;
+      int maxd = 1;
+      for (int j = 0; j < h->n_counters; j++) if (lp.counter_slot[j] == sl && h->counters[j].topo_col >= 0) maxd = std::max(maxd, h->counters[j].n_domains);
+      uint32_t bits = 0; while ((1u << bits) <= (uint32_t)maxd) bits++;        // values 0..maxd (dom + 1)
+      if (shift + bits > MULTI_PAY_BITS) { multi = false; break; }
+      mp.pay_shift[sl] = shift; mp.pay_mask[sl] = (1u << bits) - 1u; shift += bits;
+    }
+    if (smem + sizeof(LeanShared) + sizeof(MultiShared) + 1024 > h->smem_optin) multi = false;
+    if (multi) kern = (const void *)ccsim_wave_multi_kernel;
+  }
+  h->last_multi = multi ? 1 : 0;
   p.self = h->d_params;
   CK(cudaMemcpyAsync(h->d_params, &p, sizeof(DevParams), cudaMemcpyHostToDevice, s));
   int occ = 0;
-  if (batched) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_batched_kernel, block, smem));
+  if (multi) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel, block, smem));
+  else if (batched) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_batched_kernel, block, smem));
   else if (lean && faithful) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel<true>, block, smem));
   else if (lean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel<false>, block, smem));
   else if (resident) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<true>, block, smem));
   else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<false>, block, smem));
   if (occ < 1 || occ * h->sm_count < grid) return fail(h, CCSIM_ECUDA, "persistent grid %d does not fit (occupancy %d x %d SMs)", grid, occ, h->sm_count);
-  void *args[] = { (void *)&p, (void *)&lp };
+  void *args[] = { (void *)&p, (void *)&lp, (void *)&mp };
   CK(cudaEventRecord(h->ev0, s));
   CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));
   h->launches++;
@@ -1233,7 +1258,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   if (ho.error) return fail(h, CCSIM_ECUDA, "wave kernel aborted (error %d: %s)", ho.error, ho.error == 1 ? "exchange watchdog / output overflow" : "?");
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 #ifdef CCSIM_PHASE_TIMERS
-  fprintf(stderr, "[ccsim %s tile %zu B smem] ", batched ? "batched" : (lean ? "lean" : (resident ? "resident" : "streaming")), smem);
+  fprintf(stderr, "[ccsim %s tile %zu B smem] ", multi ? "multi" : batched ? "batched" : (lean ? "lean" : (resident ? "resident" : "streaming")), smem);
   fprintf(stderr, "[ccsim phases, CTA0 cycles/wave] scan=%.0f S1=%.0f publish=%.0f gather=%.0f commit=%.0f S2=%.0f (waves=%lld, %.3f ms)\n",
           (double)ho.phase_cycles[0] / ho.waves, (double)ho.phase_cycles[1] / ho.waves, (double)ho.phase_cycles[2] / ho.waves,
           (double)ho.phase_cycles[3] / ho.waves, (double)ho.phase_cycles[4] / ho.waves, (double)ho.phase_cycles[5] / ho.waves,

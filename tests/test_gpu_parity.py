@@ -279,3 +279,38 @@ def test_image_locality_only_multi_template(built):
         t.image_score = img.ctypes.data_as(abi.C.POINTER(abi.C.c_uint8))
         tm.append(t)
     check(snap, tm, max_pods=3000)
+
+
+@pytest.mark.parametrize("limit", [1, 2, 7, 64, 1001, 0])
+def test_multi_commit_waves_match_the_sequential_loop(built, limit):
+    """Multi-commit waves (ccsim_multi.cuh; picked by ENGINE_AUTO for counter-coupled templates): several reference cycles
+    per exchange, pod -> node sequence identical to one-winner-per-wave, --max-limit cuts in the middle of a wave."""
+    snap, tmpl, ctr = synth.c4(n=60000, n_existing=90000, zones=32, racks=512, regions=8)
+    want = oracle.run(snap, tmpl, ctr, max_pods=limit or 2500, threads=8)
+    got, counts, _ = gpu_run(snap, tmpl, ctr, limit or 2500, abi.ENGINE_AUTO)
+    assert got.placed == want.placed and got.stop_code == want.stop_code
+    assert np.array_equal(got.pod_node, want.pod_node)
+    if got.placed > 100:
+        assert got.waves * 3 < want.waves          # it really batched
+    assert np.array_equal(counts, np.bincount(want.pod_node, minlength=snap.n))
+
+
+def test_multi_commit_zone_anti_affinity_and_missing_keys(built):
+    """Required anti-affinity on a zone key (limit 0 on a replicated counter: one clone per zone) next to a spread constraint
+    whose key some nodes lack, run until Unschedulable: the terminal histogram comes from the state the multi-commit
+    kernel left behind."""
+    rng = np.random.default_rng(31)
+    n = 20000
+    zone = rng.integers(0, 300, n).astype(np.int32)
+    zone[rng.random(n) < 0.05] = -1
+    rack = rng.integers(0, 40, n).astype(np.int32)
+    snap = abi.Snapshot(n, rng.choice([2000, 4000, 8000], n), np.full(n, 16 * GiB), np.full(n, 20), topo=[zone, rack])
+    ctr = [abi.make_counter(0, (rng.random(300) < 0.1).astype(np.int32), inc=1),
+           abi.make_counter(1, rng.integers(0, 3, 40), inc=1)]
+    t = abi.default_template(200, 128 * MiB)
+    t.n_anti = 1
+    t.anti_counter[0] = 0
+    t.n_pts = 1
+    t.pts[0].counter, t.pts[0].max_skew, t.pts[0].self_match, t.pts[0].min_zero = 1, 3, 1, 0
+    got = check(snap, [t], ctr)
+    assert got.stop_code == abi.STOP_UNSCHEDULABLE and got.placed > 200   # nodes without the zone label are not bound by the anti-affinity term
