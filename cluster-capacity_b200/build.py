@@ -4,7 +4,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(_HERE, "csrc", "ccsim_engine.cu")]
-DEPS = SRC + [os.path.join(_HERE, "csrc", "ccsim_device.cuh"), os.path.join(_HERE, "..", "include", "ccsim.h")]
+import glob
+DEPS = SRC + sorted(glob.glob(os.path.join(_HERE, "csrc", "*.cuh"))) + [os.path.join(_HERE, "..", "include", "ccsim.h")]
 OUT = os.path.join(_HERE, "libccsim.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-lcudart", "-ldl"]
@@ -19,8 +20,6 @@ HOST_OUT = os.path.join(_HERE, "libcchost.so")
 
 def build(force=False, verbose=False):
     """libccsim.so (CUDA, sm_100a) then libcchost.so (C++ host side, links libccsim via $ORIGIN rpath)."""
-    DEPS.append(os.path.join(_HERE, "csrc", "ccsim_lean.cuh"))
-    DEPS.append(os.path.join(_HERE, "csrc", "ccsim_batched.cuh"))
     newest = max(os.path.getmtime(p) for p in DEPS)
     if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1221,9 +1221,24 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   MultiParams mp; memset(&mp, 0, sizeof(mp));
   bool multi = lean && !faithful && !batched && h->n_counters > 0 && h->max_prefer_pop == 0 && h->cfg.world == 1 &&
                h->cfg.engine == CCSIM_ENGINE_AUTO && !getenv("CCSIM_FORCE_SEQUENTIAL") && h->h_templates[0].n_aff == 0 &&
-               p.chunk <= LEAN_THREADS;
+               p.chunk <= LEAN_THREADS && h->n_global < (1 << MULTI_IDX_BITS);
   if (multi) {
     for (int j = 0; j < h->n_counters; j++) if (h->counters[j].inc < 0) multi = false;   // feasibility must be monotone within a wave
+    {
+      const ccsim_template &T = h->h_templates[0];
+      int gt = 0;
+      if (T.filter_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) for (int c = 0; c < T.n_pts; c++) if (h->counters[T.pts[c].counter].topo_col >= 0) gt++;
+      if (T.filter_enable & CCSIM_PL_INTER_POD_AFFINITY) for (int a = 0; a < T.n_anti; a++) if (h->counters[T.anti_counter[a]].topo_col >= 0) gt++;
+      if (gt > MULTI_GT) multi = false;
+      // the replay updates counters term by term: every incremented replicated counter must be read by exactly one Filter term
+      for (int j = 0; j < h->n_counters; j++) {
+        if (h->counters[j].topo_col < 0 || h->counters[j].inc == 0) continue;
+        int refs = 0;
+        if (T.filter_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) for (int c = 0; c < T.n_pts; c++) if (T.pts[c].counter == j) refs++;
+        if (T.filter_enable & CCSIM_PL_INTER_POD_AFFINITY) for (int a = 0; a < T.n_anti; a++) if (T.anti_counter[a] == j) refs++;
+        if (refs != 1) multi = false;
+      }
+    }
     uint32_t shift = 0;
     for (int sl = 0; sl < lp.n_slots && multi; sl++) {
       if (lp.slot_topo[sl] < 0) continue;
@@ -1263,6 +1278,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
           (double)ho.phase_cycles[0] / ho.waves, (double)ho.phase_cycles[1] / ho.waves, (double)ho.phase_cycles[2] / ho.waves,
           (double)ho.phase_cycles[3] / ho.waves, (double)ho.phase_cycles[4] / ho.waves, (double)ho.phase_cycles[5] / ho.waves,
           (long long)ho.waves, ms);
+  fprintf(stderr, "[ccsim phases 6/7] %.0f %.0f\n", (double)ho.phase_cycles[6] / ho.waves, (double)ho.phase_cycles[7] / ho.waves);
 #endif
   out->placed = ho.placed; out->stop_code = ho.stop_code; out->waves = ho.waves; out->evals = ho.evals; out->run_ms = ms;
   out->examined = ho.examined ? ho.examined : ho.evals;

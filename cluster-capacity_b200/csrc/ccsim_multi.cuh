@@ -27,13 +27,19 @@
 #define MULTI_PAY_BITS 39         /* payload bits for domain ids (dom+1 per topology slot) */
 #define MULTI_MORE_BIT 39
 #define MULTI_LEN_SHIFT 40
+#define MULTI_MAX_ACC 64          /* commits one wave may decide */
+#define MULTI_GT 6                /* Filter terms on replicated counters a template may have in this kernel */
 
 struct __align__(16) MultiShared {
-  unsigned long long wtop[LEAN_WARPS][MULTI_M];     // per-warp top-M keys of this wave
-  unsigned long long gkey[CCSIM_MAX_GRID][MULTI_M]; // gathered candidate keys (tag stripped) ...
-  unsigned long long gpay[CCSIM_MAX_GRID][MULTI_M]; // ... and payloads
+  uint32_t wtop[LEAN_WARPS][MULTI_M];               // per-warp top-M (compact) keys of this wave
+  int32_t gt_commit[MULTI_GT][4];                   // (16-byte aligned) per replicated-counter term: {counter base, inc, PTS constraint tracked or -1, n_present}
+  uint32_t rmax[LEAN_WARPS], rbar[LEAN_WARPS];      // replay: per-warp maxima of a round
   int32_t wfeas[LEAN_WARPS];
-  int32_t accepted, dead, pad[2];
+  int32_t gt_term[MULTI_GT];                        // indices of the Filter terms that read a replicated (non node-local) counter
+  uint32_t gt_shift[MULTI_GT], gt_mask[MULTI_GT];   // ... and where their domain id sits in the payload
+  int32_t acc_node[MULTI_MAX_ACC];                  // replay: nodes accepted in this wave, in order
+  int32_t full[MULTI_GT];                           // replay: counter cell of term q that the last commit pushed over its limit, or -2
+  int32_t n_gt, accepted, dead, stopb;
 };
 
 __shared__ MultiShared ms;
@@ -42,6 +48,19 @@ struct MultiParams {
   uint32_t pay_shift[LEAN_MAX_SLOTS];   // record slot s (a topology column) -> bit position of its dom+1 field in the payload
   uint32_t pay_mask[LEAN_MAX_SLOTS];    // field mask (0: the slot is a node-local counter, not carried)
 };
+
+// 32-bit keys for everything inside this kernel: (score+1) in bits 20..31, (2^20-1 - global index) below (needs N < 2^20 and
+// score+1 < 4096, both host-checked). Same order as pack_key (highest score, then lowest index); one REDUX per arg-max.
+#define MULTI_IDX_BITS 20
+#define MULTI_IDX_MASK ((1u << MULTI_IDX_BITS) - 1u)
+__device__ __forceinline__ uint32_t ckey(int32_t score, uint32_t gidx) { return ((uint32_t)(score + 1) << MULTI_IDX_BITS) | (MULTI_IDX_MASK - gidx); }
+__device__ __forceinline__ int32_t ckey_index(uint32_t ck) { return (int32_t)(MULTI_IDX_MASK - (ck & MULTI_IDX_MASK)); }
+
+// Shared-memory accesses of the replay loop by explicit 32-bit shared address: nvcc otherwise re-derives the CTA's shared
+// window base (S2UR SR_CgaCtaId + LEA) in front of every access inside these barrier-separated regions.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+#define MS_OFF(field) ((uint32_t)offsetof(MultiShared, field))
 
 __device__ __forceinline__ void ld_slot2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
@@ -62,6 +81,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
   const int cta = blockIdx.x;
   const int32_t lo = min(p.n, cta * p.chunk), hi = min(p.n, lo + p.chunk);
   const int32_t cnt_nodes = hi - lo;      // <= LEAN_THREADS (host-checked): one node per thread
+  // shared address of `ms`, computed once; the volatile move keeps nvcc from re-deriving it (S2UR SR_CgaCtaId) at every use
+  uint32_t msb;
+  { const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(&ms); asm volatile("mov.u32 %0, %1;" : "=r"(msb) : "r"(t0)); }
   const int su = lp.stride_u;
 
   // ---- stage the tile (once): hot AoS records + cold SoA columns (same layout as the lean kernel) ----
@@ -90,23 +112,42 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     if (dc.topo_col < 0) continue;
     for (int d = tid; d < dc.n_domains; d += LEAN_THREADS) smem_cnt[dc.smem_off + d] = dc.init[d];
   }
-  if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; ms.accepted = 0; ms.dead = 0; }
+  if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; ms.accepted = 0; ms.dead = 0; ms.stopb = 0; ms.n_gt = 0; }
   __syncthreads();
   for (int c = 0; c < ls.tmpl.n_pts; c++) lean_pts_recount(p, smem_cnt, c);
 
+#ifdef CCSIM_PHASE_TIMERS
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0;
+#endif
   long long k = 0, wv = 0;
   uint32_t wtag = 1;
   uint32_t tag = (p.epoch << 12) | wtag;
   for (;; wv++) {
+    PH_START();
     if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ls.stop = 2; __syncthreads(); break; }
     if (k > p.pod_cap) { if (tid == 0) ls.stop = 3; __syncthreads(); break; }
     if (ls.dirty) {
-      if (tid == 0) lean_build_consts(p, lp);
+      if (tid == 0) {
+        lean_build_consts(p, lp);
+        int g = 0;
+        for (int q = 0; q < ls.n_cmp_terms; q++)
+          if (ls.terms[q].cnt_off >= 0 && g < MULTI_GT) {
+            const int sl = ls.terms[q].slot - 10;
+            ms.gt_shift[g] = mp.pay_shift[sl]; ms.gt_mask[g] = mp.pay_mask[sl];
+            ms.gt_commit[g][0] = ls.terms[q].cnt_off; ms.gt_commit[g][1] = 0; ms.gt_commit[g][2] = -1; ms.gt_commit[g][3] = 0;
+            for (int j = 0; j < p.n_counters; j++)
+              if (p.counters[j].topo_col >= 0 && p.counters[j].smem_off == ls.terms[q].cnt_off) {
+                ms.gt_commit[g][1] = ls.cinfo[j].inc; ms.gt_commit[g][2] = ls.cinfo[j].pts_idx; ms.gt_commit[g][3] = ls.cinfo[j].n_present;
+              }
+            ms.gt_term[g++] = q;
+          }
+        ms.n_gt = g;
+      }
       __syncthreads();
       if (tid == 0) ls.dirty = 0;
     }
     // ---- fused Filter pass: this thread's node ----
-    unsigned long long key = 0ull;
+    uint32_t key = 0u;
     if (tid < cnt_nodes) {
       const int32_t j = tid;
       const uint4 *r = rec + (size_t)j * su;
@@ -136,50 +177,45 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
                           c_rcpu[j] + ls.tmpl.bal_cpu, c_rmem[j] + ls.tmpl.bal_mem, ls.sw);
           reinterpret_cast<int32_t *>(rec + (size_t)j * su)[9] = sc;
         }
-        key = pack_key(sc, (uint32_t)(p.node_base + lo + j));
+        key = ckey(sc, (uint32_t)(p.node_base + lo + j));
       }
     }
     // ---- the warp's M best keys (REDUX rounds; keys are unique, 0 = none) ----
     {
-      unsigned long long rem = key;
-      const int nf = __popc(__ballot_sync(0xffffffffu, key != 0ull));
+      uint32_t rem = key;
+      const int nf = __popc(__ballot_sync(0xffffffffu, key != 0u));
       if (lane == 0) ms.wfeas[warp] = nf;
       #pragma unroll
       for (int r = 0; r < MULTI_M; r++) {
-        unsigned long long v = 0ull;
+        uint32_t v = 0u;
         if (r < nf) {                         // warp-uniform: no REDUX rounds for entries that do not exist
-          v = warp_max_u64(rem);
-          if (rem == v) rem = 0ull;
+          v = __reduce_max_sync(0xffffffffu, rem);
+          if (rem == v) rem = 0u;
         }
         if (lane == 0) ms.wtop[warp][r] = v;
       }
     }
+    PH_MARK(0);
     __syncthreads();                                                    // S1
+    PH_MARK(1);
     const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
     if (warp == 0) {
-      // ---- the CTA's M best: merge of the 24 sorted warp lists, then publish (key, payload) pairs ----
-      unsigned long long e[MULTI_M];
-      #pragma unroll
-      for (int r = 0; r < MULTI_M; r++) e[r] = lane < LEAN_WARPS ? ms.wtop[lane][r] : 0ull;
+      // ---- the CTA's M best: merge of the 24 sorted warp lists (lane w walks warp w's list), then publish the pairs ----
       int32_t total = lane < LEAN_WARPS ? ms.wfeas[lane] : 0;
       total = __reduce_add_sync(0xffffffffu, total);
       int ptr = 0, L = 0;
-      unsigned long long mykey = 0ull;
-      #pragma unroll
+      uint32_t mykey = 0u;
+      uint32_t head = lane < LEAN_WARPS ? ms.wtop[lane][0] : 0u;
       for (int r = 0; r < MULTI_M; r++) {
-        unsigned long long head = 0ull;
-        #pragma unroll
-        for (int q = 0; q < MULTI_M; q++) if (q == ptr) head = e[q];
-        const unsigned long long g = warp_max_u64(head);
-        if (g != 0ull) {
-          if (head == g) ptr++;
-          if (lane == r) mykey = g;
-          L = r + 1;
-        }
+        const uint32_t g = __reduce_max_sync(0xffffffffu, head);
+        if (g == 0u) break;                    // uniform
+        if (head == g) { ptr++; head = ptr < MULTI_M ? ms.wtop[lane][ptr] : 0u; }
+        if (lane == r) mykey = g;
+        L = r + 1;
       }
       unsigned long long pay = 0ull;
       if (lane < L) {
-        const int32_t jj = (int32_t)key_index(mykey) - (p.node_base + lo);
+        const int32_t jj = ckey_index(mykey) - (p.node_base + lo);
         const int32_t *r4 = reinterpret_cast<const int32_t *>(rec + (size_t)jj * su);
         for (int s = 0; s < lp.n_slots; s++)
           if (mp.pay_mask[s]) pay |= (unsigned long long)((uint32_t)(r4[10 + s] + 1) & mp.pay_mask[s]) << mp.pay_shift[s];
@@ -187,155 +223,184 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       pay |= ((unsigned long long)L << MULTI_LEN_SHIFT) | ((unsigned long long)(total > L ? 1 : 0) << MULTI_MORE_BIT);
       unsigned long long *myslots = p.slots + ((size_t)(wv & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
       if (lane < MULTI_M) {
-        st_slot(&myslots[2 * lane], (mykey & KEY_BODY_MASK) | tagbits);
+        st_slot(&myslots[2 * lane], (unsigned long long)mykey | tagbits);
         st_slot(&myslots[2 * lane + 1], pay | tagbits);
       }
     }
-    // ---- gather: every (CTA, entry) pair is polled by one thread; all loads of the CTA are in flight together ----
+    PH_MARK(2);
+    // ---- gather: every (CTA, entry) pair is polled by one thread and stays in its registers for the replay ----
+    const int e0 = tid, e1 = tid + LEAN_THREADS;
+    unsigned long long a0w = 0ull, b0 = 0ull, a1w = 0ull, b1 = 0ull;
     {
       const unsigned long long *base = p.slots + (size_t)(wv & 1) * CCSIM_MAX_GRID * SLOT_STRIDE;
       const int tot = p.grid * MULTI_M;
-      const int e0 = tid, e1 = tid + LEAN_THREADS;
+      // (1) one lane per CTA line waits for that line's first key word — 148 pollers per line grid-wide, as in the lean kernel;
+      //     letting all 768 threads spin on their own entries (1184 pollers per line) delays the very stores they wait for
+      if (warp < (p.grid + 31) / 32) {
+        const int c = warp * 32 + lane;
+        unsigned spins = 0;
+        bool pending;
+        do {
+          pending = (c < p.grid) && ((uint32_t)(ld_slot(base + (size_t)c * SLOT_STRIDE) >> KEY_TAG_SHIFT) != tag);
+          if (++spins > WATCHDOG_SPINS) { ms.dead = 1; break; }
+        } while (__any_sync(0xffffffffu, pending));
+      }
+      __syncthreads();
+      // (2) every thread fetches its entries; words of a line are separate stores, so each is still validated by its own tag
       bool need0 = e0 < tot, need1 = e1 < tot;
-      unsigned long long a0 = 0, b0 = 0, a1 = 0, b1 = 0;
       unsigned spins = 0;
-      while (need0 | need1) {
-        if (need0) ld_slot2(base + (size_t)(e0 >> 3) * SLOT_STRIDE + 2 * (e0 & 7), a0, b0);
-        if (need1) ld_slot2(base + (size_t)(e1 >> 3) * SLOT_STRIDE + 2 * (e1 & 7), a1, b1);
-        if (need0 && (uint32_t)(a0 >> KEY_TAG_SHIFT) == tag && (uint32_t)(b0 >> KEY_TAG_SHIFT) == tag) {
-          need0 = false; ms.gkey[e0 >> 3][e0 & 7] = a0 & KEY_BODY_MASK; ms.gpay[e0 >> 3][e0 & 7] = b0 & KEY_BODY_MASK;
-        }
-        if (need1 && (uint32_t)(a1 >> KEY_TAG_SHIFT) == tag && (uint32_t)(b1 >> KEY_TAG_SHIFT) == tag) {
-          need1 = false; ms.gkey[e1 >> 3][e1 & 7] = a1 & KEY_BODY_MASK; ms.gpay[e1 >> 3][e1 & 7] = b1 & KEY_BODY_MASK;
-        }
+      while ((need0 | need1) && !ms.dead) {
+        if (need0) ld_slot2(base + (size_t)(e0 >> 3) * SLOT_STRIDE + 2 * (e0 & 7), a0w, b0);
+        if (need1) ld_slot2(base + (size_t)(e1 >> 3) * SLOT_STRIDE + 2 * (e1 & 7), a1w, b1);
+        if (need0 && (uint32_t)(a0w >> KEY_TAG_SHIFT) == tag && (uint32_t)(b0 >> KEY_TAG_SHIFT) == tag) need0 = false;
+        if (need1 && (uint32_t)(a1w >> KEY_TAG_SHIFT) == tag && (uint32_t)(b1 >> KEY_TAG_SHIFT) == tag) need1 = false;
         if (++spins > WATCHDOG_SPINS) { ms.dead = 1; break; }
       }
+      if (need0 | need1) { a0w = b0 = a1w = b1 = 0ull; }
+      b0 &= KEY_BODY_MASK; b1 &= KEY_BODY_MASK;
+      if (e0 >= tot) { a0w = 0ull; b0 = 0ull; }
+      if (e1 >= tot) { a1w = 0ull; b1 = 0ull; }
     }
-    __syncthreads();                                                    // S2
-    if (warp == 0) {
-      // ---- replay: the reference cycles k, k+1, ... this wave can decide (identical in every CTA) ----
+    const uint32_t a0 = (uint32_t)a0w, a1 = (uint32_t)a1w;      // compact keys (the tag sits above bit 44)
+    // counter cells each of my candidates depends on (-1: the node lacks the key and the term lets it pass)
+    int32_t i0[MULTI_GT], i1[MULTI_GT];
+    const int n_gt = ms.n_gt;
+    const bool has1 = (e1 & ~31) < p.grid * MULTI_M;
+    #pragma unroll
+    for (int q = 0; q < MULTI_GT; q++) {
+      i0[q] = -1; i1[q] = -1;
+      if (q < n_gt) {
+        const LeanTerm lt = ls.terms[ms.gt_term[q]];
+        const uint32_t sh = ms.gt_shift[q], mk = ms.gt_mask[q];
+        const int32_t v0 = (int32_t)((uint32_t)(b0 >> sh) & mk) - 1;
+        i0[q] = v0 >= 0 ? lt.cnt_off + v0 : -1;
+        if (has1) {          // warp-uniform: only the first grid*8 - 768 threads hold a second candidate
+          const int32_t v1 = (int32_t)((uint32_t)(b1 >> sh) & mk) - 1;
+          i1[q] = v1 >= 0 ? lt.cnt_off + v1 : -1;
+        }
+      }
+    }
+    PH_MARK(3);
+    // ---- replay: the reference cycles k, k+1, ... this wave can decide; every CTA does the same, all threads take part ----
+    // Each round: every thread re-checks its (<= 2) candidates against the CTA's counter replicas (a candidate that fails is
+    // dropped for the rest of the wave: monotone), block arg-max over the survivors, the thread holding the maximum commits.
+    bool live0 = a0 != 0u, live1 = a1 != 0u;
+    uint32_t bar = 0u;      // highest "last published key" of a list that ran dry while its CTA has more nodes
+    int32_t acc = 0;
+    const int L0 = (int)((b0 >> MULTI_LEN_SHIFT) & 15ull), L1 = (int)((b1 >> MULTI_LEN_SHIFT) & 15ull);
+    const bool more0 = (b0 >> MULTI_MORE_BIT) & 1ull, more1 = (b1 >> MULTI_MORE_BIT) & 1ull;
+    const unsigned grp = 0xffu << (lane & ~7);
+    __syncthreads();                                                    // S2: ms.dead, the counters of the previous wave's recount
+    const bool dead = ms.dead != 0;
+    // Round 0 needs no check: every published candidate passed the scan under the very counts the replicas hold now. After a
+    // commit only the candidates sitting in a counter cell that has just gone over its limit die; the committing warp
+    // names those cells (ms.full), everybody else compares. A warp whose candidates did not change keeps its maxima.
+    uint32_t wm = 0u, wb = 0u;
+    bool refresh = true;                 // warp-uniform: recompute this warp's maxima
+    for (int round = 0; !dead; round++) {
+      if (round > 0) {
+        bool died = false;
+        #pragma unroll
+        for (int q = 0; q < MULTI_GT; q++) {
+          if (q < n_gt) {
+            const int32_t f = (int32_t)lds_u32(msb + MS_OFF(full) + 4u * q);
+            if (f >= 0) {
+              if (live0 && i0[q] == f) { live0 = false; died = true; }
+              if (has1 && live1 && i1[q] == f) { live1 = false; died = true; }
+            }
+          }
+        }
+        refresh |= __any_sync(0xffffffffu, died);
+      }
+      if (refresh) {
+        const uint32_t v0 = live0 ? a0 : 0u, v1 = live1 ? a1 : 0u;
+        // a list (8 consecutive lanes) without a live entry whose CTA has unpublished feasible nodes: those rank below its last key
+        const unsigned bal0 = __ballot_sync(0xffffffffu, live0), bal1 = __ballot_sync(0xffffffffu, live1);
+        if (!(bal0 & grp) && more0 && (e0 & 7) == L0 - 1) bar = a0 > bar ? a0 : bar;
+        if (!(bal1 & grp) && more1 && (e1 & 7) == L1 - 1) bar = a1 > bar ? a1 : bar;
+        wm = __reduce_max_sync(0xffffffffu, v0 > v1 ? v0 : v1);
+        wb = __reduce_max_sync(0xffffffffu, bar);
+        if (lane == 0) { sts_u32(msb + MS_OFF(rmax) + 4u * warp, wm); sts_u32(msb + MS_OFF(rbar) + 4u * warp, wb); }
+        refresh = false;
+      }
+      __syncthreads();                                                  // A
+#ifdef CCSIM_PHASE_TIMERS
+      if (round == 0) { PH_MARK(1); } else { PH_MARK(6); }
+#endif
+      const uint32_t g = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? lds_u32(msb + MS_OFF(rmax) + 4u * lane) : 0u);
+      const uint32_t gb = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? lds_u32(msb + MS_OFF(rbar) + 4u * lane) : 0u);
+      if (g == 0u || g < gb) break;            // block-uniform: nothing left, or an unpublished node could rank above g
+      if (wm == g) {      // warp-uniform: this warp holds the winner; it commits like the lean kernel's warp 0 does
+        // ---- commit pod k+acc (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
+        const bool own0 = live0 && a0 == g, own1 = live1 && a1 == g;
+        const int ol = __ffs(__ballot_sync(0xffffffffu, own0 | own1)) - 1;
+        const unsigned long long pay = __shfl_sync(0xffffffffu, own0 ? b0 : b1, ol);
+        if (own0) live0 = false;
+        if (own1) live1 = false;
+        // Only what the next round depends on happens here: the counter cells of the winner's domains (lane q = term q; the
+        // host guarantees one term per incremented replicated counter), whether a cell went over its limit, whether a PTS
+        // minimum moved. The winner's row (NodeInfo.update, node-local counters) is brought up to date after the last round.
+        bool minchg = false;
+        if (lane < n_gt) {
+          const int4 gc = *reinterpret_cast<const int4 *>(&ms.gt_commit[lane][0]);   // {cnt_off, inc, pts_idx, n_present}
+          const int32_t lim = ls.terms[ms.gt_term[lane]].lim;
+          const int32_t v = (int32_t)((uint32_t)(pay >> ms.gt_shift[lane]) & ms.gt_mask[lane]) - 1;
+          int32_t fullcell = -2;
+          if (v >= 0) {
+            const int32_t old = smem_cnt[gc.x + v], nv = old + gc.y;
+            smem_cnt[gc.x + v] = nv;
+            if (nv > lim) fullcell = gc.x + v;             // candidates in this cell are dead from now on
+            if (gc.y && gc.z >= 0 && v < gc.w && old == ls.ptsmin[gc.z]) {
+              const int32_t left = ls.ptsnum[gc.z] - 1;
+              ls.ptsnum[gc.z] = left;
+              minchg = left <= 0;                          // the global minimum of this constraint moves: limits change, rescan
+            }
+          }
+          ms.full[lane] = fullcell;
+        }
+        bool stopb = __any_sync(0xffffffffu, minchg);
+        stopb |= (p.max_pods > 0 && k + acc + 1 >= p.max_pods);
+        stopb |= (k + acc + 1 >= p.pod_cap) | (acc + 1 >= MULTI_MAX_ACC);
+        if (lane == 0) { ms.stopb = stopb ? 1 : 0; ms.acc_node[acc] = ckey_index(g); }
+        refresh = true;
+      }
+      acc++;
+      __syncthreads();                                                  // B: counters, ms.stopb
+      PH_MARK(7);
+      if (lds_u32(msb + MS_OFF(stopb))) break;
+    }
+    __syncthreads();     // every thread has left the loop (some after barrier A, some after B)
+    // ClusterCapacityBinder.Bind + postBindHook: pod k+i -> node (plugin.go:34-53; simulator.go:297-312). Every CTA knows the
+    // whole list; CTA 0 records it.
+    if (cta == 0 && tid < acc && k + tid < p.pod_cap) p.pod_node[k + tid] = ms.acc_node[tid];
+    // ---- assume -> AssumePod -> NodeInfo.update(+1) (schedule_one.go:967-984, types.go:409-427) for the winners this CTA owns:
+    //      one thread per accepted pod (a node is accepted at most once per wave) ----
+    if (tid < acc) {
       const ccsim_template &t = ls.tmpl;
-      unsigned long long headk[CCSIM_MAX_GRID / 32];
-      int32_t ptrs[CCSIM_MAX_GRID / 32], lens[CCSIM_MAX_GRID / 32], mores[CCSIM_MAX_GRID / 32];
-      #pragma unroll
-      for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) {
-        const int c = lane + 32 * q;
-        ptrs[q] = 0; lens[q] = 0; mores[q] = 0; headk[q] = 0ull;
-        if (c < p.grid) {
-          const unsigned long long meta = ms.gpay[c][0];
-          lens[q] = (int32_t)((meta >> MULTI_LEN_SHIFT) & 15ull);
-          mores[q] = (int32_t)((meta >> MULTI_MORE_BIT) & 1ull);
-          headk[q] = lens[q] > 0 ? ms.gkey[c][0] : 0ull;
+      const int32_t w = ms.acc_node[tid] - p.node_base;
+      if (w >= lo && w < hi) {
+        const int32_t jw = w - lo;
+        const long long rc = c_rcpu[jw] + t.req_cpu, rm = c_rmem[jw] + t.req_mem;
+        const int32_t np = c_npods[jw] + 1;
+        c_rcpu[jw] = rc; c_rmem[jw] = rm; c_zcpu[jw] += t.nz_cpu; c_zmem[jw] += t.nz_mem; c_npods[jw] = np;
+        unsigned long long *r8 = reinterpret_cast<unsigned long long *>(rec + (size_t)jw * su);
+        int32_t *r4 = reinterpret_cast<int32_t *>(r8);
+        r8[2] = (unsigned long long)(c_acpu[jw] - rc);
+        r8[3] = (unsigned long long)(c_amem[jw] - rm);
+        r4[8] = c_apods[jw] - np;
+        r4[9] = -1;            // this node's NodeInfo generation changed: its memoised score is stale
+        for (int j = 0; j < p.n_counters; j++) {
+          const CommitInfo ci = ls.cinfo[j];
+          if (ci.inc && ci.local) r4[10 + lp.counter_slot[j]] += ci.inc;   // node-local counters (written back when the run ends)
         }
       }
-      const int32_t n_cmp = ls.n_cmp_terms;
-      int32_t acc = 0;
-      const bool dead = ms.dead != 0;
-      unsigned long long barrier = 0ull;      // highest "last published key" of a CTA whose list ran out while it has more nodes
-      while (!dead) {
-        // prune: a candidate that is infeasible under the current counts stays infeasible for the rest of the wave
-        // (monotone), so every lane drops such heads of its own lists at once, whatever their rank
-        #pragma unroll
-        for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) {
-          const int c = lane + 32 * q;
-          while (ptrs[q] < lens[q]) {
-            const unsigned long long py = ms.gpay[c][ptrs[q]];
-            bool bad = false;
-            for (int tq = 0; tq < n_cmp; tq++) {
-              const LeanTerm lt = ls.terms[tq];
-              if (lt.cnt_off < 0) continue;
-              const int sl = lt.slot - 10;
-              const int32_t v = (int32_t)((uint32_t)(py >> mp.pay_shift[sl]) & mp.pay_mask[sl]) - 1;
-              const bool has = v >= 0;
-              const int32_t cv = smem_cnt[lt.cnt_off + (has ? v : 0)];
-              bad |= has ? (cv > lt.lim) : (lt.miss_rejects != 0);
-            }
-            if (!bad) break;
-            ptrs[q]++;
-          }
-          if (ptrs[q] < lens[q]) headk[q] = ms.gkey[c][ptrs[q]];
-          else {
-            headk[q] = 0ull;
-            if (mores[q] && lens[q] > 0) { const unsigned long long lastk = ms.gkey[c][lens[q] - 1]; barrier = lastk > barrier ? lastk : barrier; }
-          }
-        }
-        unsigned long long h = 0ull; int hq = 0;
-        #pragma unroll
-        for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) if (headk[q] > h) { h = headk[q]; hq = q; }
-        const unsigned long long g = warp_max_u64(h);
-        if (g == 0ull) break;                                   // every published list is used up
-        // nodes a CTA did not publish have smaller keys than its last published one: g is the true maximum only above that
-        if (g < warp_max_u64(barrier)) break;
-        const int ol = __ffs(__ballot_sync(0xffffffffu, h == g)) - 1;
-        unsigned long long pay = 0ull;
-        if (lane == ol) {
-          const int c = lane + 32 * hq;
-          #pragma unroll
-          for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) if (q == hq) { pay = ms.gpay[c][ptrs[q]]; ptrs[q]++; }
-        }
-        pay = __shfl_sync(0xffffffffu, pay, ol);
-        bool stop_batch = false;
-        {
-          // ---- commit pod k+acc (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
-          const int32_t gi = (int32_t)key_index(g);
-          const int32_t w = gi - p.node_base;
-          const bool mine = (w >= lo && w < hi);
-          const int32_t jw = w - lo;
-          if (mine && lane == 31) {
-            const long long rc = c_rcpu[jw] + t.req_cpu, rm = c_rmem[jw] + t.req_mem;
-            const long long zc = c_zcpu[jw] + t.nz_cpu, zm = c_zmem[jw] + t.nz_mem;
-            const int32_t np = c_npods[jw] + 1;
-            c_rcpu[jw] = rc; c_rmem[jw] = rm; c_zcpu[jw] = zc; c_zmem[jw] = zm; c_npods[jw] = np;
-            unsigned long long *r8 = reinterpret_cast<unsigned long long *>(rec + (size_t)jw * su);
-            int32_t *r4 = reinterpret_cast<int32_t *>(r8);
-            r8[2] = (unsigned long long)(c_acpu[jw] - rc);
-            r8[3] = (unsigned long long)(c_amem[jw] - rm);
-            r4[8] = c_apods[jw] - np;
-            r4[9] = -1;
-            p.req_cpu[w] = rc; p.req_mem[w] = rm; p.nz_cpu[w] = zc; p.nz_mem[w] = zm; p.npods[w] = np;   // write through
-            if (k + acc < p.pod_cap) p.pod_node[k + acc] = gi; else ls.stop = 3;
-          }
-          bool minchg = false;
-          if (lane < p.n_counters) {
-            const int j = lane;
-            const CommitInfo ci = ls.cinfo[j];
-            if (ci.inc) {
-              const int s = lp.counter_slot[j];
-              if (ci.local) {
-                if (mine) {
-                  int32_t *r4 = reinterpret_cast<int32_t *>(rec + (size_t)jw * su);
-                  const int32_t nv = r4[10 + s] + ci.inc;
-                  r4[10 + s] = nv;
-                  p.counters[j].work[w] = nv;
-                }
-              } else {
-                const int32_t dom = (int32_t)((uint32_t)(pay >> mp.pay_shift[s]) & mp.pay_mask[s]) - 1;
-                if (dom >= 0) {
-                  int32_t *cnt = smem_cnt + p.counters[j].smem_off;
-                  const int32_t old = cnt[dom];
-                  cnt[dom] = old + ci.inc;
-                  if (ci.pts_idx >= 0 && dom < ci.n_present && old == ls.ptsmin[ci.pts_idx]) {
-                    const int32_t left = ls.ptsnum[ci.pts_idx] - 1;
-                    ls.ptsnum[ci.pts_idx] = left;
-                    minchg = left <= 0;          // the global minimum of this constraint moves: limits change, rescan
-                  }
-                }
-              }
-            }
-          }
-          acc++;
-          stop_batch |= __any_sync(0xffffffffu, minchg);
-          stop_batch |= (p.max_pods > 0 && k + acc >= p.max_pods);
-          stop_batch |= (k + acc >= p.pod_cap);
-        }
-        __syncwarp();
-        if (stop_batch) break;
-      }
-      // a PTS minimum moved: recount it here (warp 0 owns the counters during the replay) and move the term's limit, instead
-      // of a block-wide recount + rebuild of all Filter constants (filtering.go:56-69,98-137: minMatchNum / criticalPaths)
-      __syncwarp();
+    }
+    if (warp == 0) {
+      const ccsim_template &t = ls.tmpl;
+      // a PTS minimum moved: recount it here and move the term's limit, instead of a block-wide recount + rebuild of all
+      // Filter constants (filtering.go:56-69,98-137: minMatchNum / criticalPaths)
       for (int c = 0; c < t.n_pts; c++) {
-        if (t.pts[c].min_zero || ls.ptsnum[c] > 0) continue;       // uniform: shared memory, written before the __syncwarp
+        if (t.pts[c].min_zero || ls.ptsnum[c] > 0) continue;
         const DevCounter &dc = p.counters[t.pts[c].counter];
         if (dc.n_present <= 0) continue;
         const int32_t *cnt = smem_cnt + dc.smem_off;
@@ -356,11 +421,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       }
       if (lane == 0) {
         ms.accepted = acc;
+        ms.stopb = 0;
         if (dead) ls.stop = 3;
         else if (acc == 0) ls.stop = 1;          // no feasible node anywhere: the pod is unschedulable
       }
     }
+    PH_MARK(4);
     __syncthreads();                                                    // S3
+    PH_MARK(5);
     k += ms.accepted;
     if (ls.stop) break;
     for (int c = 0; c < ls.tmpl.n_pts; c++)
@@ -369,6 +437,13 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     tag = (p.epoch << 12) | wtag;
   }
 
+  // ---- write the tile back: the global columns are the snapshot-after-run (terminal diagnosis, ccsim_node_counts) ----
+  for (int32_t j = tid; j < cnt_nodes; j += LEAN_THREADS) {
+    const int32_t i = lo + j;
+    p.req_cpu[i] = c_rcpu[j]; p.req_mem[i] = c_rmem[j]; p.nz_cpu[i] = c_zcpu[j]; p.nz_mem[i] = c_zmem[j]; p.npods[i] = c_npods[j];
+    const int32_t *r4 = reinterpret_cast<const int32_t *>(rec + (size_t)j * su);
+    for (int sl = 0; sl < lp.n_slots; sl++) if (lp.slot_topo[sl] < 0) p.counters[lp.slot_counter[sl]].work[i] = r4[10 + sl];
+  }
   if (cta == 0) {
     for (int j = 0; j < p.n_counters; j++) {
       const DevCounter &dc = p.counters[j];
@@ -385,6 +460,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       o->examined = o->evals;
       for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ls.ptsmin[c];
       o->aff_total = ls.aff_total;
+#ifdef CCSIM_PHASE_TIMERS
+      for (int q = 0; q < 8; q++) o->phase_cycles[q] = ph[q];
+#endif
     }
   }
 }
