@@ -268,6 +268,7 @@ def main():
     t_total = sum(step_wall)
     # ---- end-to-end arm: host buffers -> C-ABI -> results on the host, everything inside the timed region ----
     e2e_wall = []
+    e2e_parts = [0.0, 0.0, 0.0]
     e2e_evals = 0
     d2h = 0
     for it in range(args.steps + 1):
@@ -276,11 +277,14 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         eng.load_nodes(psnap)          # H2D of every column of this rank's shard (pinned source)
+        ta = time.perf_counter()
         eng.set_templates(tmpl, ctr)   # H2D of the template table + per-domain counters
+        tb = time.perf_counter()
         r2 = eng.run(0)                # run + D2H of pod->node, histogram, counters
         torch.cuda.synchronize()
         if it > 0:                     # first iteration warms the allocator
             e2e_wall.append(time.perf_counter() - t0)
+            e2e_parts[0] += ta - t0; e2e_parts[1] += tb - ta; e2e_parts[2] += time.perf_counter() - tb
             e2e_evals += ref_equivalent_evals(r2)
             d2h = r2.placed * 4 + abi.C.sizeof(abi.Result)
     barrier()
@@ -318,7 +322,9 @@ def main():
             "physical_evals_per_sec": phys_all / t_total,
             "kernel_ms_per_step": kernel_ms / args.steps,
             "e2e": {"value": e2e_evals_all / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_bytes + ctr_bytes + len(tmpl) * abi.C.sizeof(abi.Template)),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3,
+                    "breakdown_ms_per_step": {"ccsim_load_nodes": e2e_parts[0] / args.steps * 1e3, "ccsim_set_templates": e2e_parts[1] / args.steps * 1e3,
+                                              "ccsim_run": e2e_parts[2] / args.steps * 1e3}},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

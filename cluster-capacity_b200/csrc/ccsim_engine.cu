@@ -22,6 +22,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <dlfcn.h>
+#include <map>
 #include <string>
 #include <vector>
 #include "ccsim_device.cuh"
@@ -723,6 +724,8 @@ struct ccsim_handle {
   int last_lean = 0;
   int last_batched = 0;
   int last_multi = 0;
+  std::vector<std::pair<void *, size_t>> block_cache;   // freed device blocks kept for reuse (exact size match)
+  std::map<void *, size_t> block_bytes;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -786,12 +789,19 @@ static int fail(ccsim_handle *h, int code, const char *fmt, ...) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, CCSIM_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+// Device blocks are recycled per handle: ccsim_load_nodes / ccsim_set_templates are called once per analysis by the host side,
+// usually with the same shapes as the last time, and cudaMalloc/cudaFree are slow, synchronising driver calls.
 template <typename T> static int dev_alloc(ccsim_handle *h, std::vector<void *> &pool, T **out, size_t count) {
   void *p = nullptr;
   size_t bytes = (count ? count : 1) * sizeof(T);
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e != cudaSuccess) return fail(h, CCSIM_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  for (size_t i = 0; i < h->block_cache.size(); i++)
+    if (h->block_cache[i].second == bytes) { p = h->block_cache[i].first; h->block_cache.erase(h->block_cache.begin() + i); break; }
+  if (!p) {
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(h, CCSIM_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  }
   pool.push_back(p);
+  h->block_bytes[p] = bytes;
   *out = (T *)p;
   return 0;
 }
@@ -801,7 +811,20 @@ template <typename T> static int dev_upload(ccsim_handle *h, std::vector<void *>
   if (count) CK(cudaMemcpyAsync(*out, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
-static void free_pool(std::vector<void *> &pool) { for (void *p : pool) cudaFree(p); pool.clear(); }
+// blocks of a pool go back to the handle's cache (the stream is drained first: they may still be in use)
+static void free_pool(ccsim_handle *h, std::vector<void *> &pool) {
+  if (pool.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  size_t cached = 0;
+  for (auto &b : h->block_cache) cached += b.second;
+  for (void *p : pool) {
+    const size_t bytes = h->block_bytes[p];
+    if (cached + bytes <= ((size_t)1 << 31)) { h->block_cache.push_back({p, bytes}); cached += bytes; }   // keep at most 2 GiB around
+    else { cudaFree(p); h->block_bytes.erase(p); }
+  }
+  pool.clear();
+}
+static void drop_cache(ccsim_handle *h) { for (auto &b : h->block_cache) cudaFree(b.first); h->block_cache.clear(); h->block_bytes.clear(); }
 
 extern "C" int ccsim_abi_version(void) { return CCSIM_ABI_VERSION; }
 
@@ -856,7 +879,7 @@ extern "C" void ccsim_destroy(ccsim_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
-  free_pool(h->allocs); free_pool(h->tmpl_allocs);
+  free_pool(h, h->allocs); free_pool(h, h->tmpl_allocs); drop_cache(h);
   for (int r = 0; r < CCSIM_MAX_WORLD; r++) if (h->x_peer[r] && r != h->cfg.rank) cudaIpcCloseMemHandle(h->x_peer[r]);
   cudaFree(h->d_xslots);
   cudaFree(h->d_out); cudaFree(h->d_params); cudaFree(h->d_slots); cudaFree(h->d_pod_node); cudaFree(h->d_flush);
@@ -872,7 +895,7 @@ extern "C" int ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nd) {
       nd->n_topo_cols < 0 || nd->n_topo_cols > CCSIM_MAX_TOPO_COLS)
     return fail(h, CCSIM_EINVAL, "ccsim_nodes dimensions out of range");
   CK(cudaSetDevice(h->cfg.device));
-  free_pool(h->allocs);
+  free_pool(h, h->allocs);
   h->have_nodes = false; h->have_templates = false;
   const int32_t N = nd->n_nodes;
   // node-axis shard of this rank: contiguous block of the nodeTree order
@@ -952,7 +975,7 @@ extern "C" int ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const c
   if (n_templates > 1 && n_counters > 0)
     return fail(h, CCSIM_EUNSUPPORTED, "PodTopologySpread/InterPodAffinity templates are single-template only");
   CK(cudaSetDevice(h->cfg.device));
-  free_pool(h->tmpl_allocs);
+  free_pool(h, h->tmpl_allocs);
   h->have_templates = false;
   const ccsim_nodes &nd = h->meta;
   for (int t = 0; t < n_templates; t++) {
@@ -1248,8 +1271,9 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
       if (shift + bits > MULTI_PAY_BITS) { multi = false; break; }
       mp.pay_shift[sl] = shift; mp.pay_mask[sl] = (1u << bits) - 1u; shift += bits;
     }
-    if (smem + sizeof(LeanShared) + sizeof(MultiShared) + 1024 > h->smem_optin) multi = false;
-    if (multi) kern = (const void *)ccsim_wave_multi_kernel;
+    const size_t smem_m = smem + (size_t)p.chunk_pad * 8 + 16;     // + the per-node payload column
+    if (smem_m + sizeof(LeanShared) + sizeof(MultiShared) + 1024 > h->smem_optin) multi = false;
+    if (multi) { kern = (const void *)ccsim_wave_multi_kernel; smem = smem_m; }
   }
   h->last_multi = multi ? 1 : 0;
   p.self = h->d_params;

@@ -32,6 +32,7 @@
 
 struct __align__(16) MultiShared {
   uint32_t wtop[LEAN_WARPS][MULTI_M];               // per-warp top-M (compact) keys of this wave
+  int32_t gt_c1[MULTI_GT][4];                       // (16-byte aligned) ... and {limit, payload shift, payload mask, counter base}
   int32_t gt_commit[MULTI_GT][4];                   // (16-byte aligned) per replicated-counter term: {counter base, inc, PTS constraint tracked or -1, n_present}
   uint32_t rmax[LEAN_WARPS], rbar[LEAN_WARPS];      // replay: per-warp maxima of a round
   int32_t wfeas[LEAN_WARPS];
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
   long long *c_amem = c_acpu + cp, *c_rcpu = c_amem + cp, *c_rmem = c_rcpu + cp, *c_zcpu = c_rmem + cp, *c_zmem = c_zcpu + cp;
   int32_t *c_apods = reinterpret_cast<int32_t *>(c_zmem + cp);
   int32_t *c_npods = c_apods + cp;
+  unsigned long long *c_pay = reinterpret_cast<unsigned long long *>(c_npods + cp);   // (chunk_pad is a multiple of 4: 8-byte aligned)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
@@ -104,6 +106,11 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     c_acpu[j] = ac; c_amem[j] = am; c_rcpu[j] = rc; c_rmem[j] = rm;
     c_zcpu[j] = p.nz_cpu[i]; c_zmem[j] = p.nz_mem[i];
     c_apods[j] = ap; c_npods[j] = np;
+    // the node's payload for the candidate exchange: domain id + 1 of every topology slot (static: labels do not change)
+    unsigned long long py = 0ull;
+    for (int s = 0; s < lp.n_slots; s++)
+      if (mp.pay_mask[s]) py |= (unsigned long long)((uint32_t)(r4[10 + s] + 1) & mp.pay_mask[s]) << mp.pay_shift[s];
+    c_pay[j] = py;
   }
   for (int k = tid; k < (int)(sizeof(ccsim_template) / 8); k += LEAN_THREADS)
     reinterpret_cast<unsigned long long *>(&ls.tmpl)[k] = reinterpret_cast<const unsigned long long *>(&p.templates[0])[k];
@@ -134,6 +141,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           if (ls.terms[q].cnt_off >= 0 && g < MULTI_GT) {
             const int sl = ls.terms[q].slot - 10;
             ms.gt_shift[g] = mp.pay_shift[sl]; ms.gt_mask[g] = mp.pay_mask[sl];
+            ms.gt_c1[g][0] = ls.terms[q].lim; ms.gt_c1[g][1] = (int32_t)mp.pay_shift[sl]; ms.gt_c1[g][2] = (int32_t)mp.pay_mask[sl]; ms.gt_c1[g][3] = ls.terms[q].cnt_off;
             ms.gt_commit[g][0] = ls.terms[q].cnt_off; ms.gt_commit[g][1] = 0; ms.gt_commit[g][2] = -1; ms.gt_commit[g][3] = 0;
             for (int j = 0; j < p.n_counters; j++)
               if (p.counters[j].topo_col >= 0 && p.counters[j].smem_off == ls.terms[q].cnt_off) {
@@ -214,12 +222,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         L = r + 1;
       }
       unsigned long long pay = 0ull;
-      if (lane < L) {
-        const int32_t jj = ckey_index(mykey) - (p.node_base + lo);
-        const int32_t *r4 = reinterpret_cast<const int32_t *>(rec + (size_t)jj * su);
-        for (int s = 0; s < lp.n_slots; s++)
-          if (mp.pay_mask[s]) pay |= (unsigned long long)((uint32_t)(r4[10 + s] + 1) & mp.pay_mask[s]) << mp.pay_shift[s];
-      }
+      if (lane < L) pay = c_pay[ckey_index(mykey) - (p.node_base + lo)];
       pay |= ((unsigned long long)L << MULTI_LEN_SHIFT) | ((unsigned long long)(total > L ? 1 : 0) << MULTI_MORE_BIT);
       unsigned long long *myslots = p.slots + ((size_t)(wv & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
       if (lane < MULTI_M) {
@@ -270,13 +273,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     for (int q = 0; q < MULTI_GT; q++) {
       i0[q] = -1; i1[q] = -1;
       if (q < n_gt) {
-        const LeanTerm lt = ls.terms[ms.gt_term[q]];
-        const uint32_t sh = ms.gt_shift[q], mk = ms.gt_mask[q];
-        const int32_t v0 = (int32_t)((uint32_t)(b0 >> sh) & mk) - 1;
-        i0[q] = v0 >= 0 ? lt.cnt_off + v0 : -1;
+        const int4 c1 = *reinterpret_cast<const int4 *>(&ms.gt_c1[q][0]);      // {lim, shift, mask, counter base}
+        const int32_t v0 = (int32_t)((uint32_t)(b0 >> c1.y) & (uint32_t)c1.z) - 1;
+        i0[q] = v0 >= 0 ? c1.w + v0 : -1;
         if (has1) {          // warp-uniform: only the first grid*8 - 768 threads hold a second candidate
-          const int32_t v1 = (int32_t)((uint32_t)(b1 >> sh) & mk) - 1;
-          i1[q] = v1 >= 0 ? lt.cnt_off + v1 : -1;
+          const int32_t v1 = (int32_t)((uint32_t)(b1 >> c1.y) & (uint32_t)c1.z) - 1;
+          i1[q] = v1 >= 0 ? c1.w + v1 : -1;
         }
       }
     }
@@ -343,8 +345,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         bool minchg = false;
         if (lane < n_gt) {
           const int4 gc = *reinterpret_cast<const int4 *>(&ms.gt_commit[lane][0]);   // {cnt_off, inc, pts_idx, n_present}
-          const int32_t lim = ls.terms[ms.gt_term[lane]].lim;
-          const int32_t v = (int32_t)((uint32_t)(pay >> ms.gt_shift[lane]) & ms.gt_mask[lane]) - 1;
+          const int4 c1 = *reinterpret_cast<const int4 *>(&ms.gt_c1[lane][0]);       // {lim, shift, mask, cnt_off}
+          const int32_t lim = c1.x;
+          const int32_t v = (int32_t)((uint32_t)(pay >> c1.y) & (uint32_t)c1.z) - 1;
           int32_t fullcell = -2;
           if (v >= 0) {
             const int32_t old = smem_cnt[gc.x + v], nv = old + gc.y;
@@ -375,9 +378,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     if (cta == 0 && tid < acc && k + tid < p.pod_cap) p.pod_node[k + tid] = ms.acc_node[tid];
     // ---- assume -> AssumePod -> NodeInfo.update(+1) (schedule_one.go:967-984, types.go:409-427) for the winners this CTA owns:
     //      one thread per accepted pod (a node is accepted at most once per wave) ----
-    if (tid < acc) {
+    if (tid >= 32 && tid - 32 < acc) {       // warp 1 (and up): warp 0 recounts PTS minima meanwhile
       const ccsim_template &t = ls.tmpl;
-      const int32_t w = ms.acc_node[tid] - p.node_base;
+      const int32_t w = ms.acc_node[tid - 32] - p.node_base;
       if (w >= lo && w < hi) {
         const int32_t jw = w - lo;
         const long long rc = c_rcpu[jw] + t.req_cpu, rm = c_rmem[jw] + t.req_mem;
@@ -415,6 +418,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           if (t.filter_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) {    // terms[0..n_pts) are the PTS terms, in constraint order
             const long long lim = (long long)t.pts[c].max_skew - t.pts[c].self_match + (long long)m;
             ls.terms[c].lim = lim > INT32_MAX ? INT32_MAX : (lim < INT32_MIN ? INT32_MIN : (int32_t)lim);
+            for (int q = 0; q < ms.n_gt; q++) if (ms.gt_term[q] == c) ms.gt_c1[q][0] = ls.terms[c].lim;
           }
         }
         __syncwarp();
