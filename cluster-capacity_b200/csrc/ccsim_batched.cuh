@@ -108,10 +108,11 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_batched_kernel(con
   const int64_t taint_const = (t.score_enable & CCSIM_PL_TAINT_TOLERATION) ? (int64_t)t.w_taint * 100 : 0;   // maxCount == 0 -> every node 100
 
   long long k = 0, waves = 0, extra_evals = 0;
+  bool limit_hit = false;   // postBindHook's limit (simulator.go:300-305)
   uint32_t wtag = 1;
   uint32_t tag = (p.epoch << 12) | wtag;
   for (;;) {
-    if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ls.stop = 2; __syncthreads(); break; }
+    if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }   // uniform; no shared write (slower threads may still be reading ls.stop)
     if (k > p.pod_cap) { if (tid == 0) ls.stop = 3; __syncthreads(); break; }
     // ---- fused Filter pass over the tile: one predicate-eval per node ----
     unsigned long long best = 0ull;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_batched_kernel(con
   if (cta == 0 && tid == 0) {
     DevOut *o = p.out;
     o->placed = k;
-    o->stop_code = (ls.stop == 2) ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
+    o->stop_code = limit_hit ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
     o->error = (ls.stop == 3) ? 1 : 0;
     o->waves = waves;
     o->evals = waves * (long long)p.n + extra_evals;

@@ -229,13 +229,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0;
 #endif
   long long k = 0;
+  bool limit_hit = false;   // postBindHook's limit (simulator.go:300-305)
   uint32_t wtag = 1;         // 1..4095; waves k and k+2 (same parity buffer) always differ
   uint32_t tag = (p.epoch << 12) | wtag;
   int32_t ti = 0;            // template of pod k = k % n_templates (report.go:160)
   for (;; k++) {
     PH_START();
     // postBindHook limit (pkg/framework/simulator.go:300-305): checked after the k-th pod was bound
-    if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ws.stop = 2; __syncthreads(); break; }
+    if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }   // uniform; no shared write (slower threads may still be reading ws.stop)
     if (k > p.pod_cap) { if (tid == 0) ws.stop = 3; __syncthreads(); break; }   // cannot happen (pod_cap bounds every run): never spin forever
     if (p.n_templates > 1) {
       const ccsim_template *src = &p.templates[ti];
@@ -563,9 +564,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) ccsim_wave_kernel(const DevP
     if (tid == 0) {
       DevOut *o = p.out;
       o->placed = k;
-      o->stop_code = (ws.stop == 2) ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
+      o->stop_code = limit_hit ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
       o->error = (ws.stop == 3) ? 1 : 0;
-      o->waves = (ws.stop == 2) ? k : k + 1;
+      o->waves = limit_hit ? k : k + 1;
       o->evals = o->waves * (long long)p.n;
       for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ws.ptsmin[c];
       o->aff_total = ws.aff_total;

@@ -264,11 +264,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0;
 #endif
   long long k = 0;
+  bool limit_hit = false;   // postBindHook's limit (simulator.go:300-305)
   uint32_t wtag = 1;
   uint32_t tag = (p.epoch << 12) | wtag;
   for (;; k++) {
     PH_START();
-    if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ls.stop = 2; __syncthreads(); break; }
+    if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }   // uniform; no shared write (slower threads may still be reading ls.stop)
     if (k > p.pod_cap) { if (tid == 0) ls.stop = 3; __syncthreads(); break; }   // cannot happen (pod_cap bounds every run): never spin forever
     if (ls.dirty) {   // uniform: set before the last barrier, cleared only after the barrier below (no thread can miss it)
       if (tid == 0) lean_build_consts(p, lp);
@@ -553,9 +554,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_lean_kernel(const 
     if (tid == 0) {
       DevOut *o = p.out;
       o->placed = k;
-      o->stop_code = (ls.stop == 2) ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
+      o->stop_code = limit_hit ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
       o->error = (ls.stop == 3) ? 1 : 0;
-      o->waves = (ls.stop == 2) ? k : k + 1;
+      o->waves = limit_hit ? k : k + 1;
       o->evals = o->waves * (long long)p.n;
       o->examined = FAITHFUL ? ls.examined_total : o->evals;
       for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ls.ptsmin[c];

@@ -127,11 +127,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0;
 #endif
   long long k = 0, wv = 0;
+  bool limit_hit = false;   // postBindHook's limit (simulator.go:300-305)
   uint32_t wtag = 1;
   uint32_t tag = (p.epoch << 12) | wtag;
   for (;; wv++) {
     PH_START();
-    if (p.max_pods > 0 && k >= p.max_pods) { if (tid == 0) ls.stop = 2; __syncthreads(); break; }
+    if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }   // uniform; no shared write (slower threads may still be reading ls.stop)
     if (k > p.pod_cap) { if (tid == 0) ls.stop = 3; __syncthreads(); break; }
     if (ls.dirty) {
       if (tid == 0) {
@@ -457,9 +458,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     if (tid == 0) {
       DevOut *o = p.out;
       o->placed = k;
-      o->stop_code = (ls.stop == 2) ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
+      o->stop_code = limit_hit ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
       o->error = (ls.stop == 3) ? 1 : 0;
-      o->waves = (ls.stop == 2) ? wv : wv + 1;
+      o->waves = limit_hit ? wv : wv + 1;
       o->evals = o->waves * (long long)p.n;
       o->examined = o->evals;
       for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ls.ptsmin[c];
