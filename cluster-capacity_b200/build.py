@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
         subprocess.check_call(cmd)
     newest = max([os.path.getmtime(p) for p in HOST_DEPS] + [os.path.getmtime(OUT)])
     if force or not os.path.exists(HOST_OUT) or os.path.getmtime(HOST_OUT) < newest:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", HOST_OUT] + HOST_SRC +
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-shared", "-fPIC", "-o", HOST_OUT] + HOST_SRC +
                               ["-L" + _HERE, "-lccsim", "-Wl,-rpath,$ORIGIN"])
     return OUT
 

@@ -5,6 +5,9 @@
 #include <cstdarg>
 #include <ctime>
 #include <sstream>
+#include <thread>
+#include <exception>
+#include <cstring>
 #include "../../../include/cchost.h"
 #include "encoder.hpp"
 
@@ -158,7 +161,7 @@ extern "C" int cc_new(const char *sched_config_json, const char *pod_json, int64
   try {
     cc_handle *h = new cc_handle();
     h->cfg = SchedConfig::parse(sched_config_json ? sched_config_json : "");
-    h->tmpl = Pod::parse(parse_json(pod_json));
+    h->tmpl = Pod::parse(parse_json(pod_json), /*keep_raw=*/true);
     h->max_pods = max_pods;
     h->device = device;
     if (exclude_nodes) {
@@ -174,10 +177,96 @@ static std::vector<Json> items_of(const char *text) {
   std::vector<Json> v;
   if (!text || !*text) return v;
   Json j = parse_json(text);
-  if (j.is_array()) v = j.arr;
-  else if (j.at("items").is_array()) v = j.at("items").arr;
-  else if (j.is_object()) v.push_back(j);
+  if (j.is_array()) v = std::move(j.arr);
+  else if (Json *items = const_cast<Json *>(j.find("items")); items && items->is_array()) v = std::move(items->arr);
+  else if (j.is_object()) v.push_back(std::move(j));
   return v;
+}
+
+// ---- snapshot ingest: the LISTed objects arrive as one JSON document per kind; the items are independent,
+// so their spans are located with one string-aware bracket scan and parsed + converted on all host cores. Order is kept
+// (node order feeds nodeTree, node_tree.go:51-67). Documents of another shape take the DOM path. ----
+static size_t skip_ws(const char *t, size_t n, size_t p) { while (p < n && (t[p] == ' ' || t[p] == '\n' || t[p] == '\t' || t[p] == '\r')) p++; return p; }
+static size_t skip_string(const char *t, size_t n, size_t p) {   // p at the opening quote; returns the position after the closing one
+  for (p++; p < n; p++) { if (t[p] == '\\') p++; else if (t[p] == '"') return p + 1; }
+  throw std::runtime_error("json: unterminated string");
+}
+static size_t skip_value(const char *t, size_t n, size_t p) {
+  p = skip_ws(t, n, p);
+  if (p >= n) throw std::runtime_error("json: unexpected end");
+  if (t[p] == '"') return skip_string(t, n, p);
+  if (t[p] == '{' || t[p] == '[') {
+    int depth = 0;
+    for (; p < n; p++) {
+      const char c = t[p];
+      if (c == '"') { p = skip_string(t, n, p) - 1; continue; }
+      if (c == '{' || c == '[') depth++;
+      else if (c == '}' || c == ']') { if (--depth == 0) return p + 1; }
+    }
+    throw std::runtime_error("json: unterminated value");
+  }
+  while (p < n && t[p] != ',' && t[p] != ']' && t[p] != '}' && t[p] != ' ' && t[p] != '\n' && t[p] != '\t' && t[p] != '\r') p++;
+  return p;
+}
+static bool item_spans(const char *t, size_t n, std::vector<std::pair<size_t, size_t>> &out) {
+  size_t p = skip_ws(t, n, 0);
+  if (p >= n) return false;
+  if (t[p] == '{') {          // a List object: find "items" among its members
+    p = skip_ws(t, n, p + 1);
+    bool found = false;
+    while (p < n && t[p] == '"') {
+      const size_t ke = skip_string(t, n, p);
+      const bool is_items = (ke - p == 7) && memcmp(t + p, "\"items\"", 7) == 0;
+      p = skip_ws(t, n, ke);
+      if (p >= n || t[p] != ':') return false;
+      p = skip_ws(t, n, p + 1);
+      if (is_items) { found = (p < n && t[p] == '['); break; }
+      p = skip_ws(t, n, skip_value(t, n, p));
+      if (p < n && t[p] == ',') p = skip_ws(t, n, p + 1);
+    }
+    if (!found) return false;
+  } else if (t[p] != '[') return false;
+  p = skip_ws(t, n, p + 1);
+  if (p < n && t[p] == ']') return true;
+  while (p < n) {
+    const size_t e = skip_value(t, n, p);
+    out.push_back({p, e});
+    p = skip_ws(t, n, e);
+    if (p < n && t[p] == ',') { p = skip_ws(t, n, p + 1); continue; }
+    if (p < n && t[p] == ']') return true;
+    throw std::runtime_error("json: expected , or ] in the item list");
+  }
+  throw std::runtime_error("json: unterminated item list");
+}
+
+template <class T, class F> static std::vector<T> parse_list(const char *text, F one) {
+  std::vector<T> out;
+  if (!text || !*text) return out;
+  const size_t n = strlen(text);
+  std::vector<std::pair<size_t, size_t>> spans;
+  if (!item_spans(text, n, spans)) { for (auto &j : items_of(text)) out.push_back(one(j)); return out; }
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt == 0 ? 1 : (nt > 16 ? 16 : nt);
+  if (spans.size() < 2048) nt = 1;
+  std::vector<std::vector<T>> parts(nt);
+  std::vector<std::exception_ptr> errs(nt);
+  auto work = [&](unsigned c) {
+    try {
+      const size_t per = (spans.size() + nt - 1) / nt, b = std::min(spans.size(), (size_t)c * per), e = std::min(spans.size(), b + per);
+      parts[c].reserve(e - b);
+      for (size_t i = b; i < e; i++) parts[c].push_back(one(parse_json(std::string(text + spans[i].first, spans[i].second - spans[i].first))));
+    } catch (...) { errs[c] = std::current_exception(); }
+  };
+  if (nt == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (unsigned c = 0; c < nt; c++) th.emplace_back(work, c);
+    for (auto &x : th) x.join();
+  }
+  for (auto &e : errs) if (e) std::rethrow_exception(e);
+  out.reserve(spans.size());
+  for (auto &v : parts) for (auto &x : v) out.push_back(std::move(x));
+  return out;
 }
 
 extern "C" int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const char *pods_json, const char *namespaces_json) {
@@ -185,8 +274,14 @@ extern "C" int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const 
   if (h->closed) return fail(h, CC_ESTATE, "closed");
   try {
     h->nodes.clear(); h->pods.clear(); h->ns_labels.clear(); h->workloads.clear();
-    for (auto &j : items_of(nodes_json)) h->nodes.push_back(Node::parse(j));
-    for (auto &j : items_of(pods_json)) h->pods.push_back(Pod::parse(j));
+    const bool timing = getenv("CCHOST_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    h->nodes = parse_list<Node>(nodes_json, [](const Json &j) { return Node::parse(j); });
+    auto t1 = std::chrono::steady_clock::now();
+    h->pods = parse_list<Pod>(pods_json, [](const Json &j) { return Pod::parse(j); });
+    auto t2 = std::chrono::steady_clock::now();
+    if (timing) fprintf(stderr, "[cchost] ingest: %zu nodes %.3f s, %zu pods %.3f s\n", h->nodes.size(), std::chrono::duration<double>(t1 - t0).count(),
+                        h->pods.size(), std::chrono::duration<double>(t2 - t1).count());
     for (auto &j : items_of(namespaces_json)) h->ns_labels[j.at("metadata").at("name").str()] = parse_labels(j.at("metadata").at("labels"));
     h->synced = true; h->have_enc = false; h->ran = false; h->have_report = false;
     return CC_OK;

@@ -230,9 +230,9 @@ struct Pod {
     return k;
   }
 
-  static Pod parse(const Json &j) {
+  static Pod parse(const Json &j, bool keep_raw = false) {
     Pod p;
-    p.raw = j;
+    if (keep_raw) p.raw = j;      // only the simulated pod is echoed back (report.go:60-66); existing pods are not
     const Json &md = j.at("metadata"), &sp = j.at("spec"), &st = j.at("status");
     p.name = md.at("name").str();
     p.ns = md.at("namespace").str("default");
@@ -388,7 +388,6 @@ struct Pod {
 };
 
 struct Node {
-  Json raw;
   std::string name;
   Labels labels;
   bool unschedulable = false;
@@ -399,7 +398,6 @@ struct Node {
 
   static Node parse(const Json &j) {
     Node n;
-    n.raw = j;
     n.name = j.at("metadata").at("name").str();
     n.labels = parse_labels(j.at("metadata").at("labels"));
     n.unschedulable = j.at("spec").at("unschedulable").truthy();

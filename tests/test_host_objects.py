@@ -113,3 +113,35 @@ def test_go_log_matches_libm_to_an_ulp():
     for n in list(range(2, 2000)) + [5000, 100002, 1000002]:
         a, b = objref.go_log(float(n)), math.log(float(n))
         assert abs(a - b) <= math.ulp(b), n
+
+
+def test_ingest_shapes_and_parallel_item_parsing(built):
+    """cc_sync_with_objects takes bare arrays, List objects (whatever the member order) and single objects; big lists are split at
+    item boundaries by a string-aware scan and parsed on several threads — same result, same node order."""
+    import json
+    nodes = [helpers.make_node("n%04d" % i, cpu="2", mem="4Gi", pods="10",
+                               labels={"weird": "a]b}\\\"c[{", "topology.kubernetes.io/zone": "z%d" % (i % 3)}) for i in range(2500)]
+    pods = [helpers.make_pod("p%04d" % j, cpu="500m", mem="1Gi", node="n%04d" % (j % 2500), labels={"items": "[not a list]"}) for j in range(3000)]
+    tmpl = helpers.make_pod("t", cpu="1", mem="1Gi")
+    L = fw.lib()
+
+    def encoded(nodes_doc, pods_doc):
+        cc = fw.New(None, None, tmpl, 0, [])
+        rc = L.cc_sync_with_objects(cc._h, json.dumps(nodes_doc).encode(), json.dumps(pods_doc).encode(), None)
+        assert rc == 0, L.cc_last_error(cc._h)
+        enc = cc.EncodedSnapshot()
+        cc.Close()
+        return enc["names"], enc["nodes"]["req_cpu"], enc["nodes"]["npods"]
+
+    want = encoded(nodes, pods)
+    assert want[0][:4] == ["n0000", "n0001", "n0002", "n0003"] and sum(want[2]) == 3000
+    wrapped_nodes = {"kind": "NodeList", "apiVersion": "v1", "metadata": {"items": ["decoy"], "resourceVersion": "7"}, "items": nodes}
+    wrapped_pods = {"items": pods, "kind": "PodList", "metadata": {}}
+    assert encoded(wrapped_nodes, wrapped_pods) == want
+    one = encoded(nodes[0], [])
+    assert one[0] == ["n0000"]
+    assert encoded([], [])[0] == []
+    cc = fw.New(None, None, tmpl, 0, [])
+    assert L.cc_sync_with_objects(cc._h, b'[{"metadata": {"name": "x"}', b"[]", None) != 0      # truncated document: an error, not a crash
+    assert b"json" in L.cc_last_error(cc._h)
+    cc.Close()
