@@ -15,6 +15,10 @@
 //   (b) a CTA with more feasible nodes than it published has used up its list and the next candidate's key is below that
 //       CTA's last published key (an unpublished node could rank in between),
 //   (c) the pod limit is reached (simulator.go:300-305).
+// One more precondition (host-checked): a committed node must not be able to win again inside the wave — its new score is in nobody's
+// list. The kernel therefore only takes templates whose clone blocks its own node (a self-matching required anti-affinity term on
+// the hostname: count 0 -> 1 > limit 0); a randomized differential test (tests/test_gpu_stress.py) found exactly this hole in
+// the first version. Carrying every candidate's "key after one more clone" in the payload would lift the restriction.
 // The first candidate of a wave is always accepted, so every wave makes progress; a wave without candidates is the
 // Unschedulable stop. Node-local terms (hostname anti-affinity, ...) need no re-check: a node appears once per wave.
 //
