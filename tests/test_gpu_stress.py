@@ -64,3 +64,63 @@ def test_random_coupled_templates(built, seed):
         assert got.placed == want.placed and got.stop_code == want.stop_code, (seed, kind)
         assert np.array_equal(got.pod_node, want.pod_node), (seed, kind)
         assert np.array_equal(got.reason_hist, want.reason_hist), (seed, kind)
+
+
+def random_node_local_case(seed):
+    """Templates whose predicates and scorers are node-local (tie-run batching when there is one template and no
+    PreferNoSchedule class; lean / generic kernels otherwise): taints, tolerations, selector bits, scalar resources,
+    ephemeral storage, best-effort pods, score weights, several templates."""
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.choice([700, 5000, 30000]))
+    a_cpu = rng.choice([1000, 2000, 4000, 8000, 64000], n)
+    a_mem = a_cpu * int(rng.choice([1, 2, 4])) * MiB
+    a_pods = rng.choice([4, 16, 110], n)
+    req_cpu = (rng.random(n) * 0.6 * a_cpu).astype(np.int64) // 10 * 10
+    req_mem = (rng.random(n) * 0.6 * a_mem).astype(np.int64)
+    npods = np.minimum(rng.integers(0, 30, n), a_pods).astype(np.int32)
+    taint = np.zeros(n, np.uint64)
+    for tid in range(4):
+        taint |= (rng.random(n) < 0.08).astype(np.uint64) << np.uint64(tid)
+    prefer_on = rng.random() < 0.4
+    nosched, prefer = (0b0011, 0b1100) if prefer_on else (0b1111, 0)
+    taint |= (rng.random(n) < 0.02).astype(np.uint64) << np.uint64(abi.TAINT_UNSCHEDULABLE_BIT)
+    static = (rng.random(n) < 0.5).astype(np.uint64) | ((rng.random(n) < 0.7).astype(np.uint64) << np.uint64(1))
+    scal = [(rng.integers(0, 9, n).astype(np.int64), rng.integers(0, 3, n).astype(np.int64))] if rng.random() < 0.3 else []
+    snap = abi.Snapshot(n, a_cpu, a_mem, a_pods, alloc_eph=np.full(n, 100 * GiB), req_cpu=req_cpu, req_mem=req_mem, npods=npods,
+                        scalars=scal, taint_mask=taint.reshape(1, n), taint_nosched=[nosched], taint_prefer=[prefer],
+                        static_mask=static.reshape(1, n), taint_lists=[[t for t in range(4) if (int(x) >> t) & 1] for x in taint])
+    tmpl = []
+    for _ in range(int(rng.choice([1, 1, 1, 3]))):
+        t = abi.default_template(int(rng.choice([0, 100, 250, 1500])), int(rng.choice([0, 64, 512])) * MiB)
+        if t.req_cpu == 0 and t.req_mem == 0:
+            t = abi.default_template(0, 0)
+        if rng.random() < 0.5:
+            t.flags |= abi.TF_HAS_NODE_SELECTOR
+            t.sel_mask[0] = int(rng.choice([1, 2, 3]))
+        t.tol_nosched[0] = int(rng.integers(0, 16)) & nosched
+        t.tol_prefer[0] = int(rng.integers(0, 16)) & prefer
+        if scal and rng.random() < 0.7:
+            t.req_scalar[0] = int(rng.integers(1, 3))
+        if rng.random() < 0.2:
+            t.req_eph = int(rng.integers(1, 40)) * GiB
+        if rng.random() < 0.3:
+            t.w_fit, t.w_balanced = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        tmpl.append(t)
+    return snap, tmpl, [], int(rng.choice([0, 0, 0, 57, 333, 5000]))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_node_local_templates(built, seed):
+    snap, tmpl, ctr, limit = random_node_local_case(seed)
+    cap = limit or 6000
+    want = oracle.run(snap, tmpl, ctr, max_pods=cap, threads=8)
+    engine = importlib.import_module("cluster-capacity_b200.engine")
+    for kind in (abi.ENGINE_AUTO, abi.ENGINE_SEQUENTIAL):
+        with engine.Engine(device=0, engine=kind) as eng:
+            eng.load_nodes(snap)
+            eng.set_templates(tmpl, ctr)
+            got = eng.run(cap)
+        assert got.placed == want.placed and got.stop_code == want.stop_code, (seed, kind)
+        assert np.array_equal(got.pod_node, want.pod_node), (seed, kind)
+        assert np.array_equal(got.reason_hist, want.reason_hist), (seed, kind)
+        assert (got.preempt_no_victims, got.preempt_not_helpful) == (want.preempt_no_victims, want.preempt_not_helpful), (seed, kind)
