@@ -1254,13 +1254,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
       if (T.filter_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) for (int c = 0; c < T.n_pts; c++) if (h->counters[T.pts[c].counter].topo_col >= 0) gt++;
       if (T.filter_enable & CCSIM_PL_INTER_POD_AFFINITY) for (int a = 0; a < T.n_anti; a++) if (h->counters[T.anti_counter[a]].topo_col >= 0) gt++;
       if (gt > MULTI_GT) multi = false;
-      // A candidate list is only exact if a committed node cannot win again within the wave (its new score is not in anybody's
-      // list): required when nothing makes the node infeasible after one clone. A self-matching required anti-affinity term on
-      // a node-local (hostname) counter does: count 0 -> 1 > limit 0. Everything else takes the sequential kernel.
-      bool single_use = false;
-      if (T.filter_enable & CCSIM_PL_INTER_POD_AFFINITY)
-        for (int a = 0; a < T.n_anti; a++) if (h->counters[T.anti_counter[a]].topo_col < 0 && h->counters[T.anti_counter[a]].inc > 0) single_use = true;
-      if (!single_use) multi = false;
+      // (a committed node may win again inside a wave: every candidate carries its key after one more clone, MULTI_NEXT_SHIFT)
       // the replay updates counters term by term: every incremented replicated counter must be read by exactly one Filter term
       for (int j = 0; j < h->n_counters; j++) {
         if (h->counters[j].topo_col < 0 || h->counters[j].inc == 0) continue;

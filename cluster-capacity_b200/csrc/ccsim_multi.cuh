@@ -15,10 +15,12 @@
 //   (b) a CTA with more feasible nodes than it published has used up its list and the next candidate's key is below that
 //       CTA's last published key (an unpublished node could rank in between),
 //   (c) the pod limit is reached (simulator.go:300-305).
-// One more precondition (host-checked): a committed node must not be able to win again inside the wave — its new score is in nobody's
-// list. The kernel therefore only takes templates whose clone blocks its own node (a self-matching required anti-affinity term on
-// the hostname: count 0 -> 1 > limit 0); a randomized differential test (tests/test_gpu_stress.py) found exactly this hole in
-// the first version. Carrying every candidate's "key after one more clone" in the payload would lift the restriction.
+// A committed node may win again inside the wave with its new score, which is in nobody's list (a randomized differential test,
+// tests/test_gpu_stress.py, found this hole in the first version: spread-only templates). Every published candidate therefore
+// carries, next to its domain ids, its key after one more clone (node-local Filter part + score recomputed by the publisher; 0 =
+// it would not fit). The winner comes back into the replay once with that key ("second life"); when a node wins for the second
+// time in a wave its third key is unknown and the wave ends after that commit. Entries in their second life do not keep a list
+// "alive" for rule (b): the CTA's unpublished nodes rank below its last PUBLISHED key only.
 // The first candidate of a wave is always accepted, so every wave makes progress; a wave without candidates is the
 // Unschedulable stop. Node-local terms (hostname anti-affinity, ...) need no re-check: a node appears once per wave.
 //
@@ -28,7 +30,8 @@
 #include "ccsim_lean.cuh"
 
 #define MULTI_M 8                 /* candidates per CTA and wave: 8 x 16 B = the CTA's 128-byte slot line */
-#define MULTI_PAY_BITS 39         /* payload bits for domain ids (dom+1 per topology slot) */
+#define MULTI_PAY_BITS 27         /* payload bits for domain ids (dom+1 per topology slot) */
+#define MULTI_NEXT_SHIFT 27       /* 12 bits: (score + 1) of the node after one more clone, 0 = it would not fit any more */
 #define MULTI_MORE_BIT 39
 #define MULTI_LEN_SHIFT 40
 #define MULTI_MAX_ACC 64          /* commits one wave may decide */
@@ -227,7 +230,31 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         L = r + 1;
       }
       unsigned long long pay = 0ull;
-      if (lane < L) pay = c_pay[ckey_index(mykey) - (p.node_base + lo)];
+      if (lane < L) {
+        const int32_t jj = ckey_index(mykey) - (p.node_base + lo);
+        pay = c_pay[jj];
+        // The node's key after one more clone ("second life" in the replay): the node-local part of the Filter pass and the
+        // score again, on the row as it would be after this commit (types.go:409-427). Per-domain terms are re-checked by
+        // the replay itself. 0 = the node would not take another clone.
+        const uint4 *r = rec + (size_t)jj * su;
+        const uint4 u1 = r[1], u2 = r[2];
+        const long long free_cpu = (long long)(((unsigned long long)u1.y << 32) | u1.x) - ls.tmpl.req_cpu;
+        const long long free_mem = (long long)(((unsigned long long)u1.w << 32) | u1.z) - ls.tmpl.req_mem;
+        bool ok2 = (free_cpu >= ls.eq_cpu) & (free_mem >= ls.eq_mem) & ((int32_t)u2.x - 1 >= ls.pods_need);
+        const int32_t *r4 = reinterpret_cast<const int32_t *>(r);
+        for (int q = 0; q < ls.n_cmp_terms; q++) {
+          const LeanTerm lt = ls.terms[q];
+          if (lt.cnt_off >= 0) continue;                       // replicated counters: the replay's business
+          int inc = 0;
+          for (int j = 0; j < p.n_counters; j++) if (p.counters[j].topo_col < 0 && 10 + lp.counter_slot[j] == lt.slot) inc = ls.cinfo[j].inc;
+          ok2 &= (r4[lt.slot] + inc <= lt.lim);
+        }
+        if (ok2) {
+          const int32_t sc2 = score_node(c_acpu[jj], c_amem[jj], c_zcpu[jj] + ls.tmpl.nz_cpu + ls.tmpl.least_cpu, c_zmem[jj] + ls.tmpl.nz_mem + ls.tmpl.least_mem,
+                                         c_rcpu[jj] + ls.tmpl.req_cpu + ls.tmpl.bal_cpu, c_rmem[jj] + ls.tmpl.req_mem + ls.tmpl.bal_mem, ls.sw);
+          pay |= (unsigned long long)(uint32_t)(sc2 + 1) << MULTI_NEXT_SHIFT;
+        }
+      }
       pay |= ((unsigned long long)L << MULTI_LEN_SHIFT) | ((unsigned long long)(total > L ? 1 : 0) << MULTI_MORE_BIT);
       unsigned long long *myslots = p.slots + ((size_t)(wv & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
       if (lane < MULTI_M) {
@@ -269,7 +296,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       if (e0 >= tot) { a0w = 0ull; b0 = 0ull; }
       if (e1 >= tot) { a1w = 0ull; b1 = 0ull; }
     }
-    const uint32_t a0 = (uint32_t)a0w, a1 = (uint32_t)a1w;      // compact keys (the tag sits above bit 44)
+    const uint32_t a0 = (uint32_t)a0w, a1 = (uint32_t)a1w;      // compact keys as published (the tag sits above bit 44)
+    uint32_t k0 = a0, k1 = a1;                                   // ... and as they stand in the replay (a winner comes back once with its next key)
+    bool second0 = false, second1 = false;
     // counter cells each of my candidates depends on (-1: the node lacks the key and the term lets it pass)
     int32_t i0[MULTI_GT], i1[MULTI_GT];
     const int n_gt = ms.n_gt;
@@ -320,9 +349,11 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         refresh |= __any_sync(0xffffffffu, died);
       }
       if (refresh) {
-        const uint32_t v0 = live0 ? a0 : 0u, v1 = live1 ? a1 : 0u;
+        const uint32_t v0 = live0 ? k0 : 0u, v1 = live1 ? k1 : 0u;
         // a list (8 consecutive lanes) without a live entry whose CTA has unpublished feasible nodes: those rank below its last key
-        const unsigned bal0 = __ballot_sync(0xffffffffu, live0), bal1 = __ballot_sync(0xffffffffu, live1);
+        // (only entries in their first life count: a CTA's unpublished nodes rank below its last PUBLISHED key, and a winner that
+        //  came back with its next key may well rank below that)
+        const unsigned bal0 = __ballot_sync(0xffffffffu, live0 && !second0), bal1 = __ballot_sync(0xffffffffu, live1 && !second1);
         if (!(bal0 & grp) && more0 && (e0 & 7) == L0 - 1) bar = a0 > bar ? a0 : bar;
         if (!(bal1 & grp) && more1 && (e1 & 7) == L1 - 1) bar = a1 > bar ? a1 : bar;
         wm = __reduce_max_sync(0xffffffffu, v0 > v1 ? v0 : v1);
@@ -339,11 +370,20 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       if (g == 0u || g < gb) break;            // block-uniform: nothing left, or an unpublished node could rank above g
       if (wm == g) {      // warp-uniform: this warp holds the winner; it commits like the lean kernel's warp 0 does
         // ---- commit pod k+acc (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
-        const bool own0 = live0 && a0 == g, own1 = live1 && a1 == g;
+        const bool own0 = live0 && k0 == g, own1 = live1 && k1 == g;
         const int ol = __ffs(__ballot_sync(0xffffffffu, own0 | own1)) - 1;
         const unsigned long long pay = __shfl_sync(0xffffffffu, own0 ? b0 : b1, ol);
-        if (own0) live0 = false;
-        if (own1) live1 = false;
+        // the winner comes back once with the key it has after this clone (if it still fits); when a node wins for the second
+        // time in a wave its third key is unknown: the wave ends after that commit
+        const bool was_second = __any_sync(0xffffffffu, (own0 && second0) || (own1 && second1));
+        if (own0) {
+          const uint32_t ns = (uint32_t)(b0 >> MULTI_NEXT_SHIFT) & 0xfffu;
+          if (ns && !second0) { k0 = (ns << MULTI_IDX_BITS) | (k0 & MULTI_IDX_MASK); second0 = true; } else live0 = false;
+        }
+        if (own1) {
+          const uint32_t ns = (uint32_t)(b1 >> MULTI_NEXT_SHIFT) & 0xfffu;
+          if (ns && !second1) { k1 = (ns << MULTI_IDX_BITS) | (k1 & MULTI_IDX_MASK); second1 = true; } else live1 = false;
+        }
         // Only what the next round depends on happens here: the counter cells of the winner's domains (lane q = term q; the
         // host guarantees one term per incremented replicated counter), whether a cell went over its limit, whether a PTS
         // minimum moved. The winner's row (NodeInfo.update, node-local counters) is brought up to date after the last round.
@@ -368,7 +408,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         }
         bool stopb = __any_sync(0xffffffffu, minchg);
         stopb |= (p.max_pods > 0 && k + acc + 1 >= p.max_pods);
-        stopb |= (k + acc + 1 >= p.pod_cap) | (acc + 1 >= MULTI_MAX_ACC);
+        stopb |= (k + acc + 1 >= p.pod_cap) | (acc + 1 >= MULTI_MAX_ACC) | was_second;
         if (lane == 0) { ms.stopb = stopb ? 1 : 0; ms.acc_node[acc] = ckey_index(g); }
         refresh = true;
       }
@@ -385,12 +425,17 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     //      one thread per accepted pod (a node is accepted at most once per wave) ----
     if (tid >= 32 && tid - 32 < acc) {       // warp 1 (and up): warp 0 recounts PTS minima meanwhile
       const ccsim_template &t = ls.tmpl;
-      const int32_t w = ms.acc_node[tid - 32] - p.node_base;
-      if (w >= lo && w < hi) {
+      const int i = tid - 32;
+      const int32_t w = ms.acc_node[i] - p.node_base;
+      // a node is accepted at most twice per wave, the second time as the wave's last commit: its first thread applies both
+      const bool twice = (i != acc - 1) && ms.acc_node[acc - 1] == ms.acc_node[i];
+      const bool skip = (i == acc - 1) && [&] { for (int q = 0; q < acc - 1; q++) if (ms.acc_node[q] == ms.acc_node[i]) return true; return false; }();
+      const int mult = twice ? 2 : 1;
+      if (w >= lo && w < hi && !skip) {
         const int32_t jw = w - lo;
-        const long long rc = c_rcpu[jw] + t.req_cpu, rm = c_rmem[jw] + t.req_mem;
-        const int32_t np = c_npods[jw] + 1;
-        c_rcpu[jw] = rc; c_rmem[jw] = rm; c_zcpu[jw] += t.nz_cpu; c_zmem[jw] += t.nz_mem; c_npods[jw] = np;
+        const long long rc = c_rcpu[jw] + mult * t.req_cpu, rm = c_rmem[jw] + mult * t.req_mem;
+        const int32_t np = c_npods[jw] + mult;
+        c_rcpu[jw] = rc; c_rmem[jw] = rm; c_zcpu[jw] += mult * t.nz_cpu; c_zmem[jw] += mult * t.nz_mem; c_npods[jw] = np;
         unsigned long long *r8 = reinterpret_cast<unsigned long long *>(rec + (size_t)jw * su);
         int32_t *r4 = reinterpret_cast<int32_t *>(r8);
         r8[2] = (unsigned long long)(c_acpu[jw] - rc);
@@ -399,7 +444,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         r4[9] = -1;            // this node's NodeInfo generation changed: its memoised score is stale
         for (int j = 0; j < p.n_counters; j++) {
           const CommitInfo ci = ls.cinfo[j];
-          if (ci.inc && ci.local) r4[10 + lp.counter_slot[j]] += ci.inc;   // node-local counters (written back when the run ends)
+          if (ci.inc && ci.local) r4[10 + lp.counter_slot[j]] += mult * ci.inc;   // node-local counters (written back when the run ends)
         }
       }
     }

@@ -35,9 +35,10 @@ def check(cc, ref):
     return rep
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13])
 @pytest.mark.parametrize("variant", helpers.TEMPLATE_VARIANTS)
-def test_framework_matches_object_oracle(built, variant):
-    nodes, pods = helpers.random_cluster(11, n_nodes=40, n_pods=70)
+def test_framework_matches_object_oracle(built, variant, seed):
+    nodes, pods = helpers.random_cluster(seed, n_nodes=40 + 9 * (seed - 11), n_pods=70 + 25 * (seed - 11))
     cc, ref = analyse(nodes, pods, helpers.template(variant), variant=variant)
     check(cc, ref)
 

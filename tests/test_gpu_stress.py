@@ -50,7 +50,7 @@ def random_case(seed):
     return snap, [t], ctr, limit
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(48))
 def test_random_coupled_templates(built, seed):
     snap, tmpl, ctr, limit = random_case(seed)
     cap = limit or 4000                               # keep the single-thread oracle in seconds
