@@ -14,7 +14,7 @@ GiB, MiB = 1 << 30, 1 << 20
 
 def random_case(seed):
     rng = np.random.default_rng(1000 + seed)
-    n = int(rng.choice([3000, 9000, 40000, 90000]))
+    n = int(rng.choice([200, 600, 3000, 9000, 40000, 90000, 110000]))      # 1 CTA ... the largest tile the multi-commit kernel takes
     n_topo = int(rng.integers(1, 4))
     doms = [int(rng.choice([3, 8, 40, 300, 2000])) for _ in range(n_topo)]
     topo = []
@@ -26,9 +26,12 @@ def random_case(seed):
     a_cpu = rng.choice([2000, 4000, 8000, 16000], n)
     npods = rng.integers(0, 20, n).astype(np.int32)
     req_cpu = (rng.random(n) * 0.5 * a_cpu).astype(np.int64) // 10 * 10
-    snap = abi.Snapshot(n, a_cpu, a_cpu * (2 * MiB), rng.choice([30, 60, 110], n), req_cpu=req_cpu, req_mem=req_cpu * (1 * MiB),
+    a_pods = rng.choice([30, 60, 110], n) if rng.random() < 0.7 else npods + rng.integers(0, 4, n)      # or: room for 0..3 more pods
+    snap = abi.Snapshot(n, a_cpu, a_cpu * (2 * MiB), a_pods, req_cpu=req_cpu, req_mem=req_cpu * (1 * MiB),
                         npods=npods, topo=topo)
     ctr, t = [], abi.default_template(int(rng.choice([100, 250, 700])), int(rng.choice([64, 256, 1024])) * MiB)
+    if rng.random() < 0.3:
+        t.w_fit, t.w_balanced = int(rng.integers(1, 5)), int(rng.integers(1, 5))
     n_pts = 0
     for c, d in enumerate(doms):
         init = rng.integers(0, 4, d).astype(np.int32) if rng.random() < 0.7 else np.full(d, int(rng.integers(0, 3)), np.int32)
