@@ -48,6 +48,7 @@ struct __align__(16) MultiShared {
   int32_t acc_node[MULTI_MAX_ACC];                  // replay: nodes accepted in this wave, in order
   int32_t full[MULTI_GT];                           // replay: counter cell of term q that the last commit pushed over its limit, or -2
   int32_t n_gt, accepted, dead, stopb;
+  int32_t single_use, pad_ms[3];
 };
 
 __shared__ MultiShared ms;
@@ -158,6 +159,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
             ms.gt_term[g++] = q;
           }
         ms.n_gt = g;
+        int su1 = 0;   // a self-matching required anti-affinity term on a node-local counter: count 0 -> inc > limit 0 after one clone
+        for (int q = 0; q < ls.n_cmp_terms; q++)
+          if (ls.terms[q].cnt_off < 0 && ls.terms[q].kind == LT_ANTI)
+            for (int j = 0; j < p.n_counters; j++)
+              if (p.counters[j].topo_col < 0 && 10 + lp.counter_slot[j] == ls.terms[q].slot && ls.cinfo[j].inc > 0) su1 = 1;
+        ms.single_use = su1;
       }
       __syncthreads();
       if (tid == 0) ls.dirty = 0;
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         // The node's key after one more clone ("second life" in the replay): the node-local part of the Filter pass and the
         // score again, on the row as it would be after this commit (types.go:409-427). Per-domain terms are re-checked by
         // the replay itself. 0 = the node would not take another clone.
+        if (!ms.single_use) {    // (a clone that blocks its own node — hostname anti-affinity — never has a second life)
         const uint4 *r = rec + (size_t)jj * su;
         const uint4 u1 = r[1], u2 = r[2];
         const long long free_cpu = (long long)(((unsigned long long)u1.y << 32) | u1.x) - ls.tmpl.req_cpu;
@@ -253,6 +261,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           const int32_t sc2 = score_node(c_acpu[jj], c_amem[jj], c_zcpu[jj] + ls.tmpl.nz_cpu + ls.tmpl.least_cpu, c_zmem[jj] + ls.tmpl.nz_mem + ls.tmpl.least_mem,
                                          c_rcpu[jj] + ls.tmpl.req_cpu + ls.tmpl.bal_cpu, c_rmem[jj] + ls.tmpl.req_mem + ls.tmpl.bal_mem, ls.sw);
           pay |= (unsigned long long)(uint32_t)(sc2 + 1) << MULTI_NEXT_SHIFT;
+        }
         }
       }
       pay |= ((unsigned long long)L << MULTI_LEN_SHIFT) | ((unsigned long long)(total > L ? 1 : 0) << MULTI_MORE_BIT);
