@@ -23,4 +23,11 @@ if __name__ == "__main__":
     if "c2big" in which: probe("C2 100k fit-only", *synth.c2(n=100_000), 20000, 72)
     if "c3" in which: probe("C3 50k full filters", *synth.c3(), 20000, 88)
     if "c4" in which: probe("C4 100k PTS+IPA", *synth.c4(), 0, 96)
+    if "c4spread" in which:      # spread constraints only (no hostname anti-affinity): nodes take several clones, winners can come back
+        snap, tmpl, ctr = synth.c4()
+        tmpl[0].n_anti = 0
+        probe("C4 spread-only", snap, tmpl, ctr[:3], 20000, 92)
+        os.environ["CCSIM_FORCE_SEQUENTIAL"] = "1"
+        probe("C4 spread-only, sequential", snap, tmpl, ctr[:3], 20000, 92)
+        del os.environ["CCSIM_FORCE_SEQUENTIAL"]
     if "c5" in which: probe("C5 1M x 64 templates", *synth.c5(), 6400, 72)
