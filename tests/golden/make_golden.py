@@ -25,6 +25,14 @@ def main():
             {"name": "readme_demo", "cite": "README.md:44-66", "nodes": [helpers.make_node("kube-node-%d" % i, cpu="2", mem="4Gi", pods="110") for i in range(1, 5)],
              "pods": [], "template": helpers.make_pod("small-pod", cpu="150m", mem="100Mi"), "max_pods": 0,
              "expect": {"replicas": 52, "failType": "Unschedulable", "per_node": {"kube-node-1": 13, "kube-node-2": 13, "kube-node-3": 13, "kube-node-4": 13}}},
+            # README.md:68-101: the same cluster after `examples/rc.yml` was scaled to 6 nginx replicas (150m / 100Mi each, two on
+            # kube-node-1 and kube-node-2, one on kube-node-3 and kube-node-4): 46 instances, 11 / 12 / 11 / 12
+            {"name": "readme_demo_with_rc", "cite": "README.md:68-101; examples/rc.yml",
+             "nodes": [helpers.make_node("kube-node-%d" % i, cpu="2", mem="4Gi", pods="110") for i in range(1, 5)],
+             "pods": [helpers.make_pod("nginx-%d" % j, cpu="150m", mem="100Mi", node="kube-node-%d" % nd, labels={"app": "nginx"})
+                      for j, nd in enumerate([1, 1, 2, 2, 3, 4])],
+             "template": helpers.make_pod("small-pod", cpu="150m", mem="100Mi"), "max_pods": 0,
+             "expect": {"replicas": 46, "failType": "Unschedulable", "per_node": {"kube-node-1": 11, "kube-node-2": 11, "kube-node-3": 12, "kube-node-4": 12}}},
             {"name": "test_prediction_limit", "cite": "pkg/framework/simulator_test.go:162-173,250-252",
              "nodes": [helpers.make_node("test-node-1", cpu="300m", mem="1000000000", pods="3"), helpers.make_node("test-node-2", cpu="400m", mem="2000000000", pods="3"),
                        helpers.make_node("test-node-3", cpu="1200m", mem="1000000000", pods="3")],
