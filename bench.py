@@ -140,7 +140,10 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    snap, tmpl, ctr = synth.c4()
+    if world > 1 and args.mode == "sharded":     # the same workload as our arm at this N (weak scaling: N x 100k nodes)
+        snap, tmpl, ctr = synth.c4(n=100_000 * world, n_existing=200_000 * world, racks=1024 * world)
+    else:
+        snap, tmpl, ctr = synth.c4()
     steps = max(1, min(args.steps, 3))
     evals = placed = 0
     dt = 0.0
@@ -155,7 +158,7 @@ def run_reference(args):
         "impl": "reference", "metric": "predicate-evals/sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "first %d placements of the run" % pods,
+        "config": {"workload": WORKLOAD, "nodes": snap.n, "sample": "first %d placements of the run" % pods,
                    "note": "no Go toolchain: the CPU oracle (C port of the reference loop, canonical mode) stands in for the reference"},
         "placements_per_sec": placed / dt,
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port", "usable_cores": cores,
