@@ -106,6 +106,10 @@ class JsonParser {
     std::string out;
     p_++;  // opening quote
     while (true) {
+      // fast path: copy the run up to the next quote or backslash in one go
+      const char *b = t_.data() + p_, *e = t_.data() + t_.size(), *q = b;
+      while (q < e && *q != '"' && *q != '\\') q++;
+      if (q > b) { out.append(b, (size_t)(q - b)); p_ += (size_t)(q - b); }
       if (p_ >= t_.size()) fail("unterminated string");
       char c = t_[p_++];
       if (c == '"') break;
