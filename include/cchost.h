@@ -5,6 +5,8 @@
  *                           (pkg/framework/simulator.go:107-158)
  *   cc_sync_with_objects <- (*ClusterCapacity).SyncWithClient(client)  (simulator.go:176-295): instead of a clientset the
  *                           caller hands over the LISTed objects as JSON (NodeList / PodList / NamespaceList or bare arrays)
+ *   cc_sync_workloads    <- the Services / RCs / ReplicaSets / StatefulSets part of SyncWithClient (simulator.go:217-281): optional;
+ *                           only helper.DefaultSelector reads them (system-default topology spreading)
  *   cc_run               <- (*ClusterCapacity).Run()                   (simulator.go:356-381)
  *   cc_report_json       <- (*ClusterCapacity).Report() marshalled     (simulator.go:160-170; report.go:38-98,220-233)
  *   cc_report_print      <- framework.ClusterCapacityReviewPrint(r, verbose, format)  (report.go:235-317)
