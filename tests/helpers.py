@@ -175,7 +175,7 @@ def objref_sync(sim, nodes, pods, variant=None, namespaces=()):
 
 
 def template(variant, seed=0):
-    rng = random.Random(seed)
+    del seed   # variants are deterministic; the parameter keeps the call sites symmetrical with random_cluster
     p = make_pod("small-pod", cpu="150m", mem="100Mi", labels={"app": "sim"})
     s = p["spec"]
     if variant == "selector":
@@ -258,5 +258,4 @@ def template(variant, seed=0):
         s["containers"].append({"name": "c2", "image": "y", "resources": {}})
     elif variant == "never_preempt":
         s["preemptionPolicy"] = "Never"
-    (void := rng)
     return p
