@@ -105,10 +105,10 @@ def usable_cores():
     return n
 
 
-def cpu_oracle_rate(snap, tmpl, ctr, budget_s=20.0):
-    """Times the CPU oracle on a bounded prefix of the workload. The OpenMP node-axis split is calibrated first (the
-    reference's own default is 16 goroutines, KS:apis/config/v1/defaults.go:108-110): the best of a few thread counts
-    up to the usable cores is used, so that the baseline is as strong as this host allows."""
+def calibrate_oracle(snap, tmpl, ctr):
+    """The OpenMP node-axis split is calibrated first (the reference's own default is 16 goroutines,
+    KS:apis/config/v1/defaults.go:108-110): the best of a few thread counts up to the usable cores is used, so that the
+    CPU arm is as strong as this host allows. Returns (threads, evals/s estimate, usable cores)."""
     from oracle import binding as oracle
     cores = usable_cores()
     cand = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores} | {min(cores, 16)})
@@ -120,11 +120,45 @@ def cpu_oracle_rate(snap, tmpl, ctr, budget_s=20.0):
         rate = r.evals / (time.perf_counter() - t0)
         if rate > best_rate:
             best, best_rate = c, rate
-    pods = int(max(50, min(20000, budget_s * best_rate / max(1, snap.n))))
+    return best, best_rate, cores
+
+
+def cpu_oracle_rate(snap, tmpl, ctr, budget_s=20.0, calib=None):
+    """Times the CPU oracle on the workload, bounded by a time budget: the first K placements with K = budget x calibrated
+    rate / nodes. When the analysis ends (Unschedulable) before K, this IS the whole run. Returns
+    (result, seconds, threads, usable cores, K or 0 for a whole run)."""
+    from oracle import binding as oracle
+    best, best_rate, cores = calib or calibrate_oracle(snap, tmpl, ctr)
+    pods = int(max(50, budget_s * best_rate / max(1, snap.n)))
     t0 = time.perf_counter()
     r = oracle.run(snap, tmpl, ctr, max_pods=pods, threads=best)
     dt = time.perf_counter() - t0
+    if r.stop_code == abi.STOP_UNSCHEDULABLE:
+        pods = 0
     return r, dt, best, cores, pods
+
+
+def parity_block(got, want, pods):
+    """Bit-exact comparison of the GPU result (dict: placed, stop_code, pod_node, reason_hist, preempt_no_victims) with the
+    oracle's. pods == 0: the oracle ran to the end -> everything is compared; else the first `pods` placements."""
+    gp = np.asarray(got["pod_node"])
+    wp = np.asarray(want.pod_node)
+    if pods == 0:
+        ok = (got["placed"] == want.placed and got["stop_code"] == want.stop_code and np.array_equal(gp, wp)
+              and np.array_equal(np.asarray(got["reason_hist"]), want.reason_hist)
+              and got["preempt_no_victims"] == want.preempt_no_victims)
+        k = int(want.placed)
+    else:
+        k = int(min(pods, want.placed))
+        ok = got["placed"] >= k and np.array_equal(gp[:k], wp[:k])
+    first_bad = None
+    if not ok:
+        m = min(len(gp), len(wp))
+        d = np.nonzero(gp[:m] != wp[:m])[0]
+        first_bad = int(d[0]) if len(d) else m
+    return {"ok": bool(ok), "checked_placements": k, "full_run": pods == 0,
+            "compared": "pod->node sequence" + (", placed, stop code, FitError histogram, preemption counts" if pods == 0 else " (prefix)"),
+            "against": "oracle/ccsim_oracle.c (canonical mode), same snapshot", "first_mismatch": first_bad}
 
 
 def dist_env():
@@ -148,8 +182,9 @@ def run_reference(args):
     evals = placed = 0
     dt = 0.0
     threads = cores = pods = 0
-    for _ in range(steps):
-        r, d, threads, cores, pods = cpu_oracle_rate(snap, tmpl, ctr, budget_s=15.0)
+    calib = calibrate_oracle(snap, tmpl, ctr)
+    for _ in range(steps):   # the whole analysis when it ends within ~30 s on this host, else the first K placements
+        r, d, threads, cores, pods = cpu_oracle_rate(snap, tmpl, ctr, budget_s=30.0, calib=calib)
         evals += r.evals
         placed += r.placed
         dt += d
@@ -158,11 +193,13 @@ def run_reference(args):
         "impl": "reference", "metric": "predicate-evals/sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nodes": snap.n, "sample": "first %d placements of the run" % pods,
+        "config": {"workload": WORKLOAD, "nodes": snap.n, "sample": ("first %d placements of the run" % pods) if pods else "the whole run (%d placements)" % (placed // steps),
                    "note": "no Go toolchain: the CPU oracle (C port of the reference loop, canonical mode) stands in for the reference"},
         "placements_per_sec": placed / dt,
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port", "usable_cores": cores,
-                         "sample": "first %d placements (%d evals) per step, OpenMP over the node axis, thread count calibrated" % (pods, evals // steps)},
+                         "sample": "%s (%d evals) per step; C port of the reference loop (not the Go reference), OpenMP over the node axis for filter, "
+                                   "score and arg-max, thread count calibrated" % (("first %d placements" % pods) if pods else "the whole run", evals // steps),
+                         "dram_gbs_algorithmic": val * B_EVAL / 1e9},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -203,7 +240,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", "--no-cpu-baseline", dest="no_parity", action="store_true",
+                    help="skip the oracle run (parity check of the timed configuration + cpu_baseline)")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"], help="N>1: node-sharded run or independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -266,6 +304,12 @@ def main():
         waves += res.waves
         ref_evals += ref_equivalent_evals(res)
     barrier()
+    # the result the parity check compares (sharded: per-shard histograms summed, replicated parts cross-checked between ranks)
+    if sharded_run:
+        last_result = sharded.merge_results(dist, res)
+    else:
+        last_result = {"placed": res.placed, "stop_code": res.stop_code, "pod_node": res.pod_node, "reason_hist": res.reason_hist,
+                       "preempt_no_victims": res.preempt_no_victims}
     flushes = args.steps
     launches = eng.kernel_launches() - launches0 - flushes
     t_total = sum(step_wall)
@@ -305,6 +349,7 @@ def main():
     t_total, t_e2e, kernel_ms_max = [float(x) for x in vals.tolist()]
     evals_all, placed_all, e2e_evals_all, phys_all = [float(x) for x in work.tolist()]
 
+    parity_ok = True
     if rank == 0:
         peak, peak_kind = measured_peak()
         # algorithmic bytes of a canonical run = (placed+1) x N x B_eval — every pod attempt streams every node row
@@ -341,16 +386,30 @@ def main():
                                  "achieved_physical counts one 96 B row per node and PASS actually made. The tiles are shared-memory resident: "
                                  "DRAM traffic is the snapshot once per run (traffic, from ncu, profiles/)"},
         }
-        if not args.no_cpu_baseline and world == 1:
-            rc, dtc, threads, cores, pods = cpu_oracle_rate(snap, tmpl, ctr, budget_s=15.0)
-            line["cpu_baseline"] = {"value": rc.evals / dtc, "unit": "evals/s", "cores": threads, "kind": "port", "usable_cores": cores,
-                                    "sample": "first %d placements of the same run (%d evals, %.1f s), OpenMP thread count calibrated" % (pods, rc.evals, dtc)}
+        # ---- parity on the timed configuration (and the CPU baseline: the same oracle run serves both) ----
+        # N=1: the oracle runs the WHOLE analysis of the timed snapshot when that fits ~40 s (C4: ~18 s on 16 threads) and
+        # everything is compared; N>1 (weak-scaled clusters): the first K placements within the budget are compared.
+        line["cpu_baseline"] = None
+        if not args.no_parity:
+            rc, dtc, threads, cores, pods = cpu_oracle_rate(snap, tmpl, ctr, budget_s=40.0 if world == 1 else 25.0)
+            line["parity"] = parity_block(last_result, rc, pods)
+            parity_ok = line["parity"]["ok"]
+            if world == 1:
+                line["cpu_baseline"] = {"value": rc.evals / dtc, "unit": "evals/s", "cores": threads, "kind": "port", "usable_cores": cores,
+                                        "sample": "%s of the same snapshot (%d evals, %.1f s); C port of the reference loop (not the Go reference), "
+                                                  "OpenMP over the node axis for filter, score and arg-max, thread count calibrated"
+                                                  % ("the whole run" if pods == 0 else "first %d placements" % pods, rc.evals, dtc),
+                                        "dram_gbs_algorithmic": rc.evals / dtc * B_EVAL / 1e9}
         else:
-            line["cpu_baseline"] = None
+            line["parity"] = None
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and not parity_ok:
+        sys.stderr.write("bench.py: PARITY MISMATCH against the oracle on the timed configuration\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -7,7 +7,9 @@ SRC = [os.path.join(_HERE, "csrc", "ccsim_engine.cu")]
 import glob
 DEPS = SRC + sorted(glob.glob(os.path.join(_HERE, "csrc", "*.cuh"))) + [os.path.join(_HERE, "..", "include", "ccsim.h")]
 OUT = os.path.join(_HERE, "libccsim.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+# -fmad=false: the float64 scorers (BalancedAllocation, Go's math.Log) must round every operation on its own, like Go on amd64;
+# they use __dmul_rn/__dadd_rn intrinsics already, the flag keeps a plain a*b+c written later from being contracted silently
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-lcudart", "-ldl"]
 
 

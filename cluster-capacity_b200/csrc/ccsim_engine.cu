@@ -903,6 +903,10 @@ extern "C" int ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nd) {
   const int32_t per = (N + h->cfg.world - 1) / h->cfg.world;
   const int32_t lo = std::min<int64_t>((int64_t)per * h->cfg.rank, N), hi = std::min<int64_t>((int64_t)lo + per, N);
   const int32_t n = hi - lo;
+  // every rank of a sharded run takes part in the per-wave exchange: a rank without nodes would never launch the kernel and its
+  // peers would wait for its words forever
+  if (h->cfg.world > 1 && N > 0 && (int64_t)per * (h->cfg.world - 1) >= N)
+    return fail(h, CCSIM_EUNSUPPORTED, "sharded run: %d nodes over %d ranks leaves a rank without nodes (use fewer ranks)", N, h->cfg.world);
   h->n = n; h->n_global = N; h->node_base = lo;
   h->meta = *nd;
   int rc;
@@ -1100,7 +1104,13 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   const int32_t n = h->n;
   // output capacity: no run can place more than sum(max(0, alloc_pods - npods)) pods (fit.go:567-576)
   int64_t cap = h->pod_bound + 1;
-  if (max_pods > 0 && max_pods < cap) cap = max_pods;
+  // ("Too many pods" bounds a run only while NodeResourcesFit filters: with the plugin disabled through --default-config an
+  //  unlimited run never ends in the reference either)
+  if (max_pods <= 0)
+    for (const ccsim_template &T : h->h_templates)
+      if (!(T.filter_enable & CCSIM_PL_FIT))
+        return fail(h, CCSIM_EUNSUPPORTED, "NodeResourcesFit is disabled for a template: the run is unbounded, --max-limit is required");
+  if (max_pods > 0 && (max_pods < cap || [&] { for (const ccsim_template &T : h->h_templates) if (!(T.filter_enable & CCSIM_PL_FIT)) return true; return false; }())) cap = max_pods;
   if (cap > h->pod_cap) {
     cudaFree(h->d_pod_node); h->d_pod_node = nullptr; h->pod_cap = 0;
     CK(cudaMalloc((void **)&h->d_pod_node, (size_t)cap * sizeof(int32_t)));
@@ -1318,7 +1328,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
     CK(cudaStreamSynchronize(s));
     for (int r = 0; r < CCSIM_R_TOTAL; r++) out->reason_hist[r] = (int64_t)ho.reason_hist[r];
     out->preempt_no_victims = (int64_t)ho.preempt_no_victims;
-    out->preempt_not_helpful = (int64_t)h->n_global - (int64_t)ho.preempt_no_victims;
+    out->preempt_not_helpful = (int64_t)h->n - (int64_t)ho.preempt_no_victims;   // per shard, like reason_hist: sums to N - no_victims
   }
   h->h_pod_node.resize((size_t)ho.placed);
   if (ho.placed) CK(cudaMemcpyAsync(h->h_pod_node.data(), h->d_pod_node, (size_t)ho.placed * 4, cudaMemcpyDeviceToHost, s));

@@ -389,7 +389,9 @@ class Encoder {
       e.topo.push_back(col);
       std::vector<int32_t> init(counts.begin(), counts.end());
       const bool self = hard_sel[c].matches(t_.labels);
-      add_counter(e, colidx, init, n_present, self ? 1 : 0);
+      // an Everything selector (labelSelector: {}) self-matches (filtering.go:341-344) but is never COUNTED: countPodsMatchSelector
+      // returns 0 for selector.Empty() (common.go:144-147), so committed clones do not raise the domain counts either
+      add_counter(e, colidx, init, n_present, (self && !hard_sel[c].empty()) ? 1 : 0);
       T.pts[c].counter = (int32_t)e.counters.size() - 1;
       T.pts[c].max_skew = tc.max_skew;
       T.pts[c].self_match = self ? 1 : 0;

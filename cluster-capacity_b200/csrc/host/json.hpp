@@ -76,6 +76,9 @@ class JsonParser {
  private:
   const std::string &t_;
   size_t p_ = 0;
+  int depth_ = 0;                    // nesting of the value being parsed; capped so that a hostile document cannot overflow the stack
+  static constexpr int kMaxDepth = 512;
+  struct Nest { JsonParser &p; explicit Nest(JsonParser &q) : p(q) { if (++p.depth_ > kMaxDepth) p.fail("nesting too deep"); } ~Nest() { p.depth_--; } };
   [[noreturn]] void fail(const char *m) { throw std::runtime_error(std::string("json: ") + m + " at offset " + std::to_string(p_)); }
   void ws() { while (p_ < t_.size() && (t_[p_] == ' ' || t_[p_] == '\n' || t_[p_] == '\t' || t_[p_] == '\r')) p_++; }
   Json value() {
@@ -142,6 +145,7 @@ class JsonParser {
     return out;
   }
   Json array() {
+    Nest nest(*this);
     Json a = Json::array();
     p_++;
     ws();
@@ -157,6 +161,7 @@ class JsonParser {
     return a;
   }
   Json object() {
+    Nest nest(*this);
     Json o = Json::object();
     p_++;
     ws();

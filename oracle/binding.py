@@ -33,6 +33,10 @@ def lib():
         _lib.ccsim_oracle_run.argtypes = [C.POINTER(_abi.Nodes), C.c_int32, C.POINTER(_abi.Template), C.c_int32,
                                           C.POINTER(_abi.Counter), C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(_abi.Result), _abi.P32, C.c_int64]
+        _lib.ccsim_oracle_run_ex.restype = C.c_int
+        _lib.ccsim_oracle_run_ex.argtypes = [C.POINTER(_abi.Nodes), C.c_int32, C.POINTER(_abi.Template), C.c_int32,
+                                             C.POINTER(_abi.Counter), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.POINTER(_abi.Result), _abi.P32, C.c_int64]
         _lib.ccsim_oracle_node_score.restype = C.c_int64
         _lib.ccsim_oracle_node_score.argtypes = [C.POINTER(_abi.Nodes), C.POINTER(_abi.Template), C.c_int32, C.c_int32,
                                                  _abi.P64, _abi.P64]
@@ -52,8 +56,9 @@ class OracleResult:
         self.pod_node = pod_node[: self.placed].copy()
 
 
-def run(snapshot, templates, counters=(), max_pods=0, mode=0, pct=0, threads=1, cap=None):
-    """Run the oracle loop. mode 0 = canonical, 1 = faithful (adaptive sampling + rotation)."""
+def run(snapshot, templates, counters=(), max_pods=0, mode=0, pct=0, threads=1, cap=None, memo=False):
+    """Run the oracle loop. mode 0 = canonical, 1 = faithful (adaptive sampling + rotation). memo=True memoises the node-local
+    score per (template, node) until that node is committed (identical results, for full-size parity runs; never for timing)."""
     nd = snapshot.c_struct()
     T = (_abi.Template * len(templates))(*templates)
     Cn = (_abi.Counter * max(1, len(counters)))(*counters)
@@ -61,8 +66,8 @@ def run(snapshot, templates, counters=(), max_pods=0, mode=0, pct=0, threads=1, 
         cap = max_pods if max_pods > 0 else int(snapshot.alloc_pods.astype(np.int64).sum()) + 1
     buf = np.zeros(max(1, cap), np.int32)
     res = _abi.Result()
-    rc = lib().ccsim_oracle_run(C.byref(nd), len(templates), T, len(counters), Cn, max_pods, mode, pct, threads,
-                                C.byref(res), buf.ctypes.data_as(_abi.P32), cap)
+    rc = lib().ccsim_oracle_run_ex(C.byref(nd), len(templates), T, len(counters), Cn, max_pods, mode, pct, threads, 1 if memo else 0,
+                                   C.byref(res), buf.ctypes.data_as(_abi.P32), cap)
     if rc != 0:
         raise RuntimeError("oracle rc=%d" % rc)
     return OracleResult(res, buf)

@@ -373,10 +373,25 @@ static inline int64_t score_rest(const ccsim_nodes *nd, const ostate *s, const c
   return sc;
 }
 
+/* flags bit 0 (CCSIM_ORACLE_MEMO): memoise score_rest per (template, node) and recompute it only after that node was committed.
+ * score_rest depends on the node's own Requested / NonZeroRequested and the template only, so the results are identical (a test
+ * compares both); it makes full-size parity runs affordable. The timed CPU baseline never sets it: the reference rescores every
+ * feasible node in every cycle (KS:schedule_one.go:776-886). */
+#define CCSIM_ORACLE_MEMO 1
+int ccsim_oracle_run_ex(const ccsim_nodes *nd, int32_t n_templates, const ccsim_template *tmpl,
+                        int32_t n_counters, const ccsim_counter *ctr,
+                        int64_t max_pods, int32_t mode, int32_t pct_nodes_to_score, int32_t threads, int32_t flags,
+                        ccsim_result *out, int32_t *pod_node, int64_t pod_node_cap);
 int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_template *tmpl,
                      int32_t n_counters, const ccsim_counter *ctr,
                      int64_t max_pods, int32_t mode, int32_t pct_nodes_to_score, int32_t threads,
                      ccsim_result *out, int32_t *pod_node, int64_t pod_node_cap) {
+  return ccsim_oracle_run_ex(nd, n_templates, tmpl, n_counters, ctr, max_pods, mode, pct_nodes_to_score, threads, 0, out, pod_node, pod_node_cap);
+}
+int ccsim_oracle_run_ex(const ccsim_nodes *nd, int32_t n_templates, const ccsim_template *tmpl,
+                        int32_t n_counters, const ccsim_counter *ctr,
+                        int64_t max_pods, int32_t mode, int32_t pct_nodes_to_score, int32_t threads, int32_t flags,
+                        ccsim_result *out, int32_t *pod_node, int64_t pod_node_cap) {
   const int32_t n = nd->n_nodes;
   if (n_templates < 1 || n_templates > CCSIM_MAX_TEMPLATES || n_counters > CCSIM_MAX_COUNTERS) return CCSIM_EINVAL;
   if (n_templates > 1 && n_counters > 0) return CCSIM_EUNSUPPORTED;
@@ -407,6 +422,11 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
   }
   s.aff_total = tmpl[0].aff_total_init;
 
+  int32_t *memo = NULL;                     /* [n_templates][n] memoised score_rest, -1 = stale */
+  if ((flags & CCSIM_ORACLE_MEMO) && mode == 0 && n > 0) {
+    memo = (int32_t*)malloc((size_t)n_templates * (size_t)n * 4);
+    if (memo) memset(memo, 0xff, (size_t)n_templates * (size_t)n * 4);
+  }
   int64_t *key = (int64_t*)malloc(b64);     /* per-node rest score or -1 if infeasible */
   int32_t *raw = (int32_t*)malloc((size_t)(n > 0 ? n : 1) * 4);
   int64_t placed = 0, waves = 0, evals = 0;
@@ -424,16 +444,23 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
 
     int32_t examined = n;
     int64_t feasible = 0;
+    int32_t maxraw_par = 0;   /* canonical mode: max raw TaintToleration score over the feasible nodes, reduced inside the filter loop */
     if (mode == 0) {
       /* findNodesThatPassFilters, all nodes: KS:schedule_one.go:610-693 */
       int64_t fc = 0;
-      #pragma omp parallel for schedule(static) reduction(+:fc) if(n >= 4096)
+      int32_t mr = 0;
+      #pragma omp parallel for schedule(static) reduction(+:fc) reduction(max:mr) if(n >= 4096)
       for (int32_t i = 0; i < n; i++) {
         int st = filter_node(nd, &s, t, ti, ctr, ptsmin, i, 0, NULL, NULL);
-        if (st == ST_OK) { key[i] = score_rest(nd, &s, t, i); raw[i] = (t->score_enable & CCSIM_PL_TAINT_TOLERATION) ? taint_raw(nd, t, i) : 0; fc++; }
+        if (st == ST_OK) {
+          if (memo) { int32_t *m = &memo[(size_t)ti * (size_t)n + i]; if (*m < 0) *m = (int32_t)score_rest(nd, &s, t, i); key[i] = *m; }
+          else key[i] = score_rest(nd, &s, t, i);
+          raw[i] = (t->score_enable & CCSIM_PL_TAINT_TOLERATION) ? taint_raw(nd, t, i) : 0; fc++;
+          if (raw[i] > mr) mr = raw[i];
+        }
         else key[i] = -1;
       }
-      feasible = fc;
+      feasible = fc; maxraw_par = mr;
     } else {
       int32_t want = num_feasible_nodes_to_find(n, pct_nodes_to_score);
       examined = 0;
@@ -452,8 +479,10 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
     /* prioritizeNodes + selectHost: KS:schedule_one.go:776-886,894-941; RunScorePlugins KS:framework/runtime/framework.go:1137-1244.
        TaintToleration NormalizeScore: PL:helper/normalize_score.go:28-56 (reverse=true) over the feasible set. */
     int32_t maxraw = 0;
-    if (t->score_enable & CCSIM_PL_TAINT_TOLERATION)
-      for (int32_t i = 0; i < n; i++) if (key[i] >= 0 && raw[i] > maxraw) maxraw = raw[i];
+    if (t->score_enable & CCSIM_PL_TAINT_TOLERATION) {
+      if (mode == 0) maxraw = maxraw_par;
+      else for (int32_t i = 0; i < n; i++) if (key[i] >= 0 && raw[i] > maxraw) maxraw = raw[i];
+    }
     /* NodeAffinity preferred terms: PreScore Skip when the pod has none (node_affinity.go:246-249); else
        DefaultNormalizeScore(100, reverse=false) over the feasible nodes (PL:helper/normalize_score.go:28-56) */
     const int na_on = (t->score_enable & CCSIM_PL_NODE_AFFINITY) && t->n_pref_terms > 0;
@@ -500,6 +529,38 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
         if (r > ipa_max) ipa_max = r;
       }
     int64_t best = -1; int32_t besti = -1;
+    if (mode == 0 && !na_on && !spts_on && !ipa_on && n >= 4096) {
+      /* Same arg-max as the loop below (first maximum in node order), split over the node axis like the reference's own
+         16-way parallel score pass (KS:framework/parallelize/parallelism.go:28-78): every thread keeps the first maximum of its
+         contiguous block, the blocks are combined in ascending order with a strict '>' */
+      const int tt_on = (t->score_enable & CCSIM_PL_TAINT_TOLERATION) != 0;
+      int64_t tb[256]; int32_t tbi[256]; int nth = 1;
+#ifdef _OPENMP
+      const int nthr_want = omp_get_max_threads() < 256 ? omp_get_max_threads() : 256;
+#else
+      const int nthr_want = 1;
+#endif
+      (void)nthr_want;
+      #pragma omp parallel num_threads(nthr_want)
+      {
+#ifdef _OPENMP
+        const int me = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        const int me = 0, nt = 1;
+#endif
+        const int32_t per = (n + nt - 1) / nt, lo = me * per < n ? me * per : n, hi = lo + per < n ? lo + per : n;
+        int64_t b = -1; int32_t bi = -1;
+        for (int32_t i = lo; i < hi; i++) {
+          if (key[i] < 0) continue;
+          int64_t total = key[i];
+          if (tt_on) total += (int64_t)t->w_taint * ((maxraw == 0) ? 100 : 100 - (100 * (int64_t)raw[i] / maxraw));
+          if (total > b) { b = total; bi = i; }
+        }
+        tb[me] = b; tbi[me] = bi;
+        if (me == 0) nth = nt;
+      }
+      for (int q = 0; q < nth; q++) if (tb[q] > best) { best = tb[q]; besti = tbi[q]; }
+    } else
     for (int32_t q = 0; q < n; q++) {
       int32_t i = (mode == 0) ? q : (start + q) % n;
       if (key[i] < 0) continue;
@@ -531,6 +592,7 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
     for (int q = 0; q < nd->n_scalars; q++) s.req_scalar[q][w] += t->req_scalar[q];
     s.nz_cpu[w] += t->nz_cpu; s.nz_mem[w] += t->nz_mem;
     s.npods[w] += 1;
+    if (memo) for (int q = 0; q < n_templates; q++) memo[(size_t)q * (size_t)n + w] = -1;
     if (s.placed_mask) s.placed_mask[w] |= (1ull << ti);
     /* per-domain counters: the next cycle's PreFilter recount sees this clone
        (PL:podtopologyspread/filtering.go:255-289; PL:interpodaffinity/filtering.go:234-271) */
@@ -567,7 +629,7 @@ int ccsim_oracle_run(const ccsim_nodes *nd, int32_t n_templates, const ccsim_tem
   }
   out->pod_node = pod_node;
 
-  free(key); free(raw);
+  free(key); free(raw); free(memo);
   free(s.req_cpu); free(s.req_mem); free(s.req_eph); free(s.nz_cpu); free(s.nz_mem); free(s.npods); free(s.placed_mask);
   for (int k = 0; k < nd->n_scalars; k++) free(s.req_scalar[k]);
   for (int j = 0; j < n_counters; j++) free(s.cnt[j]);

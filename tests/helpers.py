@@ -148,7 +148,7 @@ def random_cluster(seed, n_nodes=40, n_pods=60, zones=3):
 
 TEMPLATE_VARIANTS = ["plain", "selector", "tolerations", "affinity_terms", "hostports", "spread_zone", "spread_two", "anti_hostname",
                      "anti_zone", "affinity_zone", "extended", "best_effort", "init_overhead", "never_preempt", "gt_lt", "name_in", "pref_affinity", "pref_and_required",
-                     "soft_spread", "soft_and_hard", "pref_pod_affinity", "svc_default_spread", "owner_default_spread"]
+                     "soft_spread", "soft_and_hard", "pref_pod_affinity", "svc_default_spread", "owner_default_spread", "spread_everything"]
 
 
 def workloads_for(variant):
@@ -231,6 +231,11 @@ def template(variant, seed=0):
     elif variant == "spread_zone":
         s["topologySpreadConstraints"] = [{"maxSkew": 1, "topologyKey": "topology.kubernetes.io/zone", "whenUnsatisfiable": "DoNotSchedule",
                                            "labelSelector": {"matchLabels": {"app": "sim"}}}]
+    elif variant == "spread_everything":
+        # labelSelector {} = Everything: self-matches (filtering.go:341-344) but countPodsMatchSelector returns 0 for an empty
+        # selector (common.go:144-147), so the counts never move and the constraint never blocks (skew = 1 - 0)
+        s["topologySpreadConstraints"] = [{"maxSkew": 1, "topologyKey": "topology.kubernetes.io/zone", "whenUnsatisfiable": "DoNotSchedule",
+                                           "labelSelector": {}}]
     elif variant == "spread_two":
         s["topologySpreadConstraints"] = [
             {"maxSkew": 2, "topologyKey": "topology.kubernetes.io/zone", "whenUnsatisfiable": "DoNotSchedule", "labelSelector": {"matchLabels": {"app": "sim"}}},

@@ -27,6 +27,16 @@ def test_library_exports_every_declared_symbol(built):
     assert L.ccsim_abi_version() == abi.ABI_VERSION
 
 
+def test_host_library_exports_every_declared_symbol(built):
+    """include/cchost.h: every cc_* entry point the header declares is exported by libcchost.so."""
+    hdr = open(os.path.join(ROOT, "include", "cchost.h")).read()
+    names = sorted(set(re.findall(r"\b(cc_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 8, names
+    L = C.CDLL(os.path.join(ROOT, "cluster-capacity_b200", "libcchost.so"))
+    for name in names:
+        assert hasattr(L, name), name
+
+
 def test_struct_layouts_match_header(built, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s/include/ccsim.h"\n'

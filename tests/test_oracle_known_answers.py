@@ -138,3 +138,17 @@ def test_histogram_sorting_as_strings():
     # framework/types.go:816-824: "<count> <reason>" strings are sorted lexically: "10 Insufficient cpu" < "2 Too many pods"
     msg = abi.fit_error_message(12, {abi.R_INSUFFICIENT_CPU: 10, abi.R_TOO_MANY_PODS: 2}, 12, 0, lambda r: abi.REASON_TEXT[r])
     assert msg.startswith("0/12 nodes are available: 10 Insufficient cpu, 2 Too many pods. preemption: 0/12")
+
+
+@pytest.mark.parametrize("which", ["c3", "c4", "c5"])
+def test_memoised_oracle_is_identical(which):
+    """oracle.run(memo=True) (used by the full-size GPU parity tests) gives exactly the plain restatement's result, and the
+    OpenMP split of filter / score / arg-max does not depend on the thread count."""
+    synth = importlib.import_module("cluster-capacity_b200.synth")
+    snap, tmpl, ctr = {"c3": lambda: synth.c3(n=6000, prefer_taints=True), "c4": lambda: synth.c4(n=8000, n_existing=16000, zones=8, racks=64, regions=4),
+                       "c5": lambda: synth.c5(n=9000, n_templates=7)}[which]()
+    a = oracle.run(snap, tmpl, ctr, max_pods=3000, threads=1)
+    for kw in (dict(threads=1, memo=True), dict(threads=5), dict(threads=8, memo=True)):
+        b = oracle.run(snap, tmpl, ctr, max_pods=3000, **kw)
+        assert (a.placed, a.stop_code, a.evals) == (b.placed, b.stop_code, b.evals)
+        assert np.array_equal(a.pod_node, b.pod_node) and np.array_equal(a.reason_hist, b.reason_hist)
