@@ -40,7 +40,8 @@ struct DevOut {
   unsigned long long reason_hist[CCSIM_R_TOTAL];
   unsigned long long preempt_no_victims;
   unsigned long long n_diag;
-  long long phase_cycles[8];       // CCSIM_PHASE_TIMERS builds only: CTA 0's cycles per phase
+  long long phase_cycles[8];       // CTA 0's cycles per phase (multi-commit kernel: always; other kernels: CCSIM_PHASE_TIMERS builds)
+  long long stat[4];               // multi-commit kernel: [0] candidates replayed (sum over waves), [1] waves that had to raise the bar T
 };
 
 struct DevParams {
@@ -52,6 +53,9 @@ struct DevParams {
   int32_t chunk;        // nodes per CTA (contiguous ownership)
   int32_t rank, world;
   uint32_t epoch;       // run counter (1..255), folded into every exchanged word
+  uint32_t debug_flags; // CCSIM_DEBUG_FLAGS (kernel experiments): bit 0 = multi-commit waves end at every PTS minimum move
+  uint32_t xwave0;      // node-sharded runs: exchanges done by earlier runs of this handle; the double-buffer parity of the cross-GPU
+                        // buffers continues across runs, so wave 0 of a run never lands in the buffer a lagging peer CTA still reads
   long long sample_k;   // numFeasibleNodesToFind (reference sampling mode)
   // immutable columns
   const int64_t *alloc_cpu, *alloc_mem, *alloc_eph;
@@ -448,7 +452,7 @@ struct CommitInfo {
 __device__ __forceinline__ bool cross_gpu_exchange(const DevParams &p, long long k, uint32_t tag, int ncls,
                                                    unsigned long long *cbest, int lane, int cta) {
   const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
-  const size_t base = (size_t)(k & 1) * CCSIM_MAX_WORLD * SLOT_STRIDE;
+  const size_t base = (size_t)((k + p.xwave0) & 1) * CCSIM_MAX_WORLD * SLOT_STRIDE;
   if (cta == 0 && lane < p.world)
     for (int c = 0; c < ncls; c++) st_slot_sys(&p.xslots_peer[lane][base + (size_t)p.rank * SLOT_STRIDE + c], cbest[c] | tagbits);
   const unsigned long long *local = p.xslots_peer[p.rank] + base;

@@ -771,6 +771,8 @@ struct ccsim_handle {
   unsigned long long *x_peer[CCSIM_MAX_WORLD] = {};       // every rank's buffer as mapped here
   bool peers_ready = false;
   uint32_t epoch = 0;
+  uint32_t xwave0 = 0;                                    // exchanges of earlier sharded runs (buffer parity continues across runs)
+  int64_t last_stat[16] = {};                             // ccsim_run_stats
   int32_t *d_topo_full[CCSIM_MAX_TOPO_COLS] = {};
   int32_t *d_pod_node = nullptr; int64_t pod_cap = 0;
   std::vector<int32_t> h_pod_node;
@@ -856,8 +858,8 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
   cudaMalloc((void **)&h->d_out, sizeof(DevOut));
   cudaMalloc((void **)&h->d_params, sizeof(DevParams));
   cudaMalloc((void **)&h->d_slots, sizeof(unsigned long long) * 2 * CCSIM_MAX_GRID * SLOT_STRIDE);
-  cudaMalloc((void **)&h->d_xslots, sizeof(unsigned long long) * 2 * CCSIM_MAX_WORLD * SLOT_STRIDE);
-  cudaMemset(h->d_xslots, 0, sizeof(unsigned long long) * 2 * CCSIM_MAX_WORLD * SLOT_STRIDE);
+  cudaMalloc((void **)&h->d_xslots, sizeof(unsigned long long) * XSLOTS_TOTAL_WORDS);     // winner words (lean kernel) + candidate lines (multi-commit)
+  cudaMemset(h->d_xslots, 0, sizeof(unsigned long long) * XSLOTS_TOTAL_WORDS);
   h->x_peer[cfg->rank] = h->d_xslots;
   h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   cudaFuncSetAttribute(ccsim_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -868,7 +870,9 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
                        (int)(h->smem_optin - sizeof(LeanShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(LeanShared) - sizeof(BatchShared) - 1024));
-  cudaFuncSetAttribute(ccsim_wave_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(ccsim_wave_multi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(h->smem_optin - sizeof(LeanShared) - sizeof(MultiShared) - 1024));
+  cudaFuncSetAttribute(ccsim_wave_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(LeanShared) - sizeof(MultiShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(SMEM_CNT_MAX_INTS * sizeof(int32_t) + 16));
@@ -1145,7 +1149,10 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   }
   // grid: one persistent CTA per SM (fewer for tiny clusters: the exchange cost grows with the CTA count)
   int grid = std::min(h->sm_count, CCSIM_MAX_GRID);
-  const int want = (n + BLOCK_THREADS - 1) / BLOCK_THREADS;
+  // (node-sharded runs: every rank sizes the grid from the largest shard, so that all ranks launch the same grid and every
+  //  rank knows how many candidate lines its peers publish)
+  const int32_t n_grid = h->cfg.world > 1 ? (h->n_global + h->cfg.world - 1) / h->cfg.world : n;
+  const int want = (n_grid + BLOCK_THREADS - 1) / BLOCK_THREADS;
   if (want < grid) grid = want;
   if (grid < 1) grid = 1;
   h->grid = grid;
@@ -1155,6 +1162,8 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   p.chunk = (n + grid - 1) / grid;
   h->epoch = (h->epoch % 255u) + 1u;     // every rank of a sharded run calls ccsim_run the same number of times
   p.epoch = h->epoch;
+  p.xwave0 = h->xwave0;
+  p.debug_flags = getenv("CCSIM_DEBUG_FLAGS") ? (uint32_t)atoi(getenv("CCSIM_DEBUG_FLAGS")) : 0u;
   // resident mode: every column the Filter/Score pass reads is staged into shared memory once
   int n_local = 0;
   for (int j = 0; j < h->n_counters; j++) if (h->counters[j].topo_col < 0) n_local++;
@@ -1253,7 +1262,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   h->last_batched = batched ? 1 : 0;
   // multi-commit waves (ccsim_multi.cuh): one template coupled through per-domain counters, one node per thread
   MultiParams mp; memset(&mp, 0, sizeof(mp));
-  bool multi = lean && !faithful && !batched && h->n_counters > 0 && h->max_prefer_pop == 0 && h->cfg.world == 1 &&
+  bool multi = lean && !faithful && !batched && h->n_counters > 0 && h->max_prefer_pop == 0 &&
                h->cfg.engine == CCSIM_ENGINE_AUTO && !getenv("CCSIM_FORCE_SEQUENTIAL") && h->h_templates[0].n_aff == 0 &&
                p.chunk <= LEAN_THREADS && h->n_global < (1 << MULTI_IDX_BITS);
   if (multi) {
@@ -1285,13 +1294,14 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
     }
     const size_t smem_m = smem + (size_t)p.chunk_pad * 8 + 16;     // + the per-node payload column
     if (smem_m + sizeof(LeanShared) + sizeof(MultiShared) + 1024 > h->smem_optin) multi = false;
-    if (multi) { kern = (const void *)ccsim_wave_multi_kernel; smem = smem_m; }
+    if (multi) { kern = h->cfg.world > 1 ? (const void *)ccsim_wave_multi_kernel<true> : (const void *)ccsim_wave_multi_kernel<false>; smem = smem_m; }
   }
   h->last_multi = multi ? 1 : 0;
   p.self = h->d_params;
   CK(cudaMemcpyAsync(h->d_params, &p, sizeof(DevParams), cudaMemcpyHostToDevice, s));
   int occ = 0;
-  if (multi) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel, block, smem));
+  if (multi && h->cfg.world > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel<true>, block, smem));
+  else if (multi) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel<false>, block, smem));
   else if (batched) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_batched_kernel, block, smem));
   else if (lean && faithful) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel<true>, block, smem));
   else if (lean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel<false>, block, smem));
@@ -1316,6 +1326,10 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
           (long long)ho.waves, ms);
   fprintf(stderr, "[ccsim phases 6/7] %.0f %.0f\n", (double)ho.phase_cycles[6] / ho.waves, (double)ho.phase_cycles[7] / ho.waves);
 #endif
+  if (h->cfg.world > 1) h->xwave0 += (uint32_t)ho.waves;    // identical on every rank: the engines run the same waves everywhere
+  h->last_stat[0] = multi ? 3 : batched ? 2 : lean ? 1 : 0; h->last_stat[1] = ho.waves; h->last_stat[2] = ho.placed;
+  h->last_stat[3] = ho.stat[0]; h->last_stat[4] = ho.stat[1]; h->last_stat[5] = grid; h->last_stat[6] = block; h->last_stat[7] = (int64_t)smem;
+  for (int q = 0; q < 8; q++) h->last_stat[8 + q] = ho.phase_cycles[q];
   out->placed = ho.placed; out->stop_code = ho.stop_code; out->waves = ho.waves; out->evals = ho.evals; out->run_ms = ms;
   out->examined = ho.examined ? ho.examined : ho.evals;
   h->last_placed = ho.placed;
@@ -1369,6 +1383,12 @@ extern "C" int ccsim_device_info(ccsim_handle *h, int32_t *sm_count, int32_t *gr
 }
 
 extern "C" int64_t ccsim_kernel_launches(const ccsim_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int ccsim_run_stats(const ccsim_handle *h, int64_t out[16]) {
+  if (!h || !out) return CCSIM_EINVAL;
+  memcpy(out, h->last_stat, sizeof(h->last_stat));
+  return CCSIM_OK;
+}
 
 extern "C" int ccsim_flush_l2(ccsim_handle *h) {
   if (!h) return CCSIM_EINVAL;

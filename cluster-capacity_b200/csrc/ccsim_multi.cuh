@@ -1,54 +1,75 @@
 // ccsim_multi.cuh — multi-commit waves for templates coupled through per-domain counters (PodTopologySpread DoNotSchedule,
-// required pod anti-affinity): several reference scheduling cycles per grid-wide exchange, identical pod -> node sequence.
+// required pod anti-affinity): several reference scheduling cycles per grid-wide exchange, identical pod -> node sequence,
+// on one GPU or over node shards on several GPUs (the exchange then crosses NVLink inside the same kernel).
 //
 // Why it is legal. Within a stretch of cycles in which no PodTopologySpread global minimum changes, a node's feasibility
 // depends on its own row and on the match counts of its topology domains only, and it is MONOTONE: counts only grow
 // (inc >= 0), so a feasible node can become infeasible but never the reverse; a node's score changes only when the node
 // itself is committed. The winner of each cycle is therefore the highest-keyed node that is still feasible under the
 // counts as updated so far (podtopologyspread/filtering.go:311-356, interpodaffinity/filtering.go:352-432;
-// schedule_one.go:894-941 with the canonical first-max tie rule). If every CTA publishes its M best feasible nodes (the
-// exact top-M: keys are unique) together with the domain ids their feasibility depends on, every CTA can replay those
-// cycles redundantly and deterministically: walk all published candidates in descending key order, re-check the per-domain
-// terms against its own replicated counters, commit the ones that still pass (candidates that fail are dropped from all
-// lists in parallel: by monotonicity they cannot come back during the wave). The replay stops when
+// schedule_one.go:894-941 with the canonical first-max tie rule). Every CTA publishes its M best feasible nodes (the exact
+// top-M of its tile: keys are unique) with the domain ids their feasibility depends on; every CTA of every rank then
+// replays those cycles redundantly and deterministically from the same published data.
+//
+// Which published candidates may be replayed. A CTA with more than M feasible nodes has UNSEEN nodes, all keyed below its
+// M-th (last) published key. T = the largest such last key over all lists is a wave-wide bar: a candidate keyed >= T
+// outranks every unseen node of every tile, a candidate keyed below T might not. The replay therefore works on the
+// candidates keyed >= T only (compacted into shared memory) and ends when the best live key falls below T, when
 //   (a) a PTS minimum moves (limits change, rejected nodes may come back: rescan),
-//   (b) a CTA with more feasible nodes than it published has used up its list and the next candidate's key is below that
-//       CTA's last published key (an unpublished node could rank in between),
-//   (c) the pod limit is reached (simulator.go:300-305).
-// A committed node may win again inside the wave with its new score, which is in nobody's list (a randomized differential test,
-// tests/test_gpu_stress.py, found this hole in the first version: spread-only templates). Every published candidate therefore
-// carries, next to its domain ids, its key after one more clone (node-local Filter part + score recomputed by the publisher; 0 =
-// it would not fit). The winner comes back into the replay once with that key ("second life"); when a node wins for the second
-// time in a wave its third key is unknown and the wave ends after that commit. Entries in their second life do not keep a list
-// "alive" for rule (b): the CTA's unpublished nodes rank below its last PUBLISHED key only.
-// The first candidate of a wave is always accepted, so every wave makes progress; a wave without candidates is the
+//   (b) the pod limit is reached (simulator.go:300-305),
+//   (c) a node wins for the second time (see below).
+// A committed node may win again inside the wave with its new score, which is in nobody's list (a randomized differential
+// test, tests/test_gpu_stress.py, found this hole in the first version: spread-only templates). Every published candidate
+// therefore carries, next to its domain ids, its key after one more clone (node-local Filter part + score recomputed by the
+// publisher; 0 = it would not fit). The winner comes back into the replay once with that key ("second life"); when a node
+// wins for the second time in a wave its third key is unknown and the wave ends after that commit.
+// The best candidate of a wave is always >= T and feasible, so every wave makes progress; a wave without candidates is the
 // Unschedulable stop. Node-local terms (hostname anti-affinity, ...) need no re-check: a node appears once per wave.
 //
-// Exchange: one 128-byte line per CTA = M (key, payload) pairs, each word tagged (self-validating, no fences). All 24 warps
-// gather the 148 lines in one L2 round trip; warp 0 of every CTA replays.
+// Exchange: one 128-byte line per CTA = M (key, payload) pairs, each word tagged (self-validating, no fences).
+//   single GPU : lines live in the handle's slot buffer (L2), st/ld.relaxed.gpu;
+//   node shards: every CTA stores its line into EVERY rank's line buffer (CUDA IPC mappings, st.relaxed.sys.v2 over NVLink)
+//                and polls its local copy — an all-gather of world x grid lines fused into the persistent kernel.
+// Replay: ONE warp, no barrier inside: <= 8 candidates per lane in registers; a round is arg-max (REDUX) -> commit (lane q =
+//   counter term q: cell += inc, over-limit test, PTS-minimum tracking, all from registers) -> kill the candidates sitting in
+//   a cell that just filled (field compare against the shuffled cell id). ~250 cycles per reference cycle instead of the
+//   ~2000 of a block-wide round (two barriers over 24 warps); the other 23 warps wait at the barrier that ends the wave.
+//   Row updates of the winners are done by each node's own thread after that barrier (a thread owns its node).
 #pragma once
 #include "ccsim_lean.cuh"
 
 #define MULTI_M 8                 /* candidates per CTA and wave: 8 x 16 B = the CTA's 128-byte slot line */
 #define MULTI_PAY_BITS 27         /* payload bits for domain ids (dom+1 per topology slot) */
 #define MULTI_NEXT_SHIFT 27       /* 12 bits: (score + 1) of the node after one more clone, 0 = it would not fit any more */
-#define MULTI_MORE_BIT 39
-#define MULTI_LEN_SHIFT 40
+#define MULTI_MORE_BIT 32         /* key word of the last entry: the tile has more feasible nodes than it published */
 #define MULTI_MAX_ACC 64          /* commits one wave may decide */
 #define MULTI_GT 6                /* Filter terms on replicated counters a template may have in this kernel */
+#ifndef MULTI_CPT
+#define MULTI_CPT 4               /* candidates per replay lane */
+#endif
+#define MULTI_CAP (32 * MULTI_CPT)
+#define MULTI_BINS 64
+
+// cross-GPU line buffers inside every rank's exchange allocation (64-bit words): [parity][source rank][CTA][16]
+#define XLEAN_WORDS (2 * CCSIM_MAX_WORLD * SLOT_STRIDE)
+#define XLINES_OFF XLEAN_WORDS
+#define XLINES_WORDS (2 * CCSIM_MAX_WORLD * CCSIM_MAX_GRID * SLOT_STRIDE)
+#define XSLOTS_TOTAL_WORDS (XLEAN_WORDS + XLINES_WORDS)
 
 struct __align__(16) MultiShared {
   uint32_t wtop[LEAN_WARPS][MULTI_M];               // per-warp top-M (compact) keys of this wave
-  int32_t gt_c1[MULTI_GT][4];                       // (16-byte aligned) ... and {limit, payload shift, payload mask, counter base}
-  int32_t gt_commit[MULTI_GT][4];                   // (16-byte aligned) per replicated-counter term: {counter base, inc, PTS constraint tracked or -1, n_present}
-  uint32_t rmax[LEAN_WARPS], rbar[LEAN_WARPS];      // replay: per-warp maxima of a round
+  int32_t gt_c1[MULTI_GT][4];                       // per replicated-counter term: {limit, payload shift, payload mask, domains of the counter}
+  int32_t gt_commit[MULTI_GT][4];                   // ... {counter base, inc, PTS constraint tracked or -1, n_present}
+  uint32_t ckey[MULTI_CAP], cdom[MULTI_CAP], cnext[MULTI_CAP];   // the wave's candidates keyed >= T (unordered)
+  uint32_t red[LEAN_WARPS], red2[LEAN_WARPS];       // block reductions (T, best key)
+  uint32_t hist[MULTI_BINS];
   int32_t wfeas[LEAN_WARPS];
   int32_t gt_term[MULTI_GT];                        // indices of the Filter terms that read a replicated (non node-local) counter
-  uint32_t gt_shift[MULTI_GT], gt_mask[MULTI_GT];   // ... and where their domain id sits in the payload
   int32_t acc_node[MULTI_MAX_ACC];                  // replay: nodes accepted in this wave, in order
-  int32_t full[MULTI_GT];                           // replay: counter cell of term q that the last commit pushed over its limit, or -2
   int32_t n_gt, accepted, dead, stopb;
-  int32_t single_use, pad_ms[3];
+  int32_t single_use, ncand;
+  uint32_t delta, pad_ms;
+  long long ph[8], tc0, st_cand, st_overflow;       // CTA 0 / thread 0: clock cycles per phase, replay statistics
 };
 
 __shared__ MultiShared ms;
@@ -65,16 +86,36 @@ struct MultiParams {
 __device__ __forceinline__ uint32_t ckey(int32_t score, uint32_t gidx) { return ((uint32_t)(score + 1) << MULTI_IDX_BITS) | (MULTI_IDX_MASK - gidx); }
 __device__ __forceinline__ int32_t ckey_index(uint32_t ck) { return (int32_t)(MULTI_IDX_MASK - (ck & MULTI_IDX_MASK)); }
 
-// Shared-memory accesses of the replay loop by explicit 32-bit shared address: nvcc otherwise re-derives the CTA's shared
-// window base (S2UR SR_CgaCtaId + LEA) in front of every access inside these barrier-separated regions.
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-#define MS_OFF(field) ((uint32_t)offsetof(MultiShared, field))
-
-__device__ __forceinline__ void ld_slot2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+template <bool XGPU> __device__ __forceinline__ void ld_line2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  if (XGPU) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_line2_sys(unsigned long long *p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
+// warp-aggregated append of the lanes' candidates to the wave's candidate arrays (order does not matter: keys are unique)
+__device__ __forceinline__ void multi_append(bool keep, uint32_t ck, unsigned long long b, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (m) {
+    int base = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(&ms.ncand, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const int idx = base + __popc(m & ((1u << lane) - 1u));
+    if (keep && idx < MULTI_CAP) {
+      ms.ckey[idx] = ck;
+      ms.cdom[idx] = (uint32_t)b & ((1u << MULTI_PAY_BITS) - 1u);
+      ms.cnext[idx] = (uint32_t)(b >> MULTI_NEXT_SHIFT) & 0xfffu;
+    }
+  }
+}
+
+// phase timers live in shared memory (thread 0 of CTA 0 only): registers are what this kernel is short of
+#define MPH_START() do { if (cta == 0 && tid == 0) ms.tc0 = clock64(); } while (0)
+#define MPH_MARK(i) do { if (cta == 0 && tid == 0) { const long long tc1_ = clock64(); ms.ph[i] += tc1_ - ms.tc0; ms.tc0 = tc1_; } } while (0)
+
+template <bool XGPU>
 __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const DevParams p, const LeanParams lp, const MultiParams mp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t *smem_cnt = reinterpret_cast<int32_t *>(smem_raw);
@@ -91,10 +132,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
   const int cta = blockIdx.x;
   const int32_t lo = min(p.n, cta * p.chunk), hi = min(p.n, lo + p.chunk);
   const int32_t cnt_nodes = hi - lo;      // <= LEAN_THREADS (host-checked): one node per thread
-  // shared address of `ms`, computed once; the volatile move keeps nvcc from re-deriving it (S2UR SR_CgaCtaId) at every use
-  uint32_t msb;
-  { const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(&ms); asm volatile("mov.u32 %0, %1;" : "=r"(msb) : "r"(t0)); }
   const int su = lp.stride_u;
+  const int nlists = (XGPU ? p.world : 1) * p.grid;     // every rank launches the same grid (host: sized from the largest shard)
+  const int tot = nlists * MULTI_M;
 
   // ---- stage the tile (once): hot AoS records + cold SoA columns (same layout as the lean kernel) ----
   for (int32_t j = tid; j < cnt_nodes; j += LEAN_THREADS) {
@@ -127,19 +167,18 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     if (dc.topo_col < 0) continue;
     for (int d = tid; d < dc.n_domains; d += LEAN_THREADS) smem_cnt[dc.smem_off + d] = dc.init[d];
   }
-  if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; ms.accepted = 0; ms.dead = 0; ms.stopb = 0; ms.n_gt = 0; }
+  if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; ms.accepted = 0; ms.dead = 0; ms.stopb = 0; ms.n_gt = 0; ms.ncand = 0; ms.delta = 1u << MULTI_IDX_BITS;
+                  for (int q = 0; q < 8; q++) ms.ph[q] = 0; ms.tc0 = 0; ms.st_cand = 0; ms.st_overflow = 0; }
   __syncthreads();
   for (int c = 0; c < ls.tmpl.n_pts; c++) lean_pts_recount(p, smem_cnt, c);
 
-#ifdef CCSIM_PHASE_TIMERS
-  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0;
-#endif
   long long k = 0, wv = 0;
+  uint32_t delta = 1u << MULTI_IDX_BITS;     // bar distance below the best key: starts at one score level
   bool limit_hit = false;   // postBindHook's limit (simulator.go:300-305)
   uint32_t wtag = 1;
   uint32_t tag = (p.epoch << 12) | wtag;
   for (;; wv++) {
-    PH_START();
+    MPH_START();
     if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }   // uniform; no shared write (slower threads may still be reading ls.stop)
     if (k > p.pod_cap) { if (tid == 0) ls.stop = 3; __syncthreads(); break; }
     if (ls.dirty) {
@@ -149,12 +188,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         for (int q = 0; q < ls.n_cmp_terms; q++)
           if (ls.terms[q].cnt_off >= 0 && g < MULTI_GT) {
             const int sl = ls.terms[q].slot - 10;
-            ms.gt_shift[g] = mp.pay_shift[sl]; ms.gt_mask[g] = mp.pay_mask[sl];
-            ms.gt_c1[g][0] = ls.terms[q].lim; ms.gt_c1[g][1] = (int32_t)mp.pay_shift[sl]; ms.gt_c1[g][2] = (int32_t)mp.pay_mask[sl]; ms.gt_c1[g][3] = ls.terms[q].cnt_off;
+            ms.gt_c1[g][0] = ls.terms[q].lim; ms.gt_c1[g][1] = (int32_t)mp.pay_shift[sl]; ms.gt_c1[g][2] = (int32_t)mp.pay_mask[sl]; ms.gt_c1[g][3] = 0;
             ms.gt_commit[g][0] = ls.terms[q].cnt_off; ms.gt_commit[g][1] = 0; ms.gt_commit[g][2] = -1; ms.gt_commit[g][3] = 0;
             for (int j = 0; j < p.n_counters; j++)
               if (p.counters[j].topo_col >= 0 && p.counters[j].smem_off == ls.terms[q].cnt_off) {
                 ms.gt_commit[g][1] = ls.cinfo[j].inc; ms.gt_commit[g][2] = ls.cinfo[j].pts_idx; ms.gt_commit[g][3] = ls.cinfo[j].n_present;
+                ms.gt_c1[g][3] = p.counters[j].n_domains;
               }
             ms.gt_term[g++] = q;
           }
@@ -218,10 +257,11 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         if (lane == 0) ms.wtop[warp][r] = v;
       }
     }
-    PH_MARK(0);
+    MPH_MARK(0);
     __syncthreads();                                                    // S1
-    PH_MARK(1);
+    MPH_MARK(1);
     const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
+    const int par = XGPU ? (int)((wv + p.xwave0) & 1) : (int)(wv & 1);
     if (warp == 0) {
       // ---- the CTA's M best: merge of the 24 sorted warp lists (lane w walks warp w's list), then publish the pairs ----
       int32_t total = lane < LEAN_WARPS ? ms.wfeas[lane] : 0;
@@ -264,184 +304,267 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         }
         }
       }
-      pay |= ((unsigned long long)L << MULTI_LEN_SHIFT) | ((unsigned long long)(total > L ? 1 : 0) << MULTI_MORE_BIT);
-      unsigned long long *myslots = p.slots + ((size_t)(wv & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
-      if (lane < MULTI_M) {
-        st_slot(&myslots[2 * lane], (unsigned long long)mykey | tagbits);
-        st_slot(&myslots[2 * lane + 1], pay | tagbits);
+      // line layout (16 tagged words): [0] key 0  [1] key 7 | more-bit  [2..7] keys 1..6  [8..15] payloads 0..7 — the poller of a
+      // line reads words 0-1 in one 16-byte load: the list's best key and its last key (with "this tile has more feasible nodes")
+      unsigned long long kw = (unsigned long long)mykey;
+      if (lane == MULTI_M - 1 && total > L) kw |= 1ull << MULTI_MORE_BIT;
+      const int kpos = lane == 0 ? 0 : (lane == MULTI_M - 1 ? 1 : lane + 1);
+      if (!XGPU) {
+        unsigned long long *myslots = p.slots + ((size_t)par * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
+        if (lane < MULTI_M) {
+          st_slot(&myslots[kpos], kw | tagbits);
+          st_slot(&myslots[MULTI_M + lane], pay | tagbits);
+        }
+      } else {
+        // this CTA's line goes into every rank's buffer: lane -> (destination rank, entry); 8-byte stores over NVLink
+        const size_t off = XLINES_OFF + (((size_t)par * CCSIM_MAX_WORLD + p.rank) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
+        for (int base = 0; base < p.world * MULTI_M; base += 32) {
+          const int t = base + lane, e = t & (MULTI_M - 1), r = t >> 3;
+          const unsigned long long kv = __shfl_sync(0xffffffffu, kw, e);
+          const unsigned long long pv = __shfl_sync(0xffffffffu, pay, e);
+          const int kp = e == 0 ? 0 : (e == MULTI_M - 1 ? 1 : e + 1);
+          if (t < p.world * MULTI_M) {
+            st_slot_sys(p.xslots_peer[r] + off + kp, kv | tagbits);
+            st_slot_sys(p.xslots_peer[r] + off + MULTI_M + e, pv | tagbits);
+          }
+        }
       }
     }
-    PH_MARK(2);
-    // ---- gather: every (CTA, entry) pair is polled by one thread and stays in its registers for the replay ----
-    const int e0 = tid, e1 = tid + LEAN_THREADS;
-    unsigned long long a0w = 0ull, b0 = 0ull, a1w = 0ull, b1 = 0ull;
-    {
-      const unsigned long long *base = p.slots + (size_t)(wv & 1) * CCSIM_MAX_GRID * SLOT_STRIDE;
-      const int tot = p.grid * MULTI_M;
-      // (1) one lane per CTA line waits for that line's first key word — 148 pollers per line grid-wide, as in the lean kernel;
-      //     letting all 768 threads spin on their own entries (1184 pollers per line) delays the very stores they wait for
-      if (warp < (p.grid + 31) / 32) {
-        const int c = warp * 32 + lane;
-        unsigned spins = 0;
-        bool pending;
-        do {
-          pending = (c < p.grid) && ((uint32_t)(ld_slot(base + (size_t)c * SLOT_STRIDE) >> KEY_TAG_SHIFT) != tag);
-          if (++spins > WATCHDOG_SPINS) { ms.dead = 1; break; }
-        } while (__any_sync(0xffffffffu, pending));
+    MPH_MARK(2);
+    // ---- gather 1: one poller per line and CTA (like the lean kernel) waits for the line's words 0-1; T and the best key ----
+    const unsigned long long *lbase = XGPU ? p.xslots_peer[p.rank] + XLINES_OFF + (size_t)par * CCSIM_MAX_WORLD * CCSIM_MAX_GRID * SLOT_STRIDE
+                                           : p.slots + (size_t)par * CCSIM_MAX_GRID * SLOT_STRIDE;
+    // list l = (source rank l / grid, CTA l % grid) -> its line
+#define LINE_OF(l) (lbase + (XGPU ? ((size_t)((l) / p.grid) * CCSIM_MAX_GRID + (size_t)((l) % p.grid)) : (size_t)(l)) * SLOT_STRIDE)
+    uint32_t tloc = 0u, kloc = 0u;
+    for (int l = tid; l < nlists; l += LEAN_THREADS) {
+      const unsigned long long *ln = LINE_OF(l);
+      unsigned long long a, b;
+      unsigned spins = 0;
+      for (;;) {
+        ld_line2<XGPU>(ln, a, b);
+        if ((uint32_t)(a >> KEY_TAG_SHIFT) == tag && (uint32_t)(b >> KEY_TAG_SHIFT) == tag) break;
+        if (++spins > WATCHDOG_SPINS) { ms.dead = 1; a = b = 0ull; break; }
+      }
+      kloc = max(kloc, (uint32_t)a);
+      if ((b >> MULTI_MORE_BIT) & 1ull) tloc = max(tloc, (uint32_t)b);
+    }
+    tloc = __reduce_max_sync(0xffffffffu, tloc);
+    kloc = __reduce_max_sync(0xffffffffu, kloc);
+    if (lane == 0) { ms.red[warp] = tloc; ms.red2[warp] = kloc; }
+    __syncthreads();                                                    // G1 (also: ms.dead)
+    const uint32_t Tlist = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? ms.red[lane] : 0u);
+    const uint32_t kbest = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? ms.red2[lane] : 0u);
+    const bool dead = ms.dead != 0;
+    // The replay bar: T = the largest "last key" of a list whose tile has unseen feasible nodes is the lowest VALID bar; any
+    // higher bar is valid too, just more conservative. The replay holds MULTI_CAP candidates, and it rarely needs more than the
+    // best few dozen before a PTS minimum moves, so the bar is set `delta` below the best key (never below T); delta follows the
+    // previous waves (doubled when the replay ran out of candidates above an artificial bar, shrunk when too many qualified).
+    // Every CTA of every rank computes the same sequence from the same exchanged data.
+    uint32_t T = max(Tlist, kbest > delta ? kbest - delta : 0u);
+    // ---- gather 2: fetch the entries keyed >= T into shared memory (unordered; keys are unique) ----
+    int C = 0;
+    const int iters = (tot + LEAN_THREADS - 1) / LEAN_THREADS;
+    for (int pass = 0; pass < 2 && !dead; pass++) {
+      for (int it = 0; it < iters; it++) {
+        const int e = tid + it * LEAN_THREADS;
+        unsigned long long a = 0ull, b = 0ull;
+        bool keep = false;
+        if (e < tot) {
+          const unsigned long long *ln = LINE_OF(e >> 3);
+          const int ee = e & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
+          unsigned spins = 0;
+          for (;;) {       // words of a line are separate stores: each is validated by its own tag
+            a = XGPU ? ld_slot_sys(ln + kp) : ld_slot(ln + kp);
+            if ((uint32_t)(a >> KEY_TAG_SHIFT) == tag) break;
+            if (++spins > WATCHDOG_SPINS) { ms.dead = 1; a = 0ull; break; }
+          }
+          keep = (uint32_t)a != 0u && (uint32_t)a >= T;
+          if (keep) {      // payloads only of the entries that qualify
+            spins = 0;
+            for (;;) {
+              b = XGPU ? ld_slot_sys(ln + MULTI_M + ee) : ld_slot(ln + MULTI_M + ee);
+              if ((uint32_t)(b >> KEY_TAG_SHIFT) == tag) break;
+              if (++spins > WATCHDOG_SPINS) { ms.dead = 1; b = 0ull; keep = false; break; }
+            }
+          }
+        }
+        multi_append(keep, (uint32_t)a, b, lane);
+      }
+      __syncthreads();                                                  // G2
+      C = ms.ncand;
+      if (C <= MULTI_CAP || pass == 1) break;
+      // More candidates than the replay holds: raise T to the lowest of 64 equal steps between T and the best key that leaves
+      // <= MULTI_CAP candidates; every CTA sees the same data and decides alike.
+      if (tid < MULTI_BINS) ms.hist[tid] = 0u;
+      __syncthreads();
+      const unsigned long long range = (unsigned long long)(kbest - T) + 1ull;
+      for (int it = 0; it < iters; it++) {
+        const int e = tid + it * LEAN_THREADS;
+        if (e < tot) {
+          const int ee = e & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
+          const uint32_t ck = (uint32_t)(XGPU ? ld_slot_sys(LINE_OF(e >> 3) + kp) : ld_slot(LINE_OF(e >> 3) + kp));     // validated above
+          if (ck != 0u && ck >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(ck - T) * MULTI_BINS) / range)], 1u);
+        }
       }
       __syncthreads();
-      // (2) every thread fetches its entries; words of a line are separate stores, so each is still validated by its own tag
-      bool need0 = e0 < tot, need1 = e1 < tot;
-      unsigned spins = 0;
-      while ((need0 | need1) && !ms.dead) {
-        if (need0) ld_slot2(base + (size_t)(e0 >> 3) * SLOT_STRIDE + 2 * (e0 & 7), a0w, b0);
-        if (need1) ld_slot2(base + (size_t)(e1 >> 3) * SLOT_STRIDE + 2 * (e1 & 7), a1w, b1);
-        if (need0 && (uint32_t)(a0w >> KEY_TAG_SHIFT) == tag && (uint32_t)(b0 >> KEY_TAG_SHIFT) == tag) need0 = false;
-        if (need1 && (uint32_t)(a1w >> KEY_TAG_SHIFT) == tag && (uint32_t)(b1 >> KEY_TAG_SHIFT) == tag) need1 = false;
-        if (++spins > WATCHDOG_SPINS) { ms.dead = 1; break; }
-      }
-      if (need0 | need1) { a0w = b0 = a1w = b1 = 0ull; }
-      b0 &= KEY_BODY_MASK; b1 &= KEY_BODY_MASK;
-      if (e0 >= tot) { a0w = 0ull; b0 = 0ull; }
-      if (e1 >= tot) { a1w = 0ull; b1 = 0ull; }
+      int bsel = MULTI_BINS;
+      { unsigned sum = 0; for (int bq = MULTI_BINS - 1; bq >= 0; bq--) { sum += ms.hist[bq]; if (sum > (unsigned)MULTI_CAP) break; bsel = bq; } }
+      T = (bsel >= MULTI_BINS) ? kbest : T + (uint32_t)(((unsigned long long)bsel * range + (MULTI_BINS - 1)) / MULTI_BINS);
+      __syncthreads();
+      if (tid == 0) ms.ncand = 0;
+      if (cta == 0 && tid == 0) ms.st_overflow++;
+      __syncthreads();
     }
-    const uint32_t a0 = (uint32_t)a0w, a1 = (uint32_t)a1w;      // compact keys as published (the tag sits above bit 44)
-    uint32_t k0 = a0, k1 = a1;                                   // ... and as they stand in the replay (a winner comes back once with its next key)
-    bool second0 = false, second1 = false;
-    // counter cells each of my candidates depends on (-1: the node lacks the key and the term lets it pass)
-    int32_t i0[MULTI_GT], i1[MULTI_GT];
-    const int n_gt = ms.n_gt;
-    const bool has1 = (e1 & ~31) < p.grid * MULTI_M;
-    #pragma unroll
-    for (int q = 0; q < MULTI_GT; q++) {
-      i0[q] = -1; i1[q] = -1;
-      if (q < n_gt) {
-        const int4 c1 = *reinterpret_cast<const int4 *>(&ms.gt_c1[q][0]);      // {lim, shift, mask, counter base}
-        const int32_t v0 = (int32_t)((uint32_t)(b0 >> c1.y) & (uint32_t)c1.z) - 1;
-        i0[q] = v0 >= 0 ? c1.w + v0 : -1;
-        if (has1) {          // warp-uniform: only the first grid*8 - 768 threads hold a second candidate
-          const int32_t v1 = (int32_t)((uint32_t)(b1 >> c1.y) & (uint32_t)c1.z) - 1;
-          i1[q] = v1 >= 0 ? c1.w + v1 : -1;
-        }
-      }
-    }
-    PH_MARK(3);
-    // ---- replay: the reference cycles k, k+1, ... this wave can decide; every CTA does the same, all threads take part ----
-    // Each round: every thread re-checks its (<= 2) candidates against the CTA's counter replicas (a candidate that fails is
-    // dropped for the rest of the wave: monotone), block arg-max over the survivors, the thread holding the maximum commits.
-    bool live0 = a0 != 0u, live1 = a1 != 0u;
-    uint32_t bar = 0u;      // highest "last published key" of a list that ran dry while its CTA has more nodes
-    int32_t acc = 0;
-    const int L0 = (int)((b0 >> MULTI_LEN_SHIFT) & 15ull), L1 = (int)((b1 >> MULTI_LEN_SHIFT) & 15ull);
-    const bool more0 = (b0 >> MULTI_MORE_BIT) & 1ull, more1 = (b1 >> MULTI_MORE_BIT) & 1ull;
-    const unsigned grp = 0xffu << (lane & ~7);
-    __syncthreads();                                                    // S2: ms.dead, the counters of the previous wave's recount
-    const bool dead = ms.dead != 0;
-    // Round 0 needs no check: every published candidate passed the scan under the very counts the replicas hold now. After a
-    // commit only the candidates sitting in a counter cell that has just gone over its limit die; the committing warp
-    // names those cells (ms.full), everybody else compares. A warp whose candidates did not change keeps its maxima.
-    uint32_t wm = 0u, wb = 0u;
-    bool refresh = true;                 // warp-uniform: recompute this warp's maxima
-    for (int round = 0; !dead; round++) {
-      if (round > 0) {
-        bool died = false;
+    const bool overflowed = C > MULTI_CAP || T > max(Tlist, kbest > delta ? kbest - delta : 0u);
+    if (C > MULTI_CAP) C = MULTI_CAP;     // (cannot happen after the second pass: the raised T admits <= MULTI_CAP keys)
+    if (cta == 0 && tid == 0) ms.st_cand += C;
+    MPH_MARK(3);
+    // ---- replay: the reference cycles k, k+1, ... this wave can decide; every CTA does the same, in ONE warp and without a
+    //      barrier: MULTI_CPT candidates per lane in registers, lane q < n_gt also owns counter term q (its constants, and the
+    //      minimum / multiplicity of the PTS constraint it tracks, stay in registers for the whole wave) ----
+    if (warp == 0) {
+      int32_t acc = 0;
+      bool ran_dry = false;
+      if (!dead && !ms.dead) {
+        const int n_gt = ms.n_gt;
+        uint32_t ck[MULTI_CPT], cd[MULTI_CPT];
+        uint32_t second = 0u;
         #pragma unroll
-        for (int q = 0; q < MULTI_GT; q++) {
-          if (q < n_gt) {
-            const int32_t f = (int32_t)lds_u32(msb + MS_OFF(full) + 4u * q);
-            if (f >= 0) {
-              if (live0 && i0[q] == f) { live0 = false; died = true; }
-              if (has1 && live1 && i1[q] == f) { live1 = false; died = true; }
-            }
-          }
+        for (int j = 0; j < MULTI_CPT; j++) {
+          const int idx = j * 32 + lane;
+          ck[j] = 0u; cd[j] = 0u;
+          if (idx < C) { ck[j] = ms.ckey[idx]; cd[j] = ms.cdom[idx]; }
         }
-        refresh |= __any_sync(0xffffffffu, died);
-      }
-      if (refresh) {
-        const uint32_t v0 = live0 ? k0 : 0u, v1 = live1 ? k1 : 0u;
-        // a list (8 consecutive lanes) without a live entry whose CTA has unpublished feasible nodes: those rank below its last key
-        // (only entries in their first life count: a CTA's unpublished nodes rank below its last PUBLISHED key, and a winner that
-        //  came back with its next key may well rank below that)
-        const unsigned bal0 = __ballot_sync(0xffffffffu, live0 && !second0), bal1 = __ballot_sync(0xffffffffu, live1 && !second1);
-        if (!(bal0 & grp) && more0 && (e0 & 7) == L0 - 1) bar = a0 > bar ? a0 : bar;
-        if (!(bal1 & grp) && more1 && (e1 & 7) == L1 - 1) bar = a1 > bar ? a1 : bar;
-        wm = __reduce_max_sync(0xffffffffu, v0 > v1 ? v0 : v1);
-        wb = __reduce_max_sync(0xffffffffu, bar);
-        if (lane == 0) { sts_u32(msb + MS_OFF(rmax) + 4u * warp, wm); sts_u32(msb + MS_OFF(rbar) + 4u * warp, wb); }
-        refresh = false;
-      }
-      __syncthreads();                                                  // A
-#ifdef CCSIM_PHASE_TIMERS
-      if (round == 0) { PH_MARK(1); } else { PH_MARK(6); }
-#endif
-      const uint32_t g = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? lds_u32(msb + MS_OFF(rmax) + 4u * lane) : 0u);
-      const uint32_t gb = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? lds_u32(msb + MS_OFF(rbar) + 4u * lane) : 0u);
-      if (g == 0u || g < gb) break;            // block-uniform: nothing left, or an unpublished node could rank above g
-      if (wm == g) {      // warp-uniform: this warp holds the winner; it commits like the lean kernel's warp 0 does
-        // ---- commit pod k+acc (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
-        const bool own0 = live0 && k0 == g, own1 = live1 && k1 == g;
-        const int ol = __ffs(__ballot_sync(0xffffffffu, own0 | own1)) - 1;
-        const unsigned long long pay = __shfl_sync(0xffffffffu, own0 ? b0 : b1, ol);
-        // the winner comes back once with the key it has after this clone (if it still fits); when a node wins for the second
-        // time in a wave its third key is unknown: the wave ends after that commit
-        const bool was_second = __any_sync(0xffffffffu, (own0 && second0) || (own1 && second1));
-        if (own0) {
-          const uint32_t ns = (uint32_t)(b0 >> MULTI_NEXT_SHIFT) & 0xfffu;
-          if (ns && !second0) { k0 = (ns << MULTI_IDX_BITS) | (k0 & MULTI_IDX_MASK); second0 = true; } else live0 = false;
-        }
-        if (own1) {
-          const uint32_t ns = (uint32_t)(b1 >> MULTI_NEXT_SHIFT) & 0xfffu;
-          if (ns && !second1) { k1 = (ns << MULTI_IDX_BITS) | (k1 & MULTI_IDX_MASK); second1 = true; } else live1 = false;
-        }
-        // Only what the next round depends on happens here: the counter cells of the winner's domains (lane q = term q; the
-        // host guarantees one term per incremented replicated counter), whether a cell went over its limit, whether a PTS
-        // minimum moved. The winner's row (NodeInfo.update, node-local counters) is brought up to date after the last round.
-        bool minchg = false;
+        int4 gc = make_int4(0, 0, -1, 0), c1 = make_int4(0, 0, 0, 0);
+        int32_t my_min = 0, my_num = 0;
         if (lane < n_gt) {
-          const int4 gc = *reinterpret_cast<const int4 *>(&ms.gt_commit[lane][0]);   // {cnt_off, inc, pts_idx, n_present}
-          const int4 c1 = *reinterpret_cast<const int4 *>(&ms.gt_c1[lane][0]);       // {lim, shift, mask, cnt_off}
-          const int32_t lim = c1.x;
-          const int32_t v = (int32_t)((uint32_t)(pay >> c1.y) & (uint32_t)c1.z) - 1;
-          int32_t fullcell = -2;
-          if (v >= 0) {
-            const int32_t old = smem_cnt[gc.x + v], nv = old + gc.y;
-            smem_cnt[gc.x + v] = nv;
-            if (nv > lim) fullcell = gc.x + v;             // candidates in this cell are dead from now on
-            if (gc.y && gc.z >= 0 && v < gc.w && old == ls.ptsmin[gc.z]) {
-              const int32_t left = ls.ptsnum[gc.z] - 1;
-              ls.ptsnum[gc.z] = left;
-              minchg = left <= 0;                          // the global minimum of this constraint moves: limits change, rescan
+          gc = *reinterpret_cast<const int4 *>(&ms.gt_commit[lane][0]);   // {cnt_off, inc, pts_idx, n_present}
+          c1 = *reinterpret_cast<const int4 *>(&ms.gt_c1[lane][0]);       // {lim, shift, mask, n_domains}
+          if (gc.z >= 0) { my_min = ls.ptsmin[gc.z]; my_num = ls.ptsnum[gc.z]; }
+        }
+        uint32_t fmask[MULTI_GT];                    // payload field mask of term q, pre-shifted (0: no such term)
+        #pragma unroll
+        for (int q = 0; q < MULTI_GT; q++) fmask[q] = q < n_gt ? ((uint32_t)ms.gt_c1[q][2] << ms.gt_c1[q][1]) : 0u;
+        const int32_t lim_off = c1.x - my_min;       // PTS: maxSkew - selfMatch (the limit follows the global minimum)
+        bool lim_moved = false;
+        const bool single_use = ms.single_use != 0;
+        for (;;) {
+          uint32_t m = ck[0];
+          #pragma unroll
+          for (int j = 1; j < MULTI_CPT; j++) m = max(m, ck[j]);
+          const uint32_t g = __reduce_max_sync(0xffffffffu, m);
+          if (g == 0u || g < T) { ran_dry = true; break; }      // nothing left, or an unseen node could rank above g
+          // ---- commit pod k+acc (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
+          const bool mine = (m == g);
+          const int ol = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+          uint32_t dsel = 0u; int jsel = 0;
+          #pragma unroll
+          for (int j = 0; j < MULTI_CPT; j++) if (ck[j] == g) { dsel = cd[j]; jsel = j; }
+          const uint32_t pay = __shfl_sync(0xffffffffu, dsel, ol);
+          // the winner comes back once with the key it has after this clone (if it still fits); when a node wins for the second
+          // time in a wave its third key is unknown: the wave ends after that commit
+          bool sec = false;
+          if (mine) {
+            sec = (second >> jsel) & 1u;
+            const uint32_t ns = (single_use || sec) ? 0u : ms.cnext[jsel * 32 + lane];
+            const uint32_t nk = ns ? ((ns << MULTI_IDX_BITS) | (g & MULTI_IDX_MASK)) : 0u;
+            #pragma unroll
+            for (int j = 0; j < MULTI_CPT; j++) if (j == jsel) ck[j] = nk;
+            second |= 1u << jsel;
+          }
+          // Only what the next round depends on happens here: the counter cells of the winner's domains (lane q = term q; the
+          // host guarantees one term per incremented replicated counter), whether a cell went over its limit, whether a PTS
+          // minimum moved. The winner's row (NodeInfo.update, node-local counters) is brought up to date by its own thread after the wave.
+          bool minchg = false;
+          uint32_t fullf = 0u;
+          if (lane < n_gt) {
+            const int32_t v = (int32_t)((pay >> c1.y) & (uint32_t)c1.z) - 1;
+            if (v >= 0) {
+              const int32_t old = smem_cnt[gc.x + v], nv = old + gc.y;
+              smem_cnt[gc.x + v] = nv;
+              if (nv > c1.x) fullf = (uint32_t)(v + 1) << c1.y;            // candidates in this cell are dead from now on
+              if (gc.y && gc.z >= 0 && v < gc.w && old == my_min) { my_num--; minchg = my_num <= 0; }   // the global minimum of this constraint moves: limits change, rescan
             }
           }
-          ms.full[lane] = fullcell;
+          if (lane == 0) ms.acc_node[acc] = ckey_index(g);
+          acc++;
+          // A PTS minimum moved (filtering.go:56-69: minMatchNum): recount it and move the term's limit. The wave goes on unless
+          // the move changes some node's feasibility: that takes a domain whose count lies in (old limit, new limit] — nodes there
+          // were rejected by the scan (or killed earlier in this wave) and pass now. Without such a domain every verdict so far
+          // stands (the 8-region constraint of C4 moves its minimum every 8 placements and never binds).
+          bool rescan = false;
+          const unsigned mc = __ballot_sync(0xffffffffu, minchg);
+          for (unsigned nm = mc; nm; nm &= nm - 1) {
+            const int q = __ffs(nm) - 1;
+            const int32_t off = __shfl_sync(0xffffffffu, gc.x, q), npres = __shfl_sync(0xffffffffu, gc.w, q), ndom = __shfl_sync(0xffffffffu, c1.w, q);
+            const int32_t lim_old = __shfl_sync(0xffffffffu, c1.x, q), loff = __shfl_sync(0xffffffffu, lim_off, q);
+            const int32_t *cnt = smem_cnt + off;
+            int32_t mn = INT32_MAX;
+            for (int d = lane; d < npres; d += 32) mn = min(mn, cnt[d]);
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            int32_t num = 0;
+            for (int d = lane; d < npres; d += 32) num += (cnt[d] == mn);
+            num = __reduce_add_sync(0xffffffffu, num);
+            const long long liml = (long long)loff + (long long)mn;
+            const int32_t lim_new = liml > INT32_MAX ? INT32_MAX : (liml < INT32_MIN ? INT32_MIN : (int32_t)liml);
+            bool hit = false;
+            for (int d = lane; d < ndom; d += 32) { const int32_t c = cnt[d]; hit |= (c > lim_old) & (c <= lim_new); }
+            rescan |= __any_sync(0xffffffffu, hit) | (p.debug_flags & 1);
+            if (lane == q) { my_min = mn; my_num = num; c1.x = lim_new; lim_moved = true; }
+          }
+          bool stopb = __any_sync(0xffffffffu, sec) | rescan;
+          stopb |= (p.max_pods > 0 && k + acc >= p.max_pods) | (k + acc >= p.pod_cap) | (acc >= MULTI_MAX_ACC);
+          if (stopb) break;
+          // only the candidates sitting in a counter cell that this commit pushed over its limit die (monotone: for the rest of
+          // the wave); the fields of different terms are disjoint bit ranges, so one OR-reduction carries all filled cells
+          const uint32_t F = __reduce_or_sync(0xffffffffu, fullf);
+          if (F) {
+            #pragma unroll
+            for (int q = 0; q < MULTI_GT; q++) {
+              const uint32_t f = F & fmask[q];
+              if (f) {
+                #pragma unroll
+                for (int j = 0; j < MULTI_CPT; j++) if ((cd[j] & fmask[q]) == f) ck[j] = 0u;
+              }
+            }
+          }
         }
-        bool stopb = __any_sync(0xffffffffu, minchg);
-        stopb |= (p.max_pods > 0 && k + acc + 1 >= p.max_pods);
-        stopb |= (k + acc + 1 >= p.pod_cap) | (acc + 1 >= MULTI_MAX_ACC) | was_second;
-        if (lane == 0) { ms.stopb = stopb ? 1 : 0; ms.acc_node[acc] = ckey_index(g); }
-        refresh = true;
+        // the limits that moved go back to the Filter constants of the next scan
+        if (lim_moved) { ls.terms[ms.gt_term[lane]].lim = c1.x; ms.gt_c1[lane][0] = c1.x; }
+        if (lane < n_gt && gc.z >= 0) { ls.ptsmin[gc.z] = my_min; ls.ptsnum[gc.z] = my_num; }
       }
-      acc++;
-      __syncthreads();                                                  // B: counters, ms.stopb
-      PH_MARK(7);
-      if (lds_u32(msb + MS_OFF(stopb))) break;
+      if (lane == 0 && cta == 0 && (p.debug_flags & 4))
+        printf("wave %lld k=%lld acc=%d C=%d T=%08x Tlist=%08x kbest=%08x delta=%08x ran_dry=%d first=%d last=%d\n", wv, k, acc, C, T, Tlist, kbest, delta,
+               (int)ran_dry, acc ? ms.acc_node[0] : -1, acc ? ms.acc_node[acc - 1] : -1);
+      if (lane == 0) {
+        ms.accepted = acc; ms.ncand = 0;
+        // next wave's bar distance: the replay ran out of candidates above a bar that was higher than it had to be -> look further
+        // down next time; far more candidates than a wave uses -> look less far
+        uint32_t nd = delta;
+        if (ran_dry && T > Tlist) nd = delta < (1u << 30) ? delta * 2u : delta;
+        else if (overflowed) nd = max(delta / 2u, 1u << 8);
+        else if (!ran_dry && C > MULTI_CAP / 2) nd = max(delta - delta / 8u, 1u << 8);
+        ms.delta = nd;
+        if (dead || ms.dead) ls.stop = 3;
+        else if (acc == 0) ls.stop = 1;          // no feasible node anywhere: the pod is unschedulable
+      }
     }
-    __syncthreads();     // every thread has left the loop (some after barrier A, some after B)
+    __syncthreads();                                                    // R: the accepted list, counters, limits
+    MPH_MARK(4);
+    const int32_t acc = ms.accepted;
     // ClusterCapacityBinder.Bind + postBindHook: pod k+i -> node (plugin.go:34-53; simulator.go:297-312). Every CTA knows the
-    // whole list; CTA 0 records it.
+    // whole list; CTA 0 (of every rank: each keeps the whole sequence) records it.
     if (cta == 0 && tid < acc && k + tid < p.pod_cap) p.pod_node[k + tid] = ms.acc_node[tid];
-    // ---- assume -> AssumePod -> NodeInfo.update(+1) (schedule_one.go:967-984, types.go:409-427) for the winners this CTA owns:
-    //      one thread per accepted pod (a node is accepted at most once per wave) ----
-    if (tid >= 32 && tid - 32 < acc) {       // warp 1 (and up): warp 0 recounts PTS minima meanwhile
-      const ccsim_template &t = ls.tmpl;
-      const int i = tid - 32;
-      const int32_t w = ms.acc_node[i] - p.node_base;
-      // a node is accepted at most twice per wave, the second time as the wave's last commit: its first thread applies both
-      const bool twice = (i != acc - 1) && ms.acc_node[acc - 1] == ms.acc_node[i];
-      const bool skip = (i == acc - 1) && [&] { for (int q = 0; q < acc - 1; q++) if (ms.acc_node[q] == ms.acc_node[i]) return true; return false; }();
-      const int mult = twice ? 2 : 1;
-      if (w >= lo && w < hi && !skip) {
-        const int32_t jw = w - lo;
+    // ---- assume -> AssumePod -> NodeInfo.update(+1) (schedule_one.go:967-984, types.go:409-427): every thread looks for its own
+    //      node among the winners (a node is accepted at most twice per wave). Only this thread reads the row before the next S1. ----
+    if (tid < cnt_nodes && acc) {
+      const int32_t mynode = p.node_base + lo + tid;
+      int mult = 0;
+      for (int i = 0; i < acc; i++) mult += (ms.acc_node[i] == mynode);
+      if (mult) {
+        const ccsim_template &t = ls.tmpl;
+        const int32_t jw = tid;
         const long long rc = c_rcpu[jw] + mult * t.req_cpu, rm = c_rmem[jw] + mult * t.req_mem;
         const int32_t np = c_npods[jw] + mult;
         c_rcpu[jw] = rc; c_rmem[jw] = rm; c_zcpu[jw] += mult * t.nz_cpu; c_zmem[jw] += mult * t.nz_mem; c_npods[jw] = np;
@@ -457,45 +580,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         }
       }
     }
-    if (warp == 0) {
-      const ccsim_template &t = ls.tmpl;
-      // a PTS minimum moved: recount it here and move the term's limit, instead of a block-wide recount + rebuild of all
-      // Filter constants (filtering.go:56-69,98-137: minMatchNum / criticalPaths)
-      for (int c = 0; c < t.n_pts; c++) {
-        if (t.pts[c].min_zero || ls.ptsnum[c] > 0) continue;
-        const DevCounter &dc = p.counters[t.pts[c].counter];
-        if (dc.n_present <= 0) continue;
-        const int32_t *cnt = smem_cnt + dc.smem_off;
-        int32_t m = INT32_MAX;
-        for (int d = lane; d < dc.n_present; d += 32) m = min(m, cnt[d]);
-        m = __reduce_min_sync(0xffffffffu, m);
-        int32_t num = 0;
-        for (int d = lane; d < dc.n_present; d += 32) num += (cnt[d] == m);
-        num = __reduce_add_sync(0xffffffffu, num);
-        if (lane == 0) {
-          ls.ptsmin[c] = m; ls.ptsnum[c] = num;
-          if (t.filter_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) {    // terms[0..n_pts) are the PTS terms, in constraint order
-            const long long lim = (long long)t.pts[c].max_skew - t.pts[c].self_match + (long long)m;
-            ls.terms[c].lim = lim > INT32_MAX ? INT32_MAX : (lim < INT32_MIN ? INT32_MIN : (int32_t)lim);
-            for (int q = 0; q < ms.n_gt; q++) if (ms.gt_term[q] == c) ms.gt_c1[q][0] = ls.terms[c].lim;
-          }
-        }
-        __syncwarp();
-      }
-      if (lane == 0) {
-        ms.accepted = acc;
-        ms.stopb = 0;
-        if (dead) ls.stop = 3;
-        else if (acc == 0) ls.stop = 1;          // no feasible node anywhere: the pod is unschedulable
-      }
-    }
-    PH_MARK(4);
-    __syncthreads();                                                    // S3
-    PH_MARK(5);
-    k += ms.accepted;
+    MPH_MARK(5);
+    k += acc;
+    delta = ms.delta;
     if (ls.stop) break;
     for (int c = 0; c < ls.tmpl.n_pts; c++)
-      if (!ls.tmpl.pts[c].min_zero && ls.ptsnum[c] <= 0 && p.counters[ls.tmpl.pts[c].counter].n_present > 0) lean_pts_recount(p, smem_cnt, c);
+      if (!ls.tmpl.pts[c].min_zero && (ls.ptsnum[c] <= 0 || (p.debug_flags & 2)) && p.counters[ls.tmpl.pts[c].counter].n_present > 0) lean_pts_recount(p, smem_cnt, c);
     wtag = (wtag == 4095u) ? 1u : wtag + 1u;
     tag = (p.epoch << 12) | wtag;
   }
@@ -523,9 +613,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       o->examined = o->evals;
       for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ls.ptsmin[c];
       o->aff_total = ls.aff_total;
-#ifdef CCSIM_PHASE_TIMERS
-      for (int q = 0; q < 8; q++) o->phase_cycles[q] = ph[q];
-#endif
+      for (int q = 0; q < 8; q++) o->phase_cycles[q] = ms.ph[q];
+      o->stat[0] = ms.st_cand; o->stat[1] = ms.st_overflow;
     }
   }
 }

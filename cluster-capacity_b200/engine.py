@@ -16,7 +16,7 @@ _lib = None
 
 EXPORTS = ["ccsim_create", "ccsim_destroy", "ccsim_last_error", "ccsim_abi_version", "ccsim_load_nodes",
            "ccsim_set_templates", "ccsim_run", "ccsim_node_counts", "ccsim_peer_export", "ccsim_peer_import",
-           "ccsim_device_info", "ccsim_kernel_launches", "ccsim_flush_l2"]
+           "ccsim_device_info", "ccsim_kernel_launches", "ccsim_flush_l2", "ccsim_run_stats"]
 
 
 class EngineError(RuntimeError):
@@ -50,6 +50,8 @@ def lib():
         L.ccsim_kernel_launches.argtypes = [C.c_void_p]
         L.ccsim_flush_l2.restype = C.c_int
         L.ccsim_flush_l2.argtypes = [C.c_void_p]
+        L.ccsim_run_stats.restype = C.c_int
+        L.ccsim_run_stats.argtypes = [C.c_void_p, abi.P64]
         L.ccsim_peer_export.restype = C.c_int
         L.ccsim_peer_export.argtypes = [C.c_void_p, abi.PU8]
         L.ccsim_peer_import.restype = C.c_int
@@ -134,6 +136,15 @@ class Engine:
         sm, grid, block, l2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
         lib().ccsim_device_info(self._h, C.byref(sm), C.byref(grid), C.byref(block), C.byref(l2))
         return dict(sm_count=sm.value, grid=grid.value, block=block.value, l2_bytes=l2.value)
+
+    ENGINE_NAMES = ("generic", "lean sequential", "tie-run batching", "multi-commit")
+
+    def run_stats(self):
+        """Latency anatomy of the last run (see ccsim_run_stats in include/ccsim.h)."""
+        v = np.zeros(16, np.int64)
+        self._check(lib().ccsim_run_stats(self._h, v.ctypes.data_as(abi.P64)), "ccsim_run_stats")
+        return {"engine": self.ENGINE_NAMES[int(v[0])], "waves": int(v[1]), "placed": int(v[2]), "candidates": int(v[3]), "bar_raised_waves": int(v[4]),
+                "grid": int(v[5]), "block": int(v[6]), "smem_bytes": int(v[7]), "phase_cycles": [int(x) for x in v[8:16]]}
 
     def kernel_launches(self):
         return int(lib().ccsim_kernel_launches(self._h))

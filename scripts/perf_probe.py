@@ -12,10 +12,15 @@ def probe(name, snap, tmpl, ctr, limit, bytes_per_eval):
         r = eng.run(limit)
         r = eng.run(limit)
         info = eng.device_info()
+        st = eng.run_stats()
     us = r.run_ms * 1e3 / max(1, r.waves)
     print("%-28s n=%-8d grid=%-4d placed=%-8d waves=%-8d run=%9.3f ms  %6.2f us/wave  %.3g evals/s  %.0f GB/s algorithmic  (load %.1f ms)" % (
         name, snap.n, info["grid"], r.placed, r.waves, r.run_ms, us, r.evals / (r.run_ms * 1e-3),
         r.evals * bytes_per_eval / (r.run_ms * 1e-3) / 1e9, (t1 - t0) * 1e3), flush=True)
+    if st["engine"] == "multi-commit":
+        w = max(1, st["waves"])
+        print("    engine=%s  placements/wave=%.2f  candidates/wave=%.1f  bar raised in %d waves  cycles/wave (CTA 0): scan=%d S1=%d merge+publish=%d gather=%d replay=%d tail=%d  smem=%d B" % (
+            st["engine"], st["placed"] / w, st["candidates"] / w, st["bar_raised_waves"], *[c // w for c in st["phase_cycles"][:6]], st["smem_bytes"]), flush=True)
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c3", "c4", "c5"]

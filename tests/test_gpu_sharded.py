@@ -22,32 +22,45 @@ def _worker(rank, world, port, which, q):
     engine = importlib.import_module("cluster-capacity_b200.engine")
     sharded = importlib.import_module("cluster-capacity_b200.sharded")
     from oracle import binding as oracle
+    abi = importlib.import_module("cluster-capacity_b200._abi")
+    limit = 0
     if which == "c3":
         snap, tmpl, ctr = synth.c3(n=5001, prefer_taints=True)
-        limit = 0
-    else:
+    elif which == "c4":
         snap, tmpl, ctr = synth.c4(n=6000, n_existing=12000, zones=8, racks=64, regions=4)
-        limit = 0
+    elif which == "c4_wide":      # enough nodes per shard for full grids: the multi-commit replay sees 2 x 148 candidate lists
+        snap, tmpl, ctr = synth.c4(n=120_001, n_existing=200_000, zones=32, racks=1024, regions=8)
+        limit = 3000
+    else:                          # spread only: nodes take several clones, winners re-enter the replay ("second life")
+        snap, tmpl, ctr = synth.c4(n=40_000, n_existing=60_000, zones=16, racks=256, regions=4)
+        tmpl[0].n_anti = 0
+        ctr = ctr[:3]
+        limit = 2500
     torch.cuda.set_device(rank)
-    eng = engine.Engine(device=rank, rank=rank, world=world)
-    eng.load_nodes(snap)
-    eng.set_templates(tmpl, ctr)
-    eng.connect_peers(dist)
     ok = True
-    for _ in range(2):          # twice: the run epoch must keep words of the previous run from validating
-        dist.barrier()
-        res = eng.run(limit)
-        m = sharded.merge_results(dist, res)
-        want = oracle.run(snap, tmpl, ctr, max_pods=limit, threads=4)
-        ok &= (m["placed"] == want.placed and m["stop_code"] == want.stop_code and np.array_equal(m["pod_node"], want.pod_node)
-               and np.array_equal(m["reason_hist"], want.reason_hist) and m["preempt_no_victims"] == want.preempt_no_victims
-               and m["evals"] == want.evals)
+    want = oracle.run(snap, tmpl, ctr, max_pods=limit, threads=8, memo=True)
+    for kind in (abi.ENGINE_AUTO, abi.ENGINE_SEQUENTIAL):   # AUTO: multi-commit waves over the shards for counter-coupled templates
+        eng = engine.Engine(device=rank, engine=kind, rank=rank, world=world)
+        eng.load_nodes(snap)
+        eng.set_templates(tmpl, ctr)
+        eng.connect_peers(dist)
+        for it in range(3):          # several runs per handle: the run epoch / buffer parity must carry over; no host barrier in between
+            res = eng.run(limit if it != 1 else (limit or 0) // 2 + 7)
+            m = sharded.merge_results(dist, res)
+            w = want if it != 1 else oracle.run(snap, tmpl, ctr, max_pods=(limit or 0) // 2 + 7, threads=8, memo=True)
+            ok &= (m["placed"] == w.placed and m["stop_code"] == w.stop_code and np.array_equal(m["pod_node"], w.pod_node)
+                   and np.array_equal(m["reason_hist"], w.reason_hist) and m["preempt_no_victims"] == w.preempt_no_victims
+                   and m["preempt_not_helpful"] == w.preempt_not_helpful)
+            if kind == abi.ENGINE_SEQUENTIAL:
+                ok &= m["evals"] == w.evals
+            elif which.startswith("c4") or which == "spread":
+                ok &= eng.run_stats()["engine"] == "multi-commit" and (w.placed < 100 or res.waves * 2 < w.waves)
+        eng.close()
     q.put((rank, bool(ok), int(res.placed)))
-    eng.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("which", ["c3", "c4"])
+@pytest.mark.parametrize("which", ["c3", "c4", "c4_wide", "spread"])
 def test_two_gpu_sharded_matches_oracle(built, which):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
