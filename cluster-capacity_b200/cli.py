@@ -3,6 +3,7 @@ top of the GPU path:
 
     python -m cluster-capacity_b200.cli --podspec examples/pod.yaml --snapshot cluster.json [--max-limit N]
            [--exclude-nodes a,b] [--default-config cfg.yaml] [--verbose] [-o json|yaml] [--kubeconfig KUBECONFIG]
+    (--podspec may be repeated or name a directory: several podspecs are simulated round-robin, e.g. the genpod output of 64 namespaces)
 
 The analysis needs the LISTed Node/Pod/Namespace objects. `--snapshot` takes a JSON/YAML file
 {"nodes": [...], "pods": [...], "namespaces": [...]} (or a directory with nodes.json / pods.json / namespaces.json);
@@ -110,7 +111,9 @@ def list_from_cluster(kubeconfig):
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="cluster-capacity", description="Cluster-capacity is used for simulating scheduling of one or multiple pods")
     ap.add_argument("--kubeconfig", default="", help="Path to the kubeconfig file to use for the analysis.")
-    ap.add_argument("--podspec", default="", help="Path to JSON or YAML file containing pod definition.")
+    ap.add_argument("--podspec", action="append", default=[],
+                    help="Path to JSON or YAML file containing pod definition. May be repeated, or name a directory of podspec files: the pods are "
+                         "then simulated round-robin (README.md:305-306 'accept a list of pods'; template index = pod number %% #podspecs).")
     ap.add_argument("--max-limit", type=int, default=0, help="Number of instances of pod to be scheduled after which analysis stops. By default unlimited.")
     ap.add_argument("--exclude-nodes", default="", help="Exclude nodes to be scheduled")
     ap.add_argument("--default-config", default="", help="Path to JSON or YAML file containing scheduler configuration.")
@@ -126,7 +129,14 @@ def main(argv=None):
     print("Cluster capacity version %s" % VERSION)
     fw = importlib.import_module("cluster-capacity_b200.framework")
     try:
-        pod = parse_api_spec(a.podspec)
+        files = []
+        for path in a.podspec:
+            if os.path.isdir(path):
+                files += [os.path.join(path, f) for f in sorted(os.listdir(path)) if f.endswith((".yaml", ".yml", ".json"))]
+            else:
+                files.append(path)
+        pods = [parse_api_spec(f) for f in files]
+        pod = pods[0] if len(pods) == 1 else pods
         objs = load_snapshot(a.snapshot) if a.snapshot else list_from_cluster(a.kubeconfig)
         cc = fw.New(load_scheduler_config(a.default_config), None, pod, a.max_limit, [x for x in a.exclude_nodes.split(",") if x], device=a.device)
         cc.SyncWithClient(fw.ListClient(objs["nodes"], objs["pods"], objs["namespaces"], objs["services"], objs["replicationcontrollers"],

@@ -123,7 +123,10 @@ void yaml_emit(const Json &j, int indent, std::string &out) {
 
 struct cc_handle {
   SchedConfig cfg;
-  Pod tmpl;
+  Pod tmpl;                    // the first (usually only) template
+  std::vector<Pod> tmpls;      // all templates: pod k of the run is a clone of tmpls[k % T] (report.go:160)
+  std::vector<ccsim_template> enc_tmpls;          // encoded templates over the merged snapshot (T > 1)
+  std::vector<std::vector<uint8_t>> enc_images;   // their ImageLocality columns
   int64_t max_pods = 0;
   std::set<std::string> exclude;
   int device = 0;
@@ -145,23 +148,121 @@ struct cc_handle {
 static std::string g_new_err;
 static int fail(cc_handle *h, int code, const std::string &m) { if (h) h->err = m; else g_new_err = m; return code; }
 
+// 256-bit static-bit vectors as 4 words; shift left by `off` bits
+static void shl256(const uint64_t in[CCSIM_MAX_STATIC_WORDS], int off, uint64_t out[CCSIM_MAX_STATIC_WORDS]) {
+  const int ws = off >> 6, bs = off & 63;
+  for (int w = CCSIM_MAX_STATIC_WORDS - 1; w >= 0; w--) {
+    uint64_t v = 0;
+    if (w - ws >= 0) { v = in[w - ws] << bs; if (bs && w - ws - 1 >= 0) v |= in[w - ws - 1] >> (64 - bs); }
+    out[w] = v;
+  }
+}
+
+// Several templates against one snapshot (the roadmap's "list of pods", README.md:305-306; template index = k % T,
+// report.go:160): every template is encoded on its own, then the snapshots are merged — node state and the taint dictionary do
+// not depend on the template; the static predicate bits of template t move up by the bits of templates 0..t-1; extended
+// resources are the union. Per-domain counters (PodTopologySpread / InterPodAffinity terms) stay single-template.
+static void encode_list(cc_handle *h) {
+  const size_t T = h->tmpls.size();
+  std::vector<Encoded> parts;
+  parts.reserve(T);
+  for (size_t t = 0; t < T; t++) {
+    Encoder enc(h->cfg, h->tmpls[t], h->nodes, h->pods, h->ns_labels, h->exclude);
+    enc.set_workloads(&h->workloads);
+    parts.push_back(enc.encode());
+    const Encoded &e = parts.back();
+    if (!e.counters.empty()) throw Unsupported("several podspecs of which one has topology spread / pod (anti-)affinity terms or scores (single podspec only)");
+    if (!e.prefilter_msg.empty()) throw Unsupported("several podspecs of which one is rejected by PreFilter");
+    if (e.has_placed_mask) throw Unsupported("several podspecs with hostPorts");
+  }
+  Encoded &m = h->enc;
+  m = parts[0];
+  const int n = m.n;
+  // extended resources: union of the names the templates request
+  std::vector<std::string> names;
+  for (auto &e : parts) for (auto &s : e.scalar_names) if (std::find(names.begin(), names.end(), s) == names.end()) names.push_back(s);
+  if (names.size() > CCSIM_MAX_SCALARS) throw Unsupported("the podspecs request more than 4 distinct extended resources");
+  m.scalar_names = names;
+  m.alloc_scalar.assign(names.size(), std::vector<int64_t>(n, 0));
+  m.req_scalar.assign(names.size(), std::vector<int64_t>(n, 0));
+  for (size_t k = 0; k < names.size(); k++)
+    for (auto &e : parts) {
+      auto it = std::find(e.scalar_names.begin(), e.scalar_names.end(), names[k]);
+      if (it == e.scalar_names.end()) continue;
+      m.alloc_scalar[k] = e.alloc_scalar[it - e.scalar_names.begin()]; m.req_scalar[k] = e.req_scalar[it - e.scalar_names.begin()];
+      break;
+    }
+  // static bits: template t's bits start at off[t]
+  std::vector<int> off(T, 0), nbits(T, 0);
+  int total = 0;
+  for (size_t t = 0; t < T; t++) {
+    // the bits a template really uses: highest set bit over its columns (an encoder allocates them densely from 0)
+    int hi = 0;
+    for (int w = 0; w < parts[t].static_words; w++) {
+      uint64_t acc = 0;
+      for (int i = 0; i < n; i++) acc |= parts[t].static_mask[(size_t)w * n + i];
+      const ccsim_template &P = parts[t].tmpl;
+      acc |= P.sel_mask[w] | P.port_static_mask[w] | P.existing_anti_mask[w];
+      for (int k = 0; k < CCSIM_MAX_AFF_TERMS; k++) acc |= P.aff_term_mask[k][w] | P.pref_mask[k][w];
+      if (acc) hi = w * 64 + 64 - __builtin_clzll(acc);
+    }
+    if (parts[t].tmpl.prefilter_bit >= 0) hi = std::max(hi, parts[t].tmpl.prefilter_bit + 1);
+    if (parts[t].tmpl.spts_ignored_bit >= 0) hi = std::max(hi, parts[t].tmpl.spts_ignored_bit + 1);
+    off[t] = total; nbits[t] = hi; total += hi;
+  }
+  if (total > 64 * CCSIM_MAX_STATIC_WORDS) throw Unsupported("the podspecs need more than 256 static node-predicate bits together");
+  m.static_words = (total + 63) / 64;
+  m.static_mask.assign((size_t)std::max(1, m.static_words) * n, 0);
+  h->enc_tmpls.assign(T, ccsim_template());
+  h->enc_images.assign(T, std::vector<uint8_t>());
+  for (size_t t = 0; t < T; t++) {
+    const Encoded &e = parts[t];
+    if (nbits[t])
+      for (int i = 0; i < n; i++) {
+        uint64_t in[CCSIM_MAX_STATIC_WORDS] = {0, 0, 0, 0}, out[CCSIM_MAX_STATIC_WORDS];
+        for (int w = 0; w < e.static_words; w++) in[w] = e.static_mask[(size_t)w * n + i];
+        shl256(in, off[t], out);
+        for (int w = 0; w < m.static_words; w++) m.static_mask[(size_t)w * n + i] |= out[w];
+      }
+    ccsim_template P = e.tmpl;
+    auto mv = [&](uint64_t (&msk)[CCSIM_MAX_STATIC_WORDS]) { uint64_t o[CCSIM_MAX_STATIC_WORDS]; shl256(msk, off[t], o); memcpy(msk, o, sizeof(o)); };
+    mv(P.sel_mask); mv(P.port_static_mask); mv(P.existing_anti_mask);
+    for (int k = 0; k < CCSIM_MAX_AFF_TERMS; k++) { mv(P.aff_term_mask[k]); mv(P.pref_mask[k]); }
+    if (P.prefilter_bit >= 0) P.prefilter_bit += off[t];
+    if (P.spts_ignored_bit >= 0) P.spts_ignored_bit += off[t];
+    // extended resources: re-index into the union
+    int64_t rs[CCSIM_MAX_SCALARS] = {0, 0, 0, 0};
+    for (size_t k = 0; k < e.scalar_names.size(); k++) rs[std::find(names.begin(), names.end(), e.scalar_names[k]) - names.begin()] = e.tmpl.req_scalar[k];
+    memcpy(P.req_scalar, rs, sizeof(rs));
+    h->enc_images[t] = e.image_score;
+    P.image_score = h->enc_images[t].empty() ? nullptr : h->enc_images[t].data();
+    h->enc_tmpls[t] = P;
+  }
+  m.tmpl = h->enc_tmpls[0];
+}
+
 static void ensure_encoded(cc_handle *h) {
   if (h->have_enc) return;
+  if (h->tmpls.size() > 1) { encode_list(h); h->have_enc = true; return; }
   Encoder enc(h->cfg, h->tmpl, h->nodes, h->pods, h->ns_labels, h->exclude);
   enc.set_workloads(&h->workloads);
   h->enc = enc.encode();
+  h->enc_tmpls.assign(1, h->enc.tmpl);
   h->have_enc = true;
 }
 
 extern "C" const char *cc_last_error(const cc_handle *h) { return h ? h->err.c_str() : g_new_err.c_str(); }
 
-extern "C" int cc_new(const char *sched_config_json, const char *pod_json, int64_t max_pods, const char *exclude_nodes,
-                      int32_t device, cc_handle **out) {
-  if (!pod_json || !out) return fail(nullptr, CC_EINVAL, "null argument");
+static std::vector<Json> items_of(const char *text);
+
+static int new_handle(const char *sched_config_json, std::vector<Json> pods, int64_t max_pods, const char *exclude_nodes, int32_t device, cc_handle **out) {
+  if (pods.empty()) return fail(nullptr, CC_EINVAL, "no podspec");
+  if (pods.size() > CCSIM_MAX_TEMPLATES) return fail(nullptr, CC_EUNSUPPORTED, "more than 64 podspecs");
+  cc_handle *h = new cc_handle();
   try {
-    cc_handle *h = new cc_handle();
     h->cfg = SchedConfig::parse(sched_config_json ? sched_config_json : "");
-    h->tmpl = Pod::parse(parse_json(pod_json), /*keep_raw=*/true);
+    for (auto &j : pods) h->tmpls.push_back(Pod::parse(j, /*keep_raw=*/true));
+    h->tmpl = h->tmpls[0];
     h->max_pods = max_pods;
     h->device = device;
     if (exclude_nodes) {
@@ -170,7 +271,23 @@ extern "C" int cc_new(const char *sched_config_json, const char *pod_json, int64
     }
     *out = h;
     return CC_OK;
+  } catch (const std::exception &e) { delete h; return fail(nullptr, CC_EINVAL, e.what()); }
+}
+
+extern "C" int cc_new(const char *sched_config_json, const char *pod_json, int64_t max_pods, const char *exclude_nodes,
+                      int32_t device, cc_handle **out) {
+  if (!pod_json || !out) return fail(nullptr, CC_EINVAL, "null argument");
+  try {
+    std::vector<Json> one; one.push_back(parse_json(pod_json));
+    return new_handle(sched_config_json, std::move(one), max_pods, exclude_nodes, device, out);
   } catch (const std::exception &e) { return fail(nullptr, CC_EINVAL, e.what()); }
+}
+
+extern "C" int cc_new_list(const char *sched_config_json, const char *pods_json, int64_t max_pods, const char *exclude_nodes,
+                           int32_t device, cc_handle **out) {
+  if (!pods_json || !out) return fail(nullptr, CC_EINVAL, "null argument");
+  try { return new_handle(sched_config_json, items_of(pods_json), max_pods, exclude_nodes, device, out); }
+  catch (const std::exception &e) { return fail(nullptr, CC_EINVAL, e.what()); }
 }
 
 static std::vector<Json> items_of(const char *text) {
@@ -336,7 +453,7 @@ extern "C" int cc_run(cc_handle *h) {
   ccsim_result res;
   auto bail = [&](const char *what) { std::string m = std::string(what) + ": " + ccsim_last_error(eng); ccsim_destroy(eng); return fail(h, CC_EENGINE, m); };
   if ((rc = ccsim_load_nodes(eng, &nd))) return bail("ccsim_load_nodes");
-  if ((rc = ccsim_set_templates(eng, 1, &E.tmpl, (int32_t)E.counters.size(), E.counters.data()))) return bail("ccsim_set_templates");
+  if ((rc = ccsim_set_templates(eng, (int32_t)h->enc_tmpls.size(), h->enc_tmpls.data(), (int32_t)E.counters.size(), E.counters.data()))) return bail("ccsim_set_templates");
   if ((rc = ccsim_run(eng, h->max_pods, &res))) return bail("ccsim_run");
   h->pod_node.assign(res.pod_node, res.pod_node + res.placed);
   if (res.stop_code == CCSIM_STOP_LIMIT_REACHED) {
@@ -350,7 +467,8 @@ extern "C" int cc_run(cc_handle *h) {
     std::string msg = fit_error_body(E.n, hist);
     // DefaultPreemption PostFilter (default_preemption.go:132-143; preemption.go:234-279): no victims anywhere
     std::string post;
-    if (h->tmpl.preemption_policy == "Never") post = "not eligible due to preemptionPolicy=Never.";
+    const Pod &failed = h->tmpls[(size_t)res.placed % h->tmpls.size()];   // the pod that did not fit: clone of template placed % T
+    if (failed.preemption_policy == "Never") post = "not eligible due to preemptionPolicy=Never.";
     else post = fit_error_body(E.n, {{"No preemption victims found for incoming pod", res.preempt_no_victims},
                                      {"Preemption is not helpful for scheduling", res.preempt_not_helpful}});
     h->stop_reason = "Unschedulable: " + msg + " preemption: " + post;   // simulator.go:332
@@ -391,10 +509,11 @@ static int build_report(cc_handle *h) {
   if (h->have_report) return CC_OK;
   if (!h->ran) return fail(h, CC_ESTATE, "Report() before Run(): no stop reason yet (the reference panics here, report.go:102-106)");
   Json spec = Json::object();
-  Json tmpls = Json::array(); tmpls.push(h->tmpl.raw);
+  Json tmpls = Json::array();
+  Json reqs = Json::array();
+  for (auto &t : h->tmpls) { tmpls.push(t.raw); reqs.push(requirements_json(t)); }
   spec.set("templates", tmpls);
   spec.set("replicas", Json::number(h->max_pods));
-  Json reqs = Json::array(); reqs.push(requirements_json(h->tmpl));
   spec.set("podRequirements", reqs);
   Json status = Json::object();
   status.set("creationTimestamp", Json::string(rfc3339_now()));
@@ -411,18 +530,20 @@ static int build_report(cc_handle *h) {
   while (!m.empty() && m.back() == ' ') m.pop_back();
   fr.set("failMessage", Json::string(m));
   status.set("failReason", fr);
-  // parsePodsReview (report.go:146-180): ReplicasOnNodes in order of first placement
-  Json rons = Json::array();
-  {
+  // parsePodsReview (report.go:146-180): per template (pod k belongs to template k % T), ReplicasOnNodes in order of first placement
+  Json pods = Json::array();
+  const size_t T = h->tmpls.size();
+  for (size_t t = 0; t < T; t++) {
+    Json rons = Json::array();
     std::vector<int64_t> count(h->enc.n, 0); std::vector<int32_t> order;
-    for (int32_t w : h->pod_node) { if (count[w]++ == 0) order.push_back(w); }
+    for (size_t k = t; k < h->pod_node.size(); k += T) { const int32_t w = h->pod_node[k]; if (count[w]++ == 0) order.push_back(w); }
     for (int32_t w : order) { Json r = Json::object(); r.set("nodeName", Json::string(h->enc.names[w])); r.set("replicas", Json::number(count[w])); rons.push(r); }
+    Json podres = Json::object();
+    podres.set("podName", Json::string(h->tmpls[t].name));
+    podres.set("replicasOnNodes", rons);
+    podres.set("failSummary", Json::null());   // never populated by the reference (report.go:174-179)
+    pods.push(podres);
   }
-  Json podres = Json::object();
-  podres.set("podName", Json::string(h->tmpl.name));
-  podres.set("replicasOnNodes", rons);
-  podres.set("failSummary", Json::null());   // never populated by the reference (report.go:174-179)
-  Json pods = Json::array(); pods.push(podres);
   status.set("pods", pods);
   h->report = Json::object();
   h->report.set("spec", spec);
@@ -445,32 +566,38 @@ extern "C" const char *cc_report_print(cc_handle *h, int32_t verbose, const char
   if (!f.empty()) { fail(h, CC_EINVAL, "output format \"" + f + "\" not recognized"); return nullptr; }   // report.go:315
   // clusterCapacityReviewPrettyPrint (report.go:235-285)
   std::string o;
-  const Json &req = h->report.at("spec").at("podRequirements").arr[0];
   const Json &st = h->report.at("status");
-  const Json &pod = st.at("pods").arr[0];
-  long long total = 0;
-  for (auto &r : pod.at("replicasOnNodes").arr) total += r.at("replicas").i64();
-  if (verbose) {
-    o += req.at("podName").str() + " pod requirements:\n";
-    o += "\t- CPU: " + req.at("resources").at("primaryResources").at("cpu").str() + "\n";
-    o += "\t- Memory: " + req.at("resources").at("primaryResources").at("memory").str() + "\n";
-    const Json &sc = req.at("resources").at("scalarResources");
-    if (sc.is_object()) { o += "\t- ScalarResources: map["; bool fst = true; for (auto &kv : sc.obj) { if (!fst) o += " "; o += kv.first + ":" + kv.second.s; fst = false; } o += "]\n"; }
-    const Json &ns = req.at("nodeSelectors");
-    if (ns.is_object()) {   // labels.SelectorFromSet(...).String(): sorted "k=v" joined by ","
-      std::vector<std::string> kv; for (auto &p : ns.obj) kv.push_back(p.first + "=" + p.second.str());
-      std::sort(kv.begin(), kv.end());
-      o += "\t- NodeSelector: "; for (size_t i = 0; i < kv.size(); i++) { if (i) o += ","; o += kv[i]; } o += "\n";
+  if (verbose)
+    for (auto &req : h->report.at("spec").at("podRequirements").arr) {
+      o += req.at("podName").str() + " pod requirements:\n";
+      o += "\t- CPU: " + req.at("resources").at("primaryResources").at("cpu").str() + "\n";
+      o += "\t- Memory: " + req.at("resources").at("primaryResources").at("memory").str() + "\n";
+      const Json &sc = req.at("resources").at("scalarResources");
+      if (sc.is_object()) { o += "\t- ScalarResources: map["; bool fst = true; for (auto &kv : sc.obj) { if (!fst) o += " "; o += kv.first + ":" + kv.second.s; fst = false; } o += "]\n"; }
+      const Json &ns = req.at("nodeSelectors");
+      if (ns.is_object()) {   // labels.SelectorFromSet(...).String(): sorted "k=v" joined by ","
+        std::vector<std::string> kv; for (auto &p : ns.obj) kv.push_back(p.first + "=" + p.second.str());
+        std::sort(kv.begin(), kv.end());
+        o += "\t- NodeSelector: "; for (size_t i = 0; i < kv.size(); i++) { if (i) o += ","; o += kv[i]; } o += "\n";
+      }
+      o += "\n";
     }
-    o += "\n";
-    o += "The cluster can schedule " + std::to_string(total) + " instance(s) of the pod " + pod.at("podName").str() + ".\n";
+  for (auto &pod : st.at("pods").arr) {
+    long long total = 0;
+    for (auto &r : pod.at("replicasOnNodes").arr) total += r.at("replicas").i64();
+    if (verbose) o += "The cluster can schedule " + std::to_string(total) + " instance(s) of the pod " + pod.at("podName").str() + ".\n";
+    else o += std::to_string(total) + "\n";
+  }
+  if (verbose) {
     o += "\nTermination reason: " + st.at("failReason").at("failType").str() + ": " + st.at("failReason").at("failMessage").str() + "\n";
     if (st.at("replicas").i64() > 0) {
       o += "\nPod distribution among nodes:\n";
-      o += pod.at("podName").str() + "\n";
-      for (auto &r : pod.at("replicasOnNodes").arr) o += "\t- " + r.at("nodeName").str() + ": " + std::to_string(r.at("replicas").i64()) + " instance(s)\n";
+      for (auto &pod : st.at("pods").arr) {
+        o += pod.at("podName").str() + "\n";
+        for (auto &r : pod.at("replicasOnNodes").arr) o += "\t- " + r.at("nodeName").str() + ": " + std::to_string(r.at("replicas").i64()) + " instance(s)\n";
+      }
     }
-  } else o += std::to_string(total) + "\n";
+  }
   h->out = o;
   return h->out.c_str();
 }
@@ -525,6 +652,18 @@ extern "C" const char *cc_debug_encoded_snapshot(cc_handle *h) {
   static const char *d = "0123456789abcdef";
   for (size_t i = 0; i < sizeof(ccsim_template); i++) { hex += d[tb[i] >> 4]; hex += d[tb[i] & 15]; }
   j.set("template_hex", Json::string(hex));
+  {   // every template of a list run (image_score pointers are process-local: image_scores carries the columns)
+    Json th = Json::array(), is = Json::array();
+    for (size_t t = 0; t < h->enc_tmpls.size(); t++) {
+      std::string hx; const unsigned char *b = reinterpret_cast<const unsigned char *>(&h->enc_tmpls[t]);
+      for (size_t i = 0; i < sizeof(ccsim_template); i++) { hx += d[b[i] >> 4]; hx += d[b[i] & 15]; }
+      th.push(Json::string(hx));
+      Json col = Json::array();
+      if (h->tmpls.size() > 1) for (auto x : h->enc_images[t]) col.push(Json::number(x)); else for (auto x : E.image_score) col.push(Json::number(x));
+      is.push(col);
+    }
+    j.set("templates_hex", th); j.set("image_scores", is);
+  }
   Json ctr = Json::array();
   for (size_t k = 0; k < E.counters.size(); k++) {
     Json c = Json::object();

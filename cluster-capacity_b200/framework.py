@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libcchost.so")
 _lib = None
 
-EXPORTS = ["cc_new", "cc_sync_with_objects", "cc_sync_workloads", "cc_run", "cc_report_json", "cc_report_print", "cc_stop_reason",
+EXPORTS = ["cc_new", "cc_new_list", "cc_sync_with_objects", "cc_sync_workloads", "cc_run", "cc_report_json", "cc_report_print", "cc_stop_reason",
            "cc_scheduled_count", "cc_scheduled_node", "cc_close", "cc_last_error", "cc_debug_encoded_snapshot"]
 
 
@@ -37,6 +37,8 @@ def lib():
         L = C.CDLL(SO_PATH)
         L.cc_new.restype = C.c_int
         L.cc_new.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.cc_new_list.restype = C.c_int
+        L.cc_new_list.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.cc_sync_with_objects.restype = C.c_int
         L.cc_sync_with_objects.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
         L.cc_sync_workloads.restype = C.c_int
@@ -140,10 +142,15 @@ class ClusterCapacity:
 def New(kube_scheduler_config, kube_config, simulated_pod, max_pods=0, exclude_nodes=(), device=0):
     """framework.New (simulator.go:107). kube_scheduler_config: None for the default profile or a dict
     {"percentageOfNodesToScore", "disabledFilters", "disabledScores", "weights"}; kube_config is unused (kept for
-    signature parity: the analysis never talks to an API server after SyncWithClient)."""
+    signature parity: the analysis never talks to an API server after SyncWithClient).
+    simulated_pod: one v1.Pod dict, or a list of up to 64 of them (the roadmap's "list of pods", README.md:305-306: pod k of the
+    run is a clone of podspec k % T, the template index report.go:160 already uses)."""
     h = C.c_void_p()
     cfg = json.dumps(kube_scheduler_config).encode() if kube_scheduler_config else None
-    rc = lib().cc_new(cfg, json.dumps(simulated_pod).encode(), int(max_pods), ",".join(exclude_nodes).encode(), device, C.byref(h))
+    if isinstance(simulated_pod, (list, tuple)):
+        rc = lib().cc_new_list(cfg, json.dumps(list(simulated_pod)).encode(), int(max_pods), ",".join(exclude_nodes).encode(), device, C.byref(h))
+    else:
+        rc = lib().cc_new(cfg, json.dumps(simulated_pod).encode(), int(max_pods), ",".join(exclude_nodes).encode(), device, C.byref(h))
     if rc:
         raise FrameworkError("New rc=%d: %s" % (rc, lib().cc_last_error(None).decode()))
     return ClusterCapacity(h)

@@ -85,7 +85,8 @@ def retrieve_namespace_pod(namespaces, limitranges, namespace):
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="genpod", description="Generate pod based on namespace resource limits and node selector annotations")
     ap.add_argument("--kubeconfig", default="")
-    ap.add_argument("--namespace", default="", help="Cluster namespace")
+    ap.add_argument("--namespace", default="", help="Cluster namespace (a comma-separated list with --output-dir: one podspec per namespace)")
+    ap.add_argument("--output-dir", default="", help="write <namespace>.yaml|json per namespace into this directory (feeds cluster-capacity --podspec DIR)")
     ap.add_argument("--output", "-o", default="", help="Output format. One of: json|yaml")
     ap.add_argument("--snapshot", default="", help="JSON/YAML file with namespaces / limitranges lists")
     a = ap.parse_args(argv)
@@ -103,6 +104,19 @@ def main(argv=None):
         base = ["kubectl"] + (["--kubeconfig", a.kubeconfig] if a.kubeconfig else [])
         nss = json.loads(subprocess.check_output(base + ["get", "namespaces", "-o", "json"]))["items"]
         lrs = json.loads(subprocess.check_output(base + ["get", "limitranges", "-n", a.namespace, "-o", "json"]))["items"]
+    if a.output_dir:       # several namespaces -> several podspecs (the multi-template run of BASELINE config C5)
+        import os
+        os.makedirs(a.output_dir, exist_ok=True)
+        for ns in [x for x in a.namespace.split(",") if x]:
+            try:
+                pod = retrieve_namespace_pod(nss, lrs, ns)
+            except (LookupError, ValueError) as e:
+                print("Error: %s" % e)
+                return 1
+            pod["metadata"]["name"] = "cluster-capacity-stub-container-" + ns     # report rows are keyed by pod name
+            with open(os.path.join(a.output_dir, ns + (".json" if a.output == "json" else ".yaml")), "w") as f:
+                f.write(json.dumps(pod) if a.output == "json" else yaml.safe_dump(pod, default_flow_style=False, sort_keys=True))
+        return 0
     try:
         pod = retrieve_namespace_pod(nss, lrs, a.namespace)
     except (LookupError, ValueError) as e:

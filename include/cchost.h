@@ -43,6 +43,11 @@ typedef struct cc_handle cc_handle;
  * exclude_nodes: comma-separated node names (--exclude-nodes), may be NULL. device: CUDA ordinal. */
 int cc_new(const char *sched_config_json, const char *pod_json, int64_t max_pods, const char *exclude_nodes,
            int32_t device, cc_handle **out);
+/* The roadmap's "accept a list of pods" (README.md:305-306): pods_json is a JSON array (or v1 List) of up to 64 v1.Pod; pod k of
+ * the simulation is a clone of podspec k % T (the template index the report already uses, report.go:160), the run ends when
+ * one of them does not fit or at max_pods. Podspecs with topology-spread / pod-(anti-)affinity terms are single-podspec only. */
+int cc_new_list(const char *sched_config_json, const char *pods_json, int64_t max_pods, const char *exclude_nodes,
+                int32_t device, cc_handle **out);
 int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const char *pods_json, const char *namespaces_json);
 /* Optional, between cc_sync_with_objects and cc_run: the Services / ReplicationControllers / ReplicaSets / StatefulSets
  * SyncWithClient copies (simulator.go:217-281). The scheduler reads them in one place only: helper.DefaultSelector

@@ -792,9 +792,12 @@ class Simulator:
 
     def run(self):
         k = 0
-        pod = self.template
-        tols_prefer = [t for t in (pod["spec"].get("tolerations") or []) if not t.get("effect") or t["effect"] == "PreferNoSchedule"]
+        # one podspec, or a list simulated round-robin (the roadmap's "list of pods", README.md:305-306): pod k is a clone of
+        # template k % T, the index parsePodsReview already uses (report.go:160)
+        templates = self.template if isinstance(self.template, (list, tuple)) else [self.template]
         while True:
+            pod = templates[k % len(templates)]
+            tols_prefer = [t for t in (pod["spec"].get("tolerations") or []) if not t.get("effect") or t["effect"] == "PreferNoSchedule"]
             if not self.infos:
                 self.stop_reason = "Unschedulable: no nodes available to schedule pods"
                 return

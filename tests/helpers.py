@@ -24,16 +24,19 @@ def from_encoded(enc):
                         static_mask=u64(nd["static_mask"]).reshape(nd["static_words"], n) if nd["static_words"] else None,
                         topo=[np.array(t, np.int32) for t in nd["topo"]], has_placed_mask=nd["has_placed_mask"],
                         taint_lists=lists, names=enc["names"])
-    t = abi.Template()
-    raw = bytes.fromhex(enc["template_hex"])
-    assert len(raw) == C.sizeof(abi.Template)
-    C.memmove(C.byref(t), raw, len(raw))
+    ts = []
+    for k, hx in enumerate(enc.get("templates_hex") or [enc["template_hex"]]):
+        t = abi.Template()
+        raw = bytes.fromhex(hx)
+        assert len(raw) == C.sizeof(abi.Template)
+        C.memmove(C.byref(t), raw, len(raw))
+        img = np.array((enc.get("image_scores") or [enc.get("image_score") or []])[k], np.uint8)   # the hex carries a pointer of the encoding process: replace it
+        t._keep_img = img
+        t.image_score = img.ctypes.data_as(C.POINTER(C.c_uint8)) if len(img) else None
+        ts.append(t)
     ctr = [abi.make_counter(c["topo_col"], np.array(c["init"], np.int32), n_present=c["n_present"], inc=c["inc"], elig_bit=c.get("elig_bit", -1))
            for c in enc["counters"]]
-    img = np.array(enc.get("image_score") or [], np.uint8)   # template_hex carries a pointer of the encoding process: replace it
-    t._keep_img = img
-    t.image_score = img.ctypes.data_as(C.POINTER(C.c_uint8)) if len(img) else None
-    return snap, [t], ctr, nd["taint_dict"], nd["scalar_names"], enc["names"]
+    return snap, ts, ctr, nd["taint_dict"], nd["scalar_names"], enc["names"]
 
 
 def reason_text(r, taint_dict, scalar_names):
