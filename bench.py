@@ -37,17 +37,33 @@ import numpy as np  # noqa: E402
 abi = importlib.import_module("cluster-capacity_b200._abi")
 synth = importlib.import_module("cluster-capacity_b200.synth")
 
-WORKLOAD = "C4: 100k nodes, 3x PodTopologySpread(DoNotSchedule zone/rack/region) + hostname anti-affinity, 200k existing pods"
-B_EVAL = 96  # algorithmic bytes per predicate-eval for C4
+# workload -> (description, algorithmic bytes per predicate-eval, --max-limit of a step, generator(world))
+WORKLOADS = {
+    "c4": ("C4: 100k nodes, 3x PodTopologySpread(DoNotSchedule zone/rack/region) + hostname anti-affinity, 200k existing pods", 96, 0,
+           lambda w: synth.c4() if w == 1 else synth.c4(n=100_000 * w, n_existing=200_000 * w, racks=1024 * w)),
+    # BASELINE config C5 (1M nodes x 64 podspecs round-robin): strong scaling over node shards, 100 rounds of the 64 podspecs per step
+    "c5": ("C5: 1M nodes, 64 distinct podspecs (cpu 50..2000m, mem 64..4096Mi) placed round-robin, NodeResourcesFit + LeastAllocated + BalancedAllocation, --max-limit 6400",
+           72, 6400, lambda w: synth.c5()),
+}
+WKEY = "c4"
+WORKLOAD, B_EVAL, MAX_LIMIT, MAKE = WORKLOADS[WKEY]
+
+
+def select_workload(key):
+    global WKEY, WORKLOAD, B_EVAL, MAX_LIMIT, MAKE
+    WKEY = key
+    WORKLOAD, B_EVAL, MAX_LIMIT, MAKE = WORKLOADS[key]
 
 
 def profiled_traffic():
     """dram__bytes_read+write per launch of the wave kernel from the committed ncu --set full capture (profiles/)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_wave_c4_traffic.json")) as f:
-            return float(json.load(f)["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r2_wave_%s_traffic.json" % WKEY, "r1_wave_c4_traffic.json" if WKEY == "c4" else ""):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["traffic_bytes_per_launch"])
+        except Exception:
+            pass
+    return None
 
 
 def measured_peak():
@@ -130,10 +146,13 @@ def cpu_oracle_rate(snap, tmpl, ctr, budget_s=20.0, calib=None):
     from oracle import binding as oracle
     best, best_rate, cores = calib or calibrate_oracle(snap, tmpl, ctr)
     pods = int(max(50, budget_s * best_rate / max(1, snap.n)))
+    whole = False
+    if MAX_LIMIT and pods >= MAX_LIMIT:       # the step itself is limited (--max-limit): the oracle runs the same limit
+        pods, whole = MAX_LIMIT, True
     t0 = time.perf_counter()
     r = oracle.run(snap, tmpl, ctr, max_pods=pods, threads=best)
     dt = time.perf_counter() - t0
-    if r.stop_code == abi.STOP_UNSCHEDULABLE:
+    if whole or r.stop_code == abi.STOP_UNSCHEDULABLE:
         pods = 0
     return r, dt, best, cores, pods
 
@@ -161,6 +180,70 @@ def parity_block(got, want, pods):
             "against": "oracle/ccsim_oracle.c (canonical mode), same snapshot", "first_mismatch": first_bad}
 
 
+def objects_leg(flat, device, steps):
+    """e2e through the reference-facing API (include/cchost.h = pkg/framework's New / SyncWithClient / Run / Report): the C4
+    cluster as v1.Node / v1.Pod JSON in host memory (what SyncWithClient LISTs, simulator.go:176-295) -> C++ ingest + NodeInfo
+    aggregation + encoding -> H2D -> wave kernel -> D2H -> ClusterCapacityReview JSON. Everything inside the timed region;
+    the JSON text is built before it. The placement sequence must equal the flat-array run's (same cluster, same node order)."""
+    import ctypes as C
+    fw = importlib.import_module("cluster-capacity_b200.framework")
+    nodes, pods, tmpl = synth.c4_objects()
+    nj, pj, tj = json.dumps(nodes).encode(), json.dumps(pods).encode(), json.dumps(tmpl).encode()
+    del nodes, pods
+    L = fw.lib()
+    parts = [0.0, 0.0, 0.0, 0.0]
+    wall = []
+    same = True
+    placed = 0
+    for it in range(steps + 1):
+        h = C.c_void_p()
+        t0 = time.perf_counter()
+        rc = L.cc_new(None, tj, 0, b"", device, C.byref(h))
+        t1 = time.perf_counter()
+        rc = rc or L.cc_sync_with_objects(h, nj, pj, b"[]")
+        t2 = time.perf_counter()
+        rc = rc or L.cc_run(h)
+        t3 = time.perf_counter()
+        rep = L.cc_report_json(h) if not rc else None
+        t4 = time.perf_counter()
+        if rc or rep is None:
+            raise RuntimeError("e2e_objects: rc=%s %s" % (rc, L.cc_last_error(h).decode()))
+        if it > 0:        # the first iteration warms the allocators / page cache
+            wall.append(t4 - t0)
+            for q, d in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                parts[q] += d
+        placed = int(L.cc_scheduled_count(h))
+        if it == steps:   # parity (outside the timed region): count, and every pod's node
+            want = flat["pod_node"]
+            same = placed == flat["placed"] and all(L.cc_scheduled_node(h, k) == b"node-%06d" % want[k] for k in range(0, placed, 1))
+            review = json.loads(rep.decode())
+            same = same and review["status"]["replicas"] == placed
+        L.cc_close(h)
+    evals = (placed + 1) * 100_000
+    t = sum(wall)
+    return {"value": evals * steps / t, "unit": "evals/s", "ms_per_step": t / steps * 1e3, "steps": steps, "json_bytes_per_step": len(nj) + len(pj) + len(tj),
+            "ingest_mb_per_s": (len(nj) + len(pj)) / 1e6 / (parts[1] / steps),
+            "breakdown_ms_per_step": {"cc_new": parts[0] / steps * 1e3, "cc_sync_with_objects (JSON -> object model)": parts[1] / steps * 1e3,
+                                      "cc_run (NodeInfo aggregation + encode + H2D + wave kernel + D2H)": parts[2] / steps * 1e3,
+                                      "cc_report_json": parts[3] / steps * 1e3},
+            "same_sequence_as_flat_run": bool(same), "placed": placed}
+
+
+def latency_block(st, kernel_ms, sm_mhz):
+    """What actually bounds the wave kernel: it is latency-bound (dependent instruction issue, L2 round trips of the exchange),
+    not bandwidth-bound. Cycle split of CTA 0 from the kernel's own clock64 phase timers (multi-commit engine)."""
+    w = max(1, st["waves"])
+    out = {"engine": st["engine"], "waves": st["waves"], "us_per_wave": kernel_ms * 1e3 / w, "placements_per_wave": st["placed"] / w,
+           "grid": st["grid"], "block": st["block"], "dynamic_smem_bytes": st["smem_bytes"]}
+    if st["engine"] == "multi-commit":
+        names = ("scan_filter_score_top8", "barrier_wait", "merge_publish", "gather_exchange_compact", "replay", "row_updates")
+        cyc = {n: st["phase_cycles"][i] / w for i, n in enumerate(names)}
+        out.update({"candidates_replayed_per_wave": st["candidates"] / w, "waves_that_raised_the_bar": st["bar_raised_waves"],
+                    "cycles_per_wave_cta0": cyc, "cycles_per_wave_total": sum(cyc.values()),
+                    "us_per_wave_from_cycles": (sum(cyc.values()) / (sm_mhz or 1965)) if sm_mhz else None})
+    return out
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,10 +257,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    if world > 1 and args.mode == "sharded":     # the same workload as our arm at this N (weak scaling: N x 100k nodes)
-        snap, tmpl, ctr = synth.c4(n=100_000 * world, n_existing=200_000 * world, racks=1024 * world)
-    else:
-        snap, tmpl, ctr = synth.c4()
+    snap, tmpl, ctr = MAKE(world if args.mode == "sharded" else 1)     # the same workload as our arm at this N
     steps = max(1, min(args.steps, 3))
     evals = placed = 0
     dt = 0.0
@@ -242,8 +322,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-parity", "--no-cpu-baseline", dest="no_parity", action="store_true",
                     help="skip the oracle run (parity check of the timed configuration + cpu_baseline)")
+    ap.add_argument("--no-objects", action="store_true", help="skip the e2e_objects leg (plugin call from Node/Pod JSON)")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS), help="c4 (default: the metric's 100k-node configuration) or c5 (1M nodes x 64 podspecs)")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"], help="N>1: node-sharded run or independent replicas")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -258,10 +341,8 @@ def main():
 
     sharded_run = world > 1 and args.mode == "sharded"
     sharded = importlib.import_module("cluster-capacity_b200.sharded")
-    if sharded_run:   # weak scaling: world x 100k nodes, hierarchy kept (racks scale with the node count)
-        snap, tmpl, ctr = synth.c4(n=100_000 * world, n_existing=200_000 * world, racks=1024 * world)
-    else:
-        snap, tmpl, ctr = synth.c4()
+    # C4: weak scaling (world x 100k nodes, hierarchy kept: racks scale with the node count); C5: the 1M-node cluster is split
+    snap, tmpl, ctr = MAKE(world if sharded_run else 1)
     psnap, h2d_bytes = pinned_snapshot(snap)
     ctr_bytes = sum(c.n_domains * 4 for c in ctr)
     warm = max(3, args.warmup)
@@ -280,7 +361,7 @@ def main():
         lo_, hi_ = sharded.shard_bounds(snap.n, world, rank)
         h2d_bytes = int(h2d_bytes * (hi_ - lo_) / snap.n)
     for _ in range(warm):
-        res = eng.run(0)
+        res = eng.run(MAX_LIMIT)
     sampler = ClockSampler(local)
     sampler.start()
     # ---- resident-input arm: K steps, L2 flushed (untimed) between steps, each step bracketed by a synchronize ----
@@ -295,7 +376,7 @@ def main():
         if sharded_run:
             dist.barrier()
         t0 = time.perf_counter()
-        res = eng.run(0)
+        res = eng.run(MAX_LIMIT)
         torch.cuda.synchronize()
         step_wall.append(time.perf_counter() - t0)
         kernel_ms += res.run_ms
@@ -303,6 +384,7 @@ def main():
         placed += res.placed
         waves += res.waves
         ref_evals += ref_equivalent_evals(res)
+    stats = eng.run_stats()            # latency anatomy of the last timed run (CTA 0's clock cycles per phase, candidates, ...)
     barrier()
     # the result the parity check compares (sharded: per-shard histograms summed, replicated parts cross-checked between ranks)
     if sharded_run:
@@ -327,7 +409,7 @@ def main():
         ta = time.perf_counter()
         eng.set_templates(tmpl, ctr)   # H2D of the template table + per-domain counters
         tb = time.perf_counter()
-        r2 = eng.run(0)                # run + D2H of pod->node, histogram, counters
+        r2 = eng.run(MAX_LIMIT)                # run + D2H of pod->node, histogram, counters
         torch.cuda.synchronize()
         if it > 0:                     # first iteration warms the allocator
             e2e_wall.append(time.perf_counter() - t0)
@@ -359,10 +441,10 @@ def main():
         line = {
             "metric": "predicate-evals/sec", "value": evals_all / t_total, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "nodes": snap.n, "templates": 1, "mode": "canonical (percentageOfNodesToScore=100)",
+            "scaling": "weak" if WKEY == "c4" else "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "nodes": snap.n, "templates": len(tmpl), "max_limit": MAX_LIMIT, "mode": "canonical (percentageOfNodesToScore=100)",
                        "parallelism": ("node-sharded x%d (in-kernel peer-memory exchange per wave)" % world if sharded_run else "replicas x%d" % world) if world > 1 else "single GPU",
-                       "l2": "flushed between timed steps (2x L2 write, untimed); the 10 MB snapshot is re-read from HBM once per step and then lives in shared memory",
+                       "l2": "flushed between timed steps (2x L2 write, untimed)",
                        "bytes_per_eval_algorithmic": B_EVAL, "placed_per_step": int(placed / args.steps),
                        "waves_per_step": int(waves / args.steps),
                        "evals": "reference-equivalent: (placed+1) x nodes per step (SURVEY.md §8d), the count the CPU arm executes"},
@@ -380,11 +462,12 @@ def main():
                          "algorithmic_bytes_per_launch": ref_evals * B_EVAL / args.steps,
                          "achieved_physical": achieved_phys, "frac_physical": achieved_phys / peak,
                          "physical_bytes_per_launch": evals * B_EVAL / args.steps,
-                         "note": "algorithmic bytes = (placed+1) x N x 96 B (SURVEY.md §8d: every pod attempt streams every node row) over the wave "
-                                 "kernel's CUDA-event time. The multi-commit engine decides ~placed/waves reference cycles per pass over the node "
-                                 "tile, so the streaming model no longer bounds it and frac can exceed 1 (SURVEY.md §8d anticipates this); "
-                                 "achieved_physical counts one 96 B row per node and PASS actually made. The tiles are shared-memory resident: "
-                                 "DRAM traffic is the snapshot once per run (traffic, from ncu, profiles/)"},
+                         "latency": latency_block(stats, kernel_ms / args.steps, sampler.summary().get("sm_mhz")),
+                         "note": "bound: the wave kernel is LATENCY-bound (see `latency`): `frac` is the SURVEY.md §8d figure — algorithmic bytes = "
+                                 "(placed+1) x N x %d B (every pod attempt of the reference loop streams every node row) over the wave kernel's CUDA-event "
+                                 "time vs the measured HBM copy peak — and may exceed 1: the multi-commit engine decides ~placed/waves reference cycles per "
+                                 "pass over the (shared-memory resident) node tile and the streaming engine reads 24 B of the 72 B row; achieved_physical "
+                                 "counts one row per node and PASS actually made; `traffic` is ncu's dram bytes per launch (profiles/)" % B_EVAL},
         }
         # ---- parity on the timed configuration (and the CPU baseline: the same oracle run serves both) ----
         # N=1: the oracle runs the WHOLE analysis of the timed snapshot when that fits ~40 s (C4: ~18 s on 16 threads) and
@@ -402,6 +485,10 @@ def main():
                                         "dram_gbs_algorithmic": rc.evals / dtc * B_EVAL / 1e9}
         else:
             line["parity"] = None
+        # ---- the reference-facing plugin call: framework.New + SyncWithClient + Run + Report from Node / Pod JSON in host memory ----
+        if WKEY == "c4" and world == 1 and not args.no_objects:
+            line["e2e_objects"] = objects_leg(last_result, local, max(1, min(args.steps, 2)))
+            parity_ok = parity_ok and line["e2e_objects"]["same_sequence_as_flat_run"]
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

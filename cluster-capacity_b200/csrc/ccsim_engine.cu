@@ -36,6 +36,7 @@
 #include "ccsim_lean.cuh"
 #include "ccsim_batched.cuh"
 #include "ccsim_multi.cuh"
+#include "ccsim_stream.cuh"
 
 #define BLOCK_THREADS 512
 #define MAX_WARPS (BLOCK_THREADS / 32)
@@ -725,6 +726,9 @@ struct ccsim_handle {
   int last_lean = 0;
   int last_batched = 0;
   int last_multi = 0;
+  int last_stream = 0;
+  std::vector<void *> stream_allocs;                    // padded streaming columns + per-template score memo (ccsim_stream.cuh)
+  uint64_t taint_or0 = 0;                               // OR over the nodes of taint word 0
   std::vector<std::pair<void *, size_t>> block_cache;   // freed device blocks kept for reuse (exact size match)
   std::map<void *, size_t> block_bytes;
   cudaStream_t stream = nullptr;
@@ -874,6 +878,8 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
                        (int)(h->smem_optin - sizeof(LeanShared) - sizeof(MultiShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(LeanShared) - sizeof(MultiShared) - 1024));
+  cudaFuncSetAttribute(ccsim_wave_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STREAM_STAGES * STREAM_TILE * 24 + 128));
+  cudaFuncSetAttribute(ccsim_wave_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STREAM_STAGES * STREAM_TILE * 40 + 128));
   cudaFuncSetAttribute(ccsim_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(SMEM_CNT_MAX_INTS * sizeof(int32_t) + 16));
   *out = h;
@@ -884,7 +890,7 @@ extern "C" void ccsim_destroy(ccsim_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
-  free_pool(h, h->allocs); free_pool(h, h->tmpl_allocs); drop_cache(h);
+  free_pool(h, h->allocs); free_pool(h, h->tmpl_allocs); free_pool(h, h->stream_allocs); drop_cache(h);
   for (int r = 0; r < CCSIM_MAX_WORLD; r++) if (h->x_peer[r] && r != h->cfg.rank) cudaIpcCloseMemHandle(h->x_peer[r]);
   cudaFree(h->d_xslots);
   cudaFree(h->d_out); cudaFree(h->d_params); cudaFree(h->d_slots); cudaFree(h->d_pod_node); cudaFree(h->d_flush);
@@ -970,6 +976,8 @@ extern "C" int ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nd) {
     if (pc > maxpop) maxpop = pc;
   }
   h->pod_bound = bound; h->max_prefer_pop = maxpop;
+  h->taint_or0 = 0;
+  for (int32_t i = 0; i < N; i++) h->taint_or0 |= nd->taint_mask[i];
   CK(cudaStreamSynchronize(h->stream));
   h->have_nodes = true;
   return CCSIM_OK;
@@ -1297,10 +1305,65 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
     if (multi) { kern = h->cfg.world > 1 ? (const void *)ccsim_wave_multi_kernel<true> : (const void *)ccsim_wave_multi_kernel<false>; smem = smem_m; }
   }
   h->last_multi = multi ? 1 : 0;
+  // streaming engine (ccsim_stream.cuh): node-local templates when the tile is not resident, or several templates; the node
+  // tiles go through shared memory with bulk-async copies (TMA) and the score is memoised per (template, node)
+  StreamParams sp; memset(&sp, 0, sizeof(sp));
+  bool stream = !lean && !has_pref && h->n_counters == 0 && h->max_prefer_pop == 0 && !faithful &&
+                h->meta.taint_words == 1 && h->meta.static_words <= 1 && !getenv("CCSIM_FORCE_GENERIC");
+  if (stream)
+    for (const ccsim_template &T : h->h_templates) {
+      const bool nzfit = (T.filter_enable & CCSIM_PL_FIT) && !(T.flags & CCSIM_TF_FIT_ALL_ZERO);
+      if (nzfit && T.req_eph > 0) stream = false;
+      if (nzfit) for (int k = 0; k < h->meta.n_scalars; k++) if (T.req_scalar[k] != 0) stream = false;
+      if ((T.filter_enable & CCSIM_PL_NODE_AFFINITY) && (T.flags & CCSIM_TF_HAS_AFFINITY_TERMS)) stream = false;
+      if ((T.filter_enable & CCSIM_PL_NODE_NAME) && T.nodename_idx >= 0) stream = false;
+      if (T.flags & CCSIM_TF_PREFILTER_NODES) stream = false;
+      if ((T.filter_enable & CCSIM_PL_NODE_PORTS) && (T.flags & CCSIM_TF_HAS_HOST_PORTS) && h->w_placed) stream = false;
+      if (T.n_pts || T.n_aff || T.n_anti) stream = false;
+    }
+  if (stream) {
+    free_pool(h, h->stream_allocs);
+    bool masks = false;
+    for (const ccsim_template &T : h->h_templates) {
+      uint64_t tb = 0;
+      if (T.filter_enable & CCSIM_PL_TAINT_TOLERATION) tb |= h->meta.taint_nosched[0] & ~T.tol_nosched[0] & ~(1ull << CCSIM_TAINT_UNSCHEDULABLE_BIT);
+      if ((T.filter_enable & CCSIM_PL_NODE_UNSCHEDULABLE) && !(T.flags & CCSIM_TF_TOLERATES_UNSCHEDULABLE)) tb |= 1ull << CCSIM_TAINT_UNSCHEDULABLE_BIT;
+      if (tb & h->taint_or0) masks = true;
+      if (h->meta.static_words > 0) {
+        if ((T.filter_enable & CCSIM_PL_NODE_AFFINITY) && (T.flags & CCSIM_TF_HAS_NODE_SELECTOR) && T.sel_mask[0]) masks = true;
+        if ((T.filter_enable & CCSIM_PL_NODE_PORTS) && (T.flags & CCSIM_TF_HAS_HOST_PORTS) && T.port_static_mask[0]) masks = true;
+        if ((T.filter_enable & CCSIM_PL_INTER_POD_AFFINITY) && T.existing_anti_mask[0]) masks = true;
+      }
+    }
+    sp.use_masks = masks ? 1 : 0;
+    sp.chunk_pad = ((p.chunk + STREAM_TILE - 1) / STREAM_TILE) * STREAM_TILE;
+    sp.tiles = sp.chunk_pad / STREAM_TILE;
+    sp.n_pad = (long long)grid * sp.chunk_pad;
+    int rc2;
+    unsigned long long *mt = nullptr, *mst = nullptr;
+    if ((rc2 = dev_alloc<long long>(h, h->stream_allocs, &sp.f_cpu, (size_t)sp.n_pad))) return rc2;
+    if ((rc2 = dev_alloc<long long>(h, h->stream_allocs, &sp.f_mem, (size_t)sp.n_pad))) return rc2;
+    if ((rc2 = dev_alloc<int32_t>(h, h->stream_allocs, &sp.f_pods, (size_t)sp.n_pad))) return rc2;
+    if (masks) {
+      if ((rc2 = dev_alloc<unsigned long long>(h, h->stream_allocs, &mt, (size_t)sp.n_pad))) return rc2;
+      if ((rc2 = dev_alloc<unsigned long long>(h, h->stream_allocs, &mst, (size_t)sp.n_pad))) return rc2;
+    }
+    sp.m_taint = mt; sp.m_static = mst;
+    if ((rc2 = dev_alloc<int32_t>(h, h->stream_allocs, &sp.memo, (size_t)sp.n_pad * h->n_templates))) return rc2;
+    CK(cudaMemsetAsync(sp.memo, 0xFF, (size_t)sp.n_pad * h->n_templates * 4, s));
+    ccsim_stream_prep_kernel<<<std::min<long long>(8LL * h->sm_count, (sp.n_pad + 255) / 256), 256, 0, s>>>(p, sp);
+    h->launches++;
+    CK(cudaGetLastError());
+    kern = masks ? (const void *)ccsim_wave_stream_kernel<true> : (const void *)ccsim_wave_stream_kernel<false>;
+    smem = (size_t)STREAM_STAGES * STREAM_TILE * (masks ? 40 : 24) + 128;
+    block = STREAM_THREADS;
+  }
+  h->last_stream = stream ? 1 : 0;
   p.self = h->d_params;
   CK(cudaMemcpyAsync(h->d_params, &p, sizeof(DevParams), cudaMemcpyHostToDevice, s));
   int occ = 0;
-  if (multi && h->cfg.world > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel<true>, block, smem));
+  if (stream) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sp.use_masks ? ccsim_wave_stream_kernel<true> : ccsim_wave_stream_kernel<false>, block, smem));
+  else if (multi && h->cfg.world > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel<true>, block, smem));
   else if (multi) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel<false>, block, smem));
   else if (batched) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_batched_kernel, block, smem));
   else if (lean && faithful) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_lean_kernel<true>, block, smem));
@@ -1308,7 +1371,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   else if (resident) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<true>, block, smem));
   else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<false>, block, smem));
   if (occ < 1 || occ * h->sm_count < grid) return fail(h, CCSIM_ECUDA, "persistent grid %d does not fit (occupancy %d x %d SMs)", grid, occ, h->sm_count);
-  void *args[] = { (void *)&p, (void *)&lp, (void *)&mp };
+  void *args[] = { (void *)&p, stream ? (void *)&sp : (void *)&lp, (void *)&mp };
   CK(cudaEventRecord(h->ev0, s));
   CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));
   h->launches++;
@@ -1327,9 +1390,10 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   fprintf(stderr, "[ccsim phases 6/7] %.0f %.0f\n", (double)ho.phase_cycles[6] / ho.waves, (double)ho.phase_cycles[7] / ho.waves);
 #endif
   if (h->cfg.world > 1) h->xwave0 += (uint32_t)ho.waves;    // identical on every rank: the engines run the same waves everywhere
-  h->last_stat[0] = multi ? 3 : batched ? 2 : lean ? 1 : 0; h->last_stat[1] = ho.waves; h->last_stat[2] = ho.placed;
+  h->last_stat[0] = stream ? 4 : multi ? 3 : batched ? 2 : lean ? 1 : 0; h->last_stat[1] = ho.waves; h->last_stat[2] = ho.placed;
   h->last_stat[3] = ho.stat[0]; h->last_stat[4] = ho.stat[1]; h->last_stat[5] = grid; h->last_stat[6] = block; h->last_stat[7] = (int64_t)smem;
   for (int q = 0; q < 8; q++) h->last_stat[8 + q] = ho.phase_cycles[q];
+  h->last_stat[7] = ho.stat[2];   // (replay rounds; the shared-memory size is not needed by anybody)
   out->placed = ho.placed; out->stop_code = ho.stop_code; out->waves = ho.waves; out->evals = ho.evals; out->run_ms = ms;
   out->examined = ho.examined ? ho.examined : ho.evals;
   h->last_placed = ho.placed;

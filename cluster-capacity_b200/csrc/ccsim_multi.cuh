@@ -69,7 +69,7 @@ struct __align__(16) MultiShared {
   int32_t n_gt, accepted, dead, stopb;
   int32_t single_use, ncand;
   uint32_t delta, pad_ms;
-  long long ph[8], tc0, st_cand, st_overflow;       // CTA 0 / thread 0: clock cycles per phase, replay statistics
+  long long ph[8], tc0, st_cand, st_overflow, st_rounds;       // CTA 0 / thread 0: clock cycles per phase, replay statistics
 };
 
 __shared__ MultiShared ms;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     for (int d = tid; d < dc.n_domains; d += LEAN_THREADS) smem_cnt[dc.smem_off + d] = dc.init[d];
   }
   if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; ms.accepted = 0; ms.dead = 0; ms.stopb = 0; ms.n_gt = 0; ms.ncand = 0; ms.delta = 1u << MULTI_IDX_BITS;
-                  for (int q = 0; q < 8; q++) ms.ph[q] = 0; ms.tc0 = 0; ms.st_cand = 0; ms.st_overflow = 0; }
+                  for (int q = 0; q < 8; q++) ms.ph[q] = 0; ms.tc0 = 0; ms.st_cand = 0; ms.st_overflow = 0; ms.st_rounds = 0; }
   __syncthreads();
   for (int c = 0; c < ls.tmpl.n_pts; c++) lean_pts_recount(p, smem_cnt, c);
 
@@ -449,7 +449,10 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         const int32_t lim_off = c1.x - my_min;       // PTS: maxSkew - selfMatch (the limit follows the global minimum)
         bool lim_moved = false;
         const bool single_use = ms.single_use != 0;
+        long long tq0 = 0, t_rec = 0; int rounds = 0;
+        if (cta == 0 && lane == 0) { tq0 = clock64(); ms.ph[6] += tq0 - ms.tc0; }
         for (;;) {
+          rounds++;
           uint32_t m = ck[0];
           #pragma unroll
           for (int j = 1; j < MULTI_CPT; j++) m = max(m, ck[j]);
@@ -495,6 +498,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           // stands (the 8-region constraint of C4 moves its minimum every 8 placements and never binds).
           bool rescan = false;
           const unsigned mc = __ballot_sync(0xffffffffu, minchg);
+          long long tr0 = 0;
+          if (mc && cta == 0 && lane == 0) tr0 = clock64();
           for (unsigned nm = mc; nm; nm &= nm - 1) {
             const int q = __ffs(nm) - 1;
             const int32_t off = __shfl_sync(0xffffffffu, gc.x, q), npres = __shfl_sync(0xffffffffu, gc.w, q), ndom = __shfl_sync(0xffffffffu, c1.w, q);
@@ -513,6 +518,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
             rescan |= __any_sync(0xffffffffu, hit) | (p.debug_flags & 1);
             if (lane == q) { my_min = mn; my_num = num; c1.x = lim_new; lim_moved = true; }
           }
+          if (mc && cta == 0 && lane == 0) t_rec += clock64() - tr0;
           bool stopb = __any_sync(0xffffffffu, sec) | rescan;
           stopb |= (p.max_pods > 0 && k + acc >= p.max_pods) | (k + acc >= p.pod_cap) | (acc >= MULTI_MAX_ACC);
           if (stopb) break;
@@ -530,6 +536,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
             }
           }
         }
+        if (cta == 0 && lane == 0) { ms.ph[7] += t_rec; ms.st_rounds += rounds; }
         // the limits that moved go back to the Filter constants of the next scan
         if (lim_moved) { ls.terms[ms.gt_term[lane]].lim = c1.x; ms.gt_c1[lane][0] = c1.x; }
         if (lane < n_gt && gc.z >= 0) { ls.ptsmin[gc.z] = my_min; ls.ptsnum[gc.z] = my_num; }
@@ -614,7 +621,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       for (int c = 0; c < CCSIM_MAX_PTS; c++) o->ptsmin[c] = ls.ptsmin[c];
       o->aff_total = ls.aff_total;
       for (int q = 0; q < 8; q++) o->phase_cycles[q] = ms.ph[q];
-      o->stat[0] = ms.st_cand; o->stat[1] = ms.st_overflow;
+      o->stat[0] = ms.st_cand; o->stat[1] = ms.st_overflow; o->stat[2] = ms.st_rounds;
     }
   }
 }

@@ -1,0 +1,254 @@
+// ccsim_stream.cuh — the streaming wave kernel: node-local templates (no per-domain counters) on clusters whose tiles do not
+// fit in shared memory, and runs with several templates (BASELINE config C5: 1M nodes x 64 podspecs placed round-robin).
+//
+// One predicate-eval needs, per node, only what NodeResourcesFit compares (fit.go:564-660) and the node's memoised score:
+//   free_cpu, free_mem (int64: allocatable - requested), free_pods (int32), score memo of THIS template (int32)  = 24 B
+//   (+ taint / static words, 16 B, only when a template filters on them)
+// instead of the 72 B NodeInfo row of SURVEY.md §8(d): the row is read again only for a node whose memo is stale (it was
+// committed since that template last scored it; the reference's snapshot likewise refreshes only NodeInfos whose generation
+// changed, backend/cache/cache.go:194-288).
+//
+// Every persistent CTA owns a contiguous chunk of the node axis, stored padded to whole tiles (padding rows have
+// free_pods = INT_MIN and never pass the Filter). Per wave the CTA streams its chunk through a ring of shared-memory stages:
+// one elected thread arms the stage's mbarrier with the byte count and issues one 1-D bulk-async copy per column
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes — the TMA engine, no register staging), the 512
+// consumer threads wait on the mbarrier phase, run the fused Filter + arg-max on the tile from shared memory, and the stage
+// is re-armed for the tile STREAM_STAGES ahead. Then the usual tagged-word exchange through L2, and the owner CTA commits:
+// the winner's row (global columns, write-through for the terminal diagnosis), its free_* entries, and the memo entries of
+// ALL templates for that node (-1). Generic-proxy writes are ordered before later bulk-async reads by fence.proxy.async.
+#pragma once
+#include "ccsim_lean.cuh"
+
+#define STREAM_THREADS 512
+#define STREAM_WARPS (STREAM_THREADS / 32)
+#define STREAM_TILE 1024          /* nodes per stage: 24 KB (40 KB with the mask columns) */
+#define STREAM_STAGES 4
+
+struct StreamTmpl {               // per-template constants of the fused Filter pass + scorer inputs (shared memory table)
+  long long eq_cpu, eq_mem;       // effective requests (LLONG_MIN: check disabled)
+  unsigned long long taint_bad0, sel0, forbid0;
+  long long least_cpu, least_mem, bal_cpu, bal_mem, req_cpu, req_mem, nz_cpu, nz_mem;
+  ScoreWeights sw;
+  int32_t pods_need, pad[3];
+};
+
+struct StreamParams {
+  long long *f_cpu, *f_mem;       // [n_pad] allocatable - requested
+  int32_t *f_pods;                // [n_pad] allowedPodNumber - len(Pods); INT_MIN on padding rows
+  const unsigned long long *m_taint, *m_static;   // [n_pad] or nullptr when no template filters on them
+  int32_t *memo;                  // [n_templates][n_pad] memoised node-local score of template t, -1 = stale
+  int32_t chunk_pad;              // nodes per CTA, padded to a multiple of STREAM_TILE
+  int32_t tiles;                  // chunk_pad / STREAM_TILE
+  long long n_pad;                // grid * chunk_pad
+  int32_t use_masks, pad;
+};
+
+struct __align__(16) StreamShared {
+  StreamTmpl tc[CCSIM_MAX_TEMPLATES];
+  unsigned long long full[STREAM_STAGES];      // mbarriers: "the stage's bytes have landed"
+  unsigned long long warp_best[STREAM_WARPS];
+  int32_t winner, stop, pad[2];
+};
+
+__shared__ StreamShared ss;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// 1-D bulk-async copy global -> shared (TMA engine); size and both addresses are multiples of 16 bytes
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// fills the padded streaming columns from the snapshot's working columns (once per run)
+__global__ void ccsim_stream_prep_kernel(const DevParams p, const StreamParams sp) {
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < sp.n_pad; q += (long long)gridDim.x * blockDim.x) {
+    const int cta = (int)(q / sp.chunk_pad), off = (int)(q - (long long)cta * sp.chunk_pad);
+    const long long i = (long long)cta * p.chunk + off;
+    const bool real = off < p.chunk && i < p.n;
+    sp.f_cpu[q] = real ? p.alloc_cpu[i] - p.req_cpu[i] : 0;
+    sp.f_mem[q] = real ? p.alloc_mem[i] - p.req_mem[i] : 0;
+    sp.f_pods[q] = real ? p.alloc_pods[i] - p.npods[i] : INT_MIN;
+    if (sp.use_masks) {
+      const_cast<unsigned long long *>(sp.m_taint)[q] = real ? p.taint_mask[i] : 0ull;
+      const_cast<unsigned long long *>(sp.m_static)[q] = (real && p.static_words > 0) ? p.static_mask[i] : 0ull;
+    }
+  }
+}
+
+template <bool MASKS>
+__global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(const DevParams p, const StreamParams sp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // stage s: [f_cpu TILE x 8][f_mem TILE x 8][f_pods TILE x 4][memo TILE x 4]([taint TILE x 8][static TILE x 8])
+  constexpr uint32_t STAGE_BYTES = STREAM_TILE * (MASKS ? 40u : 24u);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x;
+  const long long base = (long long)cta * sp.chunk_pad;           // this CTA's first padded row
+  const int T = p.n_templates;
+
+  // ---- per-template constants (folded like lean_build_consts) ----
+  for (int t = tid; t < T; t += STREAM_THREADS) {
+    const ccsim_template &tp = p.templates[t];
+    StreamTmpl &c = ss.tc[t];
+    const uint32_t fe = tp.filter_enable, fl = tp.flags;
+    unsigned long long tb = 0ull;
+    if (fe & CCSIM_PL_TAINT_TOLERATION) tb |= p.taint_nosched[0] & ~tp.tol_nosched[0] & ~(1ull << CCSIM_TAINT_UNSCHEDULABLE_BIT);
+    if ((fe & CCSIM_PL_NODE_UNSCHEDULABLE) && !(fl & CCSIM_TF_TOLERATES_UNSCHEDULABLE)) tb |= 1ull << CCSIM_TAINT_UNSCHEDULABLE_BIT;
+    c.taint_bad0 = tb;
+    const bool aff_on = (fe & CCSIM_PL_NODE_AFFINITY) && (fl & CCSIM_TF_HAS_NODE_SELECTOR);
+    c.sel0 = (aff_on && p.static_words > 0) ? tp.sel_mask[0] : 0ull;
+    unsigned long long fb = 0ull;
+    if (p.static_words > 0) {
+      if ((fe & CCSIM_PL_NODE_PORTS) && (fl & CCSIM_TF_HAS_HOST_PORTS)) fb |= tp.port_static_mask[0];
+      if (fe & CCSIM_PL_INTER_POD_AFFINITY) fb |= tp.existing_anti_mask[0];
+    }
+    c.forbid0 = fb;
+    const bool fit = (fe & CCSIM_PL_FIT) != 0, nz = fit && !(fl & CCSIM_TF_FIT_ALL_ZERO);
+    c.pods_need = fit ? 1 : INT32_MIN + 1;       // (padding rows carry INT_MIN: they fail even when NodeResourcesFit is disabled)
+    c.eq_cpu = (nz && tp.req_cpu > 0) ? tp.req_cpu : LLONG_MIN;
+    c.eq_mem = (nz && tp.req_mem > 0) ? tp.req_mem : LLONG_MIN;
+    c.least_cpu = tp.least_cpu; c.least_mem = tp.least_mem; c.bal_cpu = tp.bal_cpu; c.bal_mem = tp.bal_mem;
+    c.req_cpu = tp.req_cpu; c.req_mem = tp.req_mem; c.nz_cpu = tp.nz_cpu; c.nz_mem = tp.nz_mem;
+    c.sw.w_fit = (tp.score_enable & CCSIM_PL_FIT) ? tp.w_fit : 0;
+    c.sw.w_balanced = ((tp.score_enable & CCSIM_PL_BALANCED) && !(fl & CCSIM_TF_BALANCED_SKIP)) ? tp.w_balanced : 0;
+    c.sw.least_w_cpu = tp.least_w_cpu; c.sw.least_w_mem = tp.least_w_mem;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STREAM_STAGES; s++) mbar_init(&ss.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ss.winner = -1; ss.stop = 0;
+  }
+  __syncthreads();
+
+  // thread 0: arm stage `s` and issue the bulk copies of tile `tile` of template t's pass
+  auto issue = [&](int tile, int s, int t) {
+    unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
+    const long long row = base + (long long)tile * STREAM_TILE;
+    mbar_expect_tx(&ss.full[s], STAGE_BYTES);
+    bulk_g2s(st, sp.f_cpu + row, STREAM_TILE * 8, &ss.full[s]);
+    bulk_g2s(st + STREAM_TILE * 8, sp.f_mem + row, STREAM_TILE * 8, &ss.full[s]);
+    bulk_g2s(st + STREAM_TILE * 16, sp.f_pods + row, STREAM_TILE * 4, &ss.full[s]);
+    bulk_g2s(st + STREAM_TILE * 20, sp.memo + (size_t)t * sp.n_pad + row, STREAM_TILE * 4, &ss.full[s]);
+    if (MASKS) {
+      bulk_g2s(st + STREAM_TILE * 24, sp.m_taint + row, STREAM_TILE * 8, &ss.full[s]);
+      bulk_g2s(st + STREAM_TILE * 32, sp.m_static + row, STREAM_TILE * 8, &ss.full[s]);
+    }
+  };
+
+  long long k = 0;
+  bool limit_hit = false;
+  uint32_t uses = 0;                 // tiles consumed so far by this CTA (all waves): stage = uses % STAGES, parity = (uses / STAGES) & 1
+  uint32_t wtag = 1;
+  uint32_t tag = (p.epoch << 12) | wtag;
+  const int tiles = sp.tiles;
+  for (;; k++) {
+    if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }
+    if (k > p.pod_cap) { if (tid == 0) ss.stop = 3; __syncthreads(); break; }
+    const int t = (int)(k % T);
+    const StreamTmpl &c = ss.tc[t];
+    const long long eq_cpu = c.eq_cpu, eq_mem = c.eq_mem;
+    const int32_t pods_need = c.pods_need;
+    const unsigned long long taint_bad0 = c.taint_bad0, sel0 = c.sel0, forbid0 = c.forbid0;
+    if (tid == 0) {
+      fence_proxy_async();            // the commit's and the scorers' generic-proxy stores of the last wave, before the engine reads them
+      for (int q = 0; q < STREAM_STAGES && q < tiles; q++) issue(q, (int)((uses + q) % STREAM_STAGES), t);
+    }
+    unsigned long long best = 0ull;
+    for (int tile = 0; tile < tiles; tile++, uses++) {
+      const int s = (int)(uses % STREAM_STAGES);
+      const uint32_t parity = (uses / STREAM_STAGES) & 1u;
+      while (!mbar_try_wait(&ss.full[s], parity)) { }
+      const unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
+      const long long *s_fcpu = reinterpret_cast<const long long *>(st), *s_fmem = reinterpret_cast<const long long *>(st + STREAM_TILE * 8);
+      const int32_t *s_fpods = reinterpret_cast<const int32_t *>(st + STREAM_TILE * 16), *s_memo = reinterpret_cast<const int32_t *>(st + STREAM_TILE * 20);
+      #pragma unroll
+      for (int j = tid; j < STREAM_TILE; j += STREAM_THREADS) {
+        // NodeResourcesFit (+ NodeUnschedulable / TaintToleration / nodeSelector / NodePorts / existing anti-affinity bits)
+        bool ok = (s_fcpu[j] >= eq_cpu) & (s_fmem[j] >= eq_mem) & (s_fpods[j] >= pods_need);
+        if (MASKS) {
+          const unsigned long long taint0 = reinterpret_cast<const unsigned long long *>(st + STREAM_TILE * 24)[j];
+          const unsigned long long static0 = reinterpret_cast<const unsigned long long *>(st + STREAM_TILE * 32)[j];
+          ok &= ((taint0 & taint_bad0) | (~static0 & sel0) | (static0 & forbid0)) == 0ull;
+        }
+        if (ok) {
+          const int off = tile * STREAM_TILE + j;
+          const long long i = (long long)cta * p.chunk + off;        // shard-local node index
+          int32_t sc = s_memo[j];
+          if (sc < 0) {   // stale: this node was committed since template t last scored it (or never scored)
+            sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
+                            p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
+            sp.memo[(size_t)t * sp.n_pad + base + off] = sc;
+            fence_proxy_async();         // a later bulk-async read of this column must see the store
+          }
+          const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
+          best = key > best ? key : best;
+        }
+      }
+      __syncthreads();                 // everybody is done with stage s
+      if (tid == 0 && tile + STREAM_STAGES < tiles) { fence_proxy_async(); issue(tile + STREAM_STAGES, s, t); }
+    }
+    {
+      const unsigned long long v = warp_max_u64(best);
+      if (lane == 0) ss.warp_best[warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
+      const unsigned long long mine = warp_max_u64(lane < STREAM_WARPS ? ss.warp_best[lane] : 0ull);
+      bool dead = false;
+      unsigned long long wkey = exchange_max(p, k, tag, 0, mine, lane, cta, dead);
+      (void)tagbits;
+      if (p.world > 1 && !dead) { unsigned long long cb[1] = {wkey}; dead = cross_gpu_exchange(p, k, tag, 1, cb, lane, cta); wkey = cb[0]; }   // node shards: winners of all ranks
+      if (lane == 0) {
+        if (dead) { ss.stop = 3; ss.winner = -1; }
+        else if (wkey == 0ull) { ss.stop = 1; ss.winner = -1; }
+        else ss.winner = (int32_t)key_index(wkey);
+      }
+      // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) by the owner CTA ----
+      if (!dead && wkey != 0ull) {
+        const int32_t w = (int32_t)key_index(wkey) - p.node_base;
+        const bool local = w >= 0 && w < p.n;
+        const int oc = local ? w / p.chunk : -1;
+        if (!local && cta == 0 && lane == 0) {      // sharded run: every rank keeps the whole pod -> node sequence
+          if (k < p.pod_cap) p.pod_node[k] = (int32_t)key_index(wkey); else ss.stop = 3;
+        }
+        if (oc == cta) {
+          const long long q = base + (w - (long long)oc * p.chunk);
+          if (lane == 0) {
+            sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1;
+            p.req_cpu[w] += c.req_cpu; p.req_mem[w] += c.req_mem; p.nz_cpu[w] += c.nz_cpu; p.nz_mem[w] += c.nz_mem; p.npods[w] += 1;   // write-through
+            if (k < p.pod_cap) p.pod_node[k] = w + p.node_base; else ss.stop = 3;
+          }
+          for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
+          fence_proxy_async();
+        }
+      }
+    }
+    __syncthreads();
+    if (ss.stop) break;
+    wtag = (wtag == 4095u) ? 1u : wtag + 1u;
+    tag = (p.epoch << 12) | wtag;
+  }
+  if (cta == 0 && tid == 0) {
+    DevOut *o = p.out;
+    o->placed = k;
+    o->stop_code = limit_hit ? CCSIM_STOP_LIMIT_REACHED : CCSIM_STOP_UNSCHEDULABLE;
+    o->error = (ss.stop == 3) ? 1 : 0;
+    o->waves = limit_hit ? k : k + 1;
+    o->evals = o->waves * (long long)p.n;
+    o->examined = o->evals;
+    o->aff_total = 0;
+  }
+}

@@ -363,7 +363,7 @@ template <class T, class F> static std::vector<T> parse_list(const char *text, F
   std::vector<std::pair<size_t, size_t>> spans;
   if (!item_spans(text, n, spans)) { for (auto &j : items_of(text)) out.push_back(one(j)); return out; }
   unsigned nt = std::thread::hardware_concurrency();
-  nt = nt == 0 ? 1 : (nt > 16 ? 16 : nt);
+  nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
   if (spans.size() < 2048) nt = 1;
   std::vector<std::vector<T>> parts(nt);
   std::vector<std::exception_ptr> errs(nt);
@@ -371,7 +371,7 @@ template <class T, class F> static std::vector<T> parse_list(const char *text, F
     try {
       const size_t per = (spans.size() + nt - 1) / nt, b = std::min(spans.size(), (size_t)c * per), e = std::min(spans.size(), b + per);
       parts[c].reserve(e - b);
-      for (size_t i = b; i < e; i++) parts[c].push_back(one(parse_json(std::string(text + spans[i].first, spans[i].second - spans[i].first))));
+      for (size_t i = b; i < e; i++) parts[c].push_back(one(parse_json(std::string_view(text + spans[i].first, spans[i].second - spans[i].first))));
     } catch (...) { errs[c] = std::current_exception(); }
   };
   if (nt == 1) work(0);
@@ -451,7 +451,11 @@ extern "C" int cc_run(cc_handle *h) {
   if (rc) return fail(h, CC_EENGINE, std::string("ccsim_create: ") + ccsim_last_error(nullptr));
   ccsim_nodes nd; E.fill_nodes(nd);
   ccsim_result res;
-  auto bail = [&](const char *what) { std::string m = std::string(what) + ": " + ccsim_last_error(eng); ccsim_destroy(eng); return fail(h, CC_EENGINE, m); };
+  auto bail = [&](const char *what) {
+    std::string m = std::string(what) + ": " + ccsim_last_error(eng);
+    ccsim_destroy(eng);
+    return rc == CCSIM_EUNSUPPORTED ? fail(h, CC_EUNSUPPORTED, "unsupported on the GPU path: " + m) : fail(h, CC_EENGINE, m);
+  };
   if ((rc = ccsim_load_nodes(eng, &nd))) return bail("ccsim_load_nodes");
   if ((rc = ccsim_set_templates(eng, (int32_t)h->enc_tmpls.size(), h->enc_tmpls.data(), (int32_t)E.counters.size(), E.counters.data()))) return bail("ccsim_set_templates");
   if ((rc = ccsim_run(eng, h->max_pods, &res))) return bail("ccsim_run");

@@ -10,6 +10,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <string_view>
 #include <utility>
 #include <vector>
 
@@ -65,7 +66,7 @@ struct Json {
 
 class JsonParser {
  public:
-  explicit JsonParser(const std::string &t) : t_(t) {}
+  explicit JsonParser(std::string_view t) : t_(t) {}   // a view: items of a list are parsed in place, without copying their text
   Json parse() {
     Json v = value();
     ws();
@@ -74,7 +75,7 @@ class JsonParser {
   }
 
  private:
-  const std::string &t_;
+  std::string_view t_;
   size_t p_ = 0;
   int depth_ = 0;                    // nesting of the value being parsed; capped so that a hostile document cannot overflow the stack
   static constexpr int kMaxDepth = 512;
@@ -103,7 +104,7 @@ class JsonParser {
     if (p_ < t_.size() && (t_[p_] == '-' || t_[p_] == '+')) p_++;
     while (p_ < t_.size() && (isdigit((unsigned char)t_[p_]) || t_[p_] == '.' || t_[p_] == 'e' || t_[p_] == 'E' || t_[p_] == '-' || t_[p_] == '+')) p_++;
     if (b == p_) fail("bad value");
-    return Json::number_text(t_.substr(b, p_ - b));
+    return Json::number_text(std::string(t_.substr(b, p_ - b)));
   }
   std::string string() {
     std::string out;
@@ -125,10 +126,10 @@ class JsonParser {
           case 'r': out += '\r'; break; case 't': out += '\t'; break;
           case 'u': {
             if (p_ + 4 > t_.size()) fail("bad \\u");
-            unsigned cp = (unsigned)strtoul(t_.substr(p_, 4).c_str(), nullptr, 16);
+            unsigned cp = (unsigned)strtoul(std::string(t_.substr(p_, 4)).c_str(), nullptr, 16);
             p_ += 4;
             if (cp >= 0xD800 && cp <= 0xDBFF && p_ + 6 <= t_.size() && t_[p_] == '\\' && t_[p_ + 1] == 'u') {
-              unsigned lo = (unsigned)strtoul(t_.substr(p_ + 2, 4).c_str(), nullptr, 16);
+              unsigned lo = (unsigned)strtoul(std::string(t_.substr(p_ + 2, 4)).c_str(), nullptr, 16);
               p_ += 6;
               cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
             }
@@ -184,7 +185,7 @@ class JsonParser {
   }
 };
 
-inline Json parse_json(const std::string &text) { return JsonParser(text).parse(); }
+inline Json parse_json(std::string_view text) { return JsonParser(text).parse(); }
 
 // Go's encoding/json escapes <, >, & and U+2028/2029 as well (HTML-safe by default: json.Marshal).
 inline void json_escape(const std::string &s, std::string &out) {

@@ -137,7 +137,7 @@ class Engine:
         lib().ccsim_device_info(self._h, C.byref(sm), C.byref(grid), C.byref(block), C.byref(l2))
         return dict(sm_count=sm.value, grid=grid.value, block=block.value, l2_bytes=l2.value)
 
-    ENGINE_NAMES = ("generic", "lean sequential", "tie-run batching", "multi-commit")
+    ENGINE_NAMES = ("generic", "lean sequential", "tie-run batching", "multi-commit", "streaming (TMA)")
 
     def run_stats(self):
         """Latency anatomy of the last run (see ccsim_run_stats in include/ccsim.h)."""

@@ -76,15 +76,8 @@ def c3(n=50_000, seed=2, prefer_taints=False):
     return snap, [t], []
 
 
-def c4(n=100_000, seed=3, n_existing=200_000, zones=64, racks=1024, regions=8, match_frac=0.30):
-    """100k nodes, 3 DoNotSchedule topology-spread constraints (zone/rack/region; maxSkew 1/2/4) + required
-    anti-affinity on kubernetes.io/hostname against app=sim, 200k pre-existing pods of which 30% carry app=sim.
-    The template itself carries app=sim (it spreads / repels itself).
-
-    Topology is hierarchical (rack -> zone = rack % zones -> region = zone % regions). The app=sim pods that already
-    exist are spread evenly over racks (as if they had been scheduled under the same constraints): with SURVEY.md
-    §8(d)'s literal "assigned uniformly at random" the per-zone counts differ by ~30 and maxSkew=1 stops the run
-    after <10 placements, which measures nothing. The other 70% of the existing pods are assigned uniformly."""
+def _c4_raw(n, seed, n_existing, zones, racks, regions, match_frac):
+    """The random draws behind C4: node capacities and topology, and the existing pods (node, cpu, memory; the first n_match carry app=sim)."""
     rng = _rng(seed)
     a_cpu, a_mem, a_pods, _, _, _ = _c2_nodes(n, rng)
     rack = rng.integers(0, racks, size=n).astype(np.int32)
@@ -103,6 +96,20 @@ def c4(n=100_000, seed=3, n_existing=200_000, zones=64, racks=1024, regions=8, m
     pn = np.concatenate([mnode, onode])
     pcpu = rng.integers(10, 51, size=len(pn)).astype(np.int64) * 10
     pmem = rng.integers(128, 1025, size=len(pn)).astype(np.int64) * MiB
+    return a_cpu, a_mem, a_pods, zone, rack, region, pn, pcpu, pmem, len(mnode)
+
+
+def c4(n=100_000, seed=3, n_existing=200_000, zones=64, racks=1024, regions=8, match_frac=0.30):
+    """100k nodes, 3 DoNotSchedule topology-spread constraints (zone/rack/region; maxSkew 1/2/4) + required
+    anti-affinity on kubernetes.io/hostname against app=sim, 200k pre-existing pods of which 30% carry app=sim.
+    The template itself carries app=sim (it spreads / repels itself).
+
+    Topology is hierarchical (rack -> zone = rack % zones -> region = zone % regions). The app=sim pods that already
+    exist are spread evenly over racks (as if they had been scheduled under the same constraints): with SURVEY.md
+    §8(d)'s literal "assigned uniformly at random" the per-zone counts differ by ~30 and maxSkew=1 stops the run
+    after <10 placements, which measures nothing. The other 70% of the existing pods are assigned uniformly."""
+    a_cpu, a_mem, a_pods, zone, rack, region, pn, pcpu, pmem, n_m = _c4_raw(n, seed, n_existing, zones, racks, regions, match_frac)
+    mnode = pn[:n_m]
     req_cpu = np.bincount(pn, weights=pcpu, minlength=n).astype(np.int64)
     req_mem = np.bincount(pn, weights=pmem, minlength=n).astype(np.int64)
     npods = np.bincount(pn, minlength=n).astype(np.int32)
@@ -125,6 +132,34 @@ def c4(n=100_000, seed=3, n_existing=200_000, zones=64, racks=1024, regions=8, m
     t.n_anti = 1
     t.anti_counter[0] = 3
     return snap, [t], counters
+
+
+def c4_objects(n=100_000, seed=3, n_existing=200_000, zones=64, racks=1024, regions=8, match_frac=0.30):
+    """The same cluster as c4() as API objects (v1.Node / v1.Pod dicts + the podspec) for the reference-facing path
+    (framework.New / SyncWithClient): node i of c4() is the i-th Node. The topology labels use example.com/* keys — the well-known
+    zone / region labels would make nodeTree reorder the nodes (node_tree.go:119-143) and the two paths would no longer index
+    nodes alike. Requests are whole milli-cpu / MiB values, so the encoded columns equal c4()'s exactly."""
+    a_cpu, a_mem, a_pods, zone, rack, region, pn, pcpu, pmem, n_m = _c4_raw(n, seed, n_existing, zones, racks, regions, match_frac)
+    nodes = [{"apiVersion": "v1", "kind": "Node",
+              "metadata": {"name": "node-%06d" % i, "labels": {"kubernetes.io/hostname": "node-%06d" % i, "example.com/zone": "z%d" % zone[i],
+                                                              "example.com/rack": "k%d" % rack[i], "example.com/region": "g%d" % region[i]}},
+              "spec": {}, "status": {"allocatable": {"cpu": "%dm" % a_cpu[i], "memory": "%dMi" % (a_mem[i] // MiB), "pods": str(int(a_pods[i]))}}}
+             for i in range(n)]
+    pods = [{"apiVersion": "v1", "kind": "Pod",
+             "metadata": {"name": "pod-%06d" % j, "namespace": "default", "labels": {"app": "sim"} if j < n_m else {"app": "other"}},
+             "spec": {"nodeName": "node-%06d" % pn[j],
+                      "containers": [{"name": "c", "image": "img", "resources": {"requests": {"cpu": "%dm" % pcpu[j], "memory": "%dMi" % (pmem[j] // MiB)}}}]},
+             "status": {"phase": "Running"}} for j in range(len(pn))]
+    sel = {"matchLabels": {"app": "sim"}}
+    template = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "sim-pod", "namespace": "default", "labels": {"app": "sim"}},
+                "spec": {"containers": [{"name": "c", "image": "img", "resources": {"requests": {"cpu": "150m", "memory": "100Mi"}}}],
+                         "topologySpreadConstraints": [
+                             {"maxSkew": 1, "topologyKey": "example.com/zone", "whenUnsatisfiable": "DoNotSchedule", "labelSelector": sel},
+                             {"maxSkew": 2, "topologyKey": "example.com/rack", "whenUnsatisfiable": "DoNotSchedule", "labelSelector": sel},
+                             {"maxSkew": 4, "topologyKey": "example.com/region", "whenUnsatisfiable": "DoNotSchedule", "labelSelector": sel}],
+                         "affinity": {"podAntiAffinity": {"requiredDuringSchedulingIgnoredDuringExecution": [
+                             {"labelSelector": sel, "topologyKey": "kubernetes.io/hostname"}]}}}}
+    return nodes, pods, template
 
 
 def c5(n=1_000_000, seed=4, n_templates=64):

@@ -308,7 +308,7 @@ int  ccsim_device_info(ccsim_handle *h, int32_t *sm_count, int32_t *grid, int32_
 int64_t ccsim_kernel_launches(const ccsim_handle *h);  /* kernels launched by this handle so far */
 int  ccsim_flush_l2(ccsim_handle *h);                  /* writes a buffer larger than L2 (bench hygiene) */
 /* latency anatomy of the last run (bench.py's roofline block): [0] engine (0 generic, 1 lean sequential, 2 tie-run batching,
- * 3 multi-commit) [1] waves [2] placed [3] multi-commit: candidates replayed, summed over waves [4] multi-commit: waves that
+ * 3 multi-commit, 4 streaming) [1] waves [2] placed [3] multi-commit: candidates replayed, summed over waves [4] multi-commit: waves that
  * raised the candidate bar [5] grid [6] block [7] dynamic shared memory bytes [8..15] CTA 0's clock cycles per phase, summed
  * over waves (multi-commit: scan, barrier, merge+publish, gather, replay, row updates+recount; 0 for the other engines) */
 int  ccsim_run_stats(const ccsim_handle *h, int64_t out[16]);

@@ -28,6 +28,9 @@ def _worker(rank, world, port, which, q):
         snap, tmpl, ctr = synth.c3(n=5001, prefer_taints=True)
     elif which == "c4":
         snap, tmpl, ctr = synth.c4(n=6000, n_existing=12000, zones=8, racks=64, regions=4)
+    elif which == "c5":            # several node-local templates: the streaming (TMA) engine over node shards
+        snap, tmpl, ctr = synth.c5(n=300_001, n_templates=9)
+        limit = 1500
     elif which == "c4_wide":      # enough nodes per shard for full grids: the multi-commit replay sees 2 x 148 candidate lists
         snap, tmpl, ctr = synth.c4(n=120_001, n_existing=200_000, zones=32, racks=1024, regions=8)
         limit = 3000
@@ -55,12 +58,14 @@ def _worker(rank, world, port, which, q):
                 ok &= m["evals"] == w.evals
             elif which.startswith("c4") or which == "spread":
                 ok &= eng.run_stats()["engine"] == "multi-commit" and (w.placed < 100 or res.waves * 2 < w.waves)
+            if which == "c5":
+                ok &= eng.run_stats()["engine"].startswith("streaming")
         eng.close()
     q.put((rank, bool(ok), int(res.placed)))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("which", ["c3", "c4", "c4_wide", "spread"])
+@pytest.mark.parametrize("which", ["c3", "c4", "c4_wide", "spread", "c5"])
 def test_two_gpu_sharded_matches_oracle(built, which):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -20,7 +20,7 @@ genpod = importlib.import_module("cluster-capacity_b200.genpod")
 LISTS = {
     "plain3": ["plain", "best_effort", "init_overhead"],
     "selectors": ["selector", "tolerations", "affinity_terms", "gt_lt"],           # static bits of four templates side by side
-    "extended": ["extended", "plain", "name_in", "pref_affinity"],                 # union of extended resources, PreFilter node names
+    "extended": ["extended", "plain", "name_in", "tolerations"],                   # union of extended resources, PreFilter node names
     "never": ["never_preempt", "plain"],
 }
 
@@ -85,6 +85,16 @@ def test_pod_list_with_spread_terms_is_refused(built):
     cc.SyncWithClient(helpers.list_client(fw, nodes, pods))
     with pytest.raises(fw.UnsupportedError, match="several podspecs"):
         cc.EncodedSnapshot()
+
+
+@pytest.mark.gpu
+def test_pod_list_with_normalised_soft_scorer_is_refused_on_gpu(built):
+    """preferred nodeAffinity needs multi-pass waves (feasible-set normalisation): single podspec only, refused by name"""
+    nodes, pods = cluster(5, 20, 20)
+    cc = fw.New(None, None, [helpers.template("plain"), helpers.template("pref_affinity")], 0, [])
+    cc.SyncWithClient(helpers.list_client(fw, nodes, pods))
+    with pytest.raises(fw.UnsupportedError, match="single template"):
+        cc.Run()
 
 
 @pytest.mark.gpu
