@@ -21,16 +21,21 @@ HOST_OUT = os.path.join(_HERE, "libcchost.so")
 
 
 def build(force=False, verbose=False):
-    """libccsim.so (CUDA, sm_100a) then libcchost.so (C++ host side, links libccsim via $ORIGIN rpath)."""
+    """libccsim.so (CUDA, sm_100a) then libcchost.so (C++ host side, links libccsim via $ORIGIN rpath).
+    CCSIM_NO_REBUILD=1 (set by GPU-box job scripts): use the shipped libraries as they are, whatever the source mtimes say."""
+    if os.environ.get("CCSIM_NO_REBUILD") and os.path.exists(OUT) and os.path.exists(HOST_OUT) and not force:
+        return OUT
     newest = max(os.path.getmtime(p) for p in DEPS)
     if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT + ".tmp"] + SRC
         subprocess.check_call(cmd)
+        os.replace(OUT + ".tmp", OUT)      # atomic: a concurrent snapshot of the tree never sees a half-written library
     newest = max([os.path.getmtime(p) for p in HOST_DEPS] + [os.path.getmtime(OUT)])
     if force or not os.path.exists(HOST_OUT) or os.path.getmtime(HOST_OUT) < newest:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-shared", "-fPIC", "-o", HOST_OUT] + HOST_SRC +
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-shared", "-fPIC", "-o", HOST_OUT + ".tmp"] + HOST_SRC +
                               ["-L" + _HERE, "-lccsim", "-Wl,-rpath,$ORIGIN"])
+        os.replace(HOST_OUT + ".tmp", HOST_OUT)
     return OUT
 
 

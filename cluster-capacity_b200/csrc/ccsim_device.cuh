@@ -556,6 +556,15 @@ __device__ __forceinline__ unsigned long long exchange_sum_fenced(const DevParam
   return s;
 }
 
+// Shared-memory accesses by explicit 32-bit shared address. nvcc otherwise re-derives the CTA's shared window base (S2UR
+// SR_CgaCtaId + ULEA, a slow special-register read) in front of accesses that follow a barrier or a divergent region; inside
+// latency-bound single-warp loops that costs more than the access itself. pin_u32 keeps the once-computed base from being
+// rematerialised.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ int32_t lds_s32(uint32_t a) { int32_t v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_s32(uint32_t a, int32_t v) { asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
 __device__ __forceinline__ bool static_bit(const DevParams &p, int32_t i, int b) {
   return (p.static_mask[(size_t)(b >> 6) * p.n + i] >> (b & 63)) & 1ull;
 }

@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
   const int32_t lo = min(p.n, cta * p.chunk), hi = min(p.n, lo + p.chunk);
   const int32_t cnt_nodes = hi - lo;      // <= LEAN_THREADS (host-checked): one node per thread
   const int su = lp.stride_u;
+  const uint32_t cnt_sa = pin_u32(smem_u32(smem_cnt)), ms_sa = pin_u32(smem_u32(&ms));   // shared bases for the replay's explicit-address accesses
+#define MS_SA(field) (ms_sa + (uint32_t)offsetof(MultiShared, field))
   const int nlists = (XGPU ? p.world : 1) * p.grid;     // every rank launches the same grid (host: sized from the largest shard)
   const int tot = nlists * MULTI_M;
 
@@ -337,6 +339,38 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     // list l = (source rank l / grid, CTA l % grid) -> its line
 #define LINE_OF(l) (lbase + (XGPU ? ((size_t)((l) / p.grid) * CCSIM_MAX_GRID + (size_t)((l) % p.grid)) : (size_t)(l)) * SLOT_STRIDE)
     uint32_t tloc = 0u, kloc = 0u;
+    // Single GPU: every thread waits for its own (<= 2) entries — key word and payload word — so that the bar and the entries cost
+    // ONE L2 round trip after the slowest CTA's line lands (measured in round 1: letting all threads poll their entries is no slower
+    // than 5 polling warps). Node shards: world x grid x 8 entries do not fit in registers; one poller per line, entries afterwards.
+    constexpr bool ONEPASS = !XGPU;
+    unsigned long long ea[2] = {0ull, 0ull}, eb[2] = {0ull, 0ull};
+    if (ONEPASS) {
+      const unsigned long long *pa[2], *pb[2];
+      bool need[2];
+      #pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int e = tid + u * LEAN_THREADS, ee = e & (MULTI_M - 1);
+        const unsigned long long *ln = lbase + (size_t)(e >> 3) * SLOT_STRIDE;
+        pa[u] = ln + (ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1)); pb[u] = ln + MULTI_M + ee;
+        need[u] = e < tot;
+      }
+      unsigned spins = 0;
+      while (need[0] | need[1]) {
+        #pragma unroll
+        for (int u = 0; u < 2; u++) if (need[u]) { ea[u] = ld_slot(pa[u]); eb[u] = ld_slot(pb[u]); }
+        #pragma unroll
+        for (int u = 0; u < 2; u++) if (need[u] && (uint32_t)(ea[u] >> KEY_TAG_SHIFT) == tag && (uint32_t)(eb[u] >> KEY_TAG_SHIFT) == tag) need[u] = false;
+        if (++spins > WATCHDOG_SPINS) { ms.dead = 1; if (need[0]) ea[0] = eb[0] = 0ull; if (need[1]) ea[1] = eb[1] = 0ull; break; }
+      }
+      #pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int e = tid + u * LEAN_THREADS, ee = e & (MULTI_M - 1);
+        if (e < tot) {
+          if (ee == 0) kloc = max(kloc, (uint32_t)ea[u]);
+          if (ee == MULTI_M - 1 && ((ea[u] >> MULTI_MORE_BIT) & 1ull)) tloc = max(tloc, (uint32_t)ea[u]);
+        }
+      }
+    } else
     for (int l = tid; l < nlists; l += LEAN_THREADS) {
       const unsigned long long *ln = LINE_OF(l);
       unsigned long long a, b;
@@ -366,6 +400,13 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     int C = 0;
     const int iters = (tot + LEAN_THREADS - 1) / LEAN_THREADS;
     for (int pass = 0; pass < 2 && !dead; pass++) {
+      if (ONEPASS && pass == 0) {           // the entries are in registers already
+        #pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const uint32_t ck = (uint32_t)ea[u];
+          if (u * LEAN_THREADS < tot) multi_append(ck != 0u && ck >= T, ck, eb[u], lane);      // (warp-uniform guard: warps beyond the entries skip)
+        }
+      } else
       for (int it = 0; it < iters; it++) {
         const int e = tid + it * LEAN_THREADS;
         unsigned long long a = 0ull, b = 0ull;
@@ -449,8 +490,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         const int32_t lim_off = c1.x - my_min;       // PTS: maxSkew - selfMatch (the limit follows the global minimum)
         bool lim_moved = false;
         const bool single_use = ms.single_use != 0;
-        long long tq0 = 0, t_rec = 0; int rounds = 0;
-        if (cta == 0 && lane == 0) { tq0 = clock64(); ms.ph[6] += tq0 - ms.tc0; }
+        // commits this wave may still decide: --max-limit (simulator.go:300-305), the output capacity, MULTI_MAX_ACC
+        long long room = p.pod_cap - k;
+        if (p.max_pods > 0 && p.max_pods - k < room) room = p.max_pods - k;
+        const int32_t acc_limit = room < MULTI_MAX_ACC ? (int32_t)room : MULTI_MAX_ACC;
+        int rounds = 0;
+        if (cta == 0 && lane == 0) ms.ph[6] += clock64() - ms.tc0;      // replay set-up
         for (;;) {
           rounds++;
           uint32_t m = ck[0];
@@ -459,22 +504,26 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           const uint32_t g = __reduce_max_sync(0xffffffffu, m);
           if (g == 0u || g < T) { ran_dry = true; break; }      // nothing left, or an unseen node could rank above g
           // ---- commit pod k+acc (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
-          const bool mine = (m == g);
-          const int ol = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-          uint32_t dsel = 0u; int jsel = 0;
+          // the owner lane contributes the winner's payload (keys are unique: exactly one lane and slot match)
+          uint32_t dsel = 0u;
           #pragma unroll
-          for (int j = 0; j < MULTI_CPT; j++) if (ck[j] == g) { dsel = cd[j]; jsel = j; }
-          const uint32_t pay = __shfl_sync(0xffffffffu, dsel, ol);
+          for (int j = 0; j < MULTI_CPT; j++) dsel = (ck[j] == g) ? cd[j] : dsel;
+          const uint32_t pay = __reduce_or_sync(0xffffffffu, dsel);
           // the winner comes back once with the key it has after this clone (if it still fits); when a node wins for the second
           // time in a wave its third key is unknown: the wave ends after that commit
           bool sec = false;
-          if (mine) {
-            sec = (second >> jsel) & 1u;
-            const uint32_t ns = (single_use || sec) ? 0u : ms.cnext[jsel * 32 + lane];
-            const uint32_t nk = ns ? ((ns << MULTI_IDX_BITS) | (g & MULTI_IDX_MASK)) : 0u;
+          if (single_use) {           // a clone blocks its own node (hostname anti-affinity): the winner just leaves
             #pragma unroll
-            for (int j = 0; j < MULTI_CPT; j++) if (j == jsel) ck[j] = nk;
-            second |= 1u << jsel;
+            for (int j = 0; j < MULTI_CPT; j++) ck[j] = (ck[j] == g) ? 0u : ck[j];
+          } else {
+            #pragma unroll
+            for (int j = 0; j < MULTI_CPT; j++)
+              if (ck[j] == g) {
+                sec = (second >> j) & 1u;
+                const uint32_t ns = sec ? 0u : (uint32_t)lds_s32(MS_SA(cnext) + 4u * (uint32_t)(j * 32 + lane));
+                ck[j] = ns ? ((ns << MULTI_IDX_BITS) | (g & MULTI_IDX_MASK)) : 0u;
+                second |= 1u << j;
+              }
           }
           // Only what the next round depends on happens here: the counter cells of the winner's domains (lane q = term q; the
           // host guarantees one term per incremented replicated counter), whether a cell went over its limit, whether a PTS
@@ -484,13 +533,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           if (lane < n_gt) {
             const int32_t v = (int32_t)((pay >> c1.y) & (uint32_t)c1.z) - 1;
             if (v >= 0) {
-              const int32_t old = smem_cnt[gc.x + v], nv = old + gc.y;
-              smem_cnt[gc.x + v] = nv;
+              const uint32_t ca = cnt_sa + 4u * (uint32_t)(gc.x + v);
+              const int32_t old = lds_s32(ca), nv = old + gc.y;
+              sts_s32(ca, nv);
               if (nv > c1.x) fullf = (uint32_t)(v + 1) << c1.y;            // candidates in this cell are dead from now on
               if (gc.y && gc.z >= 0 && v < gc.w && old == my_min) { my_num--; minchg = my_num <= 0; }   // the global minimum of this constraint moves: limits change, rescan
             }
           }
-          if (lane == 0) ms.acc_node[acc] = ckey_index(g);
+          if (lane == 0) sts_s32(MS_SA(acc_node) + 4u * (uint32_t)acc, ckey_index(g));
           acc++;
           // A PTS minimum moved (filtering.go:56-69: minMatchNum): recount it and move the term's limit. The wave goes on unless
           // the move changes some node's feasibility: that takes a domain whose count lies in (old limit, new limit] — nodes there
@@ -498,30 +548,27 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           // stands (the 8-region constraint of C4 moves its minimum every 8 placements and never binds).
           bool rescan = false;
           const unsigned mc = __ballot_sync(0xffffffffu, minchg);
-          long long tr0 = 0;
-          if (mc && cta == 0 && lane == 0) tr0 = clock64();
           for (unsigned nm = mc; nm; nm &= nm - 1) {
             const int q = __ffs(nm) - 1;
             const int32_t off = __shfl_sync(0xffffffffu, gc.x, q), npres = __shfl_sync(0xffffffffu, gc.w, q), ndom = __shfl_sync(0xffffffffu, c1.w, q);
             const int32_t lim_old = __shfl_sync(0xffffffffu, c1.x, q), loff = __shfl_sync(0xffffffffu, lim_off, q);
-            const int32_t *cnt = smem_cnt + off;
+            const uint32_t ca = cnt_sa + 4u * (uint32_t)off;
             int32_t mn = INT32_MAX;
-            for (int d = lane; d < npres; d += 32) mn = min(mn, cnt[d]);
+            #pragma unroll 1
+            for (int d = lane; d < npres; d += 32) mn = min(mn, lds_s32(ca + 4u * d));
             mn = __reduce_min_sync(0xffffffffu, mn);
-            int32_t num = 0;
-            for (int d = lane; d < npres; d += 32) num += (cnt[d] == mn);
-            num = __reduce_add_sync(0xffffffffu, num);
             const long long liml = (long long)loff + (long long)mn;
             const int32_t lim_new = liml > INT32_MAX ? INT32_MAX : (liml < INT32_MIN ? INT32_MIN : (int32_t)liml);
+            int32_t num = 0;
             bool hit = false;
-            for (int d = lane; d < ndom; d += 32) { const int32_t c = cnt[d]; hit |= (c > lim_old) & (c <= lim_new); }
+            #pragma unroll 1
+            for (int d = lane; d < ndom; d += 32) { const int32_t c = lds_s32(ca + 4u * d); num += (d < npres) & (c == mn); hit |= (c > lim_old) & (c <= lim_new); }
+            num = __reduce_add_sync(0xffffffffu, num);
             rescan |= __any_sync(0xffffffffu, hit) | (p.debug_flags & 1);
             if (lane == q) { my_min = mn; my_num = num; c1.x = lim_new; lim_moved = true; }
           }
-          if (mc && cta == 0 && lane == 0) t_rec += clock64() - tr0;
           bool stopb = __any_sync(0xffffffffu, sec) | rescan;
-          stopb |= (p.max_pods > 0 && k + acc >= p.max_pods) | (k + acc >= p.pod_cap) | (acc >= MULTI_MAX_ACC);
-          if (stopb) break;
+          if (stopb | (acc >= acc_limit)) break;
           // only the candidates sitting in a counter cell that this commit pushed over its limit die (monotone: for the rest of
           // the wave); the fields of different terms are disjoint bit ranges, so one OR-reduction carries all filled cells
           const uint32_t F = __reduce_or_sync(0xffffffffu, fullf);
@@ -536,7 +583,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
             }
           }
         }
-        if (cta == 0 && lane == 0) { ms.ph[7] += t_rec; ms.st_rounds += rounds; }
+        if (cta == 0 && lane == 0) ms.st_rounds += rounds;
         // the limits that moved go back to the Filter constants of the next scan
         if (lim_moved) { ls.terms[ms.gt_term[lane]].lim = c1.x; ms.gt_c1[lane][0] = c1.x; }
         if (lane < n_gt && gc.z >= 0) { ls.ptsmin[gc.z] = my_min; ls.ptsnum[gc.z] = my_num; }

@@ -52,7 +52,6 @@ struct __align__(16) StreamShared {
 
 __shared__ StreamShared ss;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -149,6 +148,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
 
   long long k = 0;
   bool limit_hit = false;
+  bool prefetched = false;           // the first tiles of the coming wave were requested at the end of the last one
   uint32_t uses = 0;                 // tiles consumed so far by this CTA (all waves): stage = uses % STAGES, parity = (uses / STAGES) & 1
   uint32_t wtag = 1;
   uint32_t tag = (p.epoch << 12) | wtag;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     const long long eq_cpu = c.eq_cpu, eq_mem = c.eq_mem;
     const int32_t pods_need = c.pods_need;
     const unsigned long long taint_bad0 = c.taint_bad0, sel0 = c.sel0, forbid0 = c.forbid0;
-    if (tid == 0) {
+    if (tid == 0 && !prefetched) {
       fence_proxy_async();            // the commit's and the scorers' generic-proxy stores of the last wave, before the engine reads them
       for (int q = 0; q < STREAM_STAGES && q < tiles; q++) issue(q, (int)((uses + q) % STREAM_STAGES), t);
     }
@@ -199,6 +199,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       __syncthreads();                 // everybody is done with stage s
       if (tid == 0 && tile + STREAM_STAGES < tiles) { fence_proxy_async(); issue(tile + STREAM_STAGES, s, t); }
     }
+    // The first tiles of the NEXT wave are requested now, so that the copy engine works while the exchange is in flight. They may
+    // hold the pre-commit row of this wave's winner: the owner patches its shared-memory copy after the commit (below).
+    const uint32_t uses_next = uses;           // the next wave's tile q lands in stage (uses_next + q) % STAGES
+    prefetched = !(p.max_pods > 0 && k + 1 >= p.max_pods);
+    if (tid == 0 && prefetched) {
+      fence_proxy_async();
+      const int tn = (int)((k + 1) % T);
+      for (int q = 0; q < STREAM_STAGES && q < tiles; q++) issue(q, (int)((uses_next + q) % STREAM_STAGES), tn);
+    }
     {
       const unsigned long long v = warp_max_u64(best);
       if (lane == 0) ss.warp_best[warp] = v;
@@ -233,6 +242,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
           }
           for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
           fence_proxy_async();
+          // the winner's row may already sit, pre-commit, in a stage prefetched for the next wave: wait for that copy, then patch it
+          const int off = (int)(w - (long long)oc * p.chunk), tw = off / STREAM_TILE, j = off - tw * STREAM_TILE;
+          if (prefetched && tw < STREAM_STAGES && tw < tiles && lane == 0) {
+            const uint32_t u = uses_next + (uint32_t)tw;
+            const int s = (int)(u % STREAM_STAGES);
+            while (!mbar_try_wait(&ss.full[s], (u / STREAM_STAGES) & 1u)) { }
+            unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
+            reinterpret_cast<long long *>(st)[j] = sp.f_cpu[q];
+            reinterpret_cast<long long *>(st + STREAM_TILE * 8)[j] = sp.f_mem[q];
+            reinterpret_cast<int32_t *>(st + STREAM_TILE * 16)[j] = sp.f_pods[q];
+            reinterpret_cast<int32_t *>(st + STREAM_TILE * 20)[j] = -1;
+          }
         }
       }
     }
@@ -241,6 +262,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     wtag = (wtag == 4095u) ? 1u : wtag + 1u;
     tag = (p.epoch << 12) | wtag;
   }
+  if (prefetched && tid == 0)        // copies requested for a wave that never ran: let them land before the CTA exits
+    for (int q = 0; q < STREAM_STAGES && q < tiles; q++) {
+      const uint32_t u = uses + (uint32_t)q;
+      while (!mbar_try_wait(&ss.full[u % STREAM_STAGES], (u / STREAM_STAGES) & 1u)) { }
+    }
+  __syncthreads();
   if (cta == 0 && tid == 0) {
     DevOut *o = p.out;
     o->placed = k;

@@ -41,6 +41,7 @@ def _worker(rank, world, port, which, q):
         limit = 2500
     torch.cuda.set_device(rank)
     ok = True
+    why = []
     want = oracle.run(snap, tmpl, ctr, max_pods=limit, threads=8, memo=True)
     for kind in (abi.ENGINE_AUTO, abi.ENGINE_SEQUENTIAL):   # AUTO: multi-commit waves over the shards for counter-coupled templates
         eng = engine.Engine(device=rank, engine=kind, rank=rank, world=world)
@@ -51,17 +52,24 @@ def _worker(rank, world, port, which, q):
             res = eng.run(limit if it != 1 else (limit or 0) // 2 + 7)
             m = sharded.merge_results(dist, res)
             w = want if it != 1 else oracle.run(snap, tmpl, ctr, max_pods=(limit or 0) // 2 + 7, threads=8, memo=True)
-            ok &= (m["placed"] == w.placed and m["stop_code"] == w.stop_code and np.array_equal(m["pod_node"], w.pod_node)
-                   and np.array_equal(m["reason_hist"], w.reason_hist) and m["preempt_no_victims"] == w.preempt_no_victims
-                   and m["preempt_not_helpful"] == w.preempt_not_helpful)
+            same = (m["placed"] == w.placed and m["stop_code"] == w.stop_code and np.array_equal(m["pod_node"], w.pod_node)
+                    and np.array_equal(m["reason_hist"], w.reason_hist) and m["preempt_no_victims"] == w.preempt_no_victims
+                    and m["preempt_not_helpful"] == w.preempt_not_helpful)
+            if not same:
+                why.append("engine %d run %d: placed %d/%d stop %d/%d seq_equal %s hist_equal %s preempt %d,%d / %d,%d" % (
+                    kind, it, m["placed"], w.placed, m["stop_code"], w.stop_code, np.array_equal(m["pod_node"], w.pod_node),
+                    np.array_equal(m["reason_hist"], w.reason_hist), m["preempt_no_victims"], m["preempt_not_helpful"], w.preempt_no_victims, w.preempt_not_helpful))
+            ok &= same
             if kind == abi.ENGINE_SEQUENTIAL:
+                if m["evals"] != w.evals:
+                    why.append("engine %d run %d: evals %d != %d" % (kind, it, m["evals"], w.evals))
                 ok &= m["evals"] == w.evals
             elif which.startswith("c4") or which == "spread":
                 ok &= eng.run_stats()["engine"] == "multi-commit" and (w.placed < 100 or res.waves * 2 < w.waves)
             if which == "c5":
                 ok &= eng.run_stats()["engine"].startswith("streaming")
         eng.close()
-    q.put((rank, bool(ok), int(res.placed)))
+    q.put((rank, bool(ok), int(res.placed), why))
     dist.destroy_process_group()
 
 
