@@ -774,6 +774,7 @@ struct ccsim_handle {
   unsigned long long *d_xslots = nullptr;                 // cross-GPU exchange buffer (exported over CUDA IPC)
   unsigned long long *x_peer[CCSIM_MAX_WORLD] = {};       // every rank's buffer as mapped here
   bool peers_ready = false;
+  bool peers_local = false;                               // peers are plain pointers of this process (nothing to close)
   uint32_t epoch = 0;
   uint32_t xwave0 = 0;                                    // exchanges of earlier sharded runs (buffer parity continues across runs)
   int64_t last_stat[16] = {};                             // ccsim_run_stats
@@ -878,8 +879,9 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
                        (int)(h->smem_optin - sizeof(LeanShared) - sizeof(MultiShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(h->smem_optin - sizeof(LeanShared) - sizeof(MultiShared) - 1024));
-  cudaFuncSetAttribute(ccsim_wave_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STREAM_STAGES * STREAM_TILE * 24 + 128));
-  cudaFuncSetAttribute(ccsim_wave_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STREAM_STAGES * STREAM_TILE * 40 + 128));
+  cudaFuncSetAttribute(ccsim_wave_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STREAM_STAGES * STREAM_TILE * 24 + 128));
+  cudaFuncSetAttribute(ccsim_wave_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STREAM_STAGES * STREAM_TILE * 40 + 128));
+  cudaFuncSetAttribute(ccsim_wave_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - sizeof(StreamShared) - 1024));
   cudaFuncSetAttribute(ccsim_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(SMEM_CNT_MAX_INTS * sizeof(int32_t) + 16));
   *out = h;
@@ -891,7 +893,7 @@ extern "C" void ccsim_destroy(ccsim_handle *h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   free_pool(h, h->allocs); free_pool(h, h->tmpl_allocs); free_pool(h, h->stream_allocs); drop_cache(h);
-  for (int r = 0; r < CCSIM_MAX_WORLD; r++) if (h->x_peer[r] && r != h->cfg.rank) cudaIpcCloseMemHandle(h->x_peer[r]);
+  for (int r = 0; r < CCSIM_MAX_WORLD; r++) if (h->x_peer[r] && r != h->cfg.rank && !h->peers_local) cudaIpcCloseMemHandle(h->x_peer[r]);
   cudaFree(h->d_xslots);
   cudaFree(h->d_out); cudaFree(h->d_params); cudaFree(h->d_slots); cudaFree(h->d_pod_node); cudaFree(h->d_flush);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -1308,6 +1310,7 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   // streaming engine (ccsim_stream.cuh): node-local templates when the tile is not resident, or several templates; the node
   // tiles go through shared memory with bulk-async copies (TMA) and the score is memoised per (template, node)
   StreamParams sp; memset(&sp, 0, sizeof(sp));
+  int stream_mode = 0;
   bool stream = !lean && !has_pref && h->n_counters == 0 && h->max_prefer_pop == 0 && !faithful &&
                 h->meta.taint_words == 1 && h->meta.static_words <= 1 && !getenv("CCSIM_FORCE_GENERIC");
   if (stream)
@@ -1354,15 +1357,20 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
     ccsim_stream_prep_kernel<<<std::min<long long>(8LL * h->sm_count, (sp.n_pad + 255) / 256), 256, 0, s>>>(p, sp);
     h->launches++;
     CK(cudaGetLastError());
-    kern = masks ? (const void *)ccsim_wave_stream_kernel<true> : (const void *)ccsim_wave_stream_kernel<false>;
-    smem = (size_t)STREAM_STAGES * STREAM_TILE * (masks ? 40 : 24) + 128;
+    // resident free_* columns when the chunk fits next to the memo ring (20 B per node: up to ~10k nodes per SM)
+    const size_t smem_resf = (size_t)STREAM_STAGES * STREAM_TILE * 4 + (size_t)sp.chunk_pad * 20 + 128;
+    stream_mode = masks ? 1 : ((smem_resf + sizeof(StreamShared) + 1024 <= h->smem_optin && !getenv("CCSIM_STREAM_ALL")) ? 2 : 0);
+    kern = stream_mode == 1 ? (const void *)ccsim_wave_stream_kernel<1> : stream_mode == 2 ? (const void *)ccsim_wave_stream_kernel<2> : (const void *)ccsim_wave_stream_kernel<0>;
+    smem = stream_mode == 2 ? smem_resf : (size_t)STREAM_STAGES * STREAM_TILE * (masks ? 40 : 24) + 128;
     block = STREAM_THREADS;
   }
   h->last_stream = stream ? 1 : 0;
   p.self = h->d_params;
   CK(cudaMemcpyAsync(h->d_params, &p, sizeof(DevParams), cudaMemcpyHostToDevice, s));
   int occ = 0;
-  if (stream) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sp.use_masks ? ccsim_wave_stream_kernel<true> : ccsim_wave_stream_kernel<false>, block, smem));
+  if (stream && stream_mode == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_stream_kernel<1>, block, smem));
+  else if (stream && stream_mode == 2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_stream_kernel<2>, block, smem));
+  else if (stream) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_stream_kernel<0>, block, smem));
   else if (multi && h->cfg.world > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel<true>, block, smem));
   else if (multi) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_multi_kernel<false>, block, smem));
   else if (batched) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_batched_kernel, block, smem));
@@ -1477,6 +1485,24 @@ extern "C" int ccsim_peer_export(ccsim_handle *h, uint8_t handle_out[CCSIM_IPC_H
   CK(cudaIpcGetMemHandle(&mh, h->d_xslots));
   static_assert(sizeof(mh) == CCSIM_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
   memcpy(handle_out, &mh, sizeof(mh));
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_peer_local(ccsim_handle *h, void **ptr_out) {
+  if (!h || !ptr_out) return fail(h, CCSIM_EINVAL, "null argument");
+  *ptr_out = h->d_xslots;
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_peer_import_local(ccsim_handle *h, int32_t world, void *const *ptrs) {
+  if (!h || !ptrs) return fail(h, CCSIM_EINVAL, "null argument");
+  if (world != h->cfg.world) return fail(h, CCSIM_EINVAL, "world %d != configured %d", world, h->cfg.world);
+  for (int r = 0; r < world; r++) {
+    if (!ptrs[r]) return fail(h, CCSIM_EINVAL, "null peer pointer %d", r);
+    h->x_peer[r] = r == h->cfg.rank ? h->d_xslots : (unsigned long long *)ptrs[r];
+  }
+  h->peers_local = true;
+  h->peers_ready = true;
   return CCSIM_OK;
 }
 

@@ -567,6 +567,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
             rescan |= __any_sync(0xffffffffu, hit) | (p.debug_flags & 1);
             if (lane == q) { my_min = mn; my_num = num; c1.x = lim_new; lim_moved = true; }
           }
+          if (rescan && cta == 0 && lane == 0) ms.ph[7] += 1;      // waves ended by a minimum move that changes verdicts
           bool stopb = __any_sync(0xffffffffu, sec) | rescan;
           if (stopb | (acc >= acc_limit)) break;
           // only the candidates sitting in a counter cell that this commit pushed over its limit die (monotone: for the rest of

@@ -69,7 +69,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// orders this thread's earlier generic-proxy accesses to GLOBAL memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // fills the padded streaming columns from the snapshot's working columns (once per run)
 __global__ void ccsim_stream_prep_kernel(const DevParams p, const StreamParams sp) {
@@ -87,11 +88,20 @@ __global__ void ccsim_stream_prep_kernel(const DevParams p, const StreamParams s
   }
 }
 
-template <bool MASKS>
+// MODE 0: everything streamed (24 B per node and wave); 1: + taint/static words (40 B); 2: the free_* columns of the CTA's chunk stay in
+// shared memory for the whole run (20 B per node: 1M nodes fit in the 148 SMs' shared memory) and only the score memo column of the
+// wave's template is streamed (4 B per node and wave)
+template <int MODE>
 __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(const DevParams p, const StreamParams sp) {
+  constexpr bool MASKS = MODE == 1, RESF = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // stage s: [f_cpu TILE x 8][f_mem TILE x 8][f_pods TILE x 4][memo TILE x 4]([taint TILE x 8][static TILE x 8])
-  constexpr uint32_t STAGE_BYTES = STREAM_TILE * (MASKS ? 40u : 24u);
+  constexpr uint32_t STAGE_BYTES = STREAM_TILE * (MASKS ? 40u : (RESF ? 4u : 24u));
+  constexpr uint32_t MEMO_OFF = RESF ? 0u : STREAM_TILE * 20u;      // the memo tile inside a stage
+  // RESF: resident columns behind the stage ring
+  long long *r_fcpu = reinterpret_cast<long long *>(smem_raw + STREAM_STAGES * STAGE_BYTES);
+  long long *r_fmem = r_fcpu + sp.chunk_pad;
+  int32_t *r_fpods = reinterpret_cast<int32_t *>(r_fmem + sp.chunk_pad);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
   const long long base = (long long)cta * sp.chunk_pad;           // this CTA's first padded row
@@ -124,6 +134,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     c.sw.w_balanced = ((tp.score_enable & CCSIM_PL_BALANCED) && !(fl & CCSIM_TF_BALANCED_SKIP)) ? tp.w_balanced : 0;
     c.sw.least_w_cpu = tp.least_w_cpu; c.sw.least_w_mem = tp.least_w_mem;
   }
+  if (RESF)
+    for (int j = threadIdx.x; j < sp.chunk_pad; j += STREAM_THREADS) {
+      r_fcpu[j] = sp.f_cpu[(long long)blockIdx.x * sp.chunk_pad + j]; r_fmem[j] = sp.f_mem[(long long)blockIdx.x * sp.chunk_pad + j];
+      r_fpods[j] = sp.f_pods[(long long)blockIdx.x * sp.chunk_pad + j];
+    }
   if (tid == 0) {
     for (int s = 0; s < STREAM_STAGES; s++) mbar_init(&ss.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,10 +151,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
     const long long row = base + (long long)tile * STREAM_TILE;
     mbar_expect_tx(&ss.full[s], STAGE_BYTES);
-    bulk_g2s(st, sp.f_cpu + row, STREAM_TILE * 8, &ss.full[s]);
-    bulk_g2s(st + STREAM_TILE * 8, sp.f_mem + row, STREAM_TILE * 8, &ss.full[s]);
-    bulk_g2s(st + STREAM_TILE * 16, sp.f_pods + row, STREAM_TILE * 4, &ss.full[s]);
-    bulk_g2s(st + STREAM_TILE * 20, sp.memo + (size_t)t * sp.n_pad + row, STREAM_TILE * 4, &ss.full[s]);
+    if (!RESF) {
+      bulk_g2s(st, sp.f_cpu + row, STREAM_TILE * 8, &ss.full[s]);
+      bulk_g2s(st + STREAM_TILE * 8, sp.f_mem + row, STREAM_TILE * 8, &ss.full[s]);
+      bulk_g2s(st + STREAM_TILE * 16, sp.f_pods + row, STREAM_TILE * 4, &ss.full[s]);
+    }
+    bulk_g2s(st + MEMO_OFF, sp.memo + (size_t)t * sp.n_pad + row, STREAM_TILE * 4, &ss.full[s]);
     if (MASKS) {
       bulk_g2s(st + STREAM_TILE * 24, sp.m_taint + row, STREAM_TILE * 8, &ss.full[s]);
       bulk_g2s(st + STREAM_TILE * 32, sp.m_static + row, STREAM_TILE * 8, &ss.full[s]);
@@ -166,13 +183,16 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       for (int q = 0; q < STREAM_STAGES && q < tiles; q++) issue(q, (int)((uses + q) % STREAM_STAGES), t);
     }
     unsigned long long best = 0ull;
+    bool wrote = false;
     for (int tile = 0; tile < tiles; tile++, uses++) {
       const int s = (int)(uses % STREAM_STAGES);
       const uint32_t parity = (uses / STREAM_STAGES) & 1u;
       while (!mbar_try_wait(&ss.full[s], parity)) { }
       const unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
-      const long long *s_fcpu = reinterpret_cast<const long long *>(st), *s_fmem = reinterpret_cast<const long long *>(st + STREAM_TILE * 8);
-      const int32_t *s_fpods = reinterpret_cast<const int32_t *>(st + STREAM_TILE * 16), *s_memo = reinterpret_cast<const int32_t *>(st + STREAM_TILE * 20);
+      const long long *s_fcpu = RESF ? r_fcpu + tile * STREAM_TILE : reinterpret_cast<const long long *>(st);
+      const long long *s_fmem = RESF ? r_fmem + tile * STREAM_TILE : reinterpret_cast<const long long *>(st + STREAM_TILE * 8);
+      const int32_t *s_fpods = RESF ? r_fpods + tile * STREAM_TILE : reinterpret_cast<const int32_t *>(st + STREAM_TILE * 16);
+      const int32_t *s_memo = reinterpret_cast<const int32_t *>(st + MEMO_OFF);
       #pragma unroll
       for (int j = tid; j < STREAM_TILE; j += STREAM_THREADS) {
         // NodeResourcesFit (+ NodeUnschedulable / TaintToleration / nodeSelector / NodePorts / existing anti-affinity bits)
@@ -190,15 +210,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
             sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
                             p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
             sp.memo[(size_t)t * sp.n_pad + base + off] = sc;
-            fence_proxy_async();         // a later bulk-async read of this column must see the store
+            wrote = true;                // fenced once after the pass (a later bulk-async read of this column must see the store)
           }
           const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
           best = key > best ? key : best;
         }
       }
       __syncthreads();                 // everybody is done with stage s
-      if (tid == 0 && tile + STREAM_STAGES < tiles) { fence_proxy_async(); issue(tile + STREAM_STAGES, s, t); }
+      // (no proxy fence here: the rows of a later tile were last written in an earlier wave)
+      if (tid == 0 && tile + STREAM_STAGES < tiles) issue(tile + STREAM_STAGES, s, t);
     }
+    if (wrote) fence_proxy_async();
     // The first tiles of the NEXT wave are requested now, so that the copy engine works while the exchange is in flight. They may
     // hold the pre-commit row of this wave's winner: the owner patches its shared-memory copy after the commit (below).
     const uint32_t uses_next = uses;           // the next wave's tile q lands in stage (uses_next + q) % STAGES
@@ -235,8 +257,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
         }
         if (oc == cta) {
           const long long q = base + (w - (long long)oc * p.chunk);
+          const int roff = (int)(w - (long long)oc * p.chunk);
           if (lane == 0) {
-            sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1;
+            if (RESF) { r_fcpu[roff] -= c.req_cpu; r_fmem[roff] -= c.req_mem; r_fpods[roff] -= 1; }
+            else { sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1; }
             p.req_cpu[w] += c.req_cpu; p.req_mem[w] += c.req_mem; p.nz_cpu[w] += c.nz_cpu; p.nz_mem[w] += c.nz_mem; p.npods[w] += 1;   // write-through
             if (k < p.pod_cap) p.pod_node[k] = w + p.node_base; else ss.stop = 3;
           }
@@ -249,10 +273,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
             const int s = (int)(u % STREAM_STAGES);
             while (!mbar_try_wait(&ss.full[s], (u / STREAM_STAGES) & 1u)) { }
             unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
-            reinterpret_cast<long long *>(st)[j] = sp.f_cpu[q];
-            reinterpret_cast<long long *>(st + STREAM_TILE * 8)[j] = sp.f_mem[q];
-            reinterpret_cast<int32_t *>(st + STREAM_TILE * 16)[j] = sp.f_pods[q];
-            reinterpret_cast<int32_t *>(st + STREAM_TILE * 20)[j] = -1;
+            if (!RESF) {
+              reinterpret_cast<long long *>(st)[j] = sp.f_cpu[q];
+              reinterpret_cast<long long *>(st + STREAM_TILE * 8)[j] = sp.f_mem[q];
+              reinterpret_cast<int32_t *>(st + STREAM_TILE * 16)[j] = sp.f_pods[q];
+            }
+            reinterpret_cast<int32_t *>(st + MEMO_OFF)[j] = -1;
           }
         }
       }

@@ -16,7 +16,7 @@ _lib = None
 
 EXPORTS = ["ccsim_create", "ccsim_destroy", "ccsim_last_error", "ccsim_abi_version", "ccsim_load_nodes",
            "ccsim_set_templates", "ccsim_run", "ccsim_node_counts", "ccsim_peer_export", "ccsim_peer_import",
-           "ccsim_device_info", "ccsim_kernel_launches", "ccsim_flush_l2", "ccsim_run_stats"]
+           "ccsim_device_info", "ccsim_kernel_launches", "ccsim_flush_l2", "ccsim_run_stats", "ccsim_peer_local", "ccsim_peer_import_local"]
 
 
 class EngineError(RuntimeError):
@@ -50,6 +50,10 @@ def lib():
         L.ccsim_kernel_launches.argtypes = [C.c_void_p]
         L.ccsim_flush_l2.restype = C.c_int
         L.ccsim_flush_l2.argtypes = [C.c_void_p]
+        L.ccsim_peer_local.restype = C.c_int
+        L.ccsim_peer_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ccsim_peer_import_local.restype = C.c_int
+        L.ccsim_peer_import_local.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.ccsim_run_stats.restype = C.c_int
         L.ccsim_run_stats.argtypes = [C.c_void_p, abi.P64]
         L.ccsim_peer_export.restype = C.c_int
@@ -124,6 +128,18 @@ class Engine:
         dist.all_gather(out, t)
         allh = np.concatenate([o.cpu().numpy() for o in out]).astype(np.uint8)
         self._check(lib().ccsim_peer_import(self._h, world, allh.ctypes.data_as(abi.PU8)), "ccsim_peer_import")
+
+    @staticmethod
+    def connect_local(engines):
+        """All ranks live in this process (rank r = engines[r]): hand every engine the others' exchange-buffer pointers. The
+        runs must then be started concurrently (one host thread per rank): the persistent kernels talk to each other."""
+        ptrs = (C.c_void_p * len(engines))()
+        for r, e in enumerate(engines):
+            p = C.c_void_p()
+            e._check(lib().ccsim_peer_local(e._h, C.byref(p)), "ccsim_peer_local")
+            ptrs[r] = p
+        for e in engines:
+            e._check(lib().ccsim_peer_import_local(e._h, len(engines), ptrs), "ccsim_peer_import_local")
 
     def node_counts(self, t=0):
         counts = np.zeros(max(1, self._n), np.int32)

@@ -303,6 +303,12 @@ int  ccsim_node_counts(ccsim_handle *h, int32_t t, int32_t *counts /*[n_nodes]*/
 int  ccsim_peer_export(ccsim_handle *h, uint8_t handle_out[CCSIM_IPC_HANDLE_BYTES]);
 int  ccsim_peer_import(ccsim_handle *h, int32_t world, const uint8_t *handles /* world x CCSIM_IPC_HANDLE_BYTES, rank order */);
 
+/* Peers inside ONE process (a host that drives its GPUs from one process; the single-GPU tests of the sharded engines, where all
+ * ranks share device 0): the exchange buffer's device pointer instead of an IPC handle. Ranks on different devices need peer
+ * access enabled by the caller (cudaDeviceEnablePeerAccess). */
+int  ccsim_peer_local(ccsim_handle *h, void **ptr_out);
+int  ccsim_peer_import_local(ccsim_handle *h, int32_t world, void *const *ptrs /* world pointers, rank order */);
+
 /* introspection for tests / bench */
 int  ccsim_device_info(ccsim_handle *h, int32_t *sm_count, int32_t *grid, int32_t *block, int64_t *l2_bytes);
 int64_t ccsim_kernel_launches(const ccsim_handle *h);  /* kernels launched by this handle so far */

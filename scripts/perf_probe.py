@@ -21,7 +21,7 @@ def probe(name, snap, tmpl, ctr, limit, bytes_per_eval):
         w = max(1, st["waves"])
         print("    engine=%s  placements/wave=%.2f  candidates/wave=%.1f  bar raised in %d waves  cycles/wave (CTA 0): scan=%d S1=%d merge+publish=%d gather=%d replay=%d tail=%d  smem=%d B" % (
             st["engine"], st["placed"] / w, st["candidates"] / w, st["bar_raised_waves"], *[c // w for c in st["phase_cycles"][:6]], st["smem_bytes"]), flush=True)
-        print("    replay detail: rounds/wave=%.2f  setup=%d  recount=%d cycles/wave" % (st["smem_bytes"] / w, st["phase_cycles"][6] // w, st["phase_cycles"][7] // w), flush=True)
+        print("    replay detail: rounds/wave=%.2f  setup=%d cycles/wave  waves ended by a binding minimum move: %d of %d" % (st["smem_bytes"] / w, st["phase_cycles"][6] // w, st["phase_cycles"][7], w), flush=True)
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
