@@ -23,7 +23,7 @@ def merge_results(dist, res):
     the replicated parts (placed, stop code, pod -> node sequence) agree. Returns a dict."""
     import torch
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    vec = np.concatenate([res.reason_hist.astype(np.int64), [res.preempt_no_victims, res.evals]]).astype(np.int64)
+    vec = np.concatenate([res.reason_hist.astype(np.int64), [res.preempt_not_helpful, res.preempt_no_victims, res.evals]]).astype(np.int64)
     t = torch.from_numpy(vec).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     vec = t.cpu().numpy()
@@ -36,7 +36,6 @@ def merge_results(dist, res):
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     if not bool((lo == hi).all()):
         raise RuntimeError("sharded run diverged between ranks: %s vs %s" % (lo.tolist(), hi.tolist()))
-    n_total = int(res.n_nodes)
     return {"placed": int(res.placed), "stop_code": int(res.stop_code), "pod_node": res.pod_node,
-            "reason_hist": vec[:-2], "preempt_no_victims": int(vec[-2]), "preempt_not_helpful": n_total - int(vec[-2]),
+            "reason_hist": vec[:-3], "preempt_no_victims": int(vec[-2]), "preempt_not_helpful": int(vec[-3]),   # per-shard parts: they sum up
             "evals": int(vec[-1]), "waves": int(res.waves)}

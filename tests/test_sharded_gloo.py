@@ -42,6 +42,7 @@ def _worker(rank, world, port, q):
     sub_res = oracle.run(sub, tmpl, ctr)          # the shard is full: nothing fits, only the diagnosis runs
     assert sub_res.placed == 0
     part.reason_hist, part.preempt_no_victims, part.evals = sub_res.reason_hist, sub_res.preempt_no_victims, full.waves * (hi - lo)
+    part.preempt_not_helpful = sub_res.preempt_not_helpful      # per shard, like the histogram
     merged = sharded.merge_results(dist, part)
     ok = (np.array_equal(merged["reason_hist"], full.reason_hist) and merged["preempt_no_victims"] == full.preempt_no_victims
           and merged["preempt_not_helpful"] == full.preempt_not_helpful and merged["evals"] == full.evals)
