@@ -12,6 +12,9 @@
 // and the per-template PreFilter/PreScore state is folded into ccsim_template / ccsim_counter (static bits, masks,
 // per-domain initial counts).
 #pragma once
+#include <thread>
+#include <exception>
+#include <unordered_map>
 #include <cstring>
 #include <functional>
 #include "../../../include/ccsim.h"
@@ -99,6 +102,23 @@ inline PodResource calculate_resource(const Pod &p) {
   out.non0_cpu = ic == non0.end() ? 0 : ic->second.milli_value();
   out.non0_mem = im == non0.end() ? 0 : im->second.value();
   return out;
+}
+
+// Host threads over an index range, in contiguous blocks (the per-node loops of the encoder are independent per node; anything
+// order-dependent — dictionary ids in first-seen order — stays in a serial pass over the per-node results).
+template <class F> inline void parallel_for(int n, F fn) {
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
+  if (n < 4096 || nt == 1) { for (int i = 0; i < n; i++) fn(i); return; }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> errs(nt);
+  const int per = (n + (int)nt - 1) / (int)nt;
+  for (unsigned c = 0; c < nt; c++)
+    th.emplace_back([&, c] {
+      try { for (int i = (int)c * per, e = std::min(n, i + per); i < e; i++) fn(i); } catch (...) { errs[c] = std::current_exception(); }
+    });
+  for (auto &t : th) t.join();
+  for (auto &e : errs) if (e) std::rethrow_exception(e);
 }
 
 struct Encoded {
@@ -216,7 +236,7 @@ class Encoder {
     e.alloc_pods.assign(n, 0); e.npods.assign(n, 0);
     e.alloc_scalar.assign(e.scalar_names.size(), std::vector<int64_t>(n, 0));
     e.req_scalar.assign(e.scalar_names.size(), std::vector<int64_t>(n, 0));
-    for (int i = 0; i < n; i++) {
+    parallel_for(n, [&](int i) {
       const Node &nd = *nodes_[i];
       e.names[i] = nd.name;
       for (auto &kv : nd.allocatable) {   // NewResource(node.Status.Allocatable)
@@ -233,7 +253,7 @@ class Encoder {
         for (size_t k = 0; k < e.scalar_names.size(); k++) { auto it = pr.scalar.find(e.scalar_names[k]); if (it != pr.scalar.end()) e.req_scalar[k][i] += it->second; }
         e.npods[i] += 1;
       }
-    }
+    });
     // ---- taints: dictionary in first-seen order ----
     std::map<Taint, int> tid;
     for (int i = 0; i < n; i++)
@@ -363,19 +383,25 @@ class Encoder {
       // domains: eligible nodes (all constraint keys present + inclusion policies) define TpValueToMatchNum; they get ids [0,n_present)
       std::map<std::string, int> dom_id; std::vector<int64_t> counts;
       std::vector<char> eligible(n, 0);
-      for (int i = 0; i < n; i++) {
+      std::vector<int64_t> node_cnt(n, 0);
+      parallel_for(n, [&](int i) {     // per node: eligibility and countPodsMatchSelector (common.go:144-158)
         bool all_keys = true;
         for (auto *h : hard) if (!nodes_[i]->labels.count(h->topology_key)) all_keys = false;
-        if (!all_keys) continue;
-        if (tc.node_affinity_policy == "Honor" && !required_affinity_match(i)) continue;
-        if (tc.node_taints_policy == "Honor" && untolerated(i)) continue;
+        if (!all_keys) return;
+        if (tc.node_affinity_policy == "Honor" && !required_affinity_match(i)) return;
+        if (tc.node_taints_policy == "Honor" && untolerated(i)) return;
         eligible[i] = 1;
-        const std::string &v = nodes_[i]->labels.at(tc.topology_key);
-        if (!dom_id.count(v)) { int id = (int)dom_id.size(); dom_id[v] = id; counts.push_back(0); }
-        int64_t cnt = 0;   // countPodsMatchSelector (common.go:144-158)
+        int64_t cnt = 0;
         if (!hard_sel[c].empty())
           for (auto *p : pods_on_[i]) if (!p->terminating && p->ns == t_.ns && hard_sel[c].matches(p->labels)) cnt++;
-        counts[dom_id[v]] += cnt;
+        node_cnt[i] = cnt;
+      });
+      for (int i = 0; i < n; i++) {    // domain ids in first-seen order over the eligible nodes
+        if (!eligible[i]) continue;
+        const std::string &v = nodes_[i]->labels.at(tc.topology_key);
+        auto it = dom_id.find(v);
+        if (it == dom_id.end()) { it = dom_id.emplace(v, (int)dom_id.size()).first; counts.push_back(0); }
+        counts[it->second] += node_cnt[i];
       }
       const int n_present = (int)dom_id.size();
       std::vector<int32_t> col(n, -1);
@@ -422,7 +448,8 @@ class Encoder {
         col[i] = dom_id[it->second];
       }
       std::vector<int64_t> per_node(n, 0);
-      for (int i = 0; i < n; i++) { if (col[i] < 0) continue; for (auto *p : pods_on_[i]) per_node[i] += weight(*p); counts[col[i]] += per_node[i]; }
+      parallel_for(n, [&](int i) { if (col[i] < 0) return; for (auto *p : pods_on_[i]) per_node[i] += weight(*p); });
+      for (int i = 0; i < n; i++) if (col[i] >= 0) counts[col[i]] += per_node[i];
       if (unique && n > 0) {
         std::vector<int32_t> init(per_node.begin(), per_node.end());
         add_counter(e, -1, init, n, inc);
@@ -635,7 +662,7 @@ class Encoder {
   const Pod &t_;
   const std::map<std::string, Labels> &ns_labels_;
   std::vector<const Node *> nodes_;
-  std::map<std::string, int> node_index_;
+  std::unordered_map<std::string, int> node_index_;
   std::vector<std::vector<const Pod *>> pods_on_;
   const std::vector<WorkloadSelector> *workloads_ = nullptr;
 

@@ -145,3 +145,21 @@ def test_ingest_shapes_and_parallel_item_parsing(built):
     assert L.cc_sync_with_objects(cc._h, b'[{"metadata": {"name": "x"}', b"[]", None) != 0      # truncated document: an error, not a crash
     assert b"json" in L.cc_last_error(cc._h)
     cc.Close()
+
+
+def test_c4_objects_through_the_encoder_equal_the_flat_generator(built):
+    """synth.c4_objects (v1.Node / v1.Pod dicts: what bench.py's e2e_objects leg feeds the plugin call) encodes to exactly the
+    columns synth.c4 builds directly, and both give the same placement sequence. 6000 nodes: the encoder's per-node loops take
+    their multi-threaded path (>= 4096 nodes)."""
+    synth = importlib.import_module("cluster-capacity_b200.synth")
+    kw = dict(n=6000, n_existing=12000, zones=8, racks=64, regions=4)
+    snap, tmpl, ctr = synth.c4(**kw)
+    nodes, pods, t = synth.c4_objects(**kw)
+    cc = fw.New(None, None, t, 0, [])
+    cc.SyncWithClient(fw.ListClient(nodes, pods, ()))
+    s2, T2, c2, _, _, names = helpers.from_encoded(cc.EncodedSnapshot())
+    for f in ("alloc_cpu", "alloc_mem", "alloc_pods", "req_cpu", "req_mem", "npods", "nz_cpu", "nz_mem"):
+        assert np.array_equal(getattr(snap, f), getattr(s2, f)), f
+    assert names[:2] == ["node-000000", "node-000001"] and len(c2) == len(ctr)
+    a, b = oracle.run(snap, tmpl, ctr, threads=4, memo=True), oracle.run(s2, T2, c2, threads=4, memo=True)
+    assert a.placed == b.placed > 100 and np.array_equal(a.pod_node, b.pod_node) and np.array_equal(a.reason_hist, b.reason_hist)
