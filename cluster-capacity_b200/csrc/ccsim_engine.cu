@@ -805,8 +805,10 @@ template <typename T> static int dev_alloc(ccsim_handle *h, std::vector<void *> 
   for (size_t i = 0; i < h->block_cache.size(); i++)
     if (h->block_cache[i].second == bytes) { p = h->block_cache[i].first; h->block_cache.erase(h->block_cache.begin() + i); break; }
   if (!p) {
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) return fail(h, CCSIM_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    // stream-ordered allocation: no device-wide synchronisation (a host that drives several ranks from one process may have a
+    // peer's persistent kernel running, waiting for this rank's kernel to start)
+    cudaError_t e = cudaMallocAsync(&p, bytes, h->stream);
+    if (e != cudaSuccess) return fail(h, CCSIM_ENOMEM, "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
   }
   pool.push_back(p);
   h->block_bytes[p] = bytes;
@@ -828,11 +830,15 @@ static void free_pool(ccsim_handle *h, std::vector<void *> &pool) {
   for (void *p : pool) {
     const size_t bytes = h->block_bytes[p];
     if (cached + bytes <= ((size_t)1 << 31)) { h->block_cache.push_back({p, bytes}); cached += bytes; }   // keep at most 2 GiB around
-    else { cudaFree(p); h->block_bytes.erase(p); }
+    else { cudaFreeAsync(p, h->stream); h->block_bytes.erase(p); }
   }
   pool.clear();
 }
-static void drop_cache(ccsim_handle *h) { for (auto &b : h->block_cache) cudaFree(b.first); h->block_cache.clear(); h->block_bytes.clear(); }
+static void drop_cache(ccsim_handle *h) {
+  for (auto &b : h->block_cache) cudaFreeAsync(b.first, h->stream);
+  cudaStreamSynchronize(h->stream);
+  h->block_cache.clear(); h->block_bytes.clear();
+}
 
 extern "C" int ccsim_abi_version(void) { return CCSIM_ABI_VERSION; }
 
@@ -895,7 +901,8 @@ extern "C" void ccsim_destroy(ccsim_handle *h) {
   free_pool(h, h->allocs); free_pool(h, h->tmpl_allocs); free_pool(h, h->stream_allocs); drop_cache(h);
   for (int r = 0; r < CCSIM_MAX_WORLD; r++) if (h->x_peer[r] && r != h->cfg.rank && !h->peers_local) cudaIpcCloseMemHandle(h->x_peer[r]);
   cudaFree(h->d_xslots);
-  cudaFree(h->d_out); cudaFree(h->d_params); cudaFree(h->d_slots); cudaFree(h->d_pod_node); cudaFree(h->d_flush);
+  if (h->d_pod_node) { cudaFreeAsync(h->d_pod_node, h->stream); cudaStreamSynchronize(h->stream); }
+  cudaFree(h->d_out); cudaFree(h->d_params); cudaFree(h->d_slots); cudaFree(h->d_flush);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -1126,8 +1133,9 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
         return fail(h, CCSIM_EUNSUPPORTED, "NodeResourcesFit is disabled for a template: the run is unbounded, --max-limit is required");
   if (max_pods > 0 && (max_pods < cap || [&] { for (const ccsim_template &T : h->h_templates) if (!(T.filter_enable & CCSIM_PL_FIT)) return true; return false; }())) cap = max_pods;
   if (cap > h->pod_cap) {
-    cudaFree(h->d_pod_node); h->d_pod_node = nullptr; h->pod_cap = 0;
-    CK(cudaMalloc((void **)&h->d_pod_node, (size_t)cap * sizeof(int32_t)));
+    if (h->d_pod_node) cudaFreeAsync(h->d_pod_node, h->stream);
+    h->d_pod_node = nullptr; h->pod_cap = 0;
+    CK(cudaMallocAsync((void **)&h->d_pod_node, (size_t)cap * sizeof(int32_t), h->stream));
     h->pod_cap = cap;
   }
   // restore the working copies of the mutable columns from the snapshot (a Run never changes the loaded snapshot)
