@@ -22,7 +22,8 @@
 #define STREAM_THREADS 512
 #define STREAM_WARPS (STREAM_THREADS / 32)
 #define STREAM_TILE 1024          /* nodes per stage: 24 KB (40 KB with the mask columns) */
-#define STREAM_STAGES 4
+#define STREAM_STAGES 4           /* stages of the ring when every column is streamed */
+#define STREAM_STAGES_RES 8       /* ... when only the 4-byte memo column is streamed (resident free_* columns): a whole 1M-node chunk (7 tiles) in flight */
 
 struct StreamTmpl {               // per-template constants of the fused Filter pass + scorer inputs (shared memory table)
   long long eq_cpu, eq_mem;       // effective requests (LLONG_MIN: check disabled)
@@ -45,7 +46,7 @@ struct StreamParams {
 
 struct __align__(16) StreamShared {
   StreamTmpl tc[CCSIM_MAX_TEMPLATES];
-  unsigned long long full[STREAM_STAGES];      // mbarriers: "the stage's bytes have landed"
+  unsigned long long full[STREAM_STAGES_RES];  // mbarriers: "the stage's bytes have landed"
   unsigned long long warp_best[STREAM_WARPS];
   int32_t winner, stop, pad[2];
 };
@@ -94,12 +95,13 @@ __global__ void ccsim_stream_prep_kernel(const DevParams p, const StreamParams s
 template <int MODE>
 __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(const DevParams p, const StreamParams sp) {
   constexpr bool MASKS = MODE == 1, RESF = MODE == 2;
+  constexpr int NST = RESF ? STREAM_STAGES_RES : STREAM_STAGES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // stage s: [f_cpu TILE x 8][f_mem TILE x 8][f_pods TILE x 4][memo TILE x 4]([taint TILE x 8][static TILE x 8])
   constexpr uint32_t STAGE_BYTES = STREAM_TILE * (MASKS ? 40u : (RESF ? 4u : 24u));
   constexpr uint32_t MEMO_OFF = RESF ? 0u : STREAM_TILE * 20u;      // the memo tile inside a stage
   // RESF: resident columns behind the stage ring
-  long long *r_fcpu = reinterpret_cast<long long *>(smem_raw + STREAM_STAGES * STAGE_BYTES);
+  long long *r_fcpu = reinterpret_cast<long long *>(smem_raw + NST * STAGE_BYTES);
   long long *r_fmem = r_fcpu + sp.chunk_pad;
   int32_t *r_fpods = reinterpret_cast<int32_t *>(r_fmem + sp.chunk_pad);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       r_fpods[j] = sp.f_pods[(long long)blockIdx.x * sp.chunk_pad + j];
     }
   if (tid == 0) {
-    for (int s = 0; s < STREAM_STAGES; s++) mbar_init(&ss.full[s], 1);
+    for (int s = 0; s < NST; s++) mbar_init(&ss.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     ss.winner = -1; ss.stop = 0;
   }
@@ -180,13 +182,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     const unsigned long long taint_bad0 = c.taint_bad0, sel0 = c.sel0, forbid0 = c.forbid0;
     if (tid == 0 && !prefetched) {
       fence_proxy_async();            // the commit's and the scorers' generic-proxy stores of the last wave, before the engine reads them
-      for (int q = 0; q < STREAM_STAGES && q < tiles; q++) issue(q, (int)((uses + q) % STREAM_STAGES), t);
+      for (int q = 0; q < NST && q < tiles; q++) issue(q, (int)((uses + q) % NST), t);
     }
     unsigned long long best = 0ull;
     bool wrote = false;
     for (int tile = 0; tile < tiles; tile++, uses++) {
-      const int s = (int)(uses % STREAM_STAGES);
-      const uint32_t parity = (uses / STREAM_STAGES) & 1u;
+      const int s = (int)(uses % NST);
+      const uint32_t parity = (uses / NST) & 1u;
       while (!mbar_try_wait(&ss.full[s], parity)) { }
       const unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
       const long long *s_fcpu = RESF ? r_fcpu + tile * STREAM_TILE : reinterpret_cast<const long long *>(st);
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       }
       __syncthreads();                 // everybody is done with stage s
       // (no proxy fence here: the rows of a later tile were last written in an earlier wave)
-      if (tid == 0 && tile + STREAM_STAGES < tiles) issue(tile + STREAM_STAGES, s, t);
+      if (tid == 0 && tile + NST < tiles) issue(tile + NST, s, t);
     }
     if (wrote) fence_proxy_async();
     // The first tiles of the NEXT wave are requested now, so that the copy engine works while the exchange is in flight. They may
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     if (tid == 0 && prefetched) {
       fence_proxy_async();
       const int tn = (int)((k + 1) % T);
-      for (int q = 0; q < STREAM_STAGES && q < tiles; q++) issue(q, (int)((uses_next + q) % STREAM_STAGES), tn);
+      for (int q = 0; q < NST && q < tiles; q++) issue(q, (int)((uses_next + q) % NST), tn);
     }
     {
       const unsigned long long v = warp_max_u64(best);
@@ -268,10 +270,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
           fence_proxy_async();
           // the winner's row may already sit, pre-commit, in a stage prefetched for the next wave: wait for that copy, then patch it
           const int off = (int)(w - (long long)oc * p.chunk), tw = off / STREAM_TILE, j = off - tw * STREAM_TILE;
-          if (prefetched && tw < STREAM_STAGES && tw < tiles && lane == 0) {
+          if (prefetched && tw < NST && tw < tiles && lane == 0) {
             const uint32_t u = uses_next + (uint32_t)tw;
-            const int s = (int)(u % STREAM_STAGES);
-            while (!mbar_try_wait(&ss.full[s], (u / STREAM_STAGES) & 1u)) { }
+            const int s = (int)(u % NST);
+            while (!mbar_try_wait(&ss.full[s], (u / NST) & 1u)) { }
             unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
             if (!RESF) {
               reinterpret_cast<long long *>(st)[j] = sp.f_cpu[q];
@@ -289,9 +291,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     tag = (p.epoch << 12) | wtag;
   }
   if (prefetched && tid == 0)        // copies requested for a wave that never ran: let them land before the CTA exits
-    for (int q = 0; q < STREAM_STAGES && q < tiles; q++) {
+    for (int q = 0; q < NST && q < tiles; q++) {
       const uint32_t u = uses + (uint32_t)q;
-      while (!mbar_try_wait(&ss.full[u % STREAM_STAGES], (u / STREAM_STAGES) & 1u)) { }
+      while (!mbar_try_wait(&ss.full[u % NST], (u / NST) & 1u)) { }
     }
   __syncthreads();
   if (cta == 0 && tid == 0) {

@@ -10,6 +10,7 @@
 #include <cstring>
 #include "../../../include/cchost.h"
 #include "encoder.hpp"
+#include "fastparse.hpp"
 
 using namespace cch;
 
@@ -356,12 +357,25 @@ static bool item_spans(const char *t, size_t n, std::vector<std::pair<size_t, si
   throw std::runtime_error("json: unterminated item list");
 }
 
+// one item of a LIST: the DOM-free fast path first (fastparse.hpp), the general parser when it gives up
+static Pod pod_from(std::string_view item, bool dom_only) {
+  if (!dom_only) { Pod p; if (fast::pod(item, p)) return p; }
+  return Pod::parse(parse_json(item));
+}
+static Node node_from(std::string_view item, bool dom_only) {
+  if (!dom_only) { Node n; if (fast::node(item, n)) return n; }
+  return Node::parse(parse_json(item));
+}
+
 template <class T, class F> static std::vector<T> parse_list(const char *text, F one) {
   std::vector<T> out;
   if (!text || !*text) return out;
   const size_t n = strlen(text);
   std::vector<std::pair<size_t, size_t>> spans;
-  if (!item_spans(text, n, spans)) { for (auto &j : items_of(text)) out.push_back(one(j)); return out; }
+  if (!item_spans(text, n, spans)) {   // not a list of items we can locate: DOM of the whole document, items re-serialised for `one`
+    for (auto &j : items_of(text)) { const std::string t = json_dump(j); out.push_back(one(std::string_view(t))); }
+    return out;
+  }
   unsigned nt = std::thread::hardware_concurrency();
   nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
   if (spans.size() < 2048) nt = 1;
@@ -371,7 +385,7 @@ template <class T, class F> static std::vector<T> parse_list(const char *text, F
     try {
       const size_t per = (spans.size() + nt - 1) / nt, b = std::min(spans.size(), (size_t)c * per), e = std::min(spans.size(), b + per);
       parts[c].reserve(e - b);
-      for (size_t i = b; i < e; i++) parts[c].push_back(one(parse_json(std::string_view(text + spans[i].first, spans[i].second - spans[i].first))));
+      for (size_t i = b; i < e; i++) parts[c].push_back(one(std::string_view(text + spans[i].first, spans[i].second - spans[i].first)));
     } catch (...) { errs[c] = std::current_exception(); }
   };
   if (nt == 1) work(0);
@@ -393,9 +407,10 @@ extern "C" int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const 
     h->nodes.clear(); h->pods.clear(); h->ns_labels.clear(); h->workloads.clear();
     const bool timing = getenv("CCHOST_TIMING") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
-    h->nodes = parse_list<Node>(nodes_json, [](const Json &j) { return Node::parse(j); });
+    const bool dom_only = getenv("CCHOST_DOM_ONLY") != nullptr;      // tests: the general parser for every item
+    h->nodes = parse_list<Node>(nodes_json, [&](std::string_view it) { return node_from(it, dom_only); });
     auto t1 = std::chrono::steady_clock::now();
-    h->pods = parse_list<Pod>(pods_json, [](const Json &j) { return Pod::parse(j); });
+    h->pods = parse_list<Pod>(pods_json, [&](std::string_view it) { return pod_from(it, dom_only); });
     auto t2 = std::chrono::steady_clock::now();
     if (timing) fprintf(stderr, "[cchost] ingest: %zu nodes %.3f s, %zu pods %.3f s\n", h->nodes.size(), std::chrono::duration<double>(t1 - t0).count(),
                         h->pods.size(), std::chrono::duration<double>(t2 - t1).count());

@@ -163,3 +163,31 @@ def test_c4_objects_through_the_encoder_equal_the_flat_generator(built):
     assert names[:2] == ["node-000000", "node-000001"] and len(c2) == len(ctr)
     a, b = oracle.run(snap, tmpl, ctr, threads=4, memo=True), oracle.run(s2, T2, c2, threads=4, memo=True)
     assert a.placed == b.placed > 100 and np.array_equal(a.pod_node, b.pod_node) and np.array_equal(a.reason_hist, b.reason_hist)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_fast_ingest_equals_the_general_parser(built, seed, monkeypatch):
+    """fastparse.hpp (no DOM; gives up on pods with init containers / overhead / pod affinity / escapes) against the general parser
+    (CCHOST_DOM_ONLY=1) on random clusters whose pods carry all of that: identical encoded snapshots, byte for byte."""
+    nodes, pods = helpers.random_cluster(seed, n_nodes=60, n_pods=150)
+    pods[3]["metadata"]["labels"]["quote"] = 'a"b' + chr(92) + 'c'                      # escapes: the fast path must hand the item over
+    pods[4]["metadata"]["deletionTimestamp"] = "2026-01-01T00:00:00Z"
+    pods[5]["status"]["containerStatuses"] = [{"name": "c", "resources": {"requests": {"cpu": "300m"}}, "allocatedResources": {"cpu": "300m", "memory": "64Mi"}}]
+    pods[6]["spec"]["containers"][0]["resources"]["requests"] = {"cpu": 2, "memory": "1Gi"}       # a bare JSON number as a quantity
+    nodes[2]["status"]["conditions"] = [{"type": "Ready", "status": "True", "message": 'kubelet is posting "ready" status'}]
+    nodes[3]["status"]["nodeInfo"] = {"kubeletVersion": "v1.34.1", "architecture": "amd64"}
+    out = []
+    for dom_only in (False, True):
+        if dom_only:
+            monkeypatch.setenv("CCHOST_DOM_ONLY", "1")
+        for variant in ("plain", "anti_zone", "spread_two", "pref_pod_affinity"):
+            cc = fw.New(None, None, helpers.template(variant), 0, [])
+            cc.SyncWithClient(helpers.list_client(fw, nodes, pods, variant))
+            out.append(cc.EncodedSnapshot())
+            cc.Close()
+    half = len(out) // 2
+    for a, b in zip(out[:half], out[half:]):
+        for e in (a, b):       # the template bytes end with a process-local pointer (image_score): compare everything before it
+            e["template_hex"] = e["template_hex"][:-16]
+            e["templates_hex"] = [x[:-16] for x in e["templates_hex"]]
+        assert a == b
