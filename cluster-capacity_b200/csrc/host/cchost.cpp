@@ -245,9 +245,14 @@ static void encode_list(cc_handle *h) {
 static void ensure_encoded(cc_handle *h) {
   if (h->have_enc) return;
   if (h->tmpls.size() > 1) { encode_list(h); h->have_enc = true; return; }
+  auto t0 = std::chrono::steady_clock::now();
   Encoder enc(h->cfg, h->tmpl, h->nodes, h->pods, h->ns_labels, h->exclude);
   enc.set_workloads(&h->workloads);
+  auto t1 = std::chrono::steady_clock::now();
   h->enc = enc.encode();
+  if (getenv("CCHOST_TIMING"))
+    fprintf(stderr, "[cchost] encode: node order + pod assignment %.3f s, columns / dictionaries / counters %.3f s\n",
+            std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
   h->enc_tmpls.assign(1, h->enc.tmpl);
   h->have_enc = true;
 }
