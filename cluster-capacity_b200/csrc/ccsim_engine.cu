@@ -717,6 +717,14 @@ __global__ void ccsim_flush_kernel(unsigned long long *buf, size_t n, unsigned l
 // ------------------------------------------------------------------------------------------------------------------
 // host side of the C-ABI
 // ------------------------------------------------------------------------------------------------------------------
+struct RunPlan {      // what run_prepare decided, consumed by the launch
+  bool valid = false, empty = false;
+  int64_t max_pods = 0;
+  DevParams p; LeanParams lp; MultiParams mp; StreamParams sp;
+  const void *kern = nullptr; int grid = 0, block = 0; size_t smem = 0;
+  bool stream = false, multi = false, batched = false, lean = false, resident = false;
+};
+
 struct ccsim_handle {
   ccsim_config cfg;
   int sm_count = 0;
@@ -778,6 +786,7 @@ struct ccsim_handle {
   uint32_t epoch = 0;
   uint32_t xwave0 = 0;                                    // exchanges of earlier sharded runs (buffer parity continues across runs)
   int64_t last_stat[16] = {};                             // ccsim_run_stats
+  RunPlan plan;
   int32_t *d_topo_full[CCSIM_MAX_TOPO_COLS] = {};
   int32_t *d_pod_node = nullptr; int64_t pod_cap = 0;
   std::vector<int32_t> h_pod_node;
@@ -916,7 +925,7 @@ extern "C" int ccsim_load_nodes(ccsim_handle *h, const ccsim_nodes *nd) {
     return fail(h, CCSIM_EINVAL, "ccsim_nodes dimensions out of range");
   CK(cudaSetDevice(h->cfg.device));
   free_pool(h, h->allocs);
-  h->have_nodes = false; h->have_templates = false;
+  h->have_nodes = false; h->have_templates = false; h->plan.valid = false;
   const int32_t N = nd->n_nodes;
   // node-axis shard of this rank: contiguous block of the nodeTree order
   const int32_t per = (N + h->cfg.world - 1) / h->cfg.world;
@@ -1002,7 +1011,7 @@ extern "C" int ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const c
     return fail(h, CCSIM_EUNSUPPORTED, "PodTopologySpread/InterPodAffinity templates are single-template only");
   CK(cudaSetDevice(h->cfg.device));
   free_pool(h, h->tmpl_allocs);
-  h->have_templates = false;
+  h->have_templates = false; h->plan.valid = false;
   const ccsim_nodes &nd = h->meta;
   for (int t = 0; t < n_templates; t++) {
     const ccsim_template &T = templates[t];
@@ -1115,13 +1124,15 @@ static void fill_params(ccsim_handle *h, DevParams &p, int64_t max_pods) {
   p.taint_list_off = h->d_taint_off; p.taint_list = h->d_taint_list;
 }
 
-extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
-  if (!h || !out) return fail(h, CCSIM_EINVAL, "null argument");
+// Everything a Run does before the wave kernel starts: output / streaming buffers, restoring the working columns, choosing the
+// engine, uploading the parameters. Kept apart from the launch (ccsim_prepare) for hosts that drive several ranks from one
+// process: every rank must be past its allocations before any rank's persistent kernel starts waiting for its peers.
+static int run_prepare(ccsim_handle *h, int64_t max_pods) {
   if (!h->have_nodes || !h->have_templates) return fail(h, CCSIM_ESTATE, "load_nodes and set_templates must come first");
   if (h->cfg.world > 1 && !h->peers_ready) return fail(h, CCSIM_ESTATE, "sharded run: ccsim_peer_import must come first");
   CK(cudaSetDevice(h->cfg.device));
-  memset(out, 0, sizeof(*out));
-  out->n_nodes = h->n_global;
+  RunPlan &pl = h->plan;
+  pl.valid = false; pl.empty = false; pl.max_pods = max_pods;
   const int32_t n = h->n;
   // output capacity: no run can place more than sum(max(0, alloc_pods - npods)) pods (fit.go:567-576)
   int64_t cap = h->pod_bound + 1;
@@ -1161,8 +1172,8 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   //  harmless because runs advance a per-handle epoch that is folded into the tag)
 
   if (n == 0) {   // ErrNoNodesAvailable (scheduler.go:68): nothing to evaluate; the host formats the message
-    out->placed = 0; out->stop_code = CCSIM_STOP_UNSCHEDULABLE; out->pod_node = nullptr;
     CK(cudaStreamSynchronize(s));
+    pl.empty = true; pl.valid = true;
     return CCSIM_OK;
   }
   // grid: one persistent CTA per SM (fewer for tiny clusters: the exchange cost grows with the CTA count)
@@ -1387,6 +1398,35 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   else if (resident) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<true>, block, smem));
   else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ccsim_wave_kernel<false>, block, smem));
   if (occ < 1 || occ * h->sm_count < grid) return fail(h, CCSIM_ECUDA, "persistent grid %d does not fit (occupancy %d x %d SMs)", grid, occ, h->sm_count);
+  pl.p = p; pl.lp = lp; pl.mp = mp; pl.sp = sp; pl.kern = kern; pl.grid = grid; pl.block = block; pl.smem = smem;
+  pl.stream = stream; pl.multi = multi; pl.batched = batched; pl.lean = lean; pl.resident = resident;
+  pl.valid = true;
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_prepare(ccsim_handle *h, int64_t max_pods) {
+  if (!h) return fail(h, CCSIM_EINVAL, "null argument");
+  int rc = run_prepare(h, max_pods);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));     // allocations and restores are done when this returns
+  return CCSIM_OK;
+}
+
+extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
+  if (!h || !out) return fail(h, CCSIM_EINVAL, "null argument");
+  if (!(h->plan.valid && h->plan.max_pods == max_pods)) { int rc = run_prepare(h, max_pods); if (rc) return rc; }
+  RunPlan &pl = h->plan;
+  pl.valid = false;                          // one launch per preparation: the working columns are consumed by the run
+  memset(out, 0, sizeof(*out));
+  out->n_nodes = h->n_global;
+  if (pl.empty) { out->placed = 0; out->stop_code = CCSIM_STOP_UNSCHEDULABLE; out->pod_node = nullptr; return CCSIM_OK; }
+  CK(cudaSetDevice(h->cfg.device));
+  const int32_t n = h->n;
+  cudaStream_t s = h->stream;
+  DevParams &p = pl.p; LeanParams &lp = pl.lp; MultiParams &mp = pl.mp; StreamParams &sp = pl.sp;
+  const void *kern = pl.kern; const int grid = pl.grid, block = pl.block; const size_t smem = pl.smem;
+  const bool stream = pl.stream, multi = pl.multi, batched = pl.batched, lean = pl.lean, resident = pl.resident;
+  (void)resident;
   void *args[] = { (void *)&p, stream ? (void *)&sp : (void *)&lp, (void *)&mp };
   CK(cudaEventRecord(h->ev0, s));
   CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));

@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("CCSIM_SO") or os.path.join(_HERE, "libccsim.so")   # C
 _lib = None
 
 EXPORTS = ["ccsim_create", "ccsim_destroy", "ccsim_last_error", "ccsim_abi_version", "ccsim_load_nodes",
-           "ccsim_set_templates", "ccsim_run", "ccsim_node_counts", "ccsim_peer_export", "ccsim_peer_import",
+           "ccsim_set_templates", "ccsim_run", "ccsim_prepare", "ccsim_node_counts", "ccsim_peer_export", "ccsim_peer_import",
            "ccsim_device_info", "ccsim_kernel_launches", "ccsim_flush_l2", "ccsim_run_stats", "ccsim_peer_local", "ccsim_peer_import_local"]
 
 
@@ -40,6 +40,8 @@ def lib():
         L.ccsim_load_nodes.argtypes = [C.c_void_p, C.POINTER(abi.Nodes)]
         L.ccsim_set_templates.restype = C.c_int
         L.ccsim_set_templates.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.Template), C.c_int32, C.POINTER(abi.Counter)]
+        L.ccsim_prepare.restype = C.c_int
+        L.ccsim_prepare.argtypes = [C.c_void_p, C.c_int64]
         L.ccsim_run.restype = C.c_int
         L.ccsim_run.argtypes = [C.c_void_p, C.c_int64, C.POINTER(abi.Result)]
         L.ccsim_node_counts.restype = C.c_int
@@ -109,6 +111,10 @@ class Engine:
         T = (abi.Template * len(templates))(*templates)
         Cn = (abi.Counter * max(1, len(counters)))(*counters)
         self._check(lib().ccsim_set_templates(self._h, len(templates), T, len(counters), Cn), "ccsim_set_templates")
+
+    def prepare(self, max_pods=0):
+        """The allocation / restore half of run(max_pods); see ccsim_prepare."""
+        self._check(lib().ccsim_prepare(self._h, max_pods), "ccsim_prepare")
 
     def run(self, max_pods=0):
         res = abi.Result()

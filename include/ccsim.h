@@ -288,6 +288,10 @@ int  ccsim_set_templates(ccsim_handle *h, int32_t n_templates, const ccsim_templ
 /* Run: place pods k = 0,1,2,... (template k % n_templates) until one does not fit or max_pods (>0) are placed.
  * Restores the loaded snapshot first, so it can be called repeatedly. Blocking. */
 int  ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out);
+/* Optional: everything ccsim_run(h, max_pods) does BEFORE the wave kernel starts (buffers, restoring the snapshot, engine choice),
+ * synchronously. A host that drives several ranks from one process calls it on every handle, then starts the ccsim_run calls
+ * concurrently: no rank's persistent kernel then waits for a peer that is still inside a (device-synchronising) allocation. */
+int  ccsim_prepare(ccsim_handle *h, int64_t max_pods);
 
 /* per-node number of placed pods of template t after the last run (device histogram; report.go:146-180 without the O(P*nodes) scan)
  * and the index of the first pod placed on each node (-1 none): ReplicasOnNodes is ordered by first placement. */

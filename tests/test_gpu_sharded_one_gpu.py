@@ -26,6 +26,8 @@ def run_sharded(snap, tmpl, ctr, limit, world, kind, runs):
     out = []
     for lim in runs:
         res, errs = [None] * world, []
+        for e in engs:              # every rank past its allocations before any rank's kernel starts waiting for its peers
+            e.prepare(lim)
 
         def work(r):
             try:
