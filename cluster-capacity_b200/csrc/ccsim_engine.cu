@@ -1377,7 +1377,7 @@ static int run_prepare(ccsim_handle *h, int64_t max_pods) {
     h->launches++;
     CK(cudaGetLastError());
     // resident free_* columns when the chunk fits next to the memo ring (20 B per node: up to ~10k nodes per SM)
-    const size_t smem_resf = (size_t)STREAM_STAGES_RES * STREAM_TILE * 4 + (size_t)sp.chunk_pad * 20 + 128;
+    const size_t smem_resf = (size_t)STREAM_STAGES_RES * STREAM_TILE * 4 + (size_t)sp.chunk_pad * 24 + 128;
     stream_mode = masks ? 1 : ((smem_resf + sizeof(StreamShared) + 1024 <= h->smem_optin && !getenv("CCSIM_STREAM_ALL")) ? 2 : 0);
     kern = stream_mode == 1 ? (const void *)ccsim_wave_stream_kernel<1> : stream_mode == 2 ? (const void *)ccsim_wave_stream_kernel<2> : (const void *)ccsim_wave_stream_kernel<0>;
     smem = stream_mode == 2 ? smem_resf : (size_t)STREAM_STAGES * STREAM_TILE * (masks ? 40 : 24) + 128;

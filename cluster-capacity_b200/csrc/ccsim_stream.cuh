@@ -104,6 +104,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
   long long *r_fcpu = reinterpret_cast<long long *>(smem_raw + NST * STAGE_BYTES);
   long long *r_fmem = r_fcpu + sp.chunk_pad;
   int32_t *r_fpods = reinterpret_cast<int32_t *>(r_fmem + sp.chunk_pad);
+  // RESF: a generation number per node instead of invalidating 64 memo entries at every commit: a memo entry is (generation << 12 |
+  // score + 1) and is valid only while the node's generation stands (NodeInfo.Generation, framework/types.go:409-427). The commit
+  // is then a handful of shared-memory stores: no global memo stores, no proxy fence, no patching of prefetched stages.
+  int32_t *r_gen = r_fpods + sp.chunk_pad;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
   const long long base = (long long)cta * sp.chunk_pad;           // this CTA's first padded row
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     for (int j = threadIdx.x; j < sp.chunk_pad; j += STREAM_THREADS) {
       r_fcpu[j] = sp.f_cpu[(long long)blockIdx.x * sp.chunk_pad + j]; r_fmem[j] = sp.f_mem[(long long)blockIdx.x * sp.chunk_pad + j];
       r_fpods[j] = sp.f_pods[(long long)blockIdx.x * sp.chunk_pad + j];
+      r_gen[j] = 0;
     }
   if (tid == 0) {
     for (int s = 0; s < NST; s++) mbar_init(&ss.full[s], 1);
@@ -208,10 +213,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
           const int off = tile * STREAM_TILE + j;
           const long long i = (long long)cta * p.chunk + off;        // shard-local node index
           int32_t sc = s_memo[j];
+          const int32_t gen = RESF ? r_gen[off] : 0;
+          if (RESF) sc = (sc >= 0 && (sc >> 12) == gen) ? (sc & 0xfff) - 1 : -1;
           if (sc < 0) {   // stale: this node was committed since template t last scored it (or never scored)
             sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
                             p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
-            sp.memo[(size_t)t * sp.n_pad + base + off] = sc;
+            sp.memo[(size_t)t * sp.n_pad + base + off] = RESF ? ((gen << 12) | (sc + 1)) : sc;
             wrote = true;                // fenced once after the pass (a later bulk-async read of this column must see the store)
           }
           const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
@@ -261,16 +268,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
           const long long q = base + (w - (long long)oc * p.chunk);
           const int roff = (int)(w - (long long)oc * p.chunk);
           if (lane == 0) {
-            if (RESF) { r_fcpu[roff] -= c.req_cpu; r_fmem[roff] -= c.req_mem; r_fpods[roff] -= 1; }
+            if (RESF) { r_fcpu[roff] -= c.req_cpu; r_fmem[roff] -= c.req_mem; r_fpods[roff] -= 1; r_gen[roff] = (r_gen[roff] + 1) & 0x7ffff; }
             else { sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1; }
             p.req_cpu[w] += c.req_cpu; p.req_mem[w] += c.req_mem; p.nz_cpu[w] += c.nz_cpu; p.nz_mem[w] += c.nz_mem; p.npods[w] += 1;   // write-through
             if (k < p.pod_cap) p.pod_node[k] = w + p.node_base; else ss.stop = 3;
           }
+          if (!RESF) {
           for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
           fence_proxy_async();
+          }
           // the winner's row may already sit, pre-commit, in a stage prefetched for the next wave: wait for that copy, then patch it
           const int off = (int)(w - (long long)oc * p.chunk), tw = off / STREAM_TILE, j = off - tw * STREAM_TILE;
-          if (prefetched && tw < NST && tw < tiles && lane == 0) {
+          if (!RESF && prefetched && tw < NST && tw < tiles && lane == 0) {
             const uint32_t u = uses_next + (uint32_t)tw;
             const int s = (int)(u % NST);
             while (!mbar_try_wait(&ss.full[s], (u / NST) & 1u)) { }
