@@ -1429,7 +1429,11 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   (void)resident;
   void *args[] = { (void *)&p, stream ? (void *)&sp : (void *)&lp, (void *)&mp };
   CK(cudaEventRecord(h->ev0, s));
-  CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));
+  // Cooperative launch = the driver guarantees that the whole persistent grid is co-resident (the kernels never use grid.sync()).
+  // Ranks that share a process (ccsim_peer_import_local) may share a device; cooperative launches of different streams are not
+  // run concurrently there, so those ranks use a plain launch: the occupancy check above still holds for each grid on its own.
+  if (h->peers_local) CK(cudaLaunchKernel(kern, dim3(grid), dim3(block), args, smem, s));
+  else CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));
   h->launches++;
   CK(cudaEventRecord(h->ev1, s));
   DevOut ho;

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
   uint32_t wtag = 1;
   uint32_t tag = (p.epoch << 12) | wtag;
   const int tiles = sp.tiles;
+  const bool all_in_flight = tiles <= NST;     // the whole chunk fits in the ring: no stage is reused within a pass
   for (;; k++) {
     if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }
     if (k > p.pod_cap) { if (tid == 0) ss.stop = 3; __syncthreads(); break; }
@@ -225,11 +226,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
           best = key > best ? key : best;
         }
       }
-      __syncthreads();                 // everybody is done with stage s
-      // (no proxy fence here: the rows of a later tile were last written in an earlier wave)
-      if (tid == 0 && tile + NST < tiles) issue(tile + NST, s, t);
+      if (!all_in_flight) {
+        __syncthreads();               // everybody is done with stage s
+        // (no proxy fence here: the rows of a later tile were last written in an earlier wave)
+        if (tid == 0 && tile + NST < tiles) issue(tile + NST, s, t);
+      }
     }
     if (wrote) fence_proxy_async();
+    if (all_in_flight) __syncthreads();    // no stage was reused inside the pass: one barrier before the stages are re-armed
     // The first tiles of the NEXT wave are requested now, so that the copy engine works while the exchange is in flight. They may
     // hold the pre-commit row of this wave's winner: the owner patches its shared-memory copy after the commit (below).
     const uint32_t uses_next = uses;           // the next wave's tile q lands in stage (uses_next + q) % STAGES
