@@ -274,9 +274,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
           if (lane == 0) {
             if (RESF) { r_fcpu[roff] -= c.req_cpu; r_fmem[roff] -= c.req_mem; r_fpods[roff] -= 1; r_gen[roff] = (r_gen[roff] + 1) & 0x7ffff; }
             else { sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1; }
-            p.req_cpu[w] += c.req_cpu; p.req_mem[w] += c.req_mem; p.nz_cpu[w] += c.nz_cpu; p.nz_mem[w] += c.nz_mem; p.npods[w] += 1;   // write-through
             if (k < p.pod_cap) p.pod_node[k] = w + p.node_base; else ss.stop = 3;
           }
+          // write-through of the NodeInfo row (types.go:409-427), one column per lane: the five read-modify-writes are one L2 round
+          // trip on the owner's critical path instead of five
+          if (lane == 1) p.req_cpu[w] += c.req_cpu;
+          else if (lane == 2) p.req_mem[w] += c.req_mem;
+          else if (lane == 3) p.nz_cpu[w] += c.nz_cpu;
+          else if (lane == 4) p.nz_mem[w] += c.nz_mem;
+          else if (lane == 5) p.npods[w] += 1;
           if (!RESF) {
           for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
           fence_proxy_async();
