@@ -13,8 +13,11 @@
 // per-domain initial counts).
 #pragma once
 #include <thread>
+#include <chrono>
 #include <exception>
 #include <unordered_map>
+#include <unordered_set>
+#include <string_view>
 #include <cstring>
 #include <functional>
 #include "../../../include/ccsim.h"
@@ -164,32 +167,39 @@ class Encoder {
       : cfg_(cfg), t_(tmpl), ns_labels_(ns_labels) {
     // ---- node order: nodeTree (zones in first-seen order, round-robin) ----
     std::vector<const Node *> kept;
-    for (auto &n : nodes_in) if (!exclude.count(n.name)) kept.push_back(&n);
-    std::vector<std::string> zones;
-    std::map<std::string, std::vector<const Node *>> tree;
-    std::set<std::string> seen;
-    for (auto *n : kept) {
-      if (seen.count(n->name)) continue;   // "Did not add to the NodeTree because it already exists"
-      seen.insert(n->name);
-      std::string z = n->zone_key();
-      if (!tree.count(z)) zones.push_back(z);
-      tree[z].push_back(n);
+    for (auto &n : nodes_in) if (exclude.empty() || !exclude.count(n.name)) kept.push_back(&n);
+    std::vector<std::string> zkey(kept.size());
+    parallel_for((int)kept.size(), [&](int i) { zkey[i] = kept[i]->zone_key(); });
+    std::vector<std::vector<const Node *>> tree;              // one list per zone, zones in first-seen order
+    std::unordered_map<std::string_view, int> zone_id;
+    std::unordered_set<std::string_view> seen;
+    seen.reserve(kept.size() * 2);
+    for (size_t i = 0; i < kept.size(); i++) {
+      const Node *n = kept[i];
+      if (!seen.insert(std::string_view(n->name)).second) continue;   // "Did not add to the NodeTree because it already exists"
+      auto it = zone_id.find(std::string_view(zkey[i]));
+      if (it == zone_id.end()) { it = zone_id.emplace(std::string_view(zkey[i]), (int)tree.size()).first; tree.emplace_back(); }
+      tree[it->second].push_back(n);
     }
     size_t total = seen.size(), idx = 0;
+    nodes_.reserve(total);
     while (nodes_.size() < total) {
-      for (auto &z : zones) { auto &v = tree[z]; if (idx < v.size()) nodes_.push_back(v[idx]); }
+      for (auto &v : tree) if (idx < v.size()) nodes_.push_back(v[idx]);
       idx++;
     }
-    for (size_t i = 0; i < nodes_.size(); i++) node_index_[nodes_[i]->name] = (int)i;
+    node_index_.reserve(nodes_.size() * 2);
+    for (size_t i = 0; i < nodes_.size(); i++) node_index_[std::string_view(nodes_[i]->name)] = (int)i;
     // ---- pods: non-terminal, bound to a known node ----
     pods_on_.resize(nodes_.size());
-    for (auto &p : pods_in) {
-      if (p.phase == "Succeeded" || p.phase == "Failed") continue;
-      if (p.node_name.empty()) continue;   // pending pods are not replayed (documented deviation)
-      auto it = node_index_.find(p.node_name);
-      if (it == node_index_.end()) continue;
-      pods_on_[it->second].push_back(&p);
-    }
+    std::vector<int32_t> where(pods_in.size(), -1);
+    parallel_for((int)pods_in.size(), [&](int j) {
+      const Pod &p = pods_in[j];
+      if (p.phase == "Succeeded" || p.phase == "Failed") return;
+      if (p.node_name.empty()) return;   // pending pods are not replayed (documented deviation)
+      auto it = node_index_.find(std::string_view(p.node_name));
+      if (it != node_index_.end()) where[j] = it->second;
+    });
+    for (size_t j = 0; j < pods_in.size(); j++) if (where[j] >= 0) pods_on_[where[j]].push_back(&pods_in[j]);
   }
 
   // Services / RCs / ReplicaSets / StatefulSets of the snapshot: only helper.DefaultSelector reads them (system-default spreading)
@@ -199,6 +209,14 @@ class Encoder {
     Encoded e;
     memset(&e.tmpl, 0, sizeof(e.tmpl));
     const int n = (int)nodes_.size();
+    const bool timing = getenv("CCHOST_TIMING") != nullptr;
+    auto tlast = std::chrono::steady_clock::now();
+    auto tick = [&](const char *what) {
+      if (!timing) return;
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[cchost]   encode/%s %.3f s\n", what, std::chrono::duration<double>(now - tlast).count());
+      tlast = now;
+    };
     e.n = n;
     guards();
     // ---- template request vectors (A2) ----
@@ -254,6 +272,7 @@ class Encoder {
         e.npods[i] += 1;
       }
     });
+    tick("node columns");
     // ---- taints: dictionary in first-seen order ----
     std::map<Taint, int> tid;
     for (int i = 0; i < n; i++)
@@ -283,6 +302,7 @@ class Encoder {
     }
     if (tolerations_tolerate(t_.tolerations, Taint{"node.kubernetes.io/unschedulable", "", "NoSchedule"})) T.flags |= CCSIM_TF_TOLERATES_UNSCHEDULABLE;
 
+    tick("taints");
     // ---- static bits ----
     std::vector<std::vector<char>> bits;   // bits[b][i]
     auto new_bit = [&](const std::function<bool(int)> &f) { std::vector<char> v(n); for (int i = 0; i < n; i++) v[i] = f(i) ? 1 : 0; bits.push_back(v); return (int)bits.size() - 1; };
@@ -350,6 +370,7 @@ class Encoder {
         return false;
       }));
     }
+    tick("static bits");
     // ---- PodTopologySpread hard constraints (plugin.go:257-278; common.go:86-127; filtering.go:235-308) ----
     const Labels *t_ns_labels = ns_labels_.count(t_.ns) ? &ns_labels_.at(t_.ns) : nullptr;
     std::vector<const TopologySpreadConstraint *> hard;
@@ -381,10 +402,13 @@ class Encoder {
     for (size_t c = 0; c < hard.size(); c++) {
       const TopologySpreadConstraint &tc = *hard[c];
       // domains: eligible nodes (all constraint keys present + inclusion policies) define TpValueToMatchNum; they get ids [0,n_present)
-      std::map<std::string, int> dom_id; std::vector<int64_t> counts;
+      std::unordered_map<std::string_view, int> dom_id; std::vector<int64_t> counts;
       std::vector<char> eligible(n, 0);
       std::vector<int64_t> node_cnt(n, 0);
+      std::vector<const std::string *> value(n, nullptr);    // the node's value of this constraint's key
       parallel_for(n, [&](int i) {     // per node: eligibility and countPodsMatchSelector (common.go:144-158)
+        auto vit = nodes_[i]->labels.find(tc.topology_key);
+        if (vit != nodes_[i]->labels.end()) value[i] = &vit->second;
         bool all_keys = true;
         for (auto *h : hard) if (!nodes_[i]->labels.count(h->topology_key)) all_keys = false;
         if (!all_keys) return;
@@ -396,20 +420,20 @@ class Encoder {
           for (auto *p : pods_on_[i]) if (!p->terminating && p->ns == t_.ns && hard_sel[c].matches(p->labels)) cnt++;
         node_cnt[i] = cnt;
       });
+      std::vector<int32_t> col(n, -1);
       for (int i = 0; i < n; i++) {    // domain ids in first-seen order over the eligible nodes
         if (!eligible[i]) continue;
-        const std::string &v = nodes_[i]->labels.at(tc.topology_key);
-        auto it = dom_id.find(v);
-        if (it == dom_id.end()) { it = dom_id.emplace(v, (int)dom_id.size()).first; counts.push_back(0); }
+        auto it = dom_id.find(std::string_view(*value[i]));
+        if (it == dom_id.end()) { it = dom_id.emplace(std::string_view(*value[i]), (int)dom_id.size()).first; counts.push_back(0); }
         counts[it->second] += node_cnt[i];
+        col[i] = it->second;
       }
       const int n_present = (int)dom_id.size();
-      std::vector<int32_t> col(n, -1);
       for (int i = 0; i < n; i++) {
-        auto it = nodes_[i]->labels.find(tc.topology_key);
-        if (it == nodes_[i]->labels.end()) continue;
-        if (!dom_id.count(it->second)) { int id = (int)dom_id.size(); dom_id[it->second] = id; counts.push_back(0); }   // value only on ineligible nodes: matchNum 0, never in the min
-        col[i] = dom_id[it->second];
+        if (eligible[i] || !value[i]) continue;
+        auto it = dom_id.find(std::string_view(*value[i]));
+        if (it == dom_id.end()) { it = dom_id.emplace(std::string_view(*value[i]), (int)dom_id.size()).first; counts.push_back(0); }   // value only on ineligible nodes: matchNum 0, never in the min
+        col[i] = it->second;
       }
       int colidx = (int)e.topo.size();
       e.topo.push_back(col);
@@ -424,6 +448,7 @@ class Encoder {
       T.pts[c].min_zero = n_present < tc.min_domains ? 1 : 0;
     }
     T.n_pts = (int32_t)hard.size();
+    tick("hard spread constraints");
     // ---- InterPodAffinity required terms (interpodaffinity/filtering.go:204-309) ----
     auto term_matches_pod = [&](const AffinityTerm &t, const Pod &p, const Labels *nsl) { return t.matches(p.ns, p.labels, nsl); };
     // incoming pod's terms: namespaceSelector is resolved against the namespace list and merged into Namespaces
@@ -439,13 +464,16 @@ class Encoder {
     std::vector<AffinityTerm> aff = merged(t_.aff_required), anti = merged(t_.anti_required);
     auto ipa_counter = [&](const std::string &key, const std::function<int(const Pod &)> &weight, int inc, int32_t &out_idx) {
       // one counter per topology key; node-local when every node has the key with a unique value
-      std::map<std::string, int> dom_id; std::vector<int32_t> col(n, -1); std::vector<int64_t> counts;
+      std::unordered_map<std::string_view, int> dom_id; std::vector<int32_t> col(n, -1); std::vector<int64_t> counts;
+      dom_id.reserve(1024);
+      std::vector<const std::string *> value(n, nullptr);
+      parallel_for(n, [&](int i) { auto it = nodes_[i]->labels.find(key); if (it != nodes_[i]->labels.end()) value[i] = &it->second; });
       bool unique = true;
       for (int i = 0; i < n; i++) {
-        auto it = nodes_[i]->labels.find(key);
-        if (it == nodes_[i]->labels.end()) { unique = false; continue; }
-        if (dom_id.count(it->second)) unique = false; else { int id = (int)dom_id.size(); dom_id[it->second] = id; counts.push_back(0); }
-        col[i] = dom_id[it->second];
+        if (!value[i]) { unique = false; continue; }
+        auto ins = dom_id.emplace(std::string_view(*value[i]), (int)dom_id.size());
+        if (ins.second) counts.push_back(0); else unique = false;
+        col[i] = ins.first->second;
       }
       std::vector<int64_t> per_node(n, 0);
       parallel_for(n, [&](int i) { if (col[i] < 0) return; for (auto *p : pods_on_[i]) per_node[i] += weight(*p); });
@@ -490,6 +518,7 @@ class Encoder {
       }
       T.n_anti = (int32_t)keys.size();
     }
+    tick("inter-pod (anti-)affinity counters");
     // existing pods' required anti-affinity against the incoming pod (getExistingAntiAffinityCounts): static bit
     {
       std::set<std::pair<std::string, std::string>> blocked;
@@ -506,6 +535,7 @@ class Encoder {
           return false;
         }));
     }
+    tick("existing anti-affinity");
     // ---- PodTopologySpread score: ScheduleAnyway constraints, or the system defaults when a Service / owning controller
     //      selects the pod (scoring.go:60-186; plugin.go:48-59; common.go:64-81) ----
     if (cfg_.score_enable & CCSIM_PL_POD_TOPOLOGY_SPREAD) {
@@ -643,6 +673,7 @@ class Encoder {
       }
       if (any) e.image_score = col;
     }
+    tick("soft scorers");
     if (e.topo.size() > CCSIM_MAX_TOPO_COLS || e.counters.size() > CCSIM_MAX_COUNTERS) throw Unsupported("too many topology columns");
     // ---- pack static bits ----
     if (bits.size() > 64 * CCSIM_MAX_STATIC_WORDS) throw Unsupported("too many static predicate bits");
@@ -662,7 +693,7 @@ class Encoder {
   const Pod &t_;
   const std::map<std::string, Labels> &ns_labels_;
   std::vector<const Node *> nodes_;
-  std::unordered_map<std::string, int> node_index_;
+  std::unordered_map<std::string_view, int> node_index_;   // keys view the Node objects' names (they outlive the encoder)
   std::vector<std::vector<const Pod *>> pods_on_;
   const std::vector<WorkloadSelector> *workloads_ = nullptr;
 
