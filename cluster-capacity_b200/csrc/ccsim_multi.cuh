@@ -49,6 +49,7 @@
 #endif
 #define MULTI_CAP (32 * MULTI_CPT)
 #define MULTI_BINS 64
+#define MULTI_LPT ((CCSIM_MAX_WORLD * CCSIM_MAX_GRID + LEAN_THREADS - 1) / LEAN_THREADS)   /* node shards: lines polled per thread */
 
 // cross-GPU line buffers inside every rank's exchange allocation (64-bit words): [parity][source rank][CTA][16]
 #define XLEAN_WORDS (2 * CCSIM_MAX_WORLD * SLOT_STRIDE)
@@ -92,6 +93,13 @@ template <bool XGPU> __device__ __forceinline__ void ld_line2(const unsigned lon
 }
 __device__ __forceinline__ void st_line2_sys(unsigned long long *p, unsigned long long a, unsigned long long b) {
   asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+// position of the g-th (0-based, g < 4) set bit of m, or -1
+__device__ __forceinline__ int nth_set_lane(unsigned m, int g) {
+  #pragma unroll
+  for (int i = 0; i < 3; i++) if (i < g) m &= m - 1;
+  return m ? __ffs(m) - 1 : -1;
 }
 
 // warp-aggregated append of the lanes' candidates to the wave's candidate arrays (order does not matter: keys are unique)
@@ -318,18 +326,15 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           st_slot(&myslots[MULTI_M + lane], pay | tagbits);
         }
       } else {
-        // this CTA's line goes into every rank's buffer: lane -> (destination rank, entry); 8-byte stores over NVLink
+        // this CTA's line goes into every rank's buffer as ONE 128-byte store per destination (16 lanes x 8 bytes, contiguous):
+        // two destinations per warp instruction, over NVLink
         const size_t off = XLINES_OFF + (((size_t)par * CCSIM_MAX_WORLD + p.rank) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
-        for (int base = 0; base < p.world * MULTI_M; base += 32) {
-          const int t = base + lane, e = t & (MULTI_M - 1), r = t >> 3;
-          const unsigned long long kv = __shfl_sync(0xffffffffu, kw, e);
-          const unsigned long long pv = __shfl_sync(0xffffffffu, pay, e);
-          const int kp = e == 0 ? 0 : (e == MULTI_M - 1 ? 1 : e + 1);
-          if (t < p.world * MULTI_M) {
-            st_slot_sys(p.xslots_peer[r] + off + kp, kv | tagbits);
-            st_slot_sys(p.xslots_peer[r] + off + MULTI_M + e, pv | tagbits);
-          }
-        }
+        const int wpos = lane & 15;                                                    // word of the line this lane stores
+        const int esrc = wpos >= MULTI_M ? wpos - MULTI_M : (wpos == 0 ? 0 : (wpos == 1 ? MULTI_M - 1 : wpos - 1));   // the entry it carries
+        const unsigned long long kv = __shfl_sync(0xffffffffu, kw, esrc);
+        const unsigned long long pv = __shfl_sync(0xffffffffu, pay, esrc);
+        const unsigned long long word = (wpos >= MULTI_M ? pv : kv) | tagbits;
+        for (int r = lane >> 4; r < p.world; r += 2) st_slot_sys(p.xslots_peer[r] + off + wpos, word);
       }
     }
     MPH_MARK(2);
@@ -344,6 +349,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     // than 5 polling warps). Node shards: world x grid x 8 entries do not fit in registers; one poller per line, entries afterwards.
     constexpr bool ONEPASS = !XGPU;
     unsigned long long ea[2] = {0ull, 0ull}, eb[2] = {0ull, 0ull};
+    uint32_t lk0[MULTI_LPT] = {};             // node shards: best key of the lines this thread polled
     if (ONEPASS) {
       const unsigned long long *pa[2], *pb[2];
       bool need[2];
@@ -370,18 +376,31 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           if (ee == MULTI_M - 1 && ((ea[u] >> MULTI_MORE_BIT) & 1ull)) tloc = max(tloc, (uint32_t)ea[u]);
         }
       }
-    } else
-    for (int l = tid; l < nlists; l += LEAN_THREADS) {
-      const unsigned long long *ln = LINE_OF(l);
-      unsigned long long a, b;
+    } else {
+      // node shards: thread t polls words 0-1 (best key; last key + "more") of lines t and t + LEAN_THREADS and keeps their best keys
+      bool need[MULTI_LPT];
+      unsigned long long a[MULTI_LPT], b[MULTI_LPT];
+      #pragma unroll
+      for (int u = 0; u < MULTI_LPT; u++) { need[u] = tid + u * LEAN_THREADS < nlists; a[u] = b[u] = 0ull; }
       unsigned spins = 0;
       for (;;) {
-        ld_line2<XGPU>(ln, a, b);
-        if ((uint32_t)(a >> KEY_TAG_SHIFT) == tag && (uint32_t)(b >> KEY_TAG_SHIFT) == tag) break;
-        if (++spins > WATCHDOG_SPINS) { ms.dead = 1; a = b = 0ull; break; }
+        bool any = false;
+        #pragma unroll
+        for (int u = 0; u < MULTI_LPT; u++) if (need[u]) ld_line2<XGPU>(LINE_OF(tid + u * LEAN_THREADS), a[u], b[u]);
+        #pragma unroll
+        for (int u = 0; u < MULTI_LPT; u++) {
+          if (need[u] && (uint32_t)(a[u] >> KEY_TAG_SHIFT) == tag && (uint32_t)(b[u] >> KEY_TAG_SHIFT) == tag) need[u] = false;
+          any |= need[u];
+        }
+        if (!any) break;
+        if (++spins > WATCHDOG_SPINS) { ms.dead = 1; for (int u = 0; u < MULTI_LPT; u++) if (need[u]) a[u] = b[u] = 0ull; break; }
       }
-      kloc = max(kloc, (uint32_t)a);
-      if ((b >> MULTI_MORE_BIT) & 1ull) tloc = max(tloc, (uint32_t)b);
+      #pragma unroll
+      for (int u = 0; u < MULTI_LPT; u++) {
+        lk0[u] = (uint32_t)a[u];
+        kloc = max(kloc, (uint32_t)a[u]);
+        if ((b[u] >> MULTI_MORE_BIT) & 1ull) tloc = max(tloc, (uint32_t)b[u]);
+      }
     }
     tloc = __reduce_max_sync(0xffffffffu, tloc);
     kloc = __reduce_max_sync(0xffffffffu, kloc);
@@ -407,44 +426,33 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           if (u * LEAN_THREADS < tot) multi_append(ck != 0u && ck >= T, ck, eb[u], lane);      // (warp-uniform guard: warps beyond the entries skip)
         }
       } else
-      // (the pollers have seen words 0-1 of every line: the other words are there or about to be. Key words are fetched in batches
-      //  of 8 so that their L2 / NVLink-written-memory round trips overlap instead of adding up: 13 entries per thread at world 8.)
-      for (int it0 = 0; it0 < iters; it0 += 8) {
-        unsigned long long a[8];
+      {
+        // Node shards: only the lines whose BEST key reaches the bar hold candidates (a few dozen of world x grid lines), and their
+        // pollers know which. A warp takes its qualifying lines four at a time: 8 lanes per line, lane -> entry, key word and
+        // payload word requested together (one L2 round trip; the line arrived as one 128-byte store, the tags are checked anyway).
         #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int e = tid + (it0 + u) * LEAN_THREADS;
-          a[u] = 0ull;
-          if (it0 + u < iters && e < tot) {
-            const int ee = e & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
-            a[u] = XGPU ? ld_slot_sys(LINE_OF(e >> 3) + kp) : ld_slot(LINE_OF(e >> 3) + kp);
-          }
-        }
-        #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          if (it0 + u >= iters) break;                     // block-uniform
-          const int e = tid + (it0 + u) * LEAN_THREADS;
-          unsigned long long b = 0ull;
-          bool keep = false;
-          if (e < tot) {
-            const unsigned long long *ln = LINE_OF(e >> 3);
-            const int ee = e & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
-            unsigned spins = 0;
-            while ((uint32_t)(a[u] >> KEY_TAG_SHIFT) != tag) {       // words of a line are separate stores: each is validated by its own tag
-              a[u] = XGPU ? ld_slot_sys(ln + kp) : ld_slot(ln + kp);
-              if (++spins > WATCHDOG_SPINS) { ms.dead = 1; a[u] = 0ull; break; }
-            }
-            keep = (uint32_t)a[u] != 0u && (uint32_t)a[u] >= T;
-            if (keep) {      // payloads only of the entries that qualify
-              spins = 0;
+        for (int u = 0; u < MULTI_LPT; u++) {
+          unsigned m = __ballot_sync(0xffffffffu, lk0[u] != 0u && lk0[u] >= T);
+          while (m) {                                   // warp-uniform
+            const int src = nth_set_lane(m, lane >> 3);          // the (lane / 8)-th qualifying lane of the warp, or -1
+            const bool on = src >= 0;
+            const int ee = lane & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
+            unsigned long long a = 0ull, b = 0ull;
+            bool keep = false;
+            if (on) {
+              const unsigned long long *ln = LINE_OF(warp * 32 + src + u * LEAN_THREADS);
+              unsigned spins = 0;
               for (;;) {
-                b = XGPU ? ld_slot_sys(ln + MULTI_M + ee) : ld_slot(ln + MULTI_M + ee);
-                if ((uint32_t)(b >> KEY_TAG_SHIFT) == tag) break;
-                if (++spins > WATCHDOG_SPINS) { ms.dead = 1; b = 0ull; keep = false; break; }
+                a = ld_slot_sys(ln + kp); b = ld_slot_sys(ln + MULTI_M + ee);
+                if ((uint32_t)(a >> KEY_TAG_SHIFT) == tag && (uint32_t)(b >> KEY_TAG_SHIFT) == tag) break;
+                if (++spins > WATCHDOG_SPINS) { ms.dead = 1; a = b = 0ull; break; }
               }
+              keep = (uint32_t)a != 0u && (uint32_t)a >= T;
             }
+            multi_append(keep, (uint32_t)a, b, lane);
+            #pragma unroll
+            for (int g = 0; g < 4; g++) if (m) m &= m - 1;          // the four lowest qualifying lanes are done
           }
-          multi_append(keep, (uint32_t)a[u], b, lane);
         }
       }
       __syncthreads();                                                  // G2
@@ -455,12 +463,29 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       if (tid < MULTI_BINS) ms.hist[tid] = 0u;
       __syncthreads();
       const unsigned long long range = (unsigned long long)(kbest - T) + 1ull;
-      for (int it = 0; it < iters; it++) {
-        const int e = tid + it * LEAN_THREADS;
-        if (e < tot) {
-          const int ee = e & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
-          const uint32_t ck = (uint32_t)(XGPU ? ld_slot_sys(LINE_OF(e >> 3) + kp) : ld_slot(LINE_OF(e >> 3) + kp));     // validated above
-          if (ck != 0u && ck >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(ck - T) * MULTI_BINS) / range)], 1u);
+      if (!XGPU) {
+        for (int it = 0; it < iters; it++) {
+          const int e = tid + it * LEAN_THREADS;
+          if (e < tot) {
+            const int ee = e & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
+            const uint32_t ck = (uint32_t)ld_slot(LINE_OF(e >> 3) + kp);     // validated above
+            if (ck != 0u && ck >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(ck - T) * MULTI_BINS) / range)], 1u);
+          }
+        }
+      } else {
+        #pragma unroll
+        for (int u = 0; u < MULTI_LPT; u++) {
+          unsigned m = __ballot_sync(0xffffffffu, lk0[u] != 0u && lk0[u] >= T);
+          while (m) {
+            const int src = nth_set_lane(m, lane >> 3);
+            if (src >= 0) {
+              const int ee = lane & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
+              const uint32_t ck = (uint32_t)ld_slot_sys(LINE_OF(warp * 32 + src + u * LEAN_THREADS) + kp);     // validated above
+              if (ck != 0u && ck >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(ck - T) * MULTI_BINS) / range)], 1u);
+            }
+            #pragma unroll
+            for (int g = 0; g < 4; g++) if (m) m &= m - 1;
+          }
         }
       }
       __syncthreads();

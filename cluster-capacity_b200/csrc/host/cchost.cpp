@@ -331,6 +331,77 @@ static size_t skip_value(const char *t, size_t n, size_t p) {
   while (p < n && t[p] != ',' && t[p] != ']' && t[p] != '}' && t[p] != ' ' && t[p] != '\n' && t[p] != '\t' && t[p] != '\r') p++;
   return p;
 }
+// The item list of a big document, located on all host cores. `p` is just behind the '[' of the list. Whether a byte lies inside a
+// string is the parity of the unescaped quotes before it, and in valid JSON a backslash only occurs inside strings, so "skip the
+// byte after a backslash" finds the same unescaped quotes wherever a chunk starts (chunks start behind a non-backslash byte).
+// Pass 1 (parallel): per chunk the quote parity and the bracket-depth change under both start states; a serial prefix gives
+// every chunk its true start state and depth; pass 2 (parallel): the '{' that opens depth 1 and the '}' that closes it are the
+// item boundaries. Anything unexpected (an item that is not an object, a document that ends early) returns false: the serial
+// scan then decides.
+static bool item_spans_parallel(const char *t, size_t n, size_t p, std::vector<std::pair<size_t, size_t>> &out) {
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
+  if (n - p < (4u << 20) || nt < 2) return false;
+  std::vector<size_t> cut(nt + 1);
+  cut[0] = p; cut[nt] = n;
+  for (unsigned c = 1; c < nt; c++) {
+    size_t q = p + (n - p) / nt * c;
+    while (q < n && t[q - 1] == '\\') q++;
+    cut[c] = std::max(q, cut[c - 1]);
+  }
+  struct Part { int quotes = 0; long long depth[2] = {0, 0}; };     // depth[s]: change of bracket depth when the chunk starts with state s (1: in a string)
+  std::vector<Part> part(nt);
+  auto run = [&](auto fn) {
+    std::vector<std::thread> th;
+    for (unsigned c = 0; c < nt; c++) th.emplace_back(fn, c);
+    for (auto &x : th) x.join();
+  };
+  run([&](unsigned c) {
+    Part r; int in = 0;
+    for (size_t q = cut[c]; q < cut[c + 1]; q++) {
+      const char ch = t[q];
+      if (ch == '\\') { q++; continue; }
+      if (ch == '"') { in ^= 1; r.quotes++; continue; }
+      if (ch == '{' || ch == '[') r.depth[in]++;
+      else if (ch == '}' || ch == ']') r.depth[in]--;
+    }
+    part[c] = r;
+  });
+  std::vector<int> in0(nt); std::vector<long long> d0(nt);
+  { int in = 0; long long d = 0;
+    for (unsigned c = 0; c < nt; c++) { in0[c] = in; d0[c] = d; d += part[c].depth[in]; in ^= part[c].quotes & 1; } }
+  std::vector<std::vector<size_t>> opens(nt), closes(nt);
+  std::vector<char> bad(nt, 0);
+  std::vector<size_t> list_end(nt, (size_t)-1);
+  run([&](unsigned c) {
+    int in = in0[c]; long long d = d0[c];
+    for (size_t q = cut[c]; q < cut[c + 1]; q++) {
+      const char ch = t[q];
+      if (ch == '\\') { q++; continue; }
+      if (ch == '"') { in ^= 1; if (d == 0 && !in) {} continue; }
+      if (in) continue;
+      if (ch == '{' || ch == '[') { if (d == 0) { if (ch == '{') opens[c].push_back(q); else bad[c] = 1; } d++; }
+      else if (ch == '}' || ch == ']') {
+        d--;
+        if (d == 0) closes[c].push_back(q + 1);
+        else if (d < 0) { list_end[c] = q; return; }     // the ']' of the item list: the rest of the document is not ours
+      } else if (d == 0 && ch != ',' && ch != ' ' && ch != '\n' && ch != '\t' && ch != '\r') bad[c] = 1;   // a scalar item
+    }
+  });
+  std::vector<size_t> o, e;
+  bool ended = false;
+  for (unsigned c = 0; c < nt && !ended; c++) {
+    if (bad[c]) return false;
+    o.insert(o.end(), opens[c].begin(), opens[c].end());
+    e.insert(e.end(), closes[c].begin(), closes[c].end());
+    if (list_end[c] != (size_t)-1) ended = true;
+  }
+  if (!ended || o.size() != e.size()) return false;
+  out.reserve(o.size());
+  for (size_t i = 0; i < o.size(); i++) { if (e[i] <= o[i] || (i && o[i] < e[i - 1])) return false; out.push_back({o[i], e[i]}); }
+  return true;
+}
+
 static bool item_spans(const char *t, size_t n, std::vector<std::pair<size_t, size_t>> &out) {
   size_t p = skip_ws(t, n, 0);
   if (p >= n) return false;
@@ -349,6 +420,10 @@ static bool item_spans(const char *t, size_t n, std::vector<std::pair<size_t, si
     }
     if (!found) return false;
   } else if (t[p] != '[') return false;
+  if (!getenv("CCHOST_SERIAL_SPANS")) {
+    if (item_spans_parallel(t, n, p + 1, out)) return true;
+    out.clear();
+  }
   p = skip_ws(t, n, p + 1);
   if (p < n && t[p] == ']') return true;
   while (p < n) {
@@ -384,13 +459,12 @@ template <class T, class F> static std::vector<T> parse_list(const char *text, F
   unsigned nt = std::thread::hardware_concurrency();
   nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
   if (spans.size() < 2048) nt = 1;
-  std::vector<std::vector<T>> parts(nt);
+  out.resize(spans.size());
   std::vector<std::exception_ptr> errs(nt);
   auto work = [&](unsigned c) {
     try {
       const size_t per = (spans.size() + nt - 1) / nt, b = std::min(spans.size(), (size_t)c * per), e = std::min(spans.size(), b + per);
-      parts[c].reserve(e - b);
-      for (size_t i = b; i < e; i++) parts[c].push_back(one(std::string_view(text + spans[i].first, spans[i].second - spans[i].first)));
+      for (size_t i = b; i < e; i++) out[i] = one(std::string_view(text + spans[i].first, spans[i].second - spans[i].first));
     } catch (...) { errs[c] = std::current_exception(); }
   };
   if (nt == 1) work(0);
@@ -400,8 +474,6 @@ template <class T, class F> static std::vector<T> parse_list(const char *text, F
     for (auto &x : th) x.join();
   }
   for (auto &e : errs) if (e) std::rethrow_exception(e);
-  out.reserve(spans.size());
-  for (auto &v : parts) for (auto &x : v) out.push_back(std::move(x));
   return out;
 }
 

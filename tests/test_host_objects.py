@@ -1,6 +1,7 @@
 """CPU: the C++ host encoder (libcchost) + the flat C oracle against the object-level Python oracle (oracle/objref.py)
 on random small clusters and every supported podspec feature. No GPU: the encoded snapshot is run by the C oracle."""
 import importlib
+import json
 
 import numpy as np
 import pytest
@@ -191,3 +192,29 @@ def test_fast_ingest_equals_the_general_parser(built, seed, monkeypatch):
             e["template_hex"] = e["template_hex"][:-16]
             e["templates_hex"] = [x[:-16] for x in e["templates_hex"]]
         assert a == b
+
+
+def test_parallel_item_location_equals_the_serial_scan(built, monkeypatch):
+    """Documents of more than 4 MB have their item spans located on all host cores (cchost.cpp item_spans_parallel: quote parity and
+    bracket depth per chunk, then a prefix): same encoded snapshot as the serial string-aware scan, with strings full of brackets,
+    quotes and backslashes lying wherever the chunk cuts fall."""
+    nodes, pods = helpers.random_cluster(21, n_nodes=300, n_pods=9000)
+    nasty = ['}]{[', 'a"b', chr(92), chr(92) * 2 + '"', '"]},{"', chr(92) * 3, '[[[[', '\n\t"', 'x' * 7 + chr(92)]
+    for j, p in enumerate(pods):      # annotations are skipped by the ingest: only the scanner sees them
+        p["metadata"]["annotations"] = {"note-%d" % q: nasty[(j + q) % len(nasty)] * (1 + (j + 3 * q) % 5) + "#" * ((j * 7 + q) % 90) for q in range(6)}
+    for i, n in enumerate(nodes):
+        n["metadata"]["annotations"] = {"n": nasty[i % len(nasty)] * 3}
+    assert len(json.dumps(pods)) > (4 << 20)
+    out = []
+    for serial in (False, True):
+        if serial:
+            monkeypatch.setenv("CCHOST_SERIAL_SPANS", "1")
+        cc = fw.New(None, None, helpers.template("spread_two"), 0, [])
+        cc.SyncWithClient(helpers.list_client(fw, nodes, pods, "spread_two"))
+        e = cc.EncodedSnapshot()
+        e["template_hex"] = e["template_hex"][:-16]
+        e["templates_hex"] = [x[:-16] for x in e["templates_hex"]]
+        out.append(e)
+        cc.Close()
+    assert out[0] == out[1]
+    assert sum(out[0]["nodes"]["npods"]) > 1000
