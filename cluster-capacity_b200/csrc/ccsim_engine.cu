@@ -873,6 +873,11 @@ extern "C" int ccsim_create(const ccsim_config *cfg, ccsim_handle **out) {
   if (!prop.cooperativeLaunch) { fail(nullptr, CCSIM_EUNSUPPORTED, "device lacks cooperative launch"); delete h; return CCSIM_EUNSUPPORTED; }
   h->sm_count = prop.multiProcessorCount;
   h->l2_bytes = (size_t)prop.l2CacheSize;
+  {   // the stream-ordered allocator keeps what it has mapped (default: everything goes back to the driver at the next synchronize,
+      // and every analysis would map its snapshot's memory again)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) { uint64_t keep = UINT64_MAX; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+  }
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
   cudaMalloc((void **)&h->d_out, sizeof(DevOut));

@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     int C = 0;
     const int iters = (tot + LEAN_THREADS - 1) / LEAN_THREADS;
     for (int pass = 0; pass < 2 && !dead; pass++) {
-      if (ONEPASS && pass == 0) {           // the entries are in registers already
+      if (ONEPASS) {                        // the entries are in registers already (both passes)
         #pragma unroll
         for (int u = 0; u < 2; u++) {
           const uint32_t ck = (uint32_t)ea[u];

@@ -6,6 +6,7 @@
 #include <ctime>
 #include <sstream>
 #include <thread>
+#include <mutex>
 #include <exception>
 #include <cstring>
 #include "../../../include/cchost.h"
@@ -513,6 +514,32 @@ extern "C" int cc_sync_workloads(cc_handle *h, const char *services_json, const 
   } catch (const std::exception &e) { return fail(h, CC_EINVAL, e.what()); }
 }
 
+// Engines (CUDA stream, exchange buffers, kernel attributes: ccsim_create) are kept on an idle list per (device, sampling mode) and
+// reused by later analyses of the process instead of being rebuilt for every Run; an engine that failed is destroyed, not reused.
+static std::mutex g_eng_mu;
+static std::vector<std::pair<ccsim_config, ccsim_handle *>> g_eng_idle;
+static bool same_engine_cfg(const ccsim_config &a, const ccsim_config &b) {
+  return a.device == b.device && a.sampling == b.sampling && a.pct_nodes_to_score == b.pct_nodes_to_score && a.engine == b.engine;
+}
+static ccsim_handle *engine_acquire(const ccsim_config &cfg, int &rc) {
+  {
+    std::lock_guard<std::mutex> g(g_eng_mu);
+    for (size_t i = 0; i < g_eng_idle.size(); i++)
+      if (same_engine_cfg(g_eng_idle[i].first, cfg)) { ccsim_handle *e = g_eng_idle[i].second; g_eng_idle.erase(g_eng_idle.begin() + (long)i); rc = 0; return e; }
+  }
+  ccsim_handle *e = nullptr;
+  rc = ccsim_create(&cfg, &e);
+  return rc ? nullptr : e;
+}
+static void engine_release(const ccsim_config &cfg, ccsim_handle *e) {
+  if (getenv("CCHOST_NO_ENGINE_REUSE")) { ccsim_destroy(e); return; }
+  {
+    std::lock_guard<std::mutex> g(g_eng_mu);
+    if (g_eng_idle.size() < 4) { g_eng_idle.push_back({cfg, e}); return; }
+  }
+  ccsim_destroy(e);
+}
+
 extern "C" int cc_run(cc_handle *h) {
   if (!h) return CC_EINVAL;
   if (h->closed) return fail(h, CC_ESTATE, "closed");
@@ -538,9 +565,18 @@ extern "C" int cc_run(cc_handle *h) {
   ccsim_config cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.abi_version = CCSIM_ABI_VERSION; cfg.device = h->device; cfg.engine = CCSIM_ENGINE_AUTO; cfg.rank = 0; cfg.world = 1;
   if (h->cfg.reference_sampling && h->cfg.pct_nodes_to_score != 100) { cfg.sampling = CCSIM_SAMPLING_REFERENCE; cfg.pct_nodes_to_score = h->cfg.pct_nodes_to_score; }
-  ccsim_handle *eng = nullptr;
-  int rc = ccsim_create(&cfg, &eng);
-  if (rc) return fail(h, CC_EENGINE, std::string("ccsim_create: ") + ccsim_last_error(nullptr));
+  const bool timing = getenv("CCHOST_TIMING") != nullptr;
+  auto tlast = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cchost]   run/%s %.4f s\n", what, std::chrono::duration<double>(now - tlast).count());
+    tlast = now;
+  };
+  int rc = 0;
+  ccsim_handle *eng = engine_acquire(cfg, rc);
+  if (!eng) return fail(h, CC_EENGINE, std::string("ccsim_create: ") + ccsim_last_error(nullptr));
+  tick("engine (created or taken from the idle list)");
   ccsim_nodes nd; E.fill_nodes(nd);
   ccsim_result res;
   auto bail = [&](const char *what) {
@@ -549,8 +585,11 @@ extern "C" int cc_run(cc_handle *h) {
     return rc == CCSIM_EUNSUPPORTED ? fail(h, CC_EUNSUPPORTED, "unsupported on the GPU path: " + m) : fail(h, CC_EENGINE, m);
   };
   if ((rc = ccsim_load_nodes(eng, &nd))) return bail("ccsim_load_nodes");
+  tick("ccsim_load_nodes");
   if ((rc = ccsim_set_templates(eng, (int32_t)h->enc_tmpls.size(), h->enc_tmpls.data(), (int32_t)E.counters.size(), E.counters.data()))) return bail("ccsim_set_templates");
+  tick("ccsim_set_templates");
   if ((rc = ccsim_run(eng, h->max_pods, &res))) return bail("ccsim_run");
+  tick("ccsim_run");
   h->pod_node.assign(res.pod_node, res.pod_node + res.placed);
   if (res.stop_code == CCSIM_STOP_LIMIT_REACHED) {
     h->stop_reason = "LimitReached: Maximum number of pods simulated: " + std::to_string(h->max_pods);   // simulator.go:301
@@ -569,7 +608,7 @@ extern "C" int cc_run(cc_handle *h) {
                                      {"Preemption is not helpful for scheduling", res.preempt_not_helpful}});
     h->stop_reason = "Unschedulable: " + msg + " preemption: " + post;   // simulator.go:332
   }
-  ccsim_destroy(eng);
+  engine_release(cfg, eng);
   h->ran = true;
   return CC_OK;
 }
