@@ -132,8 +132,8 @@ struct cc_handle {
   int64_t max_pods = 0;
   std::set<std::string> exclude;
   int device = 0;
-  std::vector<Node> nodes;
-  std::vector<Pod> pods;
+  ObjList<Node> nodes;
+  ObjList<Pod> pods;
   std::map<std::string, Labels> ns_labels;
   std::vector<WorkloadSelector> workloads;   // Services / RCs / ReplicaSets / StatefulSets (system-default topology spreading)
   bool synced = false, ran = false, closed = false;
@@ -448,25 +448,33 @@ static Node node_from(std::string_view item, bool dom_only) {
   return Node::parse(parse_json(item));
 }
 
-template <class T, class F> static std::vector<T> parse_list(const char *text, F one) {
-  std::vector<T> out;
+template <class T, class F> static ObjList<T> parse_list(const char *text, F one) {
+  ObjList<T> out;
   if (!text || !*text) return out;
   const size_t n = strlen(text);
   std::vector<std::pair<size_t, size_t>> spans;
   if (!item_spans(text, n, spans)) {   // not a list of items we can locate: DOM of the whole document, items re-serialised for `one`
-    for (auto &j : items_of(text)) { const std::string t = json_dump(j); out.push_back(one(std::string_view(t))); }
+    std::vector<Json> items = items_of(text);
+    T *p = out.allocate_raw(items.size());
+    std::exception_ptr err;
+    for (size_t i = 0; i < items.size(); i++) {
+      try { const std::string t = json_dump(items[i]); new (&p[i]) T(one(std::string_view(t))); }
+      catch (...) { new (&p[i]) T(); if (!err) err = std::current_exception(); }
+    }
+    if (err) std::rethrow_exception(err);
     return out;
   }
   unsigned nt = std::thread::hardware_concurrency();
   nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
   if (spans.size() < 2048) nt = 1;
-  out.resize(spans.size());
+  T *p = out.allocate_raw(spans.size());       // every element is constructed below, by the thread that parses it
   std::vector<std::exception_ptr> errs(nt);
   auto work = [&](unsigned c) {
-    try {
-      const size_t per = (spans.size() + nt - 1) / nt, b = std::min(spans.size(), (size_t)c * per), e = std::min(spans.size(), b + per);
-      for (size_t i = b; i < e; i++) out[i] = one(std::string_view(text + spans[i].first, spans[i].second - spans[i].first));
-    } catch (...) { errs[c] = std::current_exception(); }
+    const size_t per = (spans.size() + nt - 1) / nt, b = std::min(spans.size(), (size_t)c * per), e = std::min(spans.size(), b + per);
+    for (size_t i = b; i < e; i++) {
+      try { new (&p[i]) T(one(std::string_view(text + spans[i].first, spans[i].second - spans[i].first))); }
+      catch (...) { new (&p[i]) T(); if (!errs[c]) errs[c] = std::current_exception(); }
+    }
   };
   if (nt == 1) work(0);
   else {

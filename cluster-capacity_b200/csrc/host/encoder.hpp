@@ -162,7 +162,7 @@ struct Encoded {
 
 class Encoder {
  public:
-  Encoder(const SchedConfig &cfg, const Pod &tmpl, const std::vector<Node> &nodes_in, const std::vector<Pod> &pods_in,
+  Encoder(const SchedConfig &cfg, const Pod &tmpl, const ObjList<Node> &nodes_in, const ObjList<Pod> &pods_in,
           const std::map<std::string, Labels> &ns_labels, const std::set<std::string> &exclude)
       : cfg_(cfg), t_(tmpl), ns_labels_(ns_labels) {
     // ---- node order: nodeTree (zones in first-seen order, round-robin) ----

@@ -11,6 +11,7 @@
 //   GetHostPorts                          k8s.io/kubernetes/pkg/scheduler/util/utils.go:175-210
 //   PodRequests / AggregateContainerRequests  k8s.io/component-helpers/resource/helpers.go:144-251
 #pragma once
+#include <new>
 #include <algorithm>
 #include <map>
 #include <set>
@@ -169,6 +170,33 @@ struct TopologySpreadConstraint {
   std::vector<std::string> match_label_keys;
   int min_domains = 1;
   std::string node_affinity_policy = "Honor", node_taints_policy = "Ignore";
+};
+
+// The LISTed objects of a snapshot: a fixed-size array whose elements are constructed IN PLACE by the ingest threads (a
+// std::vector would value-initialise 200k x ~1 KB objects on one core before the parse even starts, and first-touch all of
+// their pages there).
+template <class T> class ObjList {
+ public:
+  ObjList() = default;
+  ObjList(const ObjList &) = delete;
+  ObjList &operator=(const ObjList &) = delete;
+  ObjList(ObjList &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  ObjList &operator=(ObjList &&o) noexcept { if (this != &o) { clear(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; } return *this; }
+  ~ObjList() { clear(); }
+  void clear() { for (size_t i = 0; i < n_; i++) p_[i].~T(); ::operator delete(p_); p_ = nullptr; n_ = 0; }
+  // raw storage for n elements: the caller constructs every one of them (placement new) before anything else touches the list
+  T *allocate_raw(size_t n) { clear(); p_ = n ? static_cast<T *>(::operator new(n * sizeof(T))) : nullptr; n_ = n; return p_; }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  const T &operator[](size_t i) const { return p_[i]; }
+  T &operator[](size_t i) { return p_[i]; }
+  const T *begin() const { return p_; }
+  const T *end() const { return p_ + n_; }
+  T *begin() { return p_; }
+  T *end() { return p_ + n_; }
+ private:
+  T *p_ = nullptr;
+  size_t n_ = 0;
 };
 
 struct Pod {
