@@ -241,6 +241,11 @@ def latency_block(st, kernel_ms, sm_mhz):
         out.update({"candidates_replayed_per_wave": st["candidates"] / w, "waves_that_raised_the_bar": st["bar_raised_waves"],
                     "cycles_per_wave_cta0": cyc, "cycles_per_wave_total": sum(cyc.values()),
                     "us_per_wave_from_cycles": (sum(cyc.values()) / (sm_mhz or 1965)) if sm_mhz else None})
+    elif st["engine"].startswith("streaming"):
+        names = ("scan_mbarrier_wait_filter_argmax", "barriers_prefetch_issue_block_argmax", "exchange_l2_round_trip", "commit_barrier")
+        cyc = {n: st["phase_cycles"][i] / w for i, n in enumerate(names)}
+        out.update({"stale_memo_rescored_per_wave_cta0": st["candidates"] / w, "cycles_per_wave_cta0": cyc, "cycles_per_wave_total": sum(cyc.values()),
+                    "us_per_wave_from_cycles": (sum(cyc.values()) / (sm_mhz or 1965)) if sm_mhz else None})
     return out
 
 

@@ -49,9 +49,12 @@ struct __align__(16) StreamShared {
   unsigned long long full[STREAM_STAGES_RES];  // mbarriers: "the stage's bytes have landed"
   unsigned long long warp_best[STREAM_WARPS];
   int32_t winner, stop, pad[2];
+  long long ph[8], tc0, n_stale;   // CTA 0 / thread 0: clock cycles per phase; stale memo entries re-scored by CTA 0
 };
 
 __shared__ StreamShared ss;
+#define SPH_START() do { if (cta == 0 && tid == 0) ss.tc0 = clock64(); } while (0)
+#define SPH_MARK(i) do { if (cta == 0 && tid == 0) { const long long t1_ = clock64(); ss.ph[i] += t1_ - ss.tc0; ss.tc0 = t1_; } } while (0)
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -150,6 +153,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     for (int s = 0; s < NST; s++) mbar_init(&ss.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     ss.winner = -1; ss.stop = 0;
+    for (int q = 0; q < 8; q++) ss.ph[q] = 0;
+    ss.n_stale = 0;
   }
   __syncthreads();
 
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       fence_proxy_async();            // the commit's and the scorers' generic-proxy stores of the last wave, before the engine reads them
       for (int q = 0; q < NST && q < tiles; q++) issue(q, (int)((uses + q) % NST), t);
     }
+    SPH_START();
     unsigned long long best = 0ull;
     bool wrote = false;
     for (int tile = 0; tile < tiles; tile++, uses++) {
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
             sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
                             p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
             sp.memo[(size_t)t * sp.n_pad + base + off] = RESF ? ((gen << 12) | (sc + 1)) : sc;
+            if (cta == 0) atomicAdd((unsigned long long *)&ss.n_stale, 1ull);
             wrote = true;                // fenced once after the pass (a later bulk-async read of this column must see the store)
           }
           const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       }
     }
     if (wrote) fence_proxy_async();
+    SPH_MARK(0);                           // scan: mbarrier waits + Filter/arg-max over the chunk
     if (all_in_flight) __syncthreads();    // no stage was reused inside the pass: one barrier before the stages are re-armed
     // The first tiles of the NEXT wave are requested now, so that the copy engine works while the exchange is in flight. They may
     // hold the pre-commit row of this wave's winner: the owner patches its shared-memory copy after the commit (below).
@@ -248,6 +256,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       if (lane == 0) ss.warp_best[warp] = v;
     }
     __syncthreads();
+    SPH_MARK(1);                           // block barriers, next wave's bulk copies issued, block arg-max
     if (warp == 0) {
       const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
       const unsigned long long mine = warp_max_u64(lane < STREAM_WARPS ? ss.warp_best[lane] : 0ull);
@@ -255,6 +264,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       unsigned long long wkey = exchange_max(p, k, tag, 0, mine, lane, cta, dead);
       (void)tagbits;
       if (p.world > 1 && !dead) { unsigned long long cb[1] = {wkey}; dead = cross_gpu_exchange(p, k, tag, 1, cb, lane, cta); wkey = cb[0]; }   // node shards: winners of all ranks
+      SPH_MARK(2);                         // exchange: own key stored, every CTA's key polled (L2 round trip + the slowest CTA)
       if (lane == 0) {
         if (dead) { ss.stop = 3; ss.winner = -1; }
         else if (wkey == 0ull) { ss.stop = 1; ss.winner = -1; }
@@ -271,25 +281,45 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
         if (oc == cta) {
           const long long q = base + (w - (long long)oc * p.chunk);
           const int roff = (int)(w - (long long)oc * p.chunk);
+          // the committed row (types.go:409-427): every lane reads the six columns (one L2 round trip, broadcast), lanes 1..5 write
+          // one column each through to global memory (the terminal diagnosis reads it), lane 0 keeps the streamed / resident copy
+          const long long a_cpu = p.alloc_cpu[w], a_mem = p.alloc_mem[w];
+          const long long n_rcpu = p.req_cpu[w] + c.req_cpu, n_rmem = p.req_mem[w] + c.req_mem;
+          const long long n_zcpu = p.nz_cpu[w] + c.nz_cpu, n_zmem = p.nz_mem[w] + c.nz_mem;
+          int32_t newgen = 0;
           if (lane == 0) {
-            if (RESF) { r_fcpu[roff] -= c.req_cpu; r_fmem[roff] -= c.req_mem; r_fpods[roff] -= 1; r_gen[roff] = (r_gen[roff] + 1) & 0x7ffff; }
+            if (RESF) { r_fcpu[roff] -= c.req_cpu; r_fmem[roff] -= c.req_mem; r_fpods[roff] -= 1; newgen = (r_gen[roff] + 1) & 0x7ffff; r_gen[roff] = newgen; }
             else { sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1; }
             if (k < p.pod_cap) p.pod_node[k] = w + p.node_base; else ss.stop = 3;
           }
-          // write-through of the NodeInfo row (types.go:409-427), one column per lane: the five read-modify-writes are one L2 round
-          // trip on the owner's critical path instead of five
-          if (lane == 1) p.req_cpu[w] += c.req_cpu;
-          else if (lane == 2) p.req_mem[w] += c.req_mem;
-          else if (lane == 3) p.nz_cpu[w] += c.nz_cpu;
-          else if (lane == 4) p.nz_mem[w] += c.nz_mem;
+          if (lane == 1) p.req_cpu[w] = n_rcpu;
+          else if (lane == 2) p.req_mem[w] = n_rmem;
+          else if (lane == 3) p.nz_cpu[w] = n_zcpu;
+          else if (lane == 4) p.nz_mem[w] = n_zmem;
           else if (lane == 5) p.npods[w] += 1;
-          if (!RESF) {
-          for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
-          fence_proxy_async();
+          int32_t patch = -1;
+          if (RESF) {
+            // Every template's memo entry of this node is re-scored NOW, by the owner (two templates per lane), under the node's new
+            // generation: a stale entry found by the scan costs a CTA an L2 round trip plus the score's divisions in the middle of
+            // its pass, and with 64 templates every wave would meet the nodes committed by the 63 waves before it.
+            newgen = __shfl_sync(0xffffffffu, newgen, 0);
+            const int tn = (int)((k + 1) % T);
+            for (int tt = lane; tt < T; tt += 32) {
+              const StreamTmpl &ct = ss.tc[tt];
+              const int32_t sc = score_node(a_cpu, a_mem, n_zcpu + ct.least_cpu, n_zmem + ct.least_mem, n_rcpu + ct.bal_cpu, n_rmem + ct.bal_mem, ct.sw);
+              const int32_t enc = (newgen << 12) | (sc + 1);
+              sp.memo[(size_t)tt * sp.n_pad + q] = enc;
+              if (tt == tn) patch = enc;
+            }
+            fence_proxy_async();           // these generic-proxy stores, before the bulk-async reads of later waves
+            patch = __shfl_sync(0xffffffffu, patch, tn & 31);
+          } else {
+            for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
+            fence_proxy_async();
           }
           // the winner's row may already sit, pre-commit, in a stage prefetched for the next wave: wait for that copy, then patch it
           const int off = (int)(w - (long long)oc * p.chunk), tw = off / STREAM_TILE, j = off - tw * STREAM_TILE;
-          if (!RESF && prefetched && tw < NST && tw < tiles && lane == 0) {
+          if (prefetched && tw < NST && tw < tiles && lane == 0) {
             const uint32_t u = uses_next + (uint32_t)tw;
             const int s = (int)(u % NST);
             while (!mbar_try_wait(&ss.full[s], (u / NST) & 1u)) { }
@@ -299,12 +329,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
               reinterpret_cast<long long *>(st + STREAM_TILE * 8)[j] = sp.f_mem[q];
               reinterpret_cast<int32_t *>(st + STREAM_TILE * 16)[j] = sp.f_pods[q];
             }
-            reinterpret_cast<int32_t *>(st + MEMO_OFF)[j] = -1;
+            reinterpret_cast<int32_t *>(st + MEMO_OFF)[j] = RESF ? patch : -1;
           }
         }
       }
     }
     __syncthreads();
+    SPH_MARK(3);                           // commit (owner CTA) + barrier
     if (ss.stop) break;
     wtag = (wtag == 4095u) ? 1u : wtag + 1u;
     tag = (p.epoch << 12) | wtag;
@@ -324,5 +355,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     o->evals = o->waves * (long long)p.n;
     o->examined = o->evals;
     o->aff_total = 0;
+    for (int q = 0; q < 8; q++) o->phase_cycles[q] = ss.ph[q];
+    o->stat[0] = ss.n_stale; o->stat[1] = 0; o->stat[2] = 0;
   }
 }
