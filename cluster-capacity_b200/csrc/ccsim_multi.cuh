@@ -49,7 +49,7 @@
 #endif
 #define MULTI_CAP (32 * MULTI_CPT)
 #define MULTI_BINS 64
-#define MULTI_LPT ((CCSIM_MAX_WORLD * CCSIM_MAX_GRID + LEAN_THREADS - 1) / LEAN_THREADS)   /* node shards: lines polled per thread */
+#define MULTI_XPT (((CCSIM_MAX_WORLD - 1) * MULTI_CAP + LEAN_THREADS - 1) / LEAN_THREADS)   /* node shards: remote candidates per thread */
 
 // cross-GPU line buffers inside every rank's exchange allocation (64-bit words): [parity][source rank][CTA][16]
 #define XLEAN_WORDS (2 * CCSIM_MAX_WORLD * SLOT_STRIDE)
@@ -69,6 +69,8 @@ struct __align__(16) MultiShared {
   int32_t acc_node[MULTI_MAX_ACC];                  // replay: nodes accepted in this wave, in order
   int32_t n_gt, accepted, dead, stopb;
   int32_t single_use, ncand;
+  int32_t xcount[CCSIM_MAX_WORLD];                  // node shards: candidates in each rank's summary
+  uint32_t xglob[4];                                // node shards: best key, T_list, bar over all ranks
   uint32_t delta, pad_ms;
   long long ph[8], tc0, st_cand, st_overflow, st_rounds;       // CTA 0 / thread 0: clock cycles per phase, replay statistics
 };
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
   const int su = lp.stride_u;
   const uint32_t cnt_sa = pin_u32(smem_u32(smem_cnt)), ms_sa = pin_u32(smem_u32(&ms));   // shared bases for the replay's explicit-address accesses
 #define MS_SA(field) (ms_sa + (uint32_t)offsetof(MultiShared, field))
-  const int nlists = (XGPU ? p.world : 1) * p.grid;     // every rank launches the same grid (host: sized from the largest shard)
+  const int nlists = p.grid;                            // lines of this GPU (node shards: every rank launches the same grid, sized from the largest shard)
   const int tot = nlists * MULTI_M;
 
   // ---- stage the tile (once): hot AoS records + cold SoA columns (same layout as the lean kernel) ----
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     __syncthreads();                                                    // S1
     MPH_MARK(1);
     const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
-    const int par = XGPU ? (int)((wv + p.xwave0) & 1) : (int)(wv & 1);
+    const int par = (int)(wv & 1);
     if (warp == 0) {
       // ---- the CTA's M best: merge of the 24 sorted warp lists (lane w walks warp w's list), then publish the pairs ----
       int32_t total = lane < LEAN_WARPS ? ms.wfeas[lane] : 0;
@@ -319,38 +321,21 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       unsigned long long kw = (unsigned long long)mykey;
       if (lane == MULTI_M - 1 && total > L) kw |= 1ull << MULTI_MORE_BIT;
       const int kpos = lane == 0 ? 0 : (lane == MULTI_M - 1 ? 1 : lane + 1);
-      if (!XGPU) {
+      {   // (node shards too: the lines stay on this GPU; what crosses NVLink is one summary per rank, below)
         unsigned long long *myslots = p.slots + ((size_t)par * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
         if (lane < MULTI_M) {
           st_slot(&myslots[kpos], kw | tagbits);
           st_slot(&myslots[MULTI_M + lane], pay | tagbits);
         }
-      } else {
-        // this CTA's line goes into every rank's buffer as ONE 128-byte store per destination (16 lanes x 8 bytes, contiguous):
-        // two destinations per warp instruction, over NVLink
-        const size_t off = XLINES_OFF + (((size_t)par * CCSIM_MAX_WORLD + p.rank) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE;
-        const int wpos = lane & 15;                                                    // word of the line this lane stores
-        const int esrc = wpos >= MULTI_M ? wpos - MULTI_M : (wpos == 0 ? 0 : (wpos == 1 ? MULTI_M - 1 : wpos - 1));   // the entry it carries
-        const unsigned long long kv = __shfl_sync(0xffffffffu, kw, esrc);
-        const unsigned long long pv = __shfl_sync(0xffffffffu, pay, esrc);
-        const unsigned long long word = (wpos >= MULTI_M ? pv : kv) | tagbits;
-        for (int r = lane >> 4; r < p.world; r += 2) st_slot_sys(p.xslots_peer[r] + off + wpos, word);
       }
     }
     MPH_MARK(2);
-    // ---- gather 1: one poller per line and CTA (like the lean kernel) waits for the line's words 0-1; T and the best key ----
-    const unsigned long long *lbase = XGPU ? p.xslots_peer[p.rank] + XLINES_OFF + (size_t)par * CCSIM_MAX_WORLD * CCSIM_MAX_GRID * SLOT_STRIDE
-                                           : p.slots + (size_t)par * CCSIM_MAX_GRID * SLOT_STRIDE;
-    // list l = (source rank l / grid, CTA l % grid) -> its line
-#define LINE_OF(l) (lbase + (XGPU ? ((size_t)((l) / p.grid) * CCSIM_MAX_GRID + (size_t)((l) % p.grid)) : (size_t)(l)) * SLOT_STRIDE)
+    // ---- gather, level 1: the lines of THIS GPU's CTAs. Every thread waits for its own (<= 2) entries — key word and payload word —
+    //      so that the bar and the entries cost ONE L2 round trip after the slowest CTA's line lands ----
+    const unsigned long long *lbase = p.slots + (size_t)par * CCSIM_MAX_GRID * SLOT_STRIDE;
     uint32_t tloc = 0u, kloc = 0u;
-    // Single GPU: every thread waits for its own (<= 2) entries — key word and payload word — so that the bar and the entries cost
-    // ONE L2 round trip after the slowest CTA's line lands (measured in round 1: letting all threads poll their entries is no slower
-    // than 5 polling warps). Node shards: world x grid x 8 entries do not fit in registers; one poller per line, entries afterwards.
-    constexpr bool ONEPASS = !XGPU;
     unsigned long long ea[2] = {0ull, 0ull}, eb[2] = {0ull, 0ull};
-    uint32_t lk0[MULTI_LPT] = {};             // node shards: best key of the lines this thread polled
-    if (ONEPASS) {
+    {
       const unsigned long long *pa[2], *pb[2];
       bool need[2];
       #pragma unroll
@@ -376,84 +361,27 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           if (ee == MULTI_M - 1 && ((ea[u] >> MULTI_MORE_BIT) & 1ull)) tloc = max(tloc, (uint32_t)ea[u]);
         }
       }
-    } else {
-      // node shards: thread t polls words 0-1 (best key; last key + "more") of lines t and t + LEAN_THREADS and keeps their best keys
-      bool need[MULTI_LPT];
-      unsigned long long a[MULTI_LPT], b[MULTI_LPT];
-      #pragma unroll
-      for (int u = 0; u < MULTI_LPT; u++) { need[u] = tid + u * LEAN_THREADS < nlists; a[u] = b[u] = 0ull; }
-      unsigned spins = 0;
-      for (;;) {
-        bool any = false;
-        #pragma unroll
-        for (int u = 0; u < MULTI_LPT; u++) if (need[u]) ld_line2<XGPU>(LINE_OF(tid + u * LEAN_THREADS), a[u], b[u]);
-        #pragma unroll
-        for (int u = 0; u < MULTI_LPT; u++) {
-          if (need[u] && (uint32_t)(a[u] >> KEY_TAG_SHIFT) == tag && (uint32_t)(b[u] >> KEY_TAG_SHIFT) == tag) need[u] = false;
-          any |= need[u];
-        }
-        if (!any) break;
-        if (++spins > WATCHDOG_SPINS) { ms.dead = 1; for (int u = 0; u < MULTI_LPT; u++) if (need[u]) a[u] = b[u] = 0ull; break; }
-      }
-      #pragma unroll
-      for (int u = 0; u < MULTI_LPT; u++) {
-        lk0[u] = (uint32_t)a[u];
-        kloc = max(kloc, (uint32_t)a[u]);
-        if ((b[u] >> MULTI_MORE_BIT) & 1ull) tloc = max(tloc, (uint32_t)b[u]);
-      }
     }
     tloc = __reduce_max_sync(0xffffffffu, tloc);
     kloc = __reduce_max_sync(0xffffffffu, kloc);
     if (lane == 0) { ms.red[warp] = tloc; ms.red2[warp] = kloc; }
     __syncthreads();                                                    // G1 (also: ms.dead)
-    const uint32_t Tlist = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? ms.red[lane] : 0u);
-    const uint32_t kbest = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? ms.red2[lane] : 0u);
-    const bool dead = ms.dead != 0;
+    uint32_t Tlist = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? ms.red[lane] : 0u);
+    uint32_t kbest = __reduce_max_sync(0xffffffffu, lane < LEAN_WARPS ? ms.red2[lane] : 0u);
+    bool dead = ms.dead != 0;
     // The replay bar: T = the largest "last key" of a list whose tile has unseen feasible nodes is the lowest VALID bar; any
     // higher bar is valid too, just more conservative. The replay holds MULTI_CAP candidates, and it rarely needs more than the
     // best few dozen before a PTS minimum moves, so the bar is set `delta` below the best key (never below T); delta follows the
     // previous waves (doubled when the replay ran out of candidates above an artificial bar, shrunk when too many qualified).
     // Every CTA of every rank computes the same sequence from the same exchanged data.
     uint32_t T = max(Tlist, kbest > delta ? kbest - delta : 0u);
-    // ---- gather 2: fetch the entries keyed >= T into shared memory (unordered; keys are unique) ----
+    // ---- the entries keyed >= T go into shared memory (unordered; keys are unique) ----
     int C = 0;
-    const int iters = (tot + LEAN_THREADS - 1) / LEAN_THREADS;
     for (int pass = 0; pass < 2 && !dead; pass++) {
-      if (ONEPASS) {                        // the entries are in registers already (both passes)
-        #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const uint32_t ck = (uint32_t)ea[u];
-          if (u * LEAN_THREADS < tot) multi_append(ck != 0u && ck >= T, ck, eb[u], lane);      // (warp-uniform guard: warps beyond the entries skip)
-        }
-      } else
-      {
-        // Node shards: only the lines whose BEST key reaches the bar hold candidates (a few dozen of world x grid lines), and their
-        // pollers know which. A warp takes its qualifying lines four at a time: 8 lanes per line, lane -> entry, key word and
-        // payload word requested together (one L2 round trip; the line arrived as one 128-byte store, the tags are checked anyway).
-        #pragma unroll
-        for (int u = 0; u < MULTI_LPT; u++) {
-          unsigned m = __ballot_sync(0xffffffffu, lk0[u] != 0u && lk0[u] >= T);
-          while (m) {                                   // warp-uniform
-            const int src = nth_set_lane(m, lane >> 3);          // the (lane / 8)-th qualifying lane of the warp, or -1
-            const bool on = src >= 0;
-            const int ee = lane & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
-            unsigned long long a = 0ull, b = 0ull;
-            bool keep = false;
-            if (on) {
-              const unsigned long long *ln = LINE_OF(warp * 32 + src + u * LEAN_THREADS);
-              unsigned spins = 0;
-              for (;;) {
-                a = ld_slot_sys(ln + kp); b = ld_slot_sys(ln + MULTI_M + ee);
-                if ((uint32_t)(a >> KEY_TAG_SHIFT) == tag && (uint32_t)(b >> KEY_TAG_SHIFT) == tag) break;
-                if (++spins > WATCHDOG_SPINS) { ms.dead = 1; a = b = 0ull; break; }
-              }
-              keep = (uint32_t)a != 0u && (uint32_t)a >= T;
-            }
-            multi_append(keep, (uint32_t)a, b, lane);
-            #pragma unroll
-            for (int g = 0; g < 4; g++) if (m) m &= m - 1;          // the four lowest qualifying lanes are done
-          }
-        }
+      #pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const uint32_t ck = (uint32_t)ea[u];
+        if (u * LEAN_THREADS < tot) multi_append(ck != 0u && ck >= T, ck, eb[u], lane);      // (warp-uniform guard: warps beyond the entries skip)
       }
       __syncthreads();                                                  // G2
       C = ms.ncand;
@@ -463,30 +391,10 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       if (tid < MULTI_BINS) ms.hist[tid] = 0u;
       __syncthreads();
       const unsigned long long range = (unsigned long long)(kbest - T) + 1ull;
-      if (!XGPU) {
-        for (int it = 0; it < iters; it++) {
-          const int e = tid + it * LEAN_THREADS;
-          if (e < tot) {
-            const int ee = e & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
-            const uint32_t ck = (uint32_t)ld_slot(LINE_OF(e >> 3) + kp);     // validated above
-            if (ck != 0u && ck >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(ck - T) * MULTI_BINS) / range)], 1u);
-          }
-        }
-      } else {
-        #pragma unroll
-        for (int u = 0; u < MULTI_LPT; u++) {
-          unsigned m = __ballot_sync(0xffffffffu, lk0[u] != 0u && lk0[u] >= T);
-          while (m) {
-            const int src = nth_set_lane(m, lane >> 3);
-            if (src >= 0) {
-              const int ee = lane & (MULTI_M - 1), kp = ee == 0 ? 0 : (ee == MULTI_M - 1 ? 1 : ee + 1);
-              const uint32_t ck = (uint32_t)ld_slot_sys(LINE_OF(warp * 32 + src + u * LEAN_THREADS) + kp);     // validated above
-              if (ck != 0u && ck >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(ck - T) * MULTI_BINS) / range)], 1u);
-            }
-            #pragma unroll
-            for (int g = 0; g < 4; g++) if (m) m &= m - 1;
-          }
-        }
+      #pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const uint32_t ck = (uint32_t)ea[u];
+        if (ck != 0u && ck >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(ck - T) * MULTI_BINS) / range)], 1u);
       }
       __syncthreads();
       int bsel = MULTI_BINS;
@@ -496,6 +404,101 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       if (tid == 0) ms.ncand = 0;
       if (cta == 0 && tid == 0) ms.st_overflow++;
       __syncthreads();
+    }
+    if (XGPU) {
+      // ---- gather, level 2 (node shards): every rank now holds ITS candidates keyed >= its bar T_r (<= MULTI_CAP of them, the same in
+      //      all of its CTAs). One summary per (source, destination) pair crosses NVLink — {best key, count, T_r, T_list_r, the
+      //      candidates} written by ONE CTA of the source as a few 128-byte stores — instead of every CTA's line going to every
+      //      rank and world x grid lines being polled by every CTA. The global bar max(max_r T_r, best - delta) is at least every
+      //      rank's own bar, so the union of the summaries holds every node keyed above it: same candidates as one GPU would see. ----
+      const int xpar = (int)((wv + p.xwave0) & 1);
+      const int Cl = C < MULTI_CAP ? C : MULTI_CAP;
+      uint32_t lkey = 0u; unsigned long long lpay = 0ull;        // this rank's candidate `tid`, kept across the shared-memory rebuild
+      if (tid < Cl) { lkey = ms.ckey[tid]; lpay = (unsigned long long)ms.cdom[tid] | ((unsigned long long)ms.cnext[tid] << MULTI_NEXT_SHIFT); }
+      if (!dead)
+        for (int d = cta; d < p.world; d += p.grid) {            // CTA d of the source writes the copy for rank d
+          if (d == p.rank) continue;
+          unsigned long long *dst = p.xslots_peer[d] + XLINES_OFF + ((size_t)xpar * CCSIM_MAX_WORLD + p.rank) * CCSIM_MAX_GRID * SLOT_STRIDE;
+          if (tid < 4 + 2 * Cl) {
+            unsigned long long v;
+            if (tid == 0) v = (unsigned long long)kbest | ((unsigned long long)Cl << 32);
+            else if (tid == 1) v = T;
+            else if (tid == 2) v = Tlist;
+            else if (tid == 3) v = 0ull;
+            else { const int ci = (tid - 4) >> 1; v = (tid & 1) ? ((unsigned long long)ms.cdom[ci] | ((unsigned long long)ms.cnext[ci] << MULTI_NEXT_SHIFT)) : (unsigned long long)ms.ckey[ci]; }
+            st_slot_sys(dst + tid, v | tagbits);
+          }
+        }
+      __syncthreads();                                                  // X0: the local candidates are in registers / on their way
+      if (tid == 0) ms.ncand = 0;
+      uint32_t xkb = kbest, xtl = Tlist, xbar = T;
+      if (tid < p.world) {
+        int cr = 0;
+        if (tid != p.rank && !dead) {
+          const unsigned long long *src = p.xslots_peer[p.rank] + XLINES_OFF + ((size_t)xpar * CCSIM_MAX_WORLD + tid) * CCSIM_MAX_GRID * SLOT_STRIDE;
+          unsigned long long a, b, c2;
+          unsigned spins = 0;
+          for (;;) {
+            ld_line2<true>(src, a, b); c2 = ld_slot_sys(src + 2);
+            if ((uint32_t)(a >> KEY_TAG_SHIFT) == tag && (uint32_t)(b >> KEY_TAG_SHIFT) == tag && (uint32_t)(c2 >> KEY_TAG_SHIFT) == tag) break;
+            if (++spins > WATCHDOG_SPINS) { ms.dead = 1; a = b = c2 = 0ull; break; }
+          }
+          xkb = (uint32_t)a; cr = (int)((a >> 32) & 0xffu); xbar = (uint32_t)b; xtl = (uint32_t)c2;
+          if (cr > MULTI_CAP) cr = MULTI_CAP;
+        }
+        ms.xcount[tid] = cr;
+      }
+      if (warp == 0) {       // (world <= 32: the pollers are lanes of warp 0; the other lanes carry this rank's own values)
+        xkb = __reduce_max_sync(0xffffffffu, xkb); xtl = __reduce_max_sync(0xffffffffu, xtl); xbar = __reduce_max_sync(0xffffffffu, xbar);
+        if (lane == 0) { ms.xglob[0] = xkb; ms.xglob[1] = xtl; ms.xglob[2] = xbar; }
+      }
+      __syncthreads();                                                  // X1
+      dead = ms.dead != 0;
+      kbest = ms.xglob[0]; Tlist = ms.xglob[1];
+      T = max(ms.xglob[2], kbest > delta ? kbest - delta : 0u);
+      // the other ranks' candidates: entry e of the concatenated summaries -> (rank, index); <= 2 per thread
+      uint32_t rkey[MULTI_XPT]; unsigned long long rpay[MULTI_XPT];
+      #pragma unroll
+      for (int u = 0; u < MULTI_XPT; u++) {
+        rkey[u] = 0u; rpay[u] = 0ull;
+        int e = tid + u * LEAN_THREADS, r = 0;
+        while (r < p.world && e >= ms.xcount[r]) { e -= ms.xcount[r]; r++; }
+        if (r < p.world && !dead) {
+          const unsigned long long *src = p.xslots_peer[p.rank] + XLINES_OFF + ((size_t)xpar * CCSIM_MAX_WORLD + r) * CCSIM_MAX_GRID * SLOT_STRIDE + 4 + 2 * e;
+          unsigned long long a, b;
+          unsigned spins = 0;
+          for (;;) {
+            ld_line2<true>(src, a, b);
+            if ((uint32_t)(a >> KEY_TAG_SHIFT) == tag && (uint32_t)(b >> KEY_TAG_SHIFT) == tag) break;
+            if (++spins > WATCHDOG_SPINS) { ms.dead = 1; a = b = 0ull; break; }
+          }
+          rkey[u] = (uint32_t)a; rpay[u] = b;
+        }
+      }
+      for (int pass = 0; pass < 2; pass++) {
+        multi_append(lkey != 0u && lkey >= T, lkey, lpay, lane);
+        #pragma unroll
+        for (int u = 0; u < MULTI_XPT; u++) multi_append(rkey[u] != 0u && rkey[u] >= T, rkey[u], rpay[u], lane);
+        __syncthreads();                                                // X2
+        C = ms.ncand;
+        if (C <= MULTI_CAP || pass == 1) break;
+        if (tid < MULTI_BINS) ms.hist[tid] = 0u;
+        __syncthreads();
+        const unsigned long long range = (unsigned long long)(kbest - T) + 1ull;
+        if (lkey != 0u && lkey >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(lkey - T) * MULTI_BINS) / range)], 1u);
+        #pragma unroll
+        for (int u = 0; u < MULTI_XPT; u++)
+          if (rkey[u] != 0u && rkey[u] >= T) atomicAdd(&ms.hist[(unsigned)(((unsigned long long)(rkey[u] - T) * MULTI_BINS) / range)], 1u);
+        __syncthreads();
+        int bsel = MULTI_BINS;
+        { unsigned sum = 0; for (int bq = MULTI_BINS - 1; bq >= 0; bq--) { sum += ms.hist[bq]; if (sum > (unsigned)MULTI_CAP) break; bsel = bq; } }
+        T = (bsel >= MULTI_BINS) ? kbest : T + (uint32_t)(((unsigned long long)bsel * range + (MULTI_BINS - 1)) / MULTI_BINS);
+        __syncthreads();
+        if (tid == 0) ms.ncand = 0;
+        if (cta == 0 && tid == 0) ms.st_overflow++;
+        __syncthreads();
+      }
+      dead = dead || ms.dead != 0;
     }
     const bool overflowed = C > MULTI_CAP || T > max(Tlist, kbest > delta ? kbest - delta : 0u);
     if (C > MULTI_CAP) C = MULTI_CAP;     // (cannot happen after the second pass: the raised T admits <= MULTI_CAP keys)
