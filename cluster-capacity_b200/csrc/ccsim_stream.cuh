@@ -48,7 +48,7 @@ struct __align__(16) StreamShared {
   StreamTmpl tc[CCSIM_MAX_TEMPLATES];
   unsigned long long full[STREAM_STAGES_RES];  // mbarriers: "the stage's bytes have landed"
   unsigned long long warp_best[STREAM_WARPS];
-  int32_t winner, stop, pad[2];
+  int32_t winner, stop, commit_seq, pad;
   long long ph[8], tc0, n_stale;   // CTA 0 / thread 0: clock cycles per phase; stale memo entries re-scored by CTA 0
 };
 
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
   if (tid == 0) {
     for (int s = 0; s < NST; s++) mbar_init(&ss.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    ss.winner = -1; ss.stop = 0;
+    ss.winner = -1; ss.stop = 0; ss.commit_seq = 0;
     for (int q = 0; q < 8; q++) ss.ph[q] = 0;
     ss.n_stale = 0;
   }
@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
 
   long long k = 0;
   bool limit_hit = false;
+  int pend_off = -1;                 // owner CTA: chunk offset of the node whose commit may still be under way when this pass starts
   bool prefetched = false;           // the first tiles of the coming wave were requested at the end of the last one
   uint32_t uses = 0;                 // tiles consumed so far by this CTA (all waves): stage = uses % STAGES, parity = (uses / STAGES) & 1
   uint32_t wtag = 1;
@@ -198,9 +199,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     SPH_START();
     unsigned long long best = 0ull;
     bool wrote = false;
-    for (int tile = 0; tile < tiles; tile++, uses++) {
-      const int s = (int)(uses % NST);
-      const uint32_t parity = (uses / NST) & 1u;
+    // in the owner CTA of the last commit the pass starts behind the winner's tile (the whole chunk is in flight: any order works),
+    // so that the commit — running in warp 0 meanwhile — is over long before anybody needs that node
+    const uint32_t ubase = uses;
+    const int rot = (all_in_flight && pend_off >= 0) ? pend_off / STREAM_TILE + 1 : 0;
+    for (int tq = 0; tq < tiles; tq++, uses++) {
+      const int tile = (tq + rot >= tiles) ? tq + rot - tiles : tq + rot;
+      const uint32_t use = ubase + (uint32_t)tile;
+      const int s = (int)(use % NST);
+      const uint32_t parity = (use / NST) & 1u;
       while (!mbar_try_wait(&ss.full[s], parity)) { }
       const unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
       const long long *s_fcpu = RESF ? r_fcpu + tile * STREAM_TILE : reinterpret_cast<const long long *>(st);
@@ -209,6 +216,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       const int32_t *s_memo = reinterpret_cast<const int32_t *>(st + MEMO_OFF);
       #pragma unroll
       for (int j = tid; j < STREAM_TILE; j += STREAM_THREADS) {
+        const int off = tile * STREAM_TILE + j;
+        if (off == pend_off) {           // the node committed a moment ago: its row, generation and memo entry are being written by warp 0
+          while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
+          __threadfence_block();
+        }
         // NodeResourcesFit (+ NodeUnschedulable / TaintToleration / nodeSelector / NodePorts / existing anti-affinity bits)
         bool ok = (s_fcpu[j] >= eq_cpu) & (s_fmem[j] >= eq_mem) & (s_fpods[j] >= pods_need);
         if (MASKS) {
@@ -217,7 +229,6 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
           ok &= ((taint0 & taint_bad0) | (~static0 & sel0) | (static0 & forbid0)) == 0ull;
         }
         if (ok) {
-          const int off = tile * STREAM_TILE + j;
           const long long i = (long long)cta * p.chunk + off;        // shard-local node index
           int32_t sc = s_memo[j];
           const int32_t gen = RESF ? r_gen[off] : 0;
@@ -270,17 +281,25 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
         else if (wkey == 0ull) { ss.stop = 1; ss.winner = -1; }
         else ss.winner = (int32_t)key_index(wkey);
       }
-      // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) by the owner CTA ----
-      if (!dead && wkey != 0ull) {
-        const int32_t w = (int32_t)key_index(wkey) - p.node_base;
-        const bool local = w >= 0 && w < p.n;
-        const int oc = local ? w / p.chunk : -1;
-        if (!local && cta == 0 && lane == 0) {      // sharded run: every rank keeps the whole pod -> node sequence
-          if (k < p.pod_cap) p.pod_node[k] = (int32_t)key_index(wkey); else ss.stop = 3;
-        }
+      if (lane == 0 && !dead && wkey != 0ull && k >= p.pod_cap) ss.stop = 3;     // no room to record the placement
+    }
+    __syncthreads();
+    SPH_MARK(3);                           // barrier: the winner is known to every thread
+    if (ss.stop) break;
+    // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) by warp 0 of the owner CTA,
+    //      AFTER the barrier: the other warps are already scanning for the next wave. Only the thread that scans the committed node
+    //      itself has to wait for the commit (ss.commit_seq); in the owner CTA the pass starts behind the winner's tile. ----
+    pend_off = -1;
+    {
+      const int32_t w = ss.winner - p.node_base;
+      const bool local = w >= 0 && w < p.n;
+      const int oc = local ? w / p.chunk : -1;
+      if (oc == cta) pend_off = (int)(w - (long long)oc * p.chunk);
+      if (warp == 0) {
+        if (!local && cta == 0 && lane == 0) p.pod_node[k] = ss.winner;      // sharded run: every rank keeps the whole pod -> node sequence
         if (oc == cta) {
           const long long q = base + (w - (long long)oc * p.chunk);
-          const int roff = (int)(w - (long long)oc * p.chunk);
+          const int roff = pend_off;
           // the committed row (types.go:409-427): every lane reads the six columns (one L2 round trip, broadcast), lanes 1..5 write
           // one column each through to global memory (the terminal diagnosis reads it), lane 0 keeps the streamed / resident copy
           const long long a_cpu = p.alloc_cpu[w], a_mem = p.alloc_mem[w];
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
           if (lane == 0) {
             if (RESF) { r_fcpu[roff] -= c.req_cpu; r_fmem[roff] -= c.req_mem; r_fpods[roff] -= 1; newgen = (r_gen[roff] + 1) & 0x7ffff; r_gen[roff] = newgen; }
             else { sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1; }
-            if (k < p.pod_cap) p.pod_node[k] = w + p.node_base; else ss.stop = 3;
+            p.pod_node[k] = w + p.node_base;
           }
           if (lane == 1) p.req_cpu[w] = n_rcpu;
           else if (lane == 2) p.req_mem[w] = n_rmem;
@@ -318,7 +337,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
             fence_proxy_async();
           }
           // the winner's row may already sit, pre-commit, in a stage prefetched for the next wave: wait for that copy, then patch it
-          const int off = (int)(w - (long long)oc * p.chunk), tw = off / STREAM_TILE, j = off - tw * STREAM_TILE;
+          const int off = roff, tw = off / STREAM_TILE, j = off - tw * STREAM_TILE;
           if (prefetched && tw < NST && tw < tiles && lane == 0) {
             const uint32_t u = uses_next + (uint32_t)tw;
             const int s = (int)(u % NST);
@@ -331,12 +350,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
             }
             reinterpret_cast<int32_t *>(st + MEMO_OFF)[j] = RESF ? patch : -1;
           }
+          __threadfence_block();
+          __syncwarp();                      // the lanes' column stores, before lane 0 announces the commit
+          if (lane == 0) *reinterpret_cast<volatile int32_t *>(&ss.commit_seq) = (int32_t)(k + 1);
         }
       }
     }
-    __syncthreads();
-    SPH_MARK(3);                           // commit (owner CTA) + barrier
-    if (ss.stop) break;
     wtag = (wtag == 4095u) ? 1u : wtag + 1u;
     tag = (p.epoch << 12) | wtag;
   }
