@@ -1383,7 +1383,7 @@ static int run_prepare(ccsim_handle *h, int64_t max_pods) {
     CK(cudaGetLastError());
     // resident free_* columns when the chunk fits next to the memo ring (20 B per node: up to ~10k nodes per SM)
     const size_t smem_resf = (size_t)STREAM_STAGES_RES * STREAM_TILE * 4 + (size_t)sp.chunk_pad * 24 + 128;
-    stream_mode = masks ? 1 : ((smem_resf + sizeof(StreamShared) + 1024 <= h->smem_optin && !getenv("CCSIM_STREAM_ALL")) ? 2 : 0);
+    stream_mode = masks ? 1 : ((smem_resf + sizeof(StreamShared) + 1024 <= h->smem_optin && sp.tiles <= STREAM_STAGES_RES && !getenv("CCSIM_STREAM_ALL")) ? 2 : 0);
     kern = stream_mode == 1 ? (const void *)ccsim_wave_stream_kernel<1> : stream_mode == 2 ? (const void *)ccsim_wave_stream_kernel<2> : (const void *)ccsim_wave_stream_kernel<0>;
     smem = stream_mode == 2 ? smem_resf : (size_t)STREAM_STAGES * STREAM_TILE * (masks ? 40 : 24) + 128;
     block = STREAM_THREADS;
@@ -1446,6 +1446,16 @@ extern "C" int ccsim_run(ccsim_handle *h, int64_t max_pods, ccsim_result *out) {
   CK(cudaStreamSynchronize(s));
   if (ho.error) return fail(h, CCSIM_ECUDA, "wave kernel aborted (error %d: %s)", ho.error, ho.error == 1 ? "exchange watchdog / output overflow" : "?");
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (stream && (p.debug_flags & 8u) && h->cfg.world == 1 && ho.waves > 0) {     // per-CTA cycle split of the streaming kernel (kernel experiments)
+    std::vector<unsigned long long> d((size_t)grid * 4);
+    CK(cudaMemcpy(d.data(), h->d_xslots + XLINES_OFF, d.size() * 8, cudaMemcpyDeviceToHost));
+    const char *nm[4] = {"mbarrier wait", "scan", "exchange", "rest"};
+    for (int q = 0; q < 4; q++) {
+      double mn = 1e30, mx = 0, sum = 0; int amx = 0, amn = 0;
+      for (int c = 0; c < grid; c++) { const double v = (double)d[(size_t)c * 4 + q] / (double)ho.waves; sum += v; if (v > mx) { mx = v; amx = c; } if (v < mn) { mn = v; amn = c; } }
+      fprintf(stderr, "[ccsim stream per-CTA cycles/wave] %-14s min %.0f (CTA %d)  mean %.0f  max %.0f (CTA %d)\n", nm[q], mn, amn, sum / grid, mx, amx);
+    }
+  }
 #ifdef CCSIM_PHASE_TIMERS
   fprintf(stderr, "[ccsim %s tile %zu B smem] ", multi ? "multi" : batched ? "batched" : (lean ? "lean" : (resident ? "resident" : "streaming")), smem);
   fprintf(stderr, "[ccsim phases, CTA0 cycles/wave] scan=%.0f S1=%.0f publish=%.0f gather=%.0f commit=%.0f S2=%.0f (waves=%lld, %.3f ms)\n",

@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
 
   long long k = 0;
   bool limit_hit = false;
+  long long dbg_t = 0, dbg_wait = 0, dbg_scan = 0, dbg_xchg = 0, dbg_rest = 0;    // CCSIM_DEBUG_FLAGS & 8: this CTA's cycle split (thread 0)
+  const bool dbg = (p.debug_flags & 8u) != 0u && tid == 0;
   int pend_off = -1;                 // owner CTA: chunk offset of the node whose commit may still be under way when this pass starts
   bool prefetched = false;           // the first tiles of the coming wave were requested at the end of the last one
   uint32_t uses = 0;                 // tiles consumed so far by this CTA (all waves): stage = uses % STAGES, parity = (uses / STAGES) & 1
@@ -197,11 +199,57 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       for (int q = 0; q < NST && q < tiles; q++) issue(q, (int)((uses + q) % NST), t);
     }
     SPH_START();
+    if (dbg) { const long long c0 = clock64(); if (dbg_t) dbg_rest += c0 - dbg_t; dbg_t = c0; }
     unsigned long long best = 0ull;
     bool wrote = false;
+    const uint32_t ubase = uses;
+    if (RESF) {
+      // ---- resident columns: the whole chunk's memo column is in flight (tile q in stage q: `uses` advances by the ring size per
+      //      wave), so the pass is ONE flat loop over the chunk with a 32-bit local key (score + 1 : 12 | ~offset : 20 — same order as
+      //      pack_key inside a CTA: highest score, then lowest index) and ~20 instructions per node; the pass is issue-bound. In the
+      //      owner CTA of the last commit it starts behind the winner's tile, so that the commit — running in warp 0 meanwhile —
+      //      is over long before anybody needs that node. ----
+      const uint32_t parity = (ubase / NST) & 1u;
+      for (int q = 0; q < tiles; q++) while (!mbar_try_wait(&ss.full[q], parity)) { }
+      if (dbg) { const long long c0 = clock64(); dbg_wait += c0 - dbg_t; dbg_t = c0; }
+      const int32_t *memo_s = reinterpret_cast<const int32_t *>(smem_raw);      // stage q = tile q: contiguous
+      const int cpad = sp.chunk_pad;
+      int off = tid + ((pend_off >= 0) ? (pend_off / STREAM_TILE + 1) * STREAM_TILE : 0);
+      if (off >= cpad) off -= cpad;
+      uint32_t best32 = 0u;
+      #pragma unroll 2
+      for (int it = 0; it < cpad; it += STREAM_THREADS) {
+        if (off == pend_off) {           // the node committed a moment ago: its row, generation and memo entry are being written by warp 0
+          while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
+          __threadfence_block();
+        }
+        const bool ok = (r_fcpu[off] >= eq_cpu) & (r_fmem[off] >= eq_mem) & (r_fpods[off] >= pods_need);
+        int32_t enc = memo_s[off];
+        const int32_t gen = r_gen[off];
+        if (ok) {
+          if ((enc >> 12) != gen) {      // never scored by this template (the run's first T waves), or — not since the owner re-scores at commit — stale
+            const long long i = (long long)cta * p.chunk + off;
+            const int32_t sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
+                                          p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
+            enc = (gen << 12) | (sc + 1);
+            sp.memo[(size_t)t * sp.n_pad + base + off] = enc;
+            if (cta == 0) atomicAdd((unsigned long long *)&ss.n_stale, 1ull);
+            wrote = true;                // fenced once after the pass (a later bulk-async read of this column must see the store)
+          }
+          const uint32_t key32 = ((uint32_t)(enc & 0xfff) << 20) | (0xfffffu - (uint32_t)off);
+          best32 = max(best32, key32);
+        }
+        off += STREAM_THREADS;
+        if (off >= cpad) off -= cpad;
+      }
+      if (best32) {
+        const int boff = (int)(0xfffffu - (best32 & 0xfffffu));
+        best = pack_key((int32_t)(best32 >> 20) - 1, (uint32_t)(p.node_base + (long long)cta * p.chunk + boff));
+      }
+      uses = ubase + NST;
+    } else {
     // in the owner CTA of the last commit the pass starts behind the winner's tile (the whole chunk is in flight: any order works),
     // so that the commit — running in warp 0 meanwhile — is over long before anybody needs that node
-    const uint32_t ubase = uses;
     const int rot = (all_in_flight && pend_off >= 0) ? pend_off / STREAM_TILE + 1 : 0;
     for (int tq = 0; tq < tiles; tq++, uses++) {
       const int tile = (tq + rot >= tiles) ? tq + rot - tiles : tq + rot;
@@ -250,7 +298,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
         if (tid == 0 && tile + NST < tiles) issue(tile + NST, s, t);
       }
     }
+    }
     if (wrote) fence_proxy_async();
+    if (dbg) { const long long c0 = clock64(); dbg_scan += c0 - dbg_t; dbg_t = c0; }
     SPH_MARK(0);                           // scan: mbarrier waits + Filter/arg-max over the chunk
     if (all_in_flight) __syncthreads();    // no stage was reused inside the pass: one barrier before the stages are re-armed
     // The first tiles of the NEXT wave are requested now, so that the copy engine works while the exchange is in flight. They may
@@ -268,6 +318,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     }
     __syncthreads();
     SPH_MARK(1);                           // block barriers, next wave's bulk copies issued, block arg-max
+    if (dbg) { const long long c0 = clock64(); dbg_rest += c0 - dbg_t; dbg_t = c0; }
     if (warp == 0) {
       const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
       const unsigned long long mine = warp_max_u64(lane < STREAM_WARPS ? ss.warp_best[lane] : 0ull);
@@ -275,6 +326,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       unsigned long long wkey = exchange_max(p, k, tag, 0, mine, lane, cta, dead);
       (void)tagbits;
       if (p.world > 1 && !dead) { unsigned long long cb[1] = {wkey}; dead = cross_gpu_exchange(p, k, tag, 1, cb, lane, cta); wkey = cb[0]; }   // node shards: winners of all ranks
+      if (dbg) { const long long c0 = clock64(); dbg_xchg += c0 - dbg_t; dbg_t = c0; }
       SPH_MARK(2);                         // exchange: own key stored, every CTA's key polled (L2 round trip + the slowest CTA)
       if (lane == 0) {
         if (dead) { ss.stop = 3; ss.winner = -1; }
@@ -365,6 +417,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
       while (!mbar_try_wait(&ss.full[u % NST], (u / NST) & 1u)) { }
     }
   __syncthreads();
+  if (dbg && p.world == 1) {          // per-CTA cycle split into the (unused at world 1) cross-GPU line buffer: the host prints min / mean / max
+    unsigned long long *d = p.xslots_peer[p.rank] + XLINES_OFF + (size_t)cta * 4;
+    d[0] = (unsigned long long)dbg_wait; d[1] = (unsigned long long)dbg_scan; d[2] = (unsigned long long)dbg_xchg; d[3] = (unsigned long long)dbg_rest;
+  }
   if (cta == 0 && tid == 0) {
     DevOut *o = p.out;
     o->placed = k;
