@@ -1386,7 +1386,7 @@ static int run_prepare(ccsim_handle *h, int64_t max_pods) {
     stream_mode = masks ? 1 : ((smem_resf + sizeof(StreamShared) + 1024 <= h->smem_optin && sp.tiles <= STREAM_STAGES_RES && !getenv("CCSIM_STREAM_ALL")) ? 2 : 0);
     kern = stream_mode == 1 ? (const void *)ccsim_wave_stream_kernel<1> : stream_mode == 2 ? (const void *)ccsim_wave_stream_kernel<2> : (const void *)ccsim_wave_stream_kernel<0>;
     smem = stream_mode == 2 ? smem_resf : (size_t)STREAM_STAGES * STREAM_TILE * (masks ? 40 : 24) + 128;
-    block = STREAM_THREADS;
+    block = STREAM_BLOCK;
   }
   h->last_stream = stream ? 1 : 0;
   p.self = h->d_params;

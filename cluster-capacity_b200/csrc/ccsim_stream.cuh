@@ -21,6 +21,7 @@
 
 #define STREAM_THREADS 512
 #define STREAM_WARPS (STREAM_THREADS / 32)
+#define STREAM_BLOCK (STREAM_THREADS + 32)   /* + the service warp: bulk-copy requests, exchange, commit */
 #define STREAM_TILE 1024          /* nodes per stage: 24 KB (40 KB with the mask columns) */
 #define STREAM_STAGES 4           /* stages of the ring when every column is streamed */
 #define STREAM_STAGES_RES 8       /* ... when only the 4-byte memo column is streamed (resident free_* columns): a whole 1M-node chunk (7 tiles) in flight */
@@ -96,7 +97,7 @@ __global__ void ccsim_stream_prep_kernel(const DevParams p, const StreamParams s
 // shared memory for the whole run (20 B per node: 1M nodes fit in the 148 SMs' shared memory) and only the score memo column of the
 // wave's template is streamed (4 B per node and wave)
 template <int MODE>
-__global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(const DevParams p, const StreamParams sp) {
+__global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(const DevParams p, const StreamParams sp) {
   constexpr bool MASKS = MODE == 1, RESF = MODE == 2;
   constexpr int NST = RESF ? STREAM_STAGES_RES : STREAM_STAGES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     c.sw.least_w_cpu = tp.least_w_cpu; c.sw.least_w_mem = tp.least_w_mem;
   }
   if (RESF)
-    for (int j = threadIdx.x; j < sp.chunk_pad; j += STREAM_THREADS) {
+    for (int j = threadIdx.x; j < sp.chunk_pad; j += STREAM_BLOCK) {
       r_fcpu[j] = sp.f_cpu[(long long)blockIdx.x * sp.chunk_pad + j]; r_fmem[j] = sp.f_mem[(long long)blockIdx.x * sp.chunk_pad + j];
       r_fpods[j] = sp.f_pods[(long long)blockIdx.x * sp.chunk_pad + j];
       r_gen[j] = 0;
@@ -179,175 +180,192 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
   bool limit_hit = false;
   long long dbg_t = 0, dbg_wait = 0, dbg_scan = 0, dbg_xchg = 0, dbg_rest = 0;    // CCSIM_DEBUG_FLAGS & 8: this CTA's cycle split (thread 0)
   const bool dbg = (p.debug_flags & 8u) != 0u && tid == 0;
+  // Warp specialisation: warps 0..15 scan; warp 16 — the SERVICE warp — requests the bulk copies, runs the exchange and commits.
+  // A wave's critical path is then scan -> barrier A -> publish / poll (one L2 round trip) -> barrier B -> next scan; the commit
+  // (row columns from L2, 64 re-scores with their divisions, 64 memo stores, a proxy fence: several thousand cycles in the owner
+  // CTA) overlaps the next pass instead of delaying the owner's next key, which every other CTA waits for.
+  const bool service = warp == STREAM_WARPS;
   int pend_off = -1;                 // owner CTA: chunk offset of the node whose commit may still be under way when this pass starts
   bool prefetched = false;           // the first tiles of the coming wave were requested at the end of the last one
+  long long pf_wave = 0;             // ... the wave they were requested for
   uint32_t uses = 0;                 // tiles consumed so far by this CTA (all waves): stage = uses % STAGES, parity = (uses / STAGES) & 1
   uint32_t wtag = 1;
   uint32_t tag = (p.epoch << 12) | wtag;
   const int tiles = sp.tiles;
   const bool all_in_flight = tiles <= NST;     // the whole chunk fits in the ring: no stage is reused within a pass
+  // RESF: the whole memo column of a wave lands on ONE mbarrier (full[0]); otherwise one barrier per stage
+  auto request_first_tiles = [&](uint32_t ubase_, int t_) {
+    fence_proxy_async();              // generic-proxy stores (commits, scorers) before the engine reads them
+    if (RESF) {
+      mbar_expect_tx(&ss.full[0], (uint32_t)tiles * STAGE_BYTES);
+      for (int q = 0; q < tiles; q++)
+        bulk_g2s(smem_raw + (size_t)q * STAGE_BYTES, sp.memo + (size_t)t_ * sp.n_pad + base + (long long)q * STREAM_TILE, STREAM_TILE * 4, &ss.full[0]);
+    } else {
+      for (int q = 0; q < NST && q < tiles; q++) issue(q, (int)((ubase_ + q) % NST), t_);
+    }
+  };
   for (;; k++) {
     if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }
     if (k > p.pod_cap) { if (tid == 0) ss.stop = 3; __syncthreads(); break; }
     const int t = (int)(k % T);
     const StreamTmpl &c = ss.tc[t];
-    const long long eq_cpu = c.eq_cpu, eq_mem = c.eq_mem;
-    const int32_t pods_need = c.pods_need;
-    const unsigned long long taint_bad0 = c.taint_bad0, sel0 = c.sel0, forbid0 = c.forbid0;
-    if (tid == 0 && !prefetched) {
-      fence_proxy_async();            // the commit's and the scorers' generic-proxy stores of the last wave, before the engine reads them
-      for (int q = 0; q < NST && q < tiles; q++) issue(q, (int)((uses + q) % NST), t);
-    }
+    const uint32_t ubase = uses;
+    if (service && lane == 0 && !prefetched) request_first_tiles(ubase, t);
     SPH_START();
     if (dbg) { const long long c0 = clock64(); if (dbg_t) dbg_rest += c0 - dbg_t; dbg_t = c0; }
-    unsigned long long best = 0ull;
-    bool wrote = false;
-    const uint32_t ubase = uses;
-    if (RESF) {
-      // ---- resident columns: the whole chunk's memo column is in flight (tile q in stage q: `uses` advances by the ring size per
-      //      wave), so the pass is ONE flat loop over the chunk with a 32-bit local key (score + 1 : 12 | ~offset : 20 — same order as
-      //      pack_key inside a CTA: highest score, then lowest index) and ~20 instructions per node; the pass is issue-bound. In the
-      //      owner CTA of the last commit it starts behind the winner's tile, so that the commit — running in warp 0 meanwhile —
-      //      is over long before anybody needs that node. ----
-      const uint32_t parity = (ubase / NST) & 1u;
-      for (int q = 0; q < tiles; q++) while (!mbar_try_wait(&ss.full[q], parity)) { }
-      if (dbg) { const long long c0 = clock64(); dbg_wait += c0 - dbg_t; dbg_t = c0; }
-      const int32_t *memo_s = reinterpret_cast<const int32_t *>(smem_raw);      // stage q = tile q: contiguous
-      const int cpad = sp.chunk_pad;
-      int off = tid + ((pend_off >= 0) ? (pend_off / STREAM_TILE + 1) * STREAM_TILE : 0);
-      if (off >= cpad) off -= cpad;
-      uint32_t best32 = 0u;
-      #pragma unroll 2
-      for (int it = 0; it < cpad; it += STREAM_THREADS) {
-        if (off == pend_off) {           // the node committed a moment ago: its row, generation and memo entry are being written by warp 0
-          while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
-          __threadfence_block();
-        }
-        const bool ok = (r_fcpu[off] >= eq_cpu) & (r_fmem[off] >= eq_mem) & (r_fpods[off] >= pods_need);
-        int32_t enc = memo_s[off];
-        const int32_t gen = r_gen[off];
-        if (ok) {
-          if ((enc >> 12) != gen) {      // never scored by this template (the run's first T waves), or — not since the owner re-scores at commit — stale
-            const long long i = (long long)cta * p.chunk + off;
-            const int32_t sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
-                                          p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
-            enc = (gen << 12) | (sc + 1);
-            sp.memo[(size_t)t * sp.n_pad + base + off] = enc;
-            if (cta == 0) atomicAdd((unsigned long long *)&ss.n_stale, 1ull);
-            wrote = true;                // fenced once after the pass (a later bulk-async read of this column must see the store)
-          }
-          const uint32_t key32 = ((uint32_t)(enc & 0xfff) << 20) | (0xfffffu - (uint32_t)off);
-          best32 = max(best32, key32);
-        }
-        off += STREAM_THREADS;
+    if (!service) {
+      const long long eq_cpu = c.eq_cpu, eq_mem = c.eq_mem;
+      const int32_t pods_need = c.pods_need;
+      unsigned long long best = 0ull;
+      bool wrote = false;
+      if (RESF) {
+        // ---- resident columns: the whole chunk's memo column is in flight (tile q in stage q), so the pass is ONE flat loop over the
+        //      chunk with a 32-bit local key (score + 1 : 12 | ~offset : 20 — same order as pack_key inside a CTA: highest score, then
+        //      lowest index). In the owner CTA of the last commit it starts behind the winner's tile, so that the commit — running
+        //      in the service warp meanwhile — is over long before anybody needs that node. ----
+        while (!mbar_try_wait(&ss.full[0], (uint32_t)(k & 1))) { }
+        if (dbg) { const long long c0 = clock64(); dbg_wait += c0 - dbg_t; dbg_t = c0; }
+        const int32_t *memo_s = reinterpret_cast<const int32_t *>(smem_raw);      // stage q = tile q: contiguous
+        const int cpad = sp.chunk_pad;
+        int off = tid + ((pend_off >= 0) ? (pend_off / STREAM_TILE + 1) * STREAM_TILE : 0);
         if (off >= cpad) off -= cpad;
-      }
-      if (best32) {
-        const int boff = (int)(0xfffffu - (best32 & 0xfffffu));
-        best = pack_key((int32_t)(best32 >> 20) - 1, (uint32_t)(p.node_base + (long long)cta * p.chunk + boff));
-      }
-      uses = ubase + NST;
-    } else {
-    // in the owner CTA of the last commit the pass starts behind the winner's tile (the whole chunk is in flight: any order works),
-    // so that the commit — running in warp 0 meanwhile — is over long before anybody needs that node
-    const int rot = (all_in_flight && pend_off >= 0) ? pend_off / STREAM_TILE + 1 : 0;
-    for (int tq = 0; tq < tiles; tq++, uses++) {
-      const int tile = (tq + rot >= tiles) ? tq + rot - tiles : tq + rot;
-      const uint32_t use = ubase + (uint32_t)tile;
-      const int s = (int)(use % NST);
-      const uint32_t parity = (use / NST) & 1u;
-      while (!mbar_try_wait(&ss.full[s], parity)) { }
-      const unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
-      const long long *s_fcpu = RESF ? r_fcpu + tile * STREAM_TILE : reinterpret_cast<const long long *>(st);
-      const long long *s_fmem = RESF ? r_fmem + tile * STREAM_TILE : reinterpret_cast<const long long *>(st + STREAM_TILE * 8);
-      const int32_t *s_fpods = RESF ? r_fpods + tile * STREAM_TILE : reinterpret_cast<const int32_t *>(st + STREAM_TILE * 16);
-      const int32_t *s_memo = reinterpret_cast<const int32_t *>(st + MEMO_OFF);
-      #pragma unroll
-      for (int j = tid; j < STREAM_TILE; j += STREAM_THREADS) {
-        const int off = tile * STREAM_TILE + j;
-        if (off == pend_off) {           // the node committed a moment ago: its row, generation and memo entry are being written by warp 0
-          while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
-          __threadfence_block();
-        }
-        // NodeResourcesFit (+ NodeUnschedulable / TaintToleration / nodeSelector / NodePorts / existing anti-affinity bits)
-        bool ok = (s_fcpu[j] >= eq_cpu) & (s_fmem[j] >= eq_mem) & (s_fpods[j] >= pods_need);
-        if (MASKS) {
-          const unsigned long long taint0 = reinterpret_cast<const unsigned long long *>(st + STREAM_TILE * 24)[j];
-          const unsigned long long static0 = reinterpret_cast<const unsigned long long *>(st + STREAM_TILE * 32)[j];
-          ok &= ((taint0 & taint_bad0) | (~static0 & sel0) | (static0 & forbid0)) == 0ull;
-        }
-        if (ok) {
-          const long long i = (long long)cta * p.chunk + off;        // shard-local node index
-          int32_t sc = s_memo[j];
-          const int32_t gen = RESF ? r_gen[off] : 0;
-          if (RESF) sc = (sc >= 0 && (sc >> 12) == gen) ? (sc & 0xfff) - 1 : -1;
-          if (sc < 0) {   // stale: this node was committed since template t last scored it (or never scored)
-            sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
-                            p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
-            sp.memo[(size_t)t * sp.n_pad + base + off] = RESF ? ((gen << 12) | (sc + 1)) : sc;
-            if (cta == 0) atomicAdd((unsigned long long *)&ss.n_stale, 1ull);
-            wrote = true;                // fenced once after the pass (a later bulk-async read of this column must see the store)
+        uint32_t best32 = 0u;
+        #pragma unroll 2
+        for (int it = 0; it < cpad; it += STREAM_THREADS) {
+          if (off == pend_off) {           // the node committed a moment ago: its row, generation and memo entry are being written by the service warp
+            while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
+            __threadfence_block();
           }
-          const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
-          best = key > best ? key : best;
+          const bool ok = (r_fcpu[off] >= eq_cpu) & (r_fmem[off] >= eq_mem) & (r_fpods[off] >= pods_need);
+          int32_t enc = memo_s[off];
+          const int32_t gen = r_gen[off];
+          if (ok) {
+            if ((enc >> 12) != gen) {      // never scored by this template (the run's first T waves); the owner re-scores at commit
+              const long long i = (long long)cta * p.chunk + off;
+              const int32_t sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
+                                            p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
+              enc = (gen << 12) | (sc + 1);
+              sp.memo[(size_t)t * sp.n_pad + base + off] = enc;
+              if (cta == 0) atomicAdd((unsigned long long *)&ss.n_stale, 1ull);
+              wrote = true;                // fenced once after the pass (a later bulk-async read of this column must see the store)
+            }
+            const uint32_t key32 = ((uint32_t)(enc & 0xfff) << 20) | (0xfffffu - (uint32_t)off);
+            best32 = max(best32, key32);
+          }
+          off += STREAM_THREADS;
+          if (off >= cpad) off -= cpad;
+        }
+        if (best32) {
+          const int boff = (int)(0xfffffu - (best32 & 0xfffffu));
+          best = pack_key((int32_t)(best32 >> 20) - 1, (uint32_t)(p.node_base + (long long)cta * p.chunk + boff));
+        }
+      } else {
+        const unsigned long long taint_bad0 = c.taint_bad0, sel0 = c.sel0, forbid0 = c.forbid0;
+        for (int tile = 0; tile < tiles; tile++) {
+          const uint32_t use = ubase + (uint32_t)tile;
+          const int s = (int)(use % NST);
+          while (!mbar_try_wait(&ss.full[s], (use / NST) & 1u)) { }
+          const unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
+          const long long *s_fcpu = reinterpret_cast<const long long *>(st);
+          const long long *s_fmem = reinterpret_cast<const long long *>(st + STREAM_TILE * 8);
+          const int32_t *s_fpods = reinterpret_cast<const int32_t *>(st + STREAM_TILE * 16);
+          const int32_t *s_memo = reinterpret_cast<const int32_t *>(st + MEMO_OFF);
+          #pragma unroll
+          for (int j = tid; j < STREAM_TILE; j += STREAM_THREADS) {
+            const int off = tile * STREAM_TILE + j;
+            if (off == pend_off) {
+              while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
+              __threadfence_block();
+            }
+            // NodeResourcesFit (+ NodeUnschedulable / TaintToleration / nodeSelector / NodePorts / existing anti-affinity bits)
+            bool ok = (s_fcpu[j] >= eq_cpu) & (s_fmem[j] >= eq_mem) & (s_fpods[j] >= pods_need);
+            if (MASKS) {
+              const unsigned long long taint0 = reinterpret_cast<const unsigned long long *>(st + STREAM_TILE * 24)[j];
+              const unsigned long long static0 = reinterpret_cast<const unsigned long long *>(st + STREAM_TILE * 32)[j];
+              ok &= ((taint0 & taint_bad0) | (~static0 & sel0) | (static0 & forbid0)) == 0ull;
+            }
+            if (ok) {
+              const long long i = (long long)cta * p.chunk + off;        // shard-local node index
+              int32_t sc = s_memo[j];
+              if (sc < 0) {   // stale: this node was committed since template t last scored it (or never scored)
+                sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
+                                p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
+                sp.memo[(size_t)t * sp.n_pad + base + off] = sc;
+                if (cta == 0) atomicAdd((unsigned long long *)&ss.n_stale, 1ull);
+                wrote = true;
+              }
+              const unsigned long long key = pack_key(sc, (uint32_t)(p.node_base + i));
+              best = key > best ? key : best;
+            }
+          }
+          if (!all_in_flight) {
+            asm volatile("bar.sync 1, %0;" ::"n"(STREAM_THREADS) : "memory");   // the scanning warps are done with stage s
+            // (no proxy fence here: the rows of a later tile were last written in an earlier wave)
+            if (tid == 0 && tile + NST < tiles) issue(tile + NST, s, t);
+          }
         }
       }
-      if (!all_in_flight) {
-        __syncthreads();               // everybody is done with stage s
-        // (no proxy fence here: the rows of a later tile were last written in an earlier wave)
-        if (tid == 0 && tile + NST < tiles) issue(tile + NST, s, t);
-      }
-    }
-    }
-    if (wrote) fence_proxy_async();
-    if (dbg) { const long long c0 = clock64(); dbg_scan += c0 - dbg_t; dbg_t = c0; }
-    SPH_MARK(0);                           // scan: mbarrier waits + Filter/arg-max over the chunk
-    if (all_in_flight) __syncthreads();    // no stage was reused inside the pass: one barrier before the stages are re-armed
-    // The first tiles of the NEXT wave are requested now, so that the copy engine works while the exchange is in flight. They may
-    // hold the pre-commit row of this wave's winner: the owner patches its shared-memory copy after the commit (below).
-    const uint32_t uses_next = uses;           // the next wave's tile q lands in stage (uses_next + q) % STAGES
-    prefetched = !(p.max_pods > 0 && k + 1 >= p.max_pods);
-    if (tid == 0 && prefetched) {
-      fence_proxy_async();
-      const int tn = (int)((k + 1) % T);
-      for (int q = 0; q < NST && q < tiles; q++) issue(q, (int)((uses_next + q) % NST), tn);
-    }
-    {
+      if (wrote) fence_proxy_async();
+      if (dbg) { const long long c0 = clock64(); dbg_scan += c0 - dbg_t; dbg_t = c0; }
       const unsigned long long v = warp_max_u64(best);
       if (lane == 0) ss.warp_best[warp] = v;
     }
-    __syncthreads();
-    SPH_MARK(1);                           // block barriers, next wave's bulk copies issued, block arg-max
+    SPH_MARK(0);                           // scan: mbarrier wait + Filter/arg-max over the chunk
+    __syncthreads();                       // A: the pass is over — warp maxima visible, stages free
+    SPH_MARK(1);                           // barrier A (the service warp's commit of the last wave included)
     if (dbg) { const long long c0 = clock64(); dbg_rest += c0 - dbg_t; dbg_t = c0; }
-    if (warp == 0) {
+    uses = ubase + (RESF ? (uint32_t)NST : (uint32_t)tiles);
+    const uint32_t uses_next = uses;           // the next wave's tile q lands in stage (uses_next + q) % STAGES
+    prefetched = !(p.max_pods > 0 && k + 1 >= p.max_pods);
+    if (prefetched) pf_wave = k + 1;
+    if (service) {
       const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
       const unsigned long long mine = warp_max_u64(lane < STREAM_WARPS ? ss.warp_best[lane] : 0ull);
+      // publish first (it is what every other CTA waits for), THEN request the next wave's tiles, then poll
+      if (lane == 0) st_slot(p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE, (mine & KEY_BODY_MASK) | tagbits);
+      if (lane == 0 && prefetched) request_first_tiles(uses_next, (int)((k + 1) % T));
       bool dead = false;
-      unsigned long long wkey = exchange_max(p, k, tag, 0, mine, lane, cta, dead);
-      (void)tagbits;
+      unsigned long long wkey = 0ull;
+      {
+        const unsigned long long *all = p.slots + (size_t)(k & 1) * CCSIM_MAX_GRID * SLOT_STRIDE;
+        unsigned long long v[CCSIM_MAX_GRID / 32];
+        unsigned spins = 0;
+        bool pending;
+        do {
+          pending = false;
+          #pragma unroll
+          for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const int b = lane + 32 * q; v[q] = (b < p.grid) ? ld_slot(&all[(size_t)b * SLOT_STRIDE]) : tagbits; }
+          #pragma unroll
+          for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) pending |= ((uint32_t)(v[q] >> KEY_TAG_SHIFT) != tag);
+          if (++spins > WATCHDOG_SPINS) { dead = true; break; }
+        } while (__any_sync(0xffffffffu, pending));
+        unsigned long long m = 0ull;
+        #pragma unroll
+        for (int q = 0; q < CCSIM_MAX_GRID / 32; q++) { const unsigned long long b = v[q] & KEY_BODY_MASK; m = b > m ? b : m; }
+        dead = __any_sync(0xffffffffu, dead);
+        wkey = warp_max_u64(m);
+      }
       if (p.world > 1 && !dead) { unsigned long long cb[1] = {wkey}; dead = cross_gpu_exchange(p, k, tag, 1, cb, lane, cta); wkey = cb[0]; }   // node shards: winners of all ranks
-      if (dbg) { const long long c0 = clock64(); dbg_xchg += c0 - dbg_t; dbg_t = c0; }
-      SPH_MARK(2);                         // exchange: own key stored, every CTA's key polled (L2 round trip + the slowest CTA)
       if (lane == 0) {
         if (dead) { ss.stop = 3; ss.winner = -1; }
         else if (wkey == 0ull) { ss.stop = 1; ss.winner = -1; }
-        else ss.winner = (int32_t)key_index(wkey);
+        else { ss.winner = (int32_t)key_index(wkey); if (k >= p.pod_cap) ss.stop = 3; }     // (no room to record the placement)
       }
-      if (lane == 0 && !dead && wkey != 0ull && k >= p.pod_cap) ss.stop = 3;     // no room to record the placement
     }
-    __syncthreads();
-    SPH_MARK(3);                           // barrier: the winner is known to every thread
+    __syncthreads();                       // B: the winner is known to every thread
+    SPH_MARK(2);                           // exchange: publish, poll every CTA's key (one L2 round trip + the slowest CTA)
+    if (dbg) { const long long c0 = clock64(); dbg_xchg += c0 - dbg_t; dbg_t = c0; }
     if (ss.stop) break;
-    // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) by warp 0 of the owner CTA,
-    //      AFTER the barrier: the other warps are already scanning for the next wave. Only the thread that scans the committed node
-    //      itself has to wait for the commit (ss.commit_seq); in the owner CTA the pass starts behind the winner's tile. ----
+    // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) by the service warp of the
+    //      owner CTA, while the scanning warps already work on the next wave. Only the thread that scans the committed node itself
+    //      waits for it (ss.commit_seq). ----
     pend_off = -1;
     {
       const int32_t w = ss.winner - p.node_base;
       const bool local = w >= 0 && w < p.n;
       const int oc = local ? w / p.chunk : -1;
       if (oc == cta) pend_off = (int)(w - (long long)oc * p.chunk);
-      if (warp == 0) {
+      if (service) {
         if (!local && cta == 0 && lane == 0) p.pod_node[k] = ss.winner;      // sharded run: every rank keeps the whole pod -> node sequence
         if (oc == cta) {
           const long long q = base + (w - (long long)oc * p.chunk);
@@ -388,12 +406,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
             for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
             fence_proxy_async();
           }
-          // the winner's row may already sit, pre-commit, in a stage prefetched for the next wave: wait for that copy, then patch it
-          const int off = roff, tw = off / STREAM_TILE, j = off - tw * STREAM_TILE;
+          // the winner's row may already sit, pre-commit, in a stage requested for the next wave: wait for that copy, then patch it
+          const int tw = roff / STREAM_TILE, j = roff - tw * STREAM_TILE;
           if (prefetched && tw < NST && tw < tiles && lane == 0) {
             const uint32_t u = uses_next + (uint32_t)tw;
-            const int s = (int)(u % NST);
-            while (!mbar_try_wait(&ss.full[s], (u / NST) & 1u)) { }
+            const int s = RESF ? tw : (int)(u % NST);
+            if (RESF) { while (!mbar_try_wait(&ss.full[0], (uint32_t)((k + 1) & 1))) { } }
+            else { while (!mbar_try_wait(&ss.full[s], (u / NST) & 1u)) { } }
             unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
             if (!RESF) {
               reinterpret_cast<long long *>(st)[j] = sp.f_cpu[q];
@@ -411,11 +430,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) ccsim_wave_stream_kernel(co
     wtag = (wtag == 4095u) ? 1u : wtag + 1u;
     tag = (p.epoch << 12) | wtag;
   }
-  if (prefetched && tid == 0)        // copies requested for a wave that never ran: let them land before the CTA exits
-    for (int q = 0; q < NST && q < tiles; q++) {
-      const uint32_t u = uses + (uint32_t)q;
-      while (!mbar_try_wait(&ss.full[u % NST], (u / NST) & 1u)) { }
-    }
+  if (prefetched && service && lane == 0) {       // copies requested for a wave that never ran: let them land before the CTA exits
+    if (RESF) { while (!mbar_try_wait(&ss.full[0], (uint32_t)(pf_wave & 1))) { } }
+    else
+      for (int q = 0; q < NST && q < tiles; q++) {
+        const uint32_t u = uses + (uint32_t)q;
+        while (!mbar_try_wait(&ss.full[u % NST], (u / NST) & 1u)) { }
+      }
+  }
   __syncthreads();
   if (dbg && p.world == 1) {          // per-CTA cycle split into the (unused at world 1) cross-GPU line buffer: the host prints min / mean / max
     unsigned long long *d = p.xslots_peer[p.rank] + XLINES_OFF + (size_t)cta * 4;
