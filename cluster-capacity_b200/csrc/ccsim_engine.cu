@@ -1381,7 +1381,7 @@ static int run_prepare(ccsim_handle *h, int64_t max_pods) {
     ccsim_stream_prep_kernel<<<std::min<long long>(8LL * h->sm_count, (sp.n_pad + 255) / 256), 256, 0, s>>>(p, sp);
     h->launches++;
     CK(cudaGetLastError());
-    // resident free_* columns when the chunk fits next to the memo ring (20 B per node: up to ~10k nodes per SM)
+    // resident free_* columns when the chunk fits next to the memo ring (24 B per node: up to ~8k nodes per SM)
     const size_t smem_resf = (size_t)STREAM_STAGES_RES * STREAM_TILE * 4 + (size_t)sp.chunk_pad * 24 + 128;
     stream_mode = masks ? 1 : ((smem_resf + sizeof(StreamShared) + 1024 <= h->smem_optin && sp.tiles <= STREAM_STAGES_RES && !getenv("CCSIM_STREAM_ALL")) ? 2 : 0);
     kern = stream_mode == 1 ? (const void *)ccsim_wave_stream_kernel<1> : stream_mode == 2 ? (const void *)ccsim_wave_stream_kernel<2> : (const void *)ccsim_wave_stream_kernel<0>;

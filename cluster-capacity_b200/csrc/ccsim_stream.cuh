@@ -21,7 +21,7 @@
 
 #define STREAM_THREADS 512
 #define STREAM_WARPS (STREAM_THREADS / 32)
-#define STREAM_BLOCK (STREAM_THREADS + 32)   /* + the service warp: bulk-copy requests, exchange, commit */
+#define STREAM_BLOCK (STREAM_THREADS + 64)   /* + two service warps: the exchange warp, and the memory warp (bulk-copy requests, commit) */
 #define STREAM_TILE 1024          /* nodes per stage: 24 KB (40 KB with the mask columns) */
 #define STREAM_STAGES 4           /* stages of the ring when every column is streamed */
 #define STREAM_STAGES_RES 8       /* ... when only the 4-byte memo column is streamed (resident free_* columns): a whole 1M-node chunk (7 tiles) in flight */
@@ -105,13 +105,11 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
   constexpr uint32_t STAGE_BYTES = STREAM_TILE * (MASKS ? 40u : (RESF ? 4u : 24u));
   constexpr uint32_t MEMO_OFF = RESF ? 0u : STREAM_TILE * 20u;      // the memo tile inside a stage
   // RESF: resident columns behind the stage ring
-  long long *r_fcpu = reinterpret_cast<long long *>(smem_raw + NST * STAGE_BYTES);
-  long long *r_fmem = r_fcpu + sp.chunk_pad;
-  int32_t *r_fpods = reinterpret_cast<int32_t *>(r_fmem + sp.chunk_pad);
-  // RESF: a generation number per node instead of invalidating 64 memo entries at every commit: a memo entry is (generation << 12 |
-  // score + 1) and is valid only while the node's generation stands (NodeInfo.Generation, framework/types.go:409-427). The commit
-  // is then a handful of shared-memory stores: no global memo stores, no proxy fence, no patching of prefetched stages.
-  int32_t *r_gen = r_fpods + sp.chunk_pad;
+  // RESF: per node {free_cpu, free_mem} (16 B: one LDS.128) and {free_pods, generation} (8 B: one LDS.64)
+  longlong2 *r_free = reinterpret_cast<longlong2 *>(smem_raw + NST * STAGE_BYTES);
+  // A generation number per node instead of invalidating 64 memo entries at every commit: a memo entry is (generation << 12 |
+  // score + 1) and is valid only while the node's generation stands (NodeInfo.Generation, framework/types.go:409-427).
+  int2 *r_pg = reinterpret_cast<int2 *>(r_free + sp.chunk_pad);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
   const long long base = (long long)cta * sp.chunk_pad;           // this CTA's first padded row
@@ -146,9 +144,8 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
   }
   if (RESF)
     for (int j = threadIdx.x; j < sp.chunk_pad; j += STREAM_BLOCK) {
-      r_fcpu[j] = sp.f_cpu[(long long)blockIdx.x * sp.chunk_pad + j]; r_fmem[j] = sp.f_mem[(long long)blockIdx.x * sp.chunk_pad + j];
-      r_fpods[j] = sp.f_pods[(long long)blockIdx.x * sp.chunk_pad + j];
-      r_gen[j] = 0;
+      r_free[j] = make_longlong2(sp.f_cpu[(long long)blockIdx.x * sp.chunk_pad + j], sp.f_mem[(long long)blockIdx.x * sp.chunk_pad + j]);
+      r_pg[j] = make_int2(sp.f_pods[(long long)blockIdx.x * sp.chunk_pad + j], 0);
     }
   if (tid == 0) {
     for (int s = 0; s < NST; s++) mbar_init(&ss.full[s], 1);
@@ -180,11 +177,12 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
   bool limit_hit = false;
   long long dbg_t = 0, dbg_wait = 0, dbg_scan = 0, dbg_xchg = 0, dbg_rest = 0;    // CCSIM_DEBUG_FLAGS & 8: this CTA's cycle split (thread 0)
   const bool dbg = (p.debug_flags & 8u) != 0u && tid == 0;
-  // Warp specialisation: warps 0..15 scan; warp 16 — the SERVICE warp — requests the bulk copies, runs the exchange and commits.
-  // A wave's critical path is then scan -> barrier A -> publish / poll (one L2 round trip) -> barrier B -> next scan; the commit
-  // (row columns from L2, 64 re-scores with their divisions, 64 memo stores, a proxy fence: several thousand cycles in the owner
-  // CTA) overlaps the next pass instead of delaying the owner's next key, which every other CTA waits for.
-  const bool service = warp == STREAM_WARPS;
+  // Warp specialisation: warps 0..15 scan; warp 16 runs the exchange (publish / poll: one L2 round trip on the critical path and
+  // nothing else); warp 17 — the memory warp — requests the bulk copies and commits. A wave's critical path is then scan ->
+  // barrier A -> publish / poll -> barrier B -> next scan; the commit (row columns from L2, 64 re-scores with their divisions, 64
+  // memo stores, a proxy fence: several thousand cycles in the owner CTA) overlaps the next pass instead of delaying the owner's
+  // next key, which every other CTA waits for.
+  const bool xwarp = warp == STREAM_WARPS, service = warp == STREAM_WARPS + 1, scanner = warp < STREAM_WARPS;
   int pend_off = -1;                 // owner CTA: chunk offset of the node whose commit may still be under way when this pass starts
   bool prefetched = false;           // the first tiles of the coming wave were requested at the end of the last one
   long long pf_wave = 0;             // ... the wave they were requested for
@@ -213,7 +211,7 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
     if (service && lane == 0 && !prefetched) request_first_tiles(ubase, t);
     SPH_START();
     if (dbg) { const long long c0 = clock64(); if (dbg_t) dbg_rest += c0 - dbg_t; dbg_t = c0; }
-    if (!service) {
+    if (scanner) {
       const long long eq_cpu = c.eq_cpu, eq_mem = c.eq_mem;
       const int32_t pods_need = c.pods_need;
       unsigned long long best = 0ull;
@@ -227,34 +225,36 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
         if (dbg) { const long long c0 = clock64(); dbg_wait += c0 - dbg_t; dbg_t = c0; }
         const int32_t *memo_s = reinterpret_cast<const int32_t *>(smem_raw);      // stage q = tile q: contiguous
         const int cpad = sp.chunk_pad;
-        int off = tid + ((pend_off >= 0) ? (pend_off / STREAM_TILE + 1) * STREAM_TILE : 0);
-        if (off >= cpad) off -= cpad;
         uint32_t best32 = 0u;
-        #pragma unroll 2
-        for (int it = 0; it < cpad; it += STREAM_THREADS) {
-          if (off == pend_off) {           // the node committed a moment ago: its row, generation and memo entry are being written by the service warp
+        auto node = [&](int off, bool check) {
+          if (check && off == pend_off) {  // the node committed a moment ago: its row, generation and memo entry are being written by the memory warp
             while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
             __threadfence_block();
           }
-          const bool ok = (r_fcpu[off] >= eq_cpu) & (r_fmem[off] >= eq_mem) & (r_fpods[off] >= pods_need);
+          const longlong2 fr = r_free[off];
+          const int2 pg = r_pg[off];
           int32_t enc = memo_s[off];
-          const int32_t gen = r_gen[off];
-          if (ok) {
-            if ((enc >> 12) != gen) {      // never scored by this template (the run's first T waves); the owner re-scores at commit
+          if ((fr.x >= eq_cpu) & (fr.y >= eq_mem) & (pg.x >= pods_need)) {
+            if ((enc >> 12) != pg.y) {     // never scored by this template (the run's first T waves); the owner re-scores at commit
               const long long i = (long long)cta * p.chunk + off;
               const int32_t sc = score_node(p.alloc_cpu[i], p.alloc_mem[i], p.nz_cpu[i] + c.least_cpu, p.nz_mem[i] + c.least_mem,
                                             p.req_cpu[i] + c.bal_cpu, p.req_mem[i] + c.bal_mem, c.sw);
-              enc = (gen << 12) | (sc + 1);
+              enc = (pg.y << 12) | (sc + 1);
               sp.memo[(size_t)t * sp.n_pad + base + off] = enc;
               if (cta == 0) atomicAdd((unsigned long long *)&ss.n_stale, 1ull);
               wrote = true;                // fenced once after the pass (a later bulk-async read of this column must see the store)
             }
-            const uint32_t key32 = ((uint32_t)(enc & 0xfff) << 20) | (0xfffffu - (uint32_t)off);
-            best32 = max(best32, key32);
+            best32 = max(best32, ((uint32_t)enc << 20) | (0xfffffu - (uint32_t)off));     // (enc << 20 keeps exactly the 12 score bits)
           }
-          off += STREAM_THREADS;
-          if (off >= cpad) off -= cpad;
-        }
+        };
+        // order: the tiles behind the pending node's tile, the tiles before it, that tile last (only there the node is looked for)
+        const int pt = (pend_off >= 0 ? pend_off / STREAM_TILE : tiles - 1) * STREAM_TILE;
+        #pragma unroll 2
+        for (int off = pt + STREAM_TILE + tid; off < cpad; off += STREAM_THREADS) node(off, false);
+        #pragma unroll 2
+        for (int off = tid; off < pt; off += STREAM_THREADS) node(off, false);
+        #pragma unroll
+        for (int off = pt + tid; off < pt + STREAM_TILE; off += STREAM_THREADS) node(off, true);
         if (best32) {
           const int boff = (int)(0xfffffu - (best32 & 0xfffffu));
           best = pack_key((int32_t)(best32 >> 20) - 1, (uint32_t)(p.node_base + (long long)cta * p.chunk + boff));
@@ -318,12 +318,11 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
     const uint32_t uses_next = uses;           // the next wave's tile q lands in stage (uses_next + q) % STAGES
     prefetched = !(p.max_pods > 0 && k + 1 >= p.max_pods);
     if (prefetched) pf_wave = k + 1;
-    if (service) {
+    if (service && lane == 0 && prefetched) request_first_tiles(uses_next, (int)((k + 1) % T));    // the next wave's memo column, while the exchange runs
+    if (xwarp) {
       const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
       const unsigned long long mine = warp_max_u64(lane < STREAM_WARPS ? ss.warp_best[lane] : 0ull);
-      // publish first (it is what every other CTA waits for), THEN request the next wave's tiles, then poll
       if (lane == 0) st_slot(p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE, (mine & KEY_BODY_MASK) | tagbits);
-      if (lane == 0 && prefetched) request_first_tiles(uses_next, (int)((k + 1) % T));
       bool dead = false;
       unsigned long long wkey = 0ull;
       {
@@ -377,7 +376,7 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
           const long long n_zcpu = p.nz_cpu[w] + c.nz_cpu, n_zmem = p.nz_mem[w] + c.nz_mem;
           int32_t newgen = 0;
           if (lane == 0) {
-            if (RESF) { r_fcpu[roff] -= c.req_cpu; r_fmem[roff] -= c.req_mem; r_fpods[roff] -= 1; newgen = (r_gen[roff] + 1) & 0x7ffff; r_gen[roff] = newgen; }
+            if (RESF) { longlong2 fr = r_free[roff]; fr.x -= c.req_cpu; fr.y -= c.req_mem; r_free[roff] = fr; int2 pg = r_pg[roff]; newgen = (pg.y + 1) & 0x7ffff; r_pg[roff] = make_int2(pg.x - 1, newgen); }
             else { sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1; }
             p.pod_node[k] = w + p.node_base;
           }
