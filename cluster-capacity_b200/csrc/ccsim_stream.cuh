@@ -21,6 +21,8 @@
 
 #define STREAM_THREADS 512
 #define STREAM_WARPS (STREAM_THREADS / 32)
+#define STREAM_WQ 8
+#define STREAM_WQ_STOP (-2)
 #define STREAM_BLOCK (STREAM_THREADS + 64)   /* + two service warps: the exchange warp, and the memory warp (bulk-copy requests, commit) */
 #define STREAM_TILE 1024          /* nodes per stage: 24 KB (40 KB with the mask columns) */
 #define STREAM_STAGES 4           /* stages of the ring when every column is streamed */
@@ -49,7 +51,9 @@ struct __align__(16) StreamShared {
   StreamTmpl tc[CCSIM_MAX_TEMPLATES];
   unsigned long long full[STREAM_STAGES_RES];  // mbarriers: "the stage's bytes have landed"
   unsigned long long warp_best[STREAM_WARPS];
-  int32_t winner, stop, commit_seq, pad;
+  int32_t winner, stop, commit_seq, commit_full;   // commit_seq / commit_full: waves whose urgent / whole commit is done (+1)
+  int32_t wq[STREAM_WQ];                            // winners handed to the commit warp (ring), STREAM_WQ_STOP ends it
+  int32_t w_seq, c_done, pad2[2];                   // winners published / consumed
   long long ph[8], tc0, n_stale;   // CTA 0 / thread 0: clock cycles per phase; stale memo entries re-scored by CTA 0
 };
 
@@ -75,6 +79,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 // orders this thread's earlier generic-proxy accesses to GLOBAL memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void bar_sync_n(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ int32_t ld_vol_s32(const int32_t *p) { return *reinterpret_cast<const volatile int32_t *>(p); }
+__device__ __forceinline__ void st_vol_s32(int32_t *p, int32_t v) { *reinterpret_cast<volatile int32_t *>(p) = v; }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // fills the padded streaming columns from the snapshot's working columns (once per run)
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
   if (tid == 0) {
     for (int s = 0; s < NST; s++) mbar_init(&ss.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    ss.winner = -1; ss.stop = 0; ss.commit_seq = 0;
+    ss.winner = -1; ss.stop = 0; ss.commit_seq = 0; ss.commit_full = 0; ss.w_seq = 0; ss.c_done = 0;
     for (int q = 0; q < 8; q++) ss.ph[q] = 0;
     ss.n_stale = 0;
   }
@@ -177,12 +184,17 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
   bool limit_hit = false;
   long long dbg_t = 0, dbg_wait = 0, dbg_scan = 0, dbg_xchg = 0, dbg_rest = 0;    // CCSIM_DEBUG_FLAGS & 8: this CTA's cycle split (thread 0)
   const bool dbg = (p.debug_flags & 8u) != 0u && tid == 0;
-  // Warp specialisation: warps 0..15 scan; warp 16 runs the exchange (publish / poll: one L2 round trip on the critical path and
-  // nothing else); warp 17 — the memory warp — requests the bulk copies and commits. A wave's critical path is then scan ->
-  // barrier A -> publish / poll -> barrier B -> next scan; the commit (row columns from L2, 64 re-scores with their divisions, 64
-  // memo stores, a proxy fence: several thousand cycles in the owner CTA) overlaps the next pass instead of delaying the owner's
-  // next key, which every other CTA waits for.
+  // Warp specialisation. Warps 0..15 SCAN. Warp 16, the EXCHANGE warp, publishes the CTA's key, requests the next wave's bulk
+  // copies and polls: a wave's critical path is scan -> barrier A -> publish / poll (one L2 round trip) -> barrier B -> next scan.
+  // Warp 17, the COMMIT warp, is decoupled from those barriers: it takes the winners from a small ring in shared memory and, when
+  // the node is this CTA's, commits it in two parts — URGENT: row columns from L2, the resident copy, the new generation, the score
+  // of the NEXT wave's template patched into the landed memo column (then `commit_seq` releases the one scanning thread that
+  // looks at this node); LAZY: write-through of the global columns, the re-scores of the other 63 templates, their memo stores,
+  // the proxy fence. A stale memo entry read by a bulk copy that overtook the lazy part is caught by the generation check.
+  // Before this split the owner CTA's next key — which every other CTA waits for — came one whole commit (several thousand
+  // cycles) late, every wave.
   const bool xwarp = warp == STREAM_WARPS, service = warp == STREAM_WARPS + 1, scanner = warp < STREAM_WARPS;
+  constexpr int SYNC_N = STREAM_THREADS + 32;      // scanning warps + exchange warp: the participants of barriers A and B
   int pend_off = -1;                 // owner CTA: chunk offset of the node whose commit may still be under way when this pass starts
   bool prefetched = false;           // the first tiles of the coming wave were requested at the end of the last one
   long long pf_wave = 0;             // ... the wave they were requested for
@@ -202,13 +214,14 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
       for (int q = 0; q < NST && q < tiles; q++) issue(q, (int)((ubase_ + q) % NST), t_);
     }
   };
+  if (!service)
   for (;; k++) {
     if (p.max_pods > 0 && k >= p.max_pods) { limit_hit = true; break; }
-    if (k > p.pod_cap) { if (tid == 0) ss.stop = 3; __syncthreads(); break; }
+    if (k > p.pod_cap) { if (tid == 0) ss.stop = 3; break; }
     const int t = (int)(k % T);
     const StreamTmpl &c = ss.tc[t];
     const uint32_t ubase = uses;
-    if (service && lane == 0 && !prefetched) request_first_tiles(ubase, t);
+    if (xwarp && lane == 0 && !prefetched) request_first_tiles(ubase, t);
     SPH_START();
     if (dbg) { const long long c0 = clock64(); if (dbg_t) dbg_rest += c0 - dbg_t; dbg_t = c0; }
     if (scanner) {
@@ -227,8 +240,8 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
         const int cpad = sp.chunk_pad;
         uint32_t best32 = 0u;
         auto node = [&](int off, bool check) {
-          if (check && off == pend_off) {  // the node committed a moment ago: its row, generation and memo entry are being written by the memory warp
-            while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
+          if (check && off == pend_off) {  // the node committed a moment ago: wait for the urgent part of its commit
+            while (ld_vol_s32(&ss.commit_seq) != (int32_t)k) { }
             __threadfence_block();
           }
           const longlong2 fr = r_free[off];
@@ -261,6 +274,9 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
         }
       } else {
         const unsigned long long taint_bad0 = c.taint_bad0, sel0 = c.sel0, forbid0 = c.forbid0;
+        // (streamed rows: tiles requested during this pass read the global columns — thread 0, which requests them, waits for the
+        //  WHOLE commit of the last wave first)
+        if (tid == 0 && pend_off >= 0) { while (ld_vol_s32(&ss.commit_full) != (int32_t)k) { } __threadfence_block(); }
         for (int tile = 0; tile < tiles; tile++) {
           const uint32_t use = ubase + (uint32_t)tile;
           const int s = (int)(use % NST);
@@ -274,7 +290,7 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
           for (int j = tid; j < STREAM_TILE; j += STREAM_THREADS) {
             const int off = tile * STREAM_TILE + j;
             if (off == pend_off) {
-              while (*reinterpret_cast<volatile int32_t *>(&ss.commit_seq) != (int32_t)k) { }
+              while (ld_vol_s32(&ss.commit_full) != (int32_t)k) { }
               __threadfence_block();
             }
             // NodeResourcesFit (+ NodeUnschedulable / TaintToleration / nodeSelector / NodePorts / existing anti-affinity bits)
@@ -299,7 +315,7 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
             }
           }
           if (!all_in_flight) {
-            asm volatile("bar.sync 1, %0;" ::"n"(STREAM_THREADS) : "memory");   // the scanning warps are done with stage s
+            bar_sync_n(3, STREAM_THREADS);   // the scanning warps are done with stage s
             // (no proxy fence here: the rows of a later tile were last written in an earlier wave)
             if (tid == 0 && tile + NST < tiles) issue(tile + NST, s, t);
           }
@@ -311,18 +327,18 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
       if (lane == 0) ss.warp_best[warp] = v;
     }
     SPH_MARK(0);                           // scan: mbarrier wait + Filter/arg-max over the chunk
-    __syncthreads();                       // A: the pass is over — warp maxima visible, stages free
-    SPH_MARK(1);                           // barrier A (the service warp's commit of the last wave included)
+    bar_sync_n(1, SYNC_N);                 // A: the pass is over — warp maxima visible, stages free
+    SPH_MARK(1);                           // barrier A
     if (dbg) { const long long c0 = clock64(); dbg_rest += c0 - dbg_t; dbg_t = c0; }
     uses = ubase + (RESF ? (uint32_t)NST : (uint32_t)tiles);
     const uint32_t uses_next = uses;           // the next wave's tile q lands in stage (uses_next + q) % STAGES
     prefetched = !(p.max_pods > 0 && k + 1 >= p.max_pods);
     if (prefetched) pf_wave = k + 1;
-    if (service && lane == 0 && prefetched) request_first_tiles(uses_next, (int)((k + 1) % T));    // the next wave's memo column, while the exchange runs
     if (xwarp) {
       const unsigned long long tagbits = (unsigned long long)tag << KEY_TAG_SHIFT;
       const unsigned long long mine = warp_max_u64(lane < STREAM_WARPS ? ss.warp_best[lane] : 0ull);
       if (lane == 0) st_slot(p.slots + ((size_t)(k & 1) * CCSIM_MAX_GRID + cta) * SLOT_STRIDE, (mine & KEY_BODY_MASK) | tagbits);
+      if (lane == 0 && prefetched) request_first_tiles(uses_next, (int)((k + 1) % T));    // the next wave's memo column, while the keys travel
       bool dead = false;
       unsigned long long wkey = 0ull;
       {
@@ -349,87 +365,111 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 1) ccsim_wave_stream_kernel(cons
         if (dead) { ss.stop = 3; ss.winner = -1; }
         else if (wkey == 0ull) { ss.stop = 1; ss.winner = -1; }
         else { ss.winner = (int32_t)key_index(wkey); if (k >= p.pod_cap) ss.stop = 3; }     // (no room to record the placement)
+        // hand the winner to the commit warp (ring of STREAM_WQ: it may lag behind, but never by more than the ring)
+        while (ld_vol_s32(&ss.c_done) + STREAM_WQ <= (int32_t)k) { }
+        ss.wq[k & (STREAM_WQ - 1)] = ss.stop ? STREAM_WQ_STOP : ss.winner;
+        __threadfence_block();
+        st_vol_s32(&ss.w_seq, (int32_t)k + 1);
       }
     }
-    __syncthreads();                       // B: the winner is known to every thread
+    bar_sync_n(2, SYNC_N);                 // B: the winner is known to every scanning thread
     SPH_MARK(2);                           // exchange: publish, poll every CTA's key (one L2 round trip + the slowest CTA)
     if (dbg) { const long long c0 = clock64(); dbg_xchg += c0 - dbg_t; dbg_t = c0; }
     if (ss.stop) break;
-    // ---- commit (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) by the service warp of the
-    //      owner CTA, while the scanning warps already work on the next wave. Only the thread that scans the committed node itself
-    //      waits for it (ss.commit_seq). ----
     pend_off = -1;
     {
       const int32_t w = ss.winner - p.node_base;
-      const bool local = w >= 0 && w < p.n;
-      const int oc = local ? w / p.chunk : -1;
-      if (oc == cta) pend_off = (int)(w - (long long)oc * p.chunk);
-      if (service) {
-        if (!local && cta == 0 && lane == 0) p.pod_node[k] = ss.winner;      // sharded run: every rank keeps the whole pod -> node sequence
-        if (oc == cta) {
-          const long long q = base + (w - (long long)oc * p.chunk);
-          const int roff = pend_off;
-          // the committed row (types.go:409-427): every lane reads the six columns (one L2 round trip, broadcast), lanes 1..5 write
-          // one column each through to global memory (the terminal diagnosis reads it), lane 0 keeps the streamed / resident copy
-          const long long a_cpu = p.alloc_cpu[w], a_mem = p.alloc_mem[w];
-          const long long n_rcpu = p.req_cpu[w] + c.req_cpu, n_rmem = p.req_mem[w] + c.req_mem;
-          const long long n_zcpu = p.nz_cpu[w] + c.nz_cpu, n_zmem = p.nz_mem[w] + c.nz_mem;
-          int32_t newgen = 0;
-          if (lane == 0) {
-            if (RESF) { longlong2 fr = r_free[roff]; fr.x -= c.req_cpu; fr.y -= c.req_mem; r_free[roff] = fr; int2 pg = r_pg[roff]; newgen = (pg.y + 1) & 0x7ffff; r_pg[roff] = make_int2(pg.x - 1, newgen); }
-            else { sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1; }
-            p.pod_node[k] = w + p.node_base;
-          }
-          if (lane == 1) p.req_cpu[w] = n_rcpu;
-          else if (lane == 2) p.req_mem[w] = n_rmem;
-          else if (lane == 3) p.nz_cpu[w] = n_zcpu;
-          else if (lane == 4) p.nz_mem[w] = n_zmem;
-          else if (lane == 5) p.npods[w] += 1;
-          int32_t patch = -1;
-          if (RESF) {
-            // Every template's memo entry of this node is re-scored NOW, by the owner (two templates per lane), under the node's new
-            // generation: a stale entry found by the scan costs a CTA an L2 round trip plus the score's divisions in the middle of
-            // its pass, and with 64 templates every wave would meet the nodes committed by the 63 waves before it.
-            newgen = __shfl_sync(0xffffffffu, newgen, 0);
-            const int tn = (int)((k + 1) % T);
-            for (int tt = lane; tt < T; tt += 32) {
-              const StreamTmpl &ct = ss.tc[tt];
-              const int32_t sc = score_node(a_cpu, a_mem, n_zcpu + ct.least_cpu, n_zmem + ct.least_mem, n_rcpu + ct.bal_cpu, n_rmem + ct.bal_mem, ct.sw);
-              const int32_t enc = (newgen << 12) | (sc + 1);
-              sp.memo[(size_t)tt * sp.n_pad + q] = enc;
-              if (tt == tn) patch = enc;
-            }
-            fence_proxy_async();           // these generic-proxy stores, before the bulk-async reads of later waves
-            patch = __shfl_sync(0xffffffffu, patch, tn & 31);
-          } else {
-            for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
-            fence_proxy_async();
-          }
-          // the winner's row may already sit, pre-commit, in a stage requested for the next wave: wait for that copy, then patch it
-          const int tw = roff / STREAM_TILE, j = roff - tw * STREAM_TILE;
-          if (prefetched && tw < NST && tw < tiles && lane == 0) {
-            const uint32_t u = uses_next + (uint32_t)tw;
-            const int s = RESF ? tw : (int)(u % NST);
-            if (RESF) { while (!mbar_try_wait(&ss.full[0], (uint32_t)((k + 1) & 1))) { } }
-            else { while (!mbar_try_wait(&ss.full[s], (u / NST) & 1u)) { } }
-            unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
-            if (!RESF) {
-              reinterpret_cast<long long *>(st)[j] = sp.f_cpu[q];
-              reinterpret_cast<long long *>(st + STREAM_TILE * 8)[j] = sp.f_mem[q];
-              reinterpret_cast<int32_t *>(st + STREAM_TILE * 16)[j] = sp.f_pods[q];
-            }
-            reinterpret_cast<int32_t *>(st + MEMO_OFF)[j] = RESF ? patch : -1;
-          }
-          __threadfence_block();
-          __syncwarp();                      // the lanes' column stores, before lane 0 announces the commit
-          if (lane == 0) *reinterpret_cast<volatile int32_t *>(&ss.commit_seq) = (int32_t)(k + 1);
-        }
-      }
+      if (w >= 0 && w < p.n && w / p.chunk == cta) pend_off = w - cta * p.chunk;
     }
     wtag = (wtag == 4095u) ? 1u : wtag + 1u;
     tag = (p.epoch << 12) | wtag;
   }
-  if (prefetched && service && lane == 0) {       // copies requested for a wave that never ran: let them land before the CTA exits
+  else {
+    // ---- the commit warp (assume -> AssumePod -> NodeInfo.update(+1): schedule_one.go:967-984, types.go:409-427) ----
+    for (long long kc = 0;; kc++) {
+      if (p.max_pods > 0 && kc >= p.max_pods) break;
+      if (kc > p.pod_cap) break;
+      while (ld_vol_s32(&ss.w_seq) <= (int32_t)kc) { }
+      __threadfence_block();
+      const int32_t wn = ss.wq[kc & (STREAM_WQ - 1)];
+      if (wn == STREAM_WQ_STOP) break;
+      const StreamTmpl &c = ss.tc[(int)(kc % T)];
+      const int32_t w = wn - p.node_base;
+      const bool local = w >= 0 && w < p.n;
+      const int oc = local ? w / p.chunk : -1;
+      if (!local && cta == 0 && lane == 0) p.pod_node[kc] = wn;      // sharded run: every rank keeps the whole pod -> node sequence
+      if (oc == cta) {
+        const int roff = w - oc * p.chunk;
+        const long long q = base + roff;
+        const bool pf = !(p.max_pods > 0 && kc + 1 >= p.max_pods);        // the next wave's first tiles were requested before this commit
+        const int tn = (int)((kc + 1) % T);
+        // URGENT: every lane reads the row columns (one L2 round trip, broadcast); lanes 1..5 write one column each through to global
+        // memory at once — a scanning thread of THIS CTA that meets a not-yet-refreshed memo entry of the node re-scores it from
+        // those columns, so they must be current before `commit_seq` says so (same SM: the L1 sees the stores)
+        const long long a_cpu = p.alloc_cpu[w], a_mem = p.alloc_mem[w];
+        const long long n_rcpu = p.req_cpu[w] + c.req_cpu, n_rmem = p.req_mem[w] + c.req_mem;
+        const long long n_zcpu = p.nz_cpu[w] + c.nz_cpu, n_zmem = p.nz_mem[w] + c.nz_mem;
+        const int32_t n_pods = p.npods[w] + 1;
+        const int tw = roff / STREAM_TILE, j = roff - tw * STREAM_TILE;
+        if (lane == 0) p.pod_node[kc] = w + p.node_base;
+        else if (lane == 1) p.req_cpu[w] = n_rcpu;
+        else if (lane == 2) p.req_mem[w] = n_rmem;
+        else if (lane == 3) p.nz_cpu[w] = n_zcpu;
+        else if (lane == 4) p.nz_mem[w] = n_zmem;
+        else if (lane == 5) p.npods[w] = n_pods;
+        __threadfence_block();
+        __syncwarp();
+        int32_t newgen = 0;
+        if (RESF) {
+          // resident copy + generation, and the next wave's memo entry of this node patched into the landed column
+          const StreamTmpl &cn = ss.tc[tn];
+          const int32_t scn = score_node(a_cpu, a_mem, n_zcpu + cn.least_cpu, n_zmem + cn.least_mem, n_rcpu + cn.bal_cpu, n_rmem + cn.bal_mem, cn.sw);
+          if (lane == 0) {
+            longlong2 fr = r_free[roff]; fr.x -= c.req_cpu; fr.y -= c.req_mem; r_free[roff] = fr;
+            const int2 pg = r_pg[roff]; newgen = (pg.y + 1) & 0x7ffff; r_pg[roff] = make_int2(pg.x - 1, newgen);
+            if (pf) {
+              while (!mbar_try_wait(&ss.full[0], (uint32_t)((kc + 1) & 1))) { }
+              reinterpret_cast<int32_t *>(smem_raw)[roff] = (newgen << 12) | (scn + 1);
+            }
+            __threadfence_block();
+            st_vol_s32(&ss.commit_seq, (int32_t)kc + 1);
+          }
+          newgen = __shfl_sync(0xffffffffu, newgen, 0);
+        } else if (lane == 0) { sp.f_cpu[q] -= c.req_cpu; sp.f_mem[q] -= c.req_mem; sp.f_pods[q] -= 1; }
+        // LAZY: the other templates' memo entries
+        if (RESF) {
+          // every template's memo entry of this node, re-scored under the new generation (two templates per lane): a stale entry met by
+          // a scan costs that CTA an L2 round trip plus the score's divisions in the middle of its pass
+          for (int tt = lane; tt < T; tt += 32) {
+            const StreamTmpl &ct = ss.tc[tt];
+            const int32_t sc = score_node(a_cpu, a_mem, n_zcpu + ct.least_cpu, n_zmem + ct.least_mem, n_rcpu + ct.bal_cpu, n_rmem + ct.bal_mem, ct.sw);
+            sp.memo[(size_t)tt * sp.n_pad + q] = (newgen << 12) | (sc + 1);
+          }
+          fence_proxy_async();             // these generic-proxy stores, before the bulk-async reads of later waves
+        } else {
+          for (int tt = lane; tt < T; tt += 32) sp.memo[(size_t)tt * sp.n_pad + q] = -1;      // this node's NodeInfo generation changed
+          fence_proxy_async();
+          // the winner's row may already sit, pre-commit, in a stage requested for the next wave: wait for that copy, then patch it
+          if (pf && tw < NST && tw < tiles && lane == 0) {
+            const uint32_t u = (uint32_t)(kc + 1) * (uint32_t)tiles + (uint32_t)tw;
+            const int s = (int)(u % NST);
+            while (!mbar_try_wait(&ss.full[s], (u / NST) & 1u)) { }
+            unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
+            reinterpret_cast<long long *>(st)[j] = sp.f_cpu[q];
+            reinterpret_cast<long long *>(st + STREAM_TILE * 8)[j] = sp.f_mem[q];
+            reinterpret_cast<int32_t *>(st + STREAM_TILE * 16)[j] = sp.f_pods[q];
+            reinterpret_cast<int32_t *>(st + MEMO_OFF)[j] = -1;
+          }
+        }
+        __threadfence_block();
+        __syncwarp();                      // the lanes' stores, before lane 0 announces the whole commit
+        if (lane == 0) st_vol_s32(&ss.commit_full, (int32_t)kc + 1);
+      }
+      __syncwarp();
+      if (lane == 0) st_vol_s32(&ss.c_done, (int32_t)kc + 1);
+    }
+  }
+  if (prefetched && xwarp && lane == 0) {         // copies requested for a wave that never ran: let them land before the CTA exits
     if (RESF) { while (!mbar_try_wait(&ss.full[0], (uint32_t)(pf_wave & 1))) { } }
     else
       for (int q = 0; q < NST && q < tiles; q++) {
