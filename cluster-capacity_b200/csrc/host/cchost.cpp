@@ -655,9 +655,9 @@ static int build_report(cc_handle *h) {
   Json tmpls = Json::array();
   Json reqs = Json::array();
   for (auto &t : h->tmpls) { tmpls.push(t.raw); reqs.push(requirements_json(t)); }
-  spec.set("templates", tmpls);
+  spec.set("templates", std::move(tmpls));
   spec.set("replicas", Json::number(h->max_pods));
-  spec.set("podRequirements", reqs);
+  spec.set("podRequirements", std::move(reqs));
   Json status = Json::object();
   status.set("creationTimestamp", Json::string(rfc3339_now()));
   status.set("replicas", Json::number((long long)h->pod_node.size()));
@@ -672,7 +672,7 @@ static int build_report(cc_handle *h) {
   while (!m.empty() && m.front() == ' ') m.erase(m.begin());
   while (!m.empty() && m.back() == ' ') m.pop_back();
   fr.set("failMessage", Json::string(m));
-  status.set("failReason", fr);
+  status.set("failReason", std::move(fr));
   // parsePodsReview (report.go:146-180): per template (pod k belongs to template k % T), ReplicasOnNodes in order of first placement
   Json pods = Json::array();
   const size_t T = h->tmpls.size();
@@ -680,17 +680,18 @@ static int build_report(cc_handle *h) {
     Json rons = Json::array();
     std::vector<int64_t> count(h->enc.n, 0); std::vector<int32_t> order;
     for (size_t k = t; k < h->pod_node.size(); k += T) { const int32_t w = h->pod_node[k]; if (count[w]++ == 0) order.push_back(w); }
-    for (int32_t w : order) { Json r = Json::object(); r.set("nodeName", Json::string(h->enc.names[w])); r.set("replicas", Json::number(count[w])); rons.push(r); }
+    rons.arr.reserve(order.size());
+    for (int32_t w : order) { Json r = Json::object(); r.obj.reserve(2); r.set("nodeName", Json::string(h->enc.names[w])); r.set("replicas", Json::number(count[w])); rons.push(std::move(r)); }
     Json podres = Json::object();
     podres.set("podName", Json::string(h->tmpls[t].name));
-    podres.set("replicasOnNodes", rons);
+    podres.set("replicasOnNodes", std::move(rons));      // (moved, not copied: one entry per node that received a clone)
     podres.set("failSummary", Json::null());   // never populated by the reference (report.go:174-179)
-    pods.push(podres);
+    pods.push(std::move(podres));
   }
-  status.set("pods", pods);
+  status.set("pods", std::move(pods));
   h->report = Json::object();
-  h->report.set("spec", spec);
-  h->report.set("status", status);
+  h->report.set("spec", std::move(spec));
+  h->report.set("status", std::move(status));
   h->have_report = true;
   return CC_OK;
 }

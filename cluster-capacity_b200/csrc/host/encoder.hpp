@@ -13,6 +13,7 @@
 // per-domain initial counts).
 #pragma once
 #include <thread>
+#include <atomic>
 #include <chrono>
 #include <exception>
 #include <unordered_map>
@@ -89,7 +90,49 @@ inline ResourceList default_non_missing() {
 }
 
 // PodInfo.CalculateResource (framework/types.go:700-734)
+inline PodResource calculate_resource_general(const Pod &p);
+// The common shape of an EXISTING pod — plain containers, no init containers / overhead / pod-level resources / resize status —
+// needs none of resourcehelper.PodRequests' list arithmetic: the pod's request of a resource is the exact sum of its containers'
+// quantities (Quantity.Add is exact; Value()/MilliValue() round the SUM up, quantity.go:812-834), and GetNonzeroRequests sees
+// every container that names no cpu / memory at 100m / 200Mi (applyNonMissing). Same numbers as the general path
+// (CCHOST_CHECK_FAST=1 computes both and compares), without a std::map per container: this runs once per pod of the snapshot.
 inline PodResource calculate_resource(const Pod &p) {
+  if (!p.init_containers.empty() || !p.overhead.empty() || !p.pod_level_requests.empty() || p.has_pod_level_requests ||
+      !p.status_resources.empty() || !p.status_allocated.empty())
+    return calculate_resource_general(p);
+  static const i128 kDefCpu = Quantity::parse("100m").nanos, kDefMem = Quantity::parse("209715200").nanos;
+  PodResource out;
+  i128 cpu = 0, mem = 0, eph = 0, z_cpu = 0, z_mem = 0;
+  bool any_cpu = false, any_mem = false;
+  std::map<std::string, i128> scalar;     // (stays empty — no allocation — unless the pod requests an extended resource)
+  for (auto &c : p.containers) {
+    bool has_cpu = false, has_mem = false;
+    for (auto &kv : c.requests) {
+      if (kv.first == "cpu") { cpu += kv.second.nanos; z_cpu += kv.second.nanos; has_cpu = true; }
+      else if (kv.first == "memory") { mem += kv.second.nanos; z_mem += kv.second.nanos; has_mem = true; }
+      else if (kv.first == "ephemeral-storage") eph += kv.second.nanos;
+      else if (kv.first == "pods") {}
+      else if (is_scalar_resource_name(kv.first)) scalar[kv.first] += kv.second.nanos;
+    }
+    if (!has_cpu) z_cpu += kDefCpu;
+    if (!has_mem) z_mem += kDefMem;
+    any_cpu = true; any_mem = true;
+  }
+  out.cpu = (int64_t)Quantity::ceil_div(cpu, Quantity::pow10(6));
+  out.mem = (int64_t)Quantity::ceil_div(mem, Quantity::pow10(9));
+  out.eph = (int64_t)Quantity::ceil_div(eph, Quantity::pow10(9));
+  for (auto &kv : scalar) out.scalar[kv.first] = (int64_t)Quantity::ceil_div(kv.second, Quantity::pow10(9));
+  out.non0_cpu = any_cpu ? (int64_t)Quantity::ceil_div(z_cpu, Quantity::pow10(6)) : 0;
+  out.non0_mem = any_mem ? (int64_t)Quantity::ceil_div(z_mem, Quantity::pow10(9)) : 0;
+  static const bool check = getenv("CCHOST_CHECK_FAST") != nullptr;
+  if (check) {
+    const PodResource g = calculate_resource_general(p);
+    if (g.cpu != out.cpu || g.mem != out.mem || g.eph != out.eph || g.scalar != out.scalar || g.non0_cpu != out.non0_cpu || g.non0_mem != out.non0_mem)
+      throw std::runtime_error("calculate_resource: fast path differs from the general path for pod " + p.ns + "/" + p.name);
+  }
+  return out;
+}
+inline PodResource calculate_resource_general(const Pod &p) {
   PodResource out;
   ResourceList req = p.requests(/*use_status=*/true, /*skip_pod_level=*/false, nullptr);
   ResourceList nm;
@@ -170,27 +213,28 @@ class Encoder {
     for (auto &n : nodes_in) if (exclude.empty() || !exclude.count(n.name)) kept.push_back(&n);
     std::vector<std::string> zkey(kept.size());
     parallel_for((int)kept.size(), [&](int i) { zkey[i] = kept[i]->zone_key(); });
-    std::vector<std::vector<const Node *>> tree;              // one list per zone, zones in first-seen order
+    // (one hash map does both jobs: "already in the tree" and, once the order is known, name -> position; references to the
+    //  mapped values stay valid while the map grows)
+    std::vector<std::vector<std::pair<const Node *, int *>>> tree;   // one list per zone, zones in first-seen order
     std::unordered_map<std::string_view, int> zone_id;
-    std::unordered_set<std::string_view> seen;
-    seen.reserve(kept.size() * 2);
+    node_index_.reserve(kept.size() * 2);
+    size_t total = 0;
     for (size_t i = 0; i < kept.size(); i++) {
       const Node *n = kept[i];
-      if (!seen.insert(std::string_view(n->name)).second) continue;   // "Did not add to the NodeTree because it already exists"
+      auto ins = node_index_.emplace(std::string_view(n->name), -1);
+      if (!ins.second) continue;   // "Did not add to the NodeTree because it already exists"
       auto it = zone_id.find(std::string_view(zkey[i]));
       if (it == zone_id.end()) { it = zone_id.emplace(std::string_view(zkey[i]), (int)tree.size()).first; tree.emplace_back(); }
-      tree[it->second].push_back(n);
+      tree[it->second].push_back({n, &ins.first->second});
+      total++;
     }
-    size_t total = seen.size(), idx = 0;
+    size_t idx = 0;
     nodes_.reserve(total);
     while (nodes_.size() < total) {
-      for (auto &v : tree) if (idx < v.size()) nodes_.push_back(v[idx]);
+      for (auto &v : tree) if (idx < v.size()) { *v[idx].second = (int)nodes_.size(); nodes_.push_back(v[idx].first); }
       idx++;
     }
-    node_index_.reserve(nodes_.size() * 2);
-    for (size_t i = 0; i < nodes_.size(); i++) node_index_[std::string_view(nodes_[i]->name)] = (int)i;
     // ---- pods: non-terminal, bound to a known node ----
-    pods_on_.resize(nodes_.size());
     std::vector<int32_t> where(pods_in.size(), -1);
     parallel_for((int)pods_in.size(), [&](int j) {
       const Pod &p = pods_in[j];
@@ -199,7 +243,7 @@ class Encoder {
       auto it = node_index_.find(std::string_view(p.node_name));
       if (it != node_index_.end()) where[j] = it->second;
     });
-    for (size_t j = 0; j < pods_in.size(); j++) if (where[j] >= 0) pods_on_[where[j]].push_back(&pods_in[j]);
+    pods_on_.build(nodes_.size(), where, pods_in);
   }
 
   // Services / RCs / ReplicaSets / StatefulSets of the snapshot: only helper.DefaultSelector reads them (system-default spreading)
@@ -399,27 +443,46 @@ class Encoder {
       for (auto &t : nodes_[i]->taints) if ((t.effect == "NoSchedule" || t.effect == "NoExecute") && !tolerations_tolerate(t_.tolerations, t)) return true;
       return false;
     };
+    // per node, for ALL hard constraints in one pass over the node's labels and pods: the node's value of each constraint's key,
+    // eligibility (every constraint key present + the constraint's inclusion policies) and countPodsMatchSelector (common.go:144-158)
+    const size_t H = hard.size();
+    std::vector<std::vector<char>> eligible_c(H, std::vector<char>(n, 0));
+    std::vector<std::vector<int64_t>> node_cnt_c(H, std::vector<int64_t>(n, 0));
+    std::vector<std::vector<const std::string *>> value_c(H, std::vector<const std::string *>(n, nullptr));
+    bool any_aff_policy = false, any_taint_policy = false;
+    for (auto *h : hard) { any_aff_policy |= h->node_affinity_policy == "Honor"; any_taint_policy |= h->node_taints_policy == "Honor"; }
+    if (H > 0)
+      parallel_for(n, [&](int i) {
+        const Node &nd = *nodes_[i];
+        bool all_keys = true;
+        for (size_t c = 0; c < H; c++) {
+          auto vit = nd.labels.find(hard[c]->topology_key);
+          if (vit != nd.labels.end()) value_c[c][i] = &vit->second; else all_keys = false;
+        }
+        if (!all_keys) return;
+        const bool aff_ok = !any_aff_policy || required_affinity_match(i);
+        const bool taint_ok = !any_taint_policy || !untolerated(i);
+        bool any = false;
+        for (size_t c = 0; c < H; c++) {
+          if (hard[c]->node_affinity_policy == "Honor" && !aff_ok) continue;
+          if (hard[c]->node_taints_policy == "Honor" && !taint_ok) continue;
+          eligible_c[c][i] = 1;
+          any |= !hard_sel[c].empty();
+        }
+        if (!any) return;
+        for (auto *p : pods_on_[i]) {
+          if (p->terminating || p->ns != t_.ns) continue;
+          for (size_t c = 0; c < H; c++)
+            if (eligible_c[c][i] && !hard_sel[c].empty() && hard_sel[c].matches(p->labels)) node_cnt_c[c][i]++;
+        }
+      });
     for (size_t c = 0; c < hard.size(); c++) {
       const TopologySpreadConstraint &tc = *hard[c];
-      // domains: eligible nodes (all constraint keys present + inclusion policies) define TpValueToMatchNum; they get ids [0,n_present)
+      // domains: eligible nodes define TpValueToMatchNum; they get ids [0,n_present)
       std::unordered_map<std::string_view, int> dom_id; std::vector<int64_t> counts;
-      std::vector<char> eligible(n, 0);
-      std::vector<int64_t> node_cnt(n, 0);
-      std::vector<const std::string *> value(n, nullptr);    // the node's value of this constraint's key
-      parallel_for(n, [&](int i) {     // per node: eligibility and countPodsMatchSelector (common.go:144-158)
-        auto vit = nodes_[i]->labels.find(tc.topology_key);
-        if (vit != nodes_[i]->labels.end()) value[i] = &vit->second;
-        bool all_keys = true;
-        for (auto *h : hard) if (!nodes_[i]->labels.count(h->topology_key)) all_keys = false;
-        if (!all_keys) return;
-        if (tc.node_affinity_policy == "Honor" && !required_affinity_match(i)) return;
-        if (tc.node_taints_policy == "Honor" && untolerated(i)) return;
-        eligible[i] = 1;
-        int64_t cnt = 0;
-        if (!hard_sel[c].empty())
-          for (auto *p : pods_on_[i]) if (!p->terminating && p->ns == t_.ns && hard_sel[c].matches(p->labels)) cnt++;
-        node_cnt[i] = cnt;
-      });
+      const std::vector<char> &eligible = eligible_c[c];
+      const std::vector<int64_t> &node_cnt = node_cnt_c[c];
+      const std::vector<const std::string *> &value = value_c[c];
       std::vector<int32_t> col(n, -1);
       for (int i = 0; i < n; i++) {    // domain ids in first-seen order over the eligible nodes
         if (!eligible[i]) continue;
@@ -465,18 +528,30 @@ class Encoder {
     auto ipa_counter = [&](const std::string &key, const std::function<int(const Pod &)> &weight, int inc, int32_t &out_idx) {
       // one counter per topology key; node-local when every node has the key with a unique value
       std::unordered_map<std::string_view, int> dom_id; std::vector<int32_t> col(n, -1); std::vector<int64_t> counts;
-      dom_id.reserve(1024);
       std::vector<const std::string *> value(n, nullptr);
       parallel_for(n, [&](int i) { auto it = nodes_[i]->labels.find(key); if (it != nodes_[i]->labels.end()) value[i] = &it->second; });
+      tick("  ipa/values");
+      // kubernetes.io/hostname-style keys: when every node's value is its own (unique) name the domains are the nodes themselves,
+      // in node order — no dictionary to build
+      std::atomic<bool> own_name{n > 0};
+      parallel_for(n, [&](int i) { if (!value[i] || *value[i] != nodes_[i]->name) own_name.store(false, std::memory_order_relaxed); });
       bool unique = true;
-      for (int i = 0; i < n; i++) {
-        if (!value[i]) { unique = false; continue; }
-        auto ins = dom_id.emplace(std::string_view(*value[i]), (int)dom_id.size());
-        if (ins.second) counts.push_back(0); else unique = false;
-        col[i] = ins.first->second;
+      if (own_name.load()) {
+        counts.assign(n, 0);
+        for (int i = 0; i < n; i++) col[i] = i;
+      } else {
+        dom_id.reserve((size_t)n);
+        for (int i = 0; i < n; i++) {
+          if (!value[i]) { unique = false; continue; }
+          auto ins = dom_id.emplace(std::string_view(*value[i]), (int)dom_id.size());
+          if (ins.second) counts.push_back(0); else unique = false;
+          col[i] = ins.first->second;
+        }
       }
+      tick("  ipa/domain ids");
       std::vector<int64_t> per_node(n, 0);
       parallel_for(n, [&](int i) { if (col[i] < 0) return; for (auto *p : pods_on_[i]) per_node[i] += weight(*p); });
+      tick("  ipa/weights");
       for (int i = 0; i < n; i++) if (col[i] >= 0) counts[col[i]] += per_node[i];
       if (unique && n > 0) {
         std::vector<int32_t> init(per_node.begin(), per_node.end());
@@ -694,7 +769,22 @@ class Encoder {
   const std::map<std::string, Labels> &ns_labels_;
   std::vector<const Node *> nodes_;
   std::unordered_map<std::string_view, int> node_index_;   // keys view the Node objects' names (they outlive the encoder)
-  std::vector<std::vector<const Pod *>> pods_on_;
+  // the pods of every node, in the order of the source list: one offsets array + one pointer array (a counting sort; a
+  // std::vector per node costs one allocation per node on one core)
+  struct PodsOn {
+    struct Range { const Pod *const *b, *const *e; const Pod *const *begin() const { return b; } const Pod *const *end() const { return e; } };
+    std::vector<uint32_t> off;
+    std::vector<const Pod *> ptr;
+    void build(size_t n_nodes, const std::vector<int32_t> &where, const ObjList<Pod> &pods) {
+      off.assign(n_nodes + 1, 0);
+      for (size_t j = 0; j < where.size(); j++) if (where[j] >= 0) off[(size_t)where[j] + 1]++;
+      for (size_t i = 0; i < n_nodes; i++) off[i + 1] += off[i];
+      ptr.resize(off[n_nodes]);
+      std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+      for (size_t j = 0; j < where.size(); j++) if (where[j] >= 0) ptr[cur[(size_t)where[j]]++] = &pods[j];
+    }
+    Range operator[](size_t i) const { return Range{ptr.data() + off[i], ptr.data() + off[i + 1]}; }
+  } pods_on_;
   const std::vector<WorkloadSelector> *workloads_ = nullptr;
 
   // helper.DefaultSelector (plugins/helper/spread.go:40-93)
