@@ -13,6 +13,7 @@
 // per-domain initial counts).
 #pragma once
 #include <thread>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <exception>
@@ -167,6 +168,49 @@ template <class F> inline void parallel_for(int n, F fn) {
   for (auto &e : errs) if (e) std::rethrow_exception(e);
 }
 
+// String -> small integer index for the encoder's dictionaries (node names, topology values): open addressing over one flat
+// array, hashes supplied by the caller — they are computed by the parallel per-node passes, so the serial first-seen-order pass that
+// assigns ids (dictionary ids are order-dependent) costs a probe and a short memcmp per node instead of a hash + a heap node.
+class FlatIndex {
+ public:
+  static uint64_t hash(std::string_view k) { return std::hash<std::string_view>()(k); }
+  void init(size_t expected) {
+    size_t cap = 16;
+    while (cap < expected * 2 + 2) cap <<= 1;
+    tab_.assign(cap, Slot{nullptr, 0, -1, 0});
+    mask_ = cap - 1; size_ = 0;
+  }
+  // the slot of `k` (inserted with value `v` when new); .second = inserted
+  std::pair<int32_t *, bool> emplace(std::string_view k, uint64_t h, int32_t v) {
+    if ((size_ + 1) * 2 > tab_.size()) grow();
+    for (size_t i = h & mask_;; i = (i + 1) & mask_) {
+      Slot &s = tab_[i];
+      if (!s.p) { s.p = k.data(); s.len = (uint32_t)k.size(); s.val = v; s.h = h; size_++; return {&s.val, true}; }
+      if (s.h == h && s.len == k.size() && memcmp(s.p, k.data(), k.size()) == 0) return {&s.val, false};
+    }
+  }
+  const int32_t *find(std::string_view k, uint64_t h) const {
+    if (tab_.empty()) return nullptr;
+    for (size_t i = h & mask_;; i = (i + 1) & mask_) {
+      const Slot &s = tab_[i];
+      if (!s.p) return nullptr;
+      if (s.h == h && s.len == k.size() && memcmp(s.p, k.data(), k.size()) == 0) return &s.val;
+    }
+  }
+  const int32_t *find(std::string_view k) const { return find(k, hash(k)); }
+  size_t size() const { return size_; }
+ private:
+  struct Slot { const char *p; uint32_t len; int32_t val; uint64_t h; };
+  void grow() {       // (pointers returned by emplace die here: callers that keep them size the table up front with init())
+    std::vector<Slot> old; old.swap(tab_);
+    tab_.assign(old.size() ? old.size() * 2 : 16, Slot{nullptr, 0, -1, 0});
+    mask_ = tab_.size() - 1;
+    for (auto &s : old) if (s.p) { size_t i = s.h & mask_; while (tab_[i].p) i = (i + 1) & mask_; tab_[i] = s; }
+  }
+  std::vector<Slot> tab_;
+  size_t mask_ = 0, size_ = 0;
+};
+
 struct Encoded {
   int32_t n = 0;
   std::vector<std::string> names;
@@ -212,20 +256,25 @@ class Encoder {
     std::vector<const Node *> kept;
     for (auto &n : nodes_in) if (exclude.empty() || !exclude.count(n.name)) kept.push_back(&n);
     std::vector<std::string> zkey(kept.size());
-    parallel_for((int)kept.size(), [&](int i) { zkey[i] = kept[i]->zone_key(); });
-    // (one hash map does both jobs: "already in the tree" and, once the order is known, name -> position; references to the
-    //  mapped values stay valid while the map grows)
-    std::vector<std::vector<std::pair<const Node *, int *>>> tree;   // one list per zone, zones in first-seen order
+    std::vector<uint64_t> nhash(kept.size());
+    parallel_for((int)kept.size(), [&](int i) { zkey[i] = kept[i]->zone_key(); nhash[i] = FlatIndex::hash(kept[i]->name); });
+    // (one index does both jobs: "already in the tree" and, once the order is known, name -> position; it is sized up front, so
+    //  the slots handed out stay where they are)
+    std::vector<std::vector<std::pair<const Node *, int32_t *>>> tree;   // one list per zone, zones in first-seen order
     std::unordered_map<std::string_view, int> zone_id;
-    node_index_.reserve(kept.size() * 2);
+    node_index_.init(kept.size());
     size_t total = 0;
+    int last_zone = -1, cur_zone = 0;
     for (size_t i = 0; i < kept.size(); i++) {
       const Node *n = kept[i];
-      auto ins = node_index_.emplace(std::string_view(n->name), -1);
+      auto ins = node_index_.emplace(std::string_view(n->name), nhash[i], -1);
       if (!ins.second) continue;   // "Did not add to the NodeTree because it already exists"
-      auto it = zone_id.find(std::string_view(zkey[i]));
-      if (it == zone_id.end()) { it = zone_id.emplace(std::string_view(zkey[i]), (int)tree.size()).first; tree.emplace_back(); }
-      tree[it->second].push_back({n, &ins.first->second});
+      if (last_zone < 0 || zkey[i] != zkey[(size_t)last_zone]) {     // (runs of nodes of one zone — or a cluster without zone labels — skip the lookup)
+        auto it = zone_id.find(std::string_view(zkey[i]));
+        if (it == zone_id.end()) { it = zone_id.emplace(std::string_view(zkey[i]), (int)tree.size()).first; tree.emplace_back(); }
+        cur_zone = it->second; last_zone = (int)i;
+      }
+      tree[(size_t)cur_zone].push_back({n, ins.first});
       total++;
     }
     size_t idx = 0;
@@ -236,14 +285,27 @@ class Encoder {
     }
     // ---- pods: non-terminal, bound to a known node ----
     std::vector<int32_t> where(pods_in.size(), -1);
+    std::vector<uint8_t> pflags(pods_in.size(), 0);   // what the rare-case passes of encode() look for, noted while the pod is in cache anyway
     parallel_for((int)pods_in.size(), [&](int j) {
       const Pod &p = pods_in[j];
       if (p.phase == "Succeeded" || p.phase == "Failed") return;
       if (p.node_name.empty()) return;   // pending pods are not replayed (documented deviation)
-      auto it = node_index_.find(std::string_view(p.node_name));
-      if (it != node_index_.end()) where[j] = it->second;
+      const int32_t *it = node_index_.find(std::string_view(p.node_name));
+      if (!it) return;
+      where[j] = *it;
+      pflags[j] = (uint8_t)((p.anti_required.empty() ? 0 : 1) | ((p.aff_required.empty() && p.aff_preferred.empty() && p.anti_preferred.empty()) ? 0 : 2) |
+                            (p.priority < t_.priority ? 4 : 0));
     });
     pods_on_.build(nodes_.size(), where, pods_in);
+    for (size_t j = 0; j < pods_in.size(); j++) {
+      if (!pflags[j]) continue;
+      if (pflags[j] & 1) anti_required_pods_.push_back({where[j], &pods_in[j]});
+      if (pflags[j] & 2) affinity_term_pods_.push_back({where[j], &pods_in[j]});
+      if (pflags[j] & 4) lower_priority_pod_ = true;
+    }
+    // node order, then source-list order within a node: the order in which a pass over pods_on_ would meet them (the topology keys of
+    // the InterPodAffinity score get their counter slots in first-seen order)
+    std::stable_sort(affinity_term_pods_.begin(), affinity_term_pods_.end(), [](auto &a, auto &b) { return a.first < b.first; });
   }
 
   // Services / RCs / ReplicaSets / StatefulSets of the snapshot: only helper.DefaultSelector reads them (system-default spreading)
@@ -449,6 +511,7 @@ class Encoder {
     std::vector<std::vector<char>> eligible_c(H, std::vector<char>(n, 0));
     std::vector<std::vector<int64_t>> node_cnt_c(H, std::vector<int64_t>(n, 0));
     std::vector<std::vector<const std::string *>> value_c(H, std::vector<const std::string *>(n, nullptr));
+    std::vector<std::vector<uint64_t>> vhash_c(H, std::vector<uint64_t>(n, 0));
     bool any_aff_policy = false, any_taint_policy = false;
     for (auto *h : hard) { any_aff_policy |= h->node_affinity_policy == "Honor"; any_taint_policy |= h->node_taints_policy == "Honor"; }
     if (H > 0)
@@ -457,7 +520,7 @@ class Encoder {
         bool all_keys = true;
         for (size_t c = 0; c < H; c++) {
           auto vit = nd.labels.find(hard[c]->topology_key);
-          if (vit != nd.labels.end()) value_c[c][i] = &vit->second; else all_keys = false;
+          if (vit != nd.labels.end()) { value_c[c][i] = &vit->second; vhash_c[c][i] = FlatIndex::hash(vit->second); } else all_keys = false;
         }
         if (!all_keys) return;
         const bool aff_ok = !any_aff_policy || required_affinity_match(i);
@@ -479,24 +542,26 @@ class Encoder {
     for (size_t c = 0; c < hard.size(); c++) {
       const TopologySpreadConstraint &tc = *hard[c];
       // domains: eligible nodes define TpValueToMatchNum; they get ids [0,n_present)
-      std::unordered_map<std::string_view, int> dom_id; std::vector<int64_t> counts;
+      FlatIndex dom_id; std::vector<int64_t> counts;
+      dom_id.init(1024);
       const std::vector<char> &eligible = eligible_c[c];
       const std::vector<int64_t> &node_cnt = node_cnt_c[c];
       const std::vector<const std::string *> &value = value_c[c];
+      const std::vector<uint64_t> &vhash = vhash_c[c];
       std::vector<int32_t> col(n, -1);
       for (int i = 0; i < n; i++) {    // domain ids in first-seen order over the eligible nodes
         if (!eligible[i]) continue;
-        auto it = dom_id.find(std::string_view(*value[i]));
-        if (it == dom_id.end()) { it = dom_id.emplace(std::string_view(*value[i]), (int)dom_id.size()).first; counts.push_back(0); }
-        counts[it->second] += node_cnt[i];
-        col[i] = it->second;
+        auto ins = dom_id.emplace(std::string_view(*value[i]), vhash[i], (int32_t)dom_id.size());
+        if (ins.second) counts.push_back(0);
+        counts[(size_t)*ins.first] += node_cnt[i];
+        col[i] = *ins.first;
       }
       const int n_present = (int)dom_id.size();
       for (int i = 0; i < n; i++) {
         if (eligible[i] || !value[i]) continue;
-        auto it = dom_id.find(std::string_view(*value[i]));
-        if (it == dom_id.end()) { it = dom_id.emplace(std::string_view(*value[i]), (int)dom_id.size()).first; counts.push_back(0); }   // value only on ineligible nodes: matchNum 0, never in the min
-        col[i] = it->second;
+        auto ins = dom_id.emplace(std::string_view(*value[i]), vhash[i], (int32_t)dom_id.size());   // value only on ineligible nodes: matchNum 0, never in the min
+        if (ins.second) counts.push_back(0);
+        col[i] = *ins.first;
       }
       int colidx = (int)e.topo.size();
       e.topo.push_back(col);
@@ -527,9 +592,10 @@ class Encoder {
     std::vector<AffinityTerm> aff = merged(t_.aff_required), anti = merged(t_.anti_required);
     auto ipa_counter = [&](const std::string &key, const std::function<int(const Pod &)> &weight, int inc, int32_t &out_idx) {
       // one counter per topology key; node-local when every node has the key with a unique value
-      std::unordered_map<std::string_view, int> dom_id; std::vector<int32_t> col(n, -1); std::vector<int64_t> counts;
+      FlatIndex dom_id; std::vector<int32_t> col(n, -1); std::vector<int64_t> counts;
       std::vector<const std::string *> value(n, nullptr);
-      parallel_for(n, [&](int i) { auto it = nodes_[i]->labels.find(key); if (it != nodes_[i]->labels.end()) value[i] = &it->second; });
+      std::vector<uint64_t> vhash(n, 0);
+      parallel_for(n, [&](int i) { auto it = nodes_[i]->labels.find(key); if (it != nodes_[i]->labels.end()) { value[i] = &it->second; vhash[i] = FlatIndex::hash(it->second); } });
       tick("  ipa/values");
       // kubernetes.io/hostname-style keys: when every node's value is its own (unique) name the domains are the nodes themselves,
       // in node order — no dictionary to build
@@ -540,12 +606,12 @@ class Encoder {
         counts.assign(n, 0);
         for (int i = 0; i < n; i++) col[i] = i;
       } else {
-        dom_id.reserve((size_t)n);
+        dom_id.init(1024);
         for (int i = 0; i < n; i++) {
           if (!value[i]) { unique = false; continue; }
-          auto ins = dom_id.emplace(std::string_view(*value[i]), (int)dom_id.size());
+          auto ins = dom_id.emplace(std::string_view(*value[i]), vhash[i], (int32_t)dom_id.size());
           if (ins.second) counts.push_back(0); else unique = false;
-          col[i] = ins.first->second;
+          col[i] = *ins.first;
         }
       }
       tick("  ipa/domain ids");
@@ -597,13 +663,14 @@ class Encoder {
     // existing pods' required anti-affinity against the incoming pod (getExistingAntiAffinityCounts): static bit
     {
       std::set<std::pair<std::string, std::string>> blocked;
-      for (int i = 0; i < n; i++)
-        for (auto *p : pods_on_[i])
-          for (auto &t : p->anti_required)
-            if (t.matches(t_.ns, t_.labels, t_ns_labels)) {
-              auto it = nodes_[i]->labels.find(t.topology_key);
-              if (it != nodes_[i]->labels.end()) blocked.insert({t.topology_key, it->second});
-            }
+      for (auto &ip : anti_required_pods_) {       // (the pods that carry such terms were listed while the pods were assigned to nodes)
+        const int i = ip.first;
+        for (auto &t : ip.second->anti_required)
+          if (t.matches(t_.ns, t_.labels, t_ns_labels)) {
+            auto it = nodes_[i]->labels.find(t.topology_key);
+            if (it != nodes_[i]->labels.end()) blocked.insert({t.topology_key, it->second});
+          }
+      }
       if (!blocked.empty())
         set_mask(T.existing_anti_mask, new_bit([&](int i) {
           for (auto &kv : nodes_[i]->labels) if (blocked.count({kv.first, kv.second})) return true;
@@ -699,12 +766,12 @@ class Encoder {
       contributions(t_, clone);
       note(clone);
       std::map<const Pod *, std::map<std::string, int64_t>> per_pod;
-      for (int i = 0; i < n; i++)
-        for (auto *p : pods_on_[i]) {
-          if (p->aff_required.empty() && p->aff_preferred.empty() && p->anti_preferred.empty() && paff.empty() && panti.empty()) continue;
-          std::map<std::string, int64_t> m; contributions(*p, m);
-          if (!m.empty()) { note(m); per_pod[p] = m; }
-        }
+      auto visit = [&](const Pod *p) {
+        std::map<std::string, int64_t> m; contributions(*p, m);
+        if (!m.empty()) { note(m); per_pod[p] = m; }
+      };
+      if (paff.empty() && panti.empty()) { for (auto &ip : affinity_term_pods_) visit(ip.second); }   // only pods with terms of their own can contribute
+      else for (int i = 0; i < n; i++) for (auto *p : pods_on_[i]) visit(p);
       if (keys.size() > CCSIM_MAX_IPA) throw Unsupported("more than 8 topology keys in pod (anti-)affinity scoring terms");
       for (size_t k = 0; k < keys.size(); k++) {
         auto w = [&](const Pod &p) { auto it = per_pod.find(&p); if (it == per_pod.end()) return 0; auto jt = it->second.find(keys[k]); return jt == it->second.end() ? 0 : (int)jt->second; };
@@ -713,7 +780,9 @@ class Encoder {
       T.n_ipa_score = (int32_t)keys.size();
     }
     // ---- ImageLocality (image_locality.go:54-131; backend/cache/cache.go:680-703): static per node ----
-    if (cfg_.score_enable & CCSIM_PL_IMAGE_LOCALITY) {
+    bool any_images = false;
+    for (int i = 0; i < n && !any_images; i++) any_images = !nodes_[i]->images.empty();
+    if ((cfg_.score_enable & CCSIM_PL_IMAGE_LOCALITY) && any_images) {      // (no image anywhere: every node scores 0)
       std::map<std::string, std::pair<int64_t, std::set<int>>> states;   // name -> (size as first registered, nodes)
       for (int i = 0; i < n; i++)
         for (auto &im : nodes_[i]->images) {
@@ -768,7 +837,7 @@ class Encoder {
   const Pod &t_;
   const std::map<std::string, Labels> &ns_labels_;
   std::vector<const Node *> nodes_;
-  std::unordered_map<std::string_view, int> node_index_;   // keys view the Node objects' names (they outlive the encoder)
+  FlatIndex node_index_;   // keys view the Node objects' names (they outlive the encoder)
   // the pods of every node, in the order of the source list: one offsets array + one pointer array (a counting sort; a
   // std::vector per node costs one allocation per node on one core)
   struct PodsOn {
@@ -785,6 +854,8 @@ class Encoder {
     }
     Range operator[](size_t i) const { return Range{ptr.data() + off[i], ptr.data() + off[i + 1]}; }
   } pods_on_;
+  std::vector<std::pair<int, const Pod *>> anti_required_pods_, affinity_term_pods_;   // (node index, pod) of the pods with such terms
+  bool lower_priority_pod_ = false;
   const std::vector<WorkloadSelector> *workloads_ = nullptr;
 
   // helper.DefaultSelector (plugins/helper/spread.go:40-93)
@@ -823,9 +894,7 @@ class Encoder {
     if (t_.has_pvc_volume) throw Unsupported("pod uses PersistentVolumeClaim/ephemeral volumes (VolumeBinding/VolumeZone/NodeVolumeLimits/VolumeRestrictions)");
     if (t_.has_resource_claims) throw Unsupported("pod uses resourceClaims (DynamicResources)");
     if (t_.has_scheduling_gates) throw Unsupported("pod has schedulingGates");
-    for (size_t i = 0; i < nodes_.size(); i++)
-      for (auto *p : pods_on_[i])
-        if (p->priority < t_.priority) throw Unsupported("an existing pod has lower priority than the simulated pod (DefaultPreemption would evict it)");
+    if (lower_priority_pod_) throw Unsupported("an existing pod has lower priority than the simulated pod (DefaultPreemption would evict it)");
   }
 };
 
