@@ -49,6 +49,8 @@
 #endif
 #define MULTI_CAP (32 * MULTI_CPT)
 #define MULTI_BINS 64
+#define MULTI_RELAX_K 8           /* look-ahead on a PTS term when at most this many of its domains still sit at the global minimum ... */
+#define MULTI_RELAX_R 3           /* ... nodes in cells up to this far over the limit are published as dormant candidates */
 #define MULTI_XPT (((CCSIM_MAX_WORLD - 1) * MULTI_CAP + LEAN_THREADS - 1) / LEAN_THREADS)   /* node shards: remote candidates per thread */
 
 // cross-GPU line buffers inside every rank's exchange allocation (64-bit words): [parity][source rank][CTA][16]
@@ -72,6 +74,8 @@ struct __align__(16) MultiShared {
   int32_t xcount[CCSIM_MAX_WORLD];                  // node shards: candidates in each rank's summary
   uint32_t xglob[4];                                // node shards: best key, T_list, bar over all ranks
   uint32_t delta, pad_ms;
+  int32_t relax[LEAN_MAX_TERMS];                    // per Filter term: this wave's look-ahead over the limit (0: strict), see "dormant candidates"
+  int32_t force_strict, st_relaxed, st_empty, pad_r;
   long long ph[8], tc0, st_cand, st_overflow, st_rounds;       // CTA 0 / thread 0: clock cycles per phase, replay statistics
 };
 
@@ -179,7 +183,8 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     if (dc.topo_col < 0) continue;
     for (int d = tid; d < dc.n_domains; d += LEAN_THREADS) smem_cnt[dc.smem_off + d] = dc.init[d];
   }
-  if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; ms.accepted = 0; ms.dead = 0; ms.stopb = 0; ms.n_gt = 0; ms.ncand = 0; ms.delta = 1u << MULTI_IDX_BITS;
+  if (tid == 0) { ls.aff_total = p.templates[0].aff_total_init; ls.winner = -1; ls.stop = 0; ls.dirty = 1; ms.accepted = 0; ms.dead = 0; ms.stopb = 0; ms.n_gt = 0; ms.ncand = 0; ms.delta = 1u << MULTI_IDX_BITS; ms.force_strict = 0; ms.st_relaxed = 0; ms.st_empty = 0;
+                  for (int q = 0; q < LEAN_MAX_TERMS; q++) ms.relax[q] = 0;
                   for (int q = 0; q < 8; q++) ms.ph[q] = 0; ms.tc0 = 0; ms.st_cand = 0; ms.st_overflow = 0; ms.st_rounds = 0; }
   __syncthreads();
   for (int c = 0; c < ls.tmpl.n_pts; c++) lean_pts_recount(p, smem_cnt, c);
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         const bool local = lt.cnt_off < 0;
         const int32_t c = local ? v : smem_cnt[lt.cnt_off + (v < 0 ? 0 : v)];
         const bool has = local | (v >= 0);
-        ok &= has ? (c <= lt.lim) : (lt.miss_rejects == 0);
+        ok &= has ? (c <= lt.lim + ms.relax[q]) : (lt.miss_rejects == 0);     // (relax > 0: closed cells close to reopening publish their nodes as dormant candidates)
       }
       if (ok) {
         if (sc < 0) {
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
     //      minimum / multiplicity of the PTS constraint it tracks, stay in registers for the whole wave) ----
     if (warp == 0) {
       int32_t acc = 0;
-      bool ran_dry = false;
+      bool ran_dry = false, any_relax = false;
       if (!dead && !ms.dead) {
         const int n_gt = ms.n_gt;
         uint32_t ck[MULTI_CPT], cd[MULTI_CPT];
@@ -538,8 +543,63 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         if (p.max_pods > 0 && p.max_pods - k < room) room = p.max_pods - k;
         const int32_t acc_limit = room < MULTI_MAX_ACC ? (int32_t)room : MULTI_MAX_ACC;
         int rounds = 0;
+        bool ended_by_rescan = false;
+        // ---- dormant candidates. A PTS term whose limit is about to move (few domains left at the global minimum) was scanned with
+        //      a look-ahead (ms.relax): nodes in cells up to MULTI_RELAX_R over the limit are in the lists too. They cannot win while
+        //      their cell is over the limit (dormant: key 0 in ck[], like a dead candidate) and wake up when a minimum move lifts the
+        //      limit over their cell — the wave then goes on instead of ending for a rescan. It still has to end when the limit
+        //      reaches a cell that was NOT published: `unpub_min` = the smallest count above limit + look-ahead at the start of the
+        //      wave (such cells are closed, so their counts stand for the whole wave).
+        //      The round loop itself is unchanged: a candidate whose cell fills is zeroed as before. Waking is a REBUILD (rare: at the
+        //      start of a look-ahead wave and after a minimum move of a look-ahead term): every slot's key is read again from the
+        //      wave's candidate arrays — first-life key, or second-life key when bit j of `second` says the slot has won already
+        //      (single-use templates: gone) — and zeroed when one of its cells is over the limit as counters and limits stand now. ----
+        int32_t rlx = 0, unpub_min = INT32_MAX;
+        if (lane < n_gt) rlx = lds_s32(MS_SA(relax) + 4u * (uint32_t)lds_s32(MS_SA(gt_term) + 4u * (uint32_t)lane));
+        any_relax = __any_sync(0xffffffffu, rlx > 0);
+        bool need_rebuild = any_relax;
+        if (any_relax) {
+          for (unsigned nm = __ballot_sync(0xffffffffu, rlx > 0); nm; nm &= nm - 1) {
+            const int q = __ffs(nm) - 1;
+            const int32_t off = __shfl_sync(0xffffffffu, gc.x, q), ndom = __shfl_sync(0xffffffffu, c1.w, q);
+            const int32_t publim = __shfl_sync(0xffffffffu, c1.x + rlx, q);
+            const uint32_t ca = cnt_sa + 4u * (uint32_t)off;
+            int32_t m = INT32_MAX;
+            #pragma unroll 1
+            for (int d = lane; d < ndom; d += 32) { const int32_t c = lds_s32(ca + 4u * d); if (c > publim) m = min(m, c); }
+            m = __reduce_min_sync(0xffffffffu, m);
+            if (lane == q) unpub_min = m;
+          }
+          if (cta == 0 && lane == 0) ms.st_relaxed++;
+        }
         if (cta == 0 && lane == 0) ms.ph[6] += clock64() - ms.tc0;      // replay set-up
         for (;;) {
+          if (need_rebuild) {       // (one call site, off the round's critical path; see "dormant candidates")
+            need_rebuild = false;
+            __syncwarp();           // the counter cells / limits written by the term lanes, before every lane reads them
+            uint32_t badm = 0u;
+            #pragma unroll 1
+            for (int q = 0; q < n_gt; q++) {
+              const int4 tg = *reinterpret_cast<const int4 *>(&ms.gt_commit[q][0]);   // {cnt_off, inc, pts_idx, n_present}
+              const int4 tc = *reinterpret_cast<const int4 *>(&ms.gt_c1[q][0]);       // {lim (kept current by lane q), shift, mask, n_domains}
+              #pragma unroll
+              for (int j = 0; j < MULTI_CPT; j++) {
+                const int32_t v = (int32_t)((cd[j] >> tc.y) & (uint32_t)tc.z) - 1;
+                if (v >= 0 && lds_s32(cnt_sa + 4u * (uint32_t)(tg.x + v)) > tc.x) badm |= 1u << j;
+              }
+            }
+            #pragma unroll
+            for (int j = 0; j < MULTI_CPT; j++) {
+              const int idx = j * 32 + lane;
+              uint32_t base = 0u;
+              if (idx < C && !((badm >> j) & 1u)) {
+                const uint32_t k0 = (uint32_t)lds_s32(MS_SA(ckey) + 4u * (uint32_t)idx);
+                if (!((second >> j) & 1u)) base = k0;
+                else if (!single_use) { const uint32_t ns = (uint32_t)lds_s32(MS_SA(cnext) + 4u * (uint32_t)idx); base = ns ? ((ns << MULTI_IDX_BITS) | (k0 & MULTI_IDX_MASK)) : 0u; }
+              }
+              ck[j] = base;
+            }
+          }
           rounds++;
           uint32_t m = ck[0];
           #pragma unroll
@@ -557,7 +617,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           bool sec = false;
           if (single_use) {           // a clone blocks its own node (hostname anti-affinity): the winner just leaves
             #pragma unroll
-            for (int j = 0; j < MULTI_CPT; j++) ck[j] = (ck[j] == g) ? 0u : ck[j];
+            for (int j = 0; j < MULTI_CPT; j++) { const bool w = ck[j] == g; ck[j] = w ? 0u : ck[j]; second |= (uint32_t)w << j; }   // (bit j: this slot has won — a rebuild leaves it out)
           } else {
             #pragma unroll
             for (int j = 0; j < MULTI_CPT; j++)
@@ -589,7 +649,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
           // the move changes some node's feasibility: that takes a domain whose count lies in (old limit, new limit] — nodes there
           // were rejected by the scan (or killed earlier in this wave) and pass now. Without such a domain every verdict so far
           // stands (the 8-region constraint of C4 moves its minimum every 8 placements and never binds).
-          bool rescan = false;
+          bool rescan = false, woke = false;
           const unsigned mc = __ballot_sync(0xffffffffu, minchg);
           for (unsigned nm = mc; nm; nm &= nm - 1) {
             const int q = __ffs(nm) - 1;
@@ -607,34 +667,65 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
             #pragma unroll 1
             for (int d = lane; d < ndom; d += 32) { const int32_t c = lds_s32(ca + 4u * d); num += (d < npres) & (c == mn); hit |= (c > lim_old) & (c <= lim_new); }
             num = __reduce_add_sync(0xffffffffu, num);
-            rescan |= __any_sync(0xffffffffu, hit) | (p.debug_flags & 1);
-            if (lane == q) { my_min = mn; my_num = num; c1.x = lim_new; lim_moved = true; }
+            // a term scanned with look-ahead published the nodes of its closed cells: the move only matters when the new limit
+            // reaches a cell that was not published; the cells in (old limit, new limit] wake their candidates up instead
+            const bool rq = __shfl_sync(0xffffffffu, rlx, q) > 0;
+            if (rq) { rescan |= (lim_new >= __shfl_sync(0xffffffffu, unpub_min, q)) | (p.debug_flags & 1); woke = true; }
+            else rescan |= __any_sync(0xffffffffu, hit) | (p.debug_flags & 1);
+            if (lane == q) { my_min = mn; my_num = num; c1.x = lim_new; lim_moved = true; sts_s32(MS_SA(gt_c1) + 16u * (uint32_t)q, lim_new); }
           }
-          if (rescan && cta == 0 && lane == 0) ms.ph[7] += 1;      // waves ended by a minimum move that changes verdicts
+          need_rebuild = woke & !rescan;
+          // (no statistics, special registers or kernel parameters are touched inside the round loop: one S2R on this dependent
+          //  chain costs as much as ten ALU instructions)
           bool stopb = __any_sync(0xffffffffu, sec) | rescan;
-          if (stopb | (acc >= acc_limit)) break;
+          if (stopb | (acc >= acc_limit)) { ended_by_rescan = rescan; break; }
           // only the candidates sitting in a counter cell that this commit pushed over its limit die (monotone: for the rest of
           // the wave); the fields of different terms are disjoint bit ranges, so one OR-reduction carries all filled cells
-          const uint32_t F = __reduce_or_sync(0xffffffffu, fullf);
+          // (the rebuild at the top of the next round sets every candidate as counters and limits stand by then — `fullf` was taken
+          //  against the limits before the move)
+          const uint32_t F = woke ? 0u : __reduce_or_sync(0xffffffffu, fullf);
           if (F) {
             #pragma unroll
             for (int q = 0; q < MULTI_GT; q++) {
               const uint32_t f = F & fmask[q];
               if (f) {
                 #pragma unroll
-                for (int j = 0; j < MULTI_CPT; j++) if ((cd[j] & fmask[q]) == f) ck[j] = 0u;
+                for (int j = 0; j < MULTI_CPT; j++)
+                  if ((cd[j] & fmask[q]) == f) ck[j] = 0u;     // (dead — in a look-ahead wave: dormant, a rebuild may bring it back)
               }
             }
           }
         }
-        if (cta == 0 && lane == 0) ms.st_rounds += rounds;
+        if (cta == 0 && lane == 0) { ms.st_rounds += rounds; if (ended_by_rescan) ms.ph[7] += 1; }      // (ph[7]: waves ended by a minimum move that changes verdicts)
+        // ---- the next wave's look-ahead, per PTS term on a replicated counter: its limit is about to move (<= MULTI_RELAX_K present
+        //      domains left at the minimum) and the closed domains are not the majority (their nodes would crowd the live ones out of
+        //      the tiles' top-M lists). A look-ahead wave that could not place anything is repeated strictly. Every CTA of every rank
+        //      decides alike (same counters, same replay). ----
+        {
+          const bool strict_next = (acc == 0 && any_relax) || (p.debug_flags & 16u);
+          const bool elig = lane < n_gt && gc.z >= 0 && gc.y > 0 && my_num <= MULTI_RELAX_K && c1.x < INT32_MAX - 2 * MULTI_RELAX_R && !strict_next;
+          int32_t nrl = 0;
+          for (unsigned nm = __ballot_sync(0xffffffffu, elig); nm; nm &= nm - 1) {
+            const int q = __ffs(nm) - 1;
+            const int32_t off = __shfl_sync(0xffffffffu, gc.x, q), npres = __shfl_sync(0xffffffffu, gc.w, q), lim = __shfl_sync(0xffffffffu, c1.x, q);
+            const uint32_t ca = cnt_sa + 4u * (uint32_t)off;
+            int32_t closed = 0;
+            #pragma unroll 1
+            for (int d = lane; d < npres; d += 32) closed += lds_s32(ca + 4u * d) > lim;
+            closed = __reduce_add_sync(0xffffffffu, closed);
+            if (lane == q && 2 * closed <= npres) nrl = MULTI_RELAX_R;
+          }
+          if (p.debug_flags & 32u) nrl = (lane < n_gt && gc.z >= 0 && gc.y > 0 && c1.x < INT32_MAX - 2 * MULTI_RELAX_R && !strict_next) ? MULTI_RELAX_R : 0;   // tests: look-ahead on every PTS term, every wave
+          if (lane < n_gt) sts_s32(MS_SA(relax) + 4u * (uint32_t)lds_s32(MS_SA(gt_term) + 4u * (uint32_t)lane), nrl);
+          if (cta == 0 && lane == 0 && acc == 0 && any_relax) ms.st_empty++;
+        }
         // the limits that moved go back to the Filter constants of the next scan
         if (lim_moved) { ls.terms[ms.gt_term[lane]].lim = c1.x; ms.gt_c1[lane][0] = c1.x; }
         if (lane < n_gt && gc.z >= 0) { ls.ptsmin[gc.z] = my_min; ls.ptsnum[gc.z] = my_num; }
       }
       if (lane == 0 && cta == 0 && (p.debug_flags & 4))
-        printf("wave %lld k=%lld acc=%d C=%d T=%08x Tlist=%08x kbest=%08x delta=%08x ran_dry=%d first=%d last=%d\n", wv, k, acc, C, T, Tlist, kbest, delta,
-               (int)ran_dry, acc ? ms.acc_node[0] : -1, acc ? ms.acc_node[acc - 1] : -1);
+        printf("wave %lld k=%lld acc=%d C=%d T=%08x Tlist=%08x kbest=%08x delta=%08x ran_dry=%d look_ahead=%d first=%d last=%d\n", wv, k, acc, C, T, Tlist, kbest, delta,
+               (int)ran_dry, (int)any_relax, acc ? ms.acc_node[0] : -1, acc ? ms.acc_node[acc - 1] : -1);
       if (lane == 0) {
         ms.accepted = acc; ms.ncand = 0;
         // next wave's bar distance: the replay ran out of candidates above a bar that was higher than it had to be -> look further
@@ -645,7 +736,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
         else if (!ran_dry && C > MULTI_CAP / 2) nd = max(delta - delta / 8u, 1u << 8);
         ms.delta = nd;
         if (dead || ms.dead) ls.stop = 3;
-        else if (acc == 0) ls.stop = 1;          // no feasible node anywhere: the pod is unschedulable
+        else if (acc == 0 && !any_relax) ls.stop = 1;          // no feasible node anywhere: the pod is unschedulable (after a look-ahead wave: rescan strictly first)
       }
     }
     __syncthreads();                                                    // R: the accepted list, counters, limits
@@ -713,6 +804,9 @@ __global__ void __launch_bounds__(LEAN_THREADS, 1) ccsim_wave_multi_kernel(const
       o->aff_total = ls.aff_total;
       for (int q = 0; q < 8; q++) o->phase_cycles[q] = ms.ph[q];
       o->stat[0] = ms.st_cand; o->stat[1] = ms.st_overflow; o->stat[2] = ms.st_rounds;
+      if (p.debug_flags & 8u)
+        printf("multi-commit replay: waves %lld rounds %lld look-ahead waves %d (without a placement: %d) | cycles: replay %lld set-up %lld\n",
+               limit_hit ? wv : wv + 1, ms.st_rounds, ms.st_relaxed, ms.st_empty, ms.ph[4], ms.ph[6]);
     }
   }
 }

@@ -340,8 +340,7 @@ static size_t skip_value(const char *t, size_t n, size_t p) {
 // item boundaries. Anything unexpected (an item that is not an object, a document that ends early) returns false: the serial
 // scan then decides.
 static bool item_spans_parallel(const char *t, size_t n, size_t p, std::vector<std::pair<size_t, size_t>> &out) {
-  unsigned nt = std::thread::hardware_concurrency();
-  nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
+  unsigned nt = host_threads();
   if (n - p < (4u << 20) || nt < 2) return false;
   std::vector<size_t> cut(nt + 1);
   cut[0] = p; cut[nt] = n;
@@ -438,14 +437,23 @@ static bool item_spans(const char *t, size_t n, std::vector<std::pair<size_t, si
   throw std::runtime_error("json: unterminated item list");
 }
 
-// one item of a LIST: the DOM-free fast path first (fastparse.hpp), the general parser when it gives up
-static Pod pod_from(std::string_view item, bool dom_only) {
-  if (!dom_only) { Pod p; if (fast::pod(item, p)) return p; }
-  return Pod::parse(parse_json(item));
+// one item of a LIST, constructed IN PLACE (an object is ~1 KB of strings, vectors and maps: no temporary, no move): the DOM-free
+// fast path first (fastparse.hpp), the general parser when it gives up
+static void pod_into(Pod *dst, std::string_view item, bool dom_only) {
+  if (!dom_only) {
+    new (dst) Pod();
+    try { if (fast::pod(item, *dst)) return; } catch (...) { dst->~Pod(); throw; }
+    dst->~Pod();
+  }
+  new (dst) Pod(Pod::parse(parse_json(item)));
 }
-static Node node_from(std::string_view item, bool dom_only) {
-  if (!dom_only) { Node n; if (fast::node(item, n)) return n; }
-  return Node::parse(parse_json(item));
+static void node_into(Node *dst, std::string_view item, bool dom_only) {
+  if (!dom_only) {
+    new (dst) Node();
+    try { if (fast::node(item, *dst)) return; } catch (...) { dst->~Node(); throw; }
+    dst->~Node();
+  }
+  new (dst) Node(Node::parse(parse_json(item)));
 }
 
 template <class T, class F> static ObjList<T> parse_list(const char *text, F one) {
@@ -458,21 +466,20 @@ template <class T, class F> static ObjList<T> parse_list(const char *text, F one
     T *p = out.allocate_raw(items.size());
     std::exception_ptr err;
     for (size_t i = 0; i < items.size(); i++) {
-      try { const std::string t = json_dump(items[i]); new (&p[i]) T(one(std::string_view(t))); }
+      try { const std::string t = json_dump(items[i]); one(&p[i], std::string_view(t)); }
       catch (...) { new (&p[i]) T(); if (!err) err = std::current_exception(); }
     }
     if (err) std::rethrow_exception(err);
     return out;
   }
-  unsigned nt = std::thread::hardware_concurrency();
-  nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
+  unsigned nt = host_threads();
   if (spans.size() < 2048) nt = 1;
   T *p = out.allocate_raw(spans.size());       // every element is constructed below, by the thread that parses it
   std::vector<std::exception_ptr> errs(nt);
   auto work = [&](unsigned c) {
     const size_t per = (spans.size() + nt - 1) / nt, b = std::min(spans.size(), (size_t)c * per), e = std::min(spans.size(), b + per);
     for (size_t i = b; i < e; i++) {
-      try { new (&p[i]) T(one(std::string_view(text + spans[i].first, spans[i].second - spans[i].first))); }
+      try { one(&p[i], std::string_view(text + spans[i].first, spans[i].second - spans[i].first)); }
       catch (...) { new (&p[i]) T(); if (!errs[c]) errs[c] = std::current_exception(); }
     }
   };
@@ -494,9 +501,9 @@ extern "C" int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const 
     const bool timing = getenv("CCHOST_TIMING") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
     const bool dom_only = getenv("CCHOST_DOM_ONLY") != nullptr;      // tests: the general parser for every item
-    h->nodes = parse_list<Node>(nodes_json, [&](std::string_view it) { return node_from(it, dom_only); });
+    h->nodes = parse_list<Node>(nodes_json, [&](Node *dst, std::string_view it) { node_into(dst, it, dom_only); });
     auto t1 = std::chrono::steady_clock::now();
-    h->pods = parse_list<Pod>(pods_json, [&](std::string_view it) { return pod_from(it, dom_only); });
+    h->pods = parse_list<Pod>(pods_json, [&](Pod *dst, std::string_view it) { pod_into(dst, it, dom_only); });
     auto t2 = std::chrono::steady_clock::now();
     if (timing) fprintf(stderr, "[cchost] ingest: %zu nodes %.3f s, %zu pods %.3f s\n", h->nodes.size(), std::chrono::duration<double>(t1 - t0).count(),
                         h->pods.size(), std::chrono::duration<double>(t2 - t1).count());

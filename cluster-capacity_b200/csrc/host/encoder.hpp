@@ -153,9 +153,19 @@ inline PodResource calculate_resource_general(const Pod &p) {
 
 // Host threads over an index range, in contiguous blocks (the per-node loops of the encoder are independent per node; anything
 // order-dependent — dictionary ids in first-seen order — stays in a serial pass over the per-node results).
+// host threads for the ingest and the encoder: the hardware's, at most 64 (CCHOST_THREADS overrides; the passes are bound by
+// memory allocation and cache misses on the object model, more threads than that only add contention)
+inline unsigned host_threads() {
+  static const unsigned nt = [] {
+    if (const char *e = getenv("CCHOST_THREADS")) { const int v = atoi(e); if (v > 0) return (unsigned)(v > 256 ? 256 : v); }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw == 0 ? 1u : (hw > 64 ? 64u : hw);
+  }();
+  return nt;
+}
+
 template <class F> inline void parallel_for(int n, F fn) {
-  unsigned nt = std::thread::hardware_concurrency();
-  nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
+  unsigned nt = host_threads();
   if (n < 4096 || nt == 1) { for (int i = 0; i < n; i++) fn(i); return; }
   std::vector<std::thread> th;
   std::vector<std::exception_ptr> errs(nt);

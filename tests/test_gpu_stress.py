@@ -69,6 +69,25 @@ def test_random_coupled_templates(built, seed):
         assert np.array_equal(got.reason_hist, want.reason_hist), (seed, kind)
 
 
+@pytest.mark.parametrize("seed", range(48))
+def test_random_coupled_templates_forced_look_ahead(built, seed, monkeypatch):
+    """The multi-commit kernel with its look-ahead forced on for every PodTopologySpread term in every wave (CCSIM_DEBUG_FLAGS=32):
+    candidates published from closed cells start dormant, wake up when a minimum move lifts the limit over their cell, crowd the
+    tiles' lists (waves without a placement are repeated strictly) — the pod -> node sequence must not change."""
+    snap, tmpl, ctr, limit = random_case(seed)
+    cap = limit or 4000
+    want = oracle.run(snap, tmpl, ctr, max_pods=cap, threads=8)
+    engine = importlib.import_module("cluster-capacity_b200.engine")
+    monkeypatch.setenv("CCSIM_DEBUG_FLAGS", "32")
+    with engine.Engine(device=0, engine=abi.ENGINE_AUTO) as eng:
+        eng.load_nodes(snap)
+        eng.set_templates(tmpl, ctr)
+        got = eng.run(cap)
+    assert got.placed == want.placed and got.stop_code == want.stop_code, seed
+    assert np.array_equal(got.pod_node, want.pod_node), seed
+    assert np.array_equal(got.reason_hist, want.reason_hist), seed
+
+
 def random_node_local_case(seed):
     """Templates whose predicates and scorers are node-local (tie-run batching when there is one template and no
     PreferNoSchedule class; lean / generic kernels otherwise): taints, tolerations, selector bits, scalar resources,
