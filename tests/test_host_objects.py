@@ -218,3 +218,53 @@ def test_parallel_item_location_equals_the_serial_scan(built, monkeypatch):
         cc.Close()
     assert out[0] == out[1]
     assert sum(out[0]["nodes"]["npods"]) > 1000
+
+
+def test_calculate_resource_fast_path_equals_the_general_path(built):
+    """CCHOST_CHECK_FAST=1 makes the encoder compute every existing pod's resources twice — the exact-sum fast path for plain pods and
+    resourcehelper.PodRequests' list arithmetic (types.go:700-734) — and fail on any difference. The switch is read once per process:
+    the object-level cases (init containers, sidecars, overhead, pod-level resources, sub-milli quantities, extended resources) run in
+    a child interpreter with it set."""
+    import os, subprocess, sys
+    env = dict(os.environ, CCHOST_CHECK_FAST="1", CCSIM_NO_REBUILD="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_host_objects.py"), "-q", "-x", "-m", "not gpu",
+                        "-k", "encoder_matches_object_oracle or quantities_round_up or c4_objects or readme_demo"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(here), timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_calculate_resource_fast_path_random_request_shapes(built):
+    """... and random container shapes aimed at the rounding rules: 0-3 containers, requests missing per resource, sub-milli cpu
+    ("0.5m", "1500u", "3n"), fractional memory ("1.5", "129Mi", "1e3"), extended resources, ephemeral storage."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import importlib, json, random, sys
+        sys.path.insert(0, %r)
+        fw = importlib.import_module("cluster-capacity_b200.framework")
+        rnd = random.Random(7)
+        cpus = ["0.5m", "1500u", "3n", "100m", "1", "0.25", "2500m", "0"]
+        mems = ["1.5", "129Mi", "1e3", "1Gi", "200M", "0", "123456789"]
+        def container(k):
+            req = {}
+            if rnd.random() < 0.7: req["cpu"] = rnd.choice(cpus)
+            if rnd.random() < 0.7: req["memory"] = rnd.choice(mems)
+            if rnd.random() < 0.2: req["ephemeral-storage"] = rnd.choice(["1Gi", "500M", "1.5"])
+            if rnd.random() < 0.2: req["example.com/gpu"] = str(rnd.randint(1, 3))
+            c = {"name": "c%%d" %% k, "image": "img"}
+            if req or rnd.random() < 0.5: c["resources"] = {"requests": req}
+            return c
+        nodes = [{"metadata": {"name": "n%%d" %% i, "labels": {"kubernetes.io/hostname": "n%%d" %% i}}, "spec": {},
+                  "status": {"allocatable": {"cpu": "64", "memory": "256Gi", "pods": "110", "example.com/gpu": "8", "ephemeral-storage": "1Ti"}}} for i in range(20)]
+        pods = [{"metadata": {"name": "p%%d" %% j, "namespace": "default"}, "spec": {"nodeName": "n%%d" %% rnd.randrange(20),
+                 "containers": [container(k) for k in range(rnd.randint(0, 3))]}, "status": {"phase": "Running"}} for j in range(400)]
+        tmpl = {"metadata": {"name": "t", "namespace": "default"}, "spec": {"containers": [{"name": "c", "image": "img",
+                "resources": {"requests": {"cpu": "100m", "memory": "64Mi", "example.com/gpu": "1"}}}]}}
+        cc = fw.New(None, None, tmpl, 0, [])
+        cc.SyncWithClient(fw.ListClient(nodes=nodes, pods=pods))
+        enc = cc.EncodedSnapshot()
+        assert sum(enc["nodes"]["npods"]) == 400
+        print("ok")
+    ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CCHOST_CHECK_FAST="1", CCSIM_NO_REBUILD="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
