@@ -141,6 +141,8 @@ def main(argv=None):
         cc = fw.New(load_scheduler_config(a.default_config), None, pod, a.max_limit, [x for x in a.exclude_nodes.split(",") if x], device=a.device)
         cc.SyncWithClient(fw.ListClient(objs["nodes"], objs["pods"], objs["namespaces"], objs["services"], objs["replicationcontrollers"],
                                         objs["replicasets"], objs["statefulsets"]))
+        for w in cc.Warnings():
+            print("warning: " + w, file=sys.stderr)
         cc.Run()
         fw.ClusterCapacityReviewPrint(cc, a.verbose, a.output)
     except (fw.FrameworkError, OSError, subprocess.CalledProcessError) as e:   # the reference prints the error and exits 0 (server.go:68-71)

@@ -144,7 +144,8 @@ struct cc_handle {
   std::string stop_reason;
   Json report;   // cached like c.report (simulator.go:161-169)
   bool have_report = false;
-  std::string err, out;
+  std::string err, out, warn;
+  int64_t pending_skipped = 0;   // pods of the snapshot without spec.nodeName (not terminal): not replayed, reported by cc_warnings
 };
 
 static std::string g_new_err;
@@ -507,6 +508,8 @@ extern "C" int cc_sync_with_objects(cc_handle *h, const char *nodes_json, const 
     auto t2 = std::chrono::steady_clock::now();
     if (timing) fprintf(stderr, "[cchost] ingest: %zu nodes %.3f s, %zu pods %.3f s\n", h->nodes.size(), std::chrono::duration<double>(t1 - t0).count(),
                         h->pods.size(), std::chrono::duration<double>(t2 - t1).count());
+    h->pending_skipped = 0;
+    for (auto &p : h->pods) if (p.node_name.empty() && p.phase != "Succeeded" && p.phase != "Failed") h->pending_skipped++;
     for (auto &j : items_of(namespaces_json)) h->ns_labels[j.at("metadata").at("name").str()] = parse_labels(j.at("metadata").at("labels"));
     h->synced = true; h->have_enc = false; h->ran = false; h->have_report = false;
     return CC_OK;
@@ -753,6 +756,14 @@ extern "C" const char *cc_report_print(cc_handle *h, int32_t verbose, const char
   return h->out.c_str();
 }
 
+extern "C" const char *cc_warnings(cc_handle *h) {
+  if (!h) return "";
+  h->warn.clear();
+  if (h->pending_skipped > 0)
+    h->warn += std::to_string(h->pending_skipped) + " pending pod(s) of the snapshot (no spec.nodeName) were left out: the reference would let its embedded scheduler bind "
+               "them and count each as a simulated instance (pkg/framework/simulator.go:193-200,297-312), with no defined order\n";
+  return h->warn.c_str();
+}
 extern "C" const char *cc_stop_reason(cc_handle *h) { return h ? h->stop_reason.c_str() : nullptr; }
 extern "C" int64_t cc_scheduled_count(cc_handle *h) { return h ? (int64_t)h->pod_node.size() : 0; }
 extern "C" const char *cc_scheduled_node(cc_handle *h, int64_t k) {

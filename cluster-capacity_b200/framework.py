@@ -18,7 +18,7 @@ SO_PATH = os.path.join(_HERE, "libcchost.so")
 _lib = None
 
 EXPORTS = ["cc_new", "cc_new_list", "cc_sync_with_objects", "cc_sync_workloads", "cc_run", "cc_report_json", "cc_report_print", "cc_stop_reason",
-           "cc_scheduled_count", "cc_scheduled_node", "cc_close", "cc_last_error", "cc_debug_encoded_snapshot"]
+           "cc_scheduled_count", "cc_scheduled_node", "cc_close", "cc_last_error", "cc_warnings", "cc_debug_encoded_snapshot"]
 
 
 class FrameworkError(RuntimeError):
@@ -45,7 +45,7 @@ def lib():
         L.cc_sync_workloads.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
         L.cc_run.restype = C.c_int
         L.cc_run.argtypes = [C.c_void_p]
-        for f in ("cc_report_json", "cc_stop_reason", "cc_last_error", "cc_debug_encoded_snapshot"):
+        for f in ("cc_report_json", "cc_stop_reason", "cc_last_error", "cc_warnings", "cc_debug_encoded_snapshot"):
             getattr(L, f).restype = C.c_char_p
             getattr(L, f).argtypes = [C.c_void_p]
         L.cc_report_print.restype = C.c_char_p
@@ -115,6 +115,10 @@ class ClusterCapacity:
 
     def StopReason(self):
         return lib().cc_stop_reason(self._h).decode()
+
+    def Warnings(self):
+        """Deviations from what the reference would have done with this snapshot (cc_warnings): a list of lines, usually empty."""
+        return [l for l in lib().cc_warnings(self._h).decode().split("\n") if l]
 
     def ScheduledPods(self):
         """Node name of every simulated pod, in placement order (ScheduledPods()[k].Spec.NodeName)."""

@@ -268,3 +268,28 @@ def test_calculate_resource_fast_path_random_request_shapes(built):
     ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CCHOST_CHECK_FAST="1", CCSIM_NO_REBUILD="1"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_pending_pods_are_left_out_and_reported(built):
+    """Pending pods of the source cluster (no spec.nodeName) are not replayed — the reference would bind them through its binder
+    and count them as simulated instances in no defined order (simulator.go:193-200,297-312) — and cc_warnings says how many."""
+    nodes, pods = helpers.random_cluster(5, n_nodes=10, n_pods=12)
+    tmpl = helpers.template("plain", 5)
+    base, seq0, sr0 = run_both(nodes, pods, tmpl)
+    pending = [{"metadata": {"name": "pend-%d" % i, "namespace": "default"}, "spec": {"containers": [{"name": "c", "image": "i",
+                "resources": {"requests": {"cpu": "4", "memory": "1Gi"}}}]}, "status": {"phase": "Pending"}} for i in range(3)]
+    done = [{"metadata": {"name": "done", "namespace": "default"}, "spec": {"containers": []}, "status": {"phase": "Succeeded"}}]
+    cc = fw.New(None, None, tmpl, 0, [])
+    cc.SyncWithClient(helpers.list_client(fw, nodes, pods + pending + done, None))
+    w = cc.Warnings()
+    n_pending = sum(1 for p in pods + pending + done if not p["spec"].get("nodeName") and p.get("status", {}).get("phase") not in ("Succeeded", "Failed"))
+    assert n_pending >= 3 and len(w) == 1 and w[0].startswith("%d pending pod(s)" % n_pending)
+    enc = cc.EncodedSnapshot()
+    snap, T, ctr, tdict, snames, names = helpers.from_encoded(enc)
+    got = oracle.run(snap, T, ctr, max_pods=0)
+    assert [names[i] for i in got.pod_node.tolist()] == seq0      # same result as without them
+    cc.Close()
+    cc = fw.New(None, None, tmpl, 0, [])
+    cc.SyncWithClient(helpers.list_client(fw, nodes, [p for p in pods if p["spec"].get("nodeName")], None))
+    assert cc.Warnings() == []
+    cc.Close()
