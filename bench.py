@@ -57,7 +57,9 @@ def select_workload(key):
 
 def profiled_traffic():
     """dram__bytes_read+write per launch of the wave kernel from the committed ncu --set full capture (profiles/)."""
-    for name in ("r2_wave_%s_traffic.json" % WKEY, "r1_wave_c4_traffic.json" if WKEY == "c4" else ""):
+    # (C5: the capture is of an earlier build of the streaming kernel — 53 ms per launch — with the same DRAM-side behaviour: the
+    #  4-byte memo column of the wave's template, 4 MB, comes from HBM every wave because the 64 columns, 256 MB, do not fit the L2)
+    for name in ("r2_wave_%s_traffic.json" % WKEY, "r2_stream_%s_traffic.json" % WKEY, "r1_wave_c4_traffic.json" if WKEY == "c4" else ""):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 return float(json.load(f)["traffic_bytes_per_launch"])
