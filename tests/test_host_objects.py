@@ -166,6 +166,21 @@ def test_c4_objects_through_the_encoder_equal_the_flat_generator(built):
     assert a.placed == b.placed > 100 and np.array_equal(a.pod_node, b.pod_node) and np.array_equal(a.reason_hist, b.reason_hist)
 
 
+def test_large_topology_dictionaries(built):
+    """More distinct topology values than the encoder's dictionaries are first sized for (the flat index grows while ids are being
+    handed out in first-seen order): 2500 racks over 40000 nodes; same columns, counters and placement sequence as the flat generator."""
+    synth = importlib.import_module("cluster-capacity_b200.synth")
+    kw = dict(n=40000, n_existing=25000, zones=50, racks=2500, regions=5, match_frac=0.5)
+    snap, tmpl, ctr = synth.c4(**kw)
+    nodes, pods, t = synth.c4_objects(**kw)
+    cc = fw.New(None, None, t, 0, [])
+    cc.SyncWithClient(fw.ListClient(nodes, pods, ()))
+    s2, T2, c2, _, _, names = helpers.from_encoded(cc.EncodedSnapshot())
+    assert len(c2) == len(ctr) and sorted(c.n_domains for c in c2)[-2] == 2500
+    a, b = oracle.run(snap, tmpl, ctr, threads=4, memo=True), oracle.run(s2, T2, c2, threads=4, memo=True)
+    assert a.placed == b.placed > 100 and np.array_equal(a.pod_node, b.pod_node) and np.array_equal(a.reason_hist, b.reason_hist)
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
 def test_fast_ingest_equals_the_general_parser(built, seed, monkeypatch):
     """fastparse.hpp (no DOM; gives up on pods with init containers / overhead / pod affinity / escapes) against the general parser
