@@ -35,6 +35,11 @@
 //   a cell that just filled (field compare against the shuffled cell id). ~250 cycles per reference cycle instead of the
 //   ~2000 of a block-wide round (two barriers over 24 warps); the other 23 warps wait at the barrier that ends the wave.
 //   Row updates of the winners are done by each node's own thread after that barrier (a thread owns its node).
+// Look-ahead waves: a PodTopologySpread minimum move that REOPENS closed domains would end the wave (the reopened nodes were
+//   rejected by the scan and are in nobody's list). When a term's limit is about to move, the scan publishes the nodes of its
+//   closed cells too; they sit in the replay as dormant candidates (key 0) and are rebuilt from the wave's candidate arrays when
+//   the move comes — see "dormant candidates" in the replay. C4: 3654 -> 2260 waves (scripts/wave_sim.py models the wave structure
+//   on the CPU and was used to choose the rule).
 #pragma once
 #include "ccsim_lean.cuh"
 
