@@ -352,11 +352,7 @@ static bool item_spans_parallel(const char *t, size_t n, size_t p, std::vector<s
   }
   struct Part { int quotes = 0; long long depth[2] = {0, 0}; };     // depth[s]: change of bracket depth when the chunk starts with state s (1: in a string)
   std::vector<Part> part(nt);
-  auto run = [&](auto fn) {
-    std::vector<std::thread> th;
-    for (unsigned c = 0; c < nt; c++) th.emplace_back(fn, c);
-    for (auto &x : th) x.join();
-  };
+  auto run = [&](auto fn) { HostPool::instance().run(nt, fn); };
   run([&](unsigned c) {
     Part r; int in = 0;
     for (size_t q = cut[c]; q < cut[c + 1]; q++) {
@@ -484,12 +480,7 @@ template <class T, class F> static ObjList<T> parse_list(const char *text, F one
       catch (...) { new (&p[i]) T(); if (!errs[c]) errs[c] = std::current_exception(); }
     }
   };
-  if (nt == 1) work(0);
-  else {
-    std::vector<std::thread> th;
-    for (unsigned c = 0; c < nt; c++) th.emplace_back(work, c);
-    for (auto &x : th) x.join();
-  }
+  HostPool::instance().run(nt, work);
   for (auto &e : errs) if (e) std::rethrow_exception(e);
   return out;
 }

@@ -13,6 +13,9 @@
 // per-domain initial counts).
 #pragma once
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <pthread.h>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -164,18 +167,85 @@ inline unsigned host_threads() {
   return nt;
 }
 
+// A persistent pool for the host passes. One analysis of the C4 cluster makes ~13 parallel passes (item location x2 and item parsing for
+// nodes and pods, node / pod hashing, NodeInfo aggregation, one pass per constraint family ...); creating and joining 64 threads costs
+// 1.5-2.5 ms each time, more than most of those passes take. Workers are created on first use and parked on a condition variable; the
+// calling thread takes tasks too. One job at a time per process (callers from several host threads queue up); a task that starts a job
+// itself runs it inline. The pool is never destroyed (no destructor-order trouble at process exit), and a forked child starts a new one.
+class HostPool {
+ public:
+  static HostPool &instance() {
+    HostPool *p = slot().load(std::memory_order_acquire);
+    if (!p) {
+      static std::mutex mk;
+      std::lock_guard<std::mutex> g(mk);
+      p = slot().load(std::memory_order_acquire);
+      if (!p) {
+        static std::once_flag once;
+        std::call_once(once, [] { pthread_atfork(nullptr, nullptr, [] { slot().store(nullptr, std::memory_order_release); }); });
+        p = new HostPool();
+        slot().store(p, std::memory_order_release);
+      }
+    }
+    return *p;
+  }
+  // fn(c) for every c in [0, n_tasks), on up to n_tasks threads; returns when all are done; the first exception is rethrown
+  void run(unsigned n_tasks, const std::function<void(unsigned)> &fn) {
+    if (n_tasks == 0) return;
+    if (n_tasks == 1 || in_task()) { for (unsigned c = 0; c < n_tasks; c++) fn(c); return; }
+    std::lock_guard<std::mutex> serial(run_mu_);
+    std::unique_lock<std::mutex> lk(mu_);
+    while (n_workers_ + 1 < n_tasks && n_workers_ < kMaxWorkers) { std::thread(&HostPool::worker, this).detach(); n_workers_++; }
+    fn_ = &fn; n_ = n_tasks; next_ = 0; remaining_ = n_tasks; err_ = nullptr; gen_++;
+    cv_work_.notify_all();
+    drain(lk);                                            // the caller works too
+    cv_done_.wait(lk, [&] { return remaining_ == 0; });
+    fn_ = nullptr;
+    std::exception_ptr e = err_; err_ = nullptr;
+    lk.unlock();
+    if (e) std::rethrow_exception(e);
+  }
+ private:
+  static constexpr unsigned kMaxWorkers = 255;
+  static std::atomic<HostPool *> &slot() { static std::atomic<HostPool *> s{nullptr}; return s; }
+  static bool &in_task() { static thread_local bool f = false; return f; }
+  // takes tasks of the current job until none is left (mu_ held on entry and on exit)
+  void drain(std::unique_lock<std::mutex> &lk) {
+    while (next_ < n_) {
+      const unsigned c = next_++;
+      const std::function<void(unsigned)> *f = fn_;
+      lk.unlock();
+      in_task() = true;
+      std::exception_ptr e;
+      try { (*f)(c); } catch (...) { e = std::current_exception(); }
+      in_task() = false;
+      lk.lock();
+      if (e && !err_) err_ = e;
+      if (--remaining_ == 0) cv_done_.notify_all();
+    }
+  }
+  void worker() {
+    std::unique_lock<std::mutex> lk(mu_);
+    uint64_t seen = 0;
+    for (;;) {
+      cv_work_.wait(lk, [&] { return gen_ != seen; });
+      seen = gen_;
+      drain(lk);
+    }
+  }
+  std::mutex run_mu_, mu_;
+  std::condition_variable cv_work_, cv_done_;
+  const std::function<void(unsigned)> *fn_ = nullptr;
+  unsigned n_ = 0, next_ = 0, remaining_ = 0, n_workers_ = 0;
+  uint64_t gen_ = 0;
+  std::exception_ptr err_;
+};
+
 template <class F> inline void parallel_for(int n, F fn) {
   unsigned nt = host_threads();
   if (n < 4096 || nt == 1) { for (int i = 0; i < n; i++) fn(i); return; }
-  std::vector<std::thread> th;
-  std::vector<std::exception_ptr> errs(nt);
   const int per = (n + (int)nt - 1) / (int)nt;
-  for (unsigned c = 0; c < nt; c++)
-    th.emplace_back([&, c] {
-      try { for (int i = (int)c * per, e = std::min(n, i + per); i < e; i++) fn(i); } catch (...) { errs[c] = std::current_exception(); }
-    });
-  for (auto &t : th) t.join();
-  for (auto &e : errs) if (e) std::rethrow_exception(e);
+  HostPool::instance().run(nt, [&](unsigned c) { for (int i = (int)c * per, e = std::min(n, i + per); i < e; i++) fn(i); });
 }
 
 // String -> small integer index for the encoder's dictionaries (node names, topology values): open addressing over one flat
