@@ -11,6 +11,11 @@
  *   cc_report_json       <- (*ClusterCapacity).Report() marshalled     (simulator.go:160-170; report.go:38-98,220-233)
  *   cc_report_print      <- framework.ClusterCapacityReviewPrint(r, verbose, format)  (report.go:235-317)
  *   cc_close             <- (*ClusterCapacity).Close()                 (simulator.go:314-325), idempotent
+ *   cc_new_list          <- the roadmap's "accept a list of pods" (README.md:305-306): framework.New with several podspecs, pod k of the
+ *                           run is a clone of podspec k % T (the template index parsePodsReview uses, report.go:160)
+ *   cc_stop_reason / cc_scheduled_count / cc_scheduled_node <- Status{StopReason, Pods} as the callers of Report() read them
+ *                           (simulator.go:90-93; ScheduledPods in the reference's tests, simulator_test.go:226-240)
+ *   cc_warnings          <- nothing in the reference: what this analysis left out that the reference would have done (pending pods)
  *
  * What SyncWithClient+Run do internally here: aggregate NodeInfo exactly as the scheduler cache would
  * (framework/types.go:409-427,700-734), order nodes as nodeTree.list() (backend/cache/node_tree.go:119-143),
