@@ -1,8 +1,10 @@
-"""CPU model of the multi-commit wave structure on C4 (design tool, not a test): replays the exact reference sequence while grouping it
+"""CPU model of the multi-commit wave structure on C4 (design tool; tests/test_wave_model.py checks its sequences against the oracle): replays the exact reference sequence while grouping it
 into waves the way ccsim_multi.cuh does — per-tile top-M publication, the bar T, the candidate cap, kill-on-full-cell, waves that go on
 across non-binding PTS minimum moves — and reports placements per wave and why waves end, for alternative tile layouts / M / caps.
 
-    python scripts/wave_sim.py [--layout contiguous|interleaved] [--m 8] [--cap 128] [--nodelta] [--waves N]
+    python scripts/wave_sim.py [--layout contiguous|interleaved] [--m 8] [--cap 128] [--nodelta] [--waves N] [--relax a,b,c]
+    KNUM=8 RMAX=3 CF=1 python scripts/wave_sim.py        # the look-ahead rule ccsim_multi.cuh ships (MULTI_RELAX_K / MULTI_RELAX_R)
+The placement sequence goes to $WAVE_SIM_OUT (.npy).
 
 C4 specifics used: hostname anti-affinity makes every node single-use, so a node's score never changes during the run."""
 import argparse, importlib, os, sys
@@ -18,6 +20,10 @@ ap.add_argument("--grid", type=int, default=148)
 ap.add_argument("--nodelta", action="store_true")
 ap.add_argument("--waves", type=int, default=0)
 ap.add_argument("--n", type=int, default=100_000)
+ap.add_argument("--existing", type=int, default=200_000)
+ap.add_argument("--zones", type=int, default=64)
+ap.add_argument("--racks", type=int, default=1024)
+ap.add_argument("--regions", type=int, default=8)
 ap.add_argument("--perdomain", type=int, default=-1, help="publish the best node per open domain of this constraint (0 zone, 1 rack, 2 region) instead of the top-M")
 ap.add_argument("--relax", default="0,0,0", help="look-ahead per constraint: nodes whose cell is at most this far over the limit are published as dormant candidates")
 args = ap.parse_args()
@@ -26,7 +32,7 @@ ADAPT = os.environ.get("ADAPT") == "1"; KNUM = int(os.environ.get("KNUM", "0"));
 if ADAPT: R = [0, 0, 0]
 cool = [0, 0, 0]; pen = [4, 4, 4]; RMAX = int(os.environ.get("RMAX", "2"))
 
-snap, tmpl, ctr = synth.c4(n=args.n)
+snap, tmpl, ctr = synth.c4(n=args.n, n_existing=args.existing, zones=args.zones, racks=args.racks, regions=args.regions)
 t = tmpl[0]
 n = snap.n
 a_cpu = np.asarray(snap.alloc_cpu, dtype=np.int64); a_mem = np.asarray(snap.alloc_mem, dtype=np.int64)
@@ -164,4 +170,4 @@ print("waves without a placement (relaxed scan hid the feasible nodes):", empty_
 print("final R", R, "pen", pen)
 print("rescans by constraint (zone, rack, region):", resc_by)
 print("placements/wave percentiles 10/50/90/max:", np.percentile(h, [10, 50, 90]).tolist(), int(h.max()))
-np.save("/tmp/wave_sim_seq.npy", np.array(seq, dtype=np.int64))
+np.save(os.environ.get("WAVE_SIM_OUT", "/tmp/wave_sim_seq.npy"), np.array(seq, dtype=np.int64))
