@@ -14,6 +14,7 @@
 #pragma once
 #include <thread>
 #include <mutex>
+#include <system_error>
 #include <condition_variable>
 #include <pthread.h>
 #include <algorithm>
@@ -195,7 +196,10 @@ class HostPool {
     if (n_tasks == 1 || in_task()) { for (unsigned c = 0; c < n_tasks; c++) fn(c); return; }
     std::lock_guard<std::mutex> serial(run_mu_);
     std::unique_lock<std::mutex> lk(mu_);
-    while (n_workers_ + 1 < n_tasks && n_workers_ < kMaxWorkers) { std::thread(&HostPool::worker, this).detach(); n_workers_++; }
+    while (n_workers_ + 1 < n_tasks && n_workers_ < kMaxWorkers) {
+      try { std::thread(&HostPool::worker, this).detach(); } catch (const std::system_error &) { break; }   // (thread limit reached: fewer workers, same result)
+      n_workers_++;
+    }
     fn_ = &fn; n_ = n_tasks; next_ = 0; remaining_ = n_tasks; err_ = nullptr; gen_++;
     cv_work_.notify_all();
     drain(lk);                                            // the caller works too
