@@ -333,6 +333,109 @@ static size_t skip_value(const char *t, size_t n, size_t p) {
   while (p < n && t[p] != ',' && t[p] != ']' && t[p] != '}' && t[p] != ' ' && t[p] != '\n' && t[p] != '\t' && t[p] != '\r') p++;
   return p;
 }
+// The two passes of item_spans_parallel over one chunk [q, end). Scalar reference versions first; the AVX2 versions below do the same
+// 32 bytes at a time from compare masks (quotes, brackets: '[' / ']' fold onto '{' / '}' with bit 5 set; a 32-byte block that holds
+// a backslash, and in pass 2 everything between two items, goes through the scalar code) and are tested against them.
+struct SpanPart { int quotes = 0; long long depth[2] = {0, 0}; };   // depth[s]: change of bracket depth over the bytes seen in relative string state s
+static inline void span_pass1_byte(const char *t, size_t &q, int &in, SpanPart &r) {
+  const char ch = t[q];
+  if (ch == '\\') { q++; return; }
+  if (ch == '"') { in ^= 1; r.quotes++; return; }
+  if (ch == '{' || ch == '[') r.depth[in]++;
+  else if (ch == '}' || ch == ']') r.depth[in]--;
+}
+static void span_pass1_scalar(const char *t, size_t q, size_t end, SpanPart &r) {
+  int in = 0;
+  for (; q < end; q++) span_pass1_byte(t, q, in, r);
+}
+struct SpanEmit { std::vector<size_t> opens, closes; char bad = 0; size_t list_end = (size_t)-1; };
+// one byte of pass 2; returns false when the ']' of the item list was met (the rest of the document is not ours)
+static inline bool span_pass2_byte(const char *t, size_t &q, int &in, long long &d, SpanEmit &e) {
+  const char ch = t[q];
+  if (ch == '\\') { q++; return true; }
+  if (ch == '"') { in ^= 1; return true; }
+  if (in) return true;
+  if (ch == '{' || ch == '[') { if (d == 0) { if (ch == '{') e.opens.push_back(q); else e.bad = 1; } d++; }
+  else if (ch == '}' || ch == ']') {
+    d--;
+    if (d == 0) e.closes.push_back(q + 1);
+    else if (d < 0) { e.list_end = q; return false; }
+  } else if (d == 0 && ch != ',' && ch != ' ' && ch != '\n' && ch != '\t' && ch != '\r') e.bad = 1;   // a scalar item
+  return true;
+}
+static void span_pass2_scalar(const char *t, size_t q, size_t end, int in, long long d, SpanEmit &e) {
+  for (; q < end; q++) if (!span_pass2_byte(t, q, in, d, e)) return;
+}
+#if defined(__x86_64__)
+#include <immintrin.h>
+static inline uint32_t prefix_xor32(uint32_t x) { x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; return x; }
+__attribute__((target("avx2,popcnt"))) static void span_pass1_avx2(const char *t, size_t q, size_t end, SpanPart &r) {
+  const __m256i quote = _mm256_set1_epi8('"'), bslash = _mm256_set1_epi8('\\'), open = _mm256_set1_epi8('{'), close = _mm256_set1_epi8('}');
+  const __m256i bit5 = _mm256_set1_epi8(0x20);
+  int in = 0;
+  while (q < end) {
+    if (q + 32 <= end) {
+      const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(t + q));
+      if (!_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, bslash))) {
+        const __m256i w = _mm256_or_si256(v, bit5);
+        const uint32_t Q = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, quote));
+        const uint32_t O = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(w, open)), C = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(w, close));
+        uint32_t S = prefix_xor32(Q);            // bit i: an odd number of quotes in bytes 0..i (a bracket is not a quote: inclusive = exclusive there)
+        if (in) S = ~S;
+        r.depth[0] += __builtin_popcount(O & ~S) - __builtin_popcount(C & ~S);
+        r.depth[1] += __builtin_popcount(O & S) - __builtin_popcount(C & S);
+        const int nq = __builtin_popcount(Q);
+        r.quotes += nq; in ^= nq & 1;
+        q += 32;
+        continue;
+      }
+    }
+    const size_t stop = std::min(end, q + 32);   // a block with a backslash, or the tail: byte by byte
+    for (; q < stop; q++) span_pass1_byte(t, q, in, r);
+  }
+}
+__attribute__((target("avx2,popcnt"))) static void span_pass2_avx2(const char *t, size_t q, size_t end, int in, long long d, SpanEmit &e) {
+  const __m256i quote = _mm256_set1_epi8('"'), bslash = _mm256_set1_epi8('\\'), open = _mm256_set1_epi8('{'), close = _mm256_set1_epi8('}');
+  const __m256i bit5 = _mm256_set1_epi8(0x20);
+  while (q < end) {
+    if (d > 0 && q + 32 <= end) {                // inside an item: only quotes and brackets matter
+      const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(t + q));
+      if (!_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, bslash))) {
+        const __m256i w = _mm256_or_si256(v, bit5);
+        const uint32_t Q = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, quote));
+        const uint32_t O = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(w, open)), C = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(w, close));
+        uint32_t S = prefix_xor32(Q);
+        if (in) S = ~S;
+        uint32_t B = (O | C) & ~S;               // brackets outside strings, in order
+        bool left = false;
+        while (B) {
+          const int i = __builtin_ctz(B);
+          B &= B - 1;
+          if ((O >> i) & 1u) d++;
+          else if (--d == 0) {                   // the item ends here: what follows, up to the next '{', is looked at byte by byte
+            e.closes.push_back(q + (size_t)i + 1);
+            in = 0; q += (size_t)i + 1; left = true;
+            break;
+          }
+        }
+        if (!left) { in ^= __builtin_popcount(Q) & 1; q += 32; }
+        continue;
+      }
+      const size_t stop = q + 32;                // a block with a backslash: byte by byte
+      for (; q < stop; q++) if (!span_pass2_byte(t, q, in, d, e)) return;
+      continue;
+    }
+    if (!span_pass2_byte(t, q, in, d, e)) return;
+    q++;
+  }
+}
+static bool span_simd() { static const bool on = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt") && !getenv("CCHOST_NO_SIMD"); return on; }
+#else
+static bool span_simd() { return false; }
+static void span_pass1_avx2(const char *, size_t, size_t, SpanPart &) {}
+static void span_pass2_avx2(const char *, size_t, size_t, int, long long, SpanEmit &) {}
+#endif
+
 // The item list of a big document, located on all host cores. `p` is just behind the '[' of the list. Whether a byte lies inside a
 // string is the parity of the unescaped quotes before it, and in valid JSON a backslash only occurs inside strings, so "skip the
 // byte after a backslash" finds the same unescaped quotes wherever a chunk starts (chunks start behind a non-backslash byte).
@@ -350,48 +453,35 @@ static bool item_spans_parallel(const char *t, size_t n, size_t p, std::vector<s
     while (q < n && t[q - 1] == '\\') q++;
     cut[c] = std::max(q, cut[c - 1]);
   }
-  struct Part { int quotes = 0; long long depth[2] = {0, 0}; };     // depth[s]: change of bracket depth when the chunk starts with state s (1: in a string)
-  std::vector<Part> part(nt);
+  std::vector<SpanPart> part(nt);
   auto run = [&](auto fn) { HostPool::instance().run(nt, fn); };
+  const auto T0 = std::chrono::steady_clock::now();
+  const bool simd = span_simd();
   run([&](unsigned c) {
-    Part r; int in = 0;
-    for (size_t q = cut[c]; q < cut[c + 1]; q++) {
-      const char ch = t[q];
-      if (ch == '\\') { q++; continue; }
-      if (ch == '"') { in ^= 1; r.quotes++; continue; }
-      if (ch == '{' || ch == '[') r.depth[in]++;
-      else if (ch == '}' || ch == ']') r.depth[in]--;
-    }
+    SpanPart r;
+    if (simd) span_pass1_avx2(t, cut[c], cut[c + 1], r); else span_pass1_scalar(t, cut[c], cut[c + 1], r);
     part[c] = r;
   });
+  const auto T1 = std::chrono::steady_clock::now();
   std::vector<int> in0(nt); std::vector<long long> d0(nt);
   { int in = 0; long long d = 0;
     for (unsigned c = 0; c < nt; c++) { in0[c] = in; d0[c] = d; d += part[c].depth[in]; in ^= part[c].quotes & 1; } }
-  std::vector<std::vector<size_t>> opens(nt), closes(nt);
-  std::vector<char> bad(nt, 0);
-  std::vector<size_t> list_end(nt, (size_t)-1);
+  std::vector<SpanEmit> em(nt);
   run([&](unsigned c) {
-    int in = in0[c]; long long d = d0[c];
-    for (size_t q = cut[c]; q < cut[c + 1]; q++) {
-      const char ch = t[q];
-      if (ch == '\\') { q++; continue; }
-      if (ch == '"') { in ^= 1; if (d == 0 && !in) {} continue; }
-      if (in) continue;
-      if (ch == '{' || ch == '[') { if (d == 0) { if (ch == '{') opens[c].push_back(q); else bad[c] = 1; } d++; }
-      else if (ch == '}' || ch == ']') {
-        d--;
-        if (d == 0) closes[c].push_back(q + 1);
-        else if (d < 0) { list_end[c] = q; return; }     // the ']' of the item list: the rest of the document is not ours
-      } else if (d == 0 && ch != ',' && ch != ' ' && ch != '\n' && ch != '\t' && ch != '\r') bad[c] = 1;   // a scalar item
-    }
+    if (simd) span_pass2_avx2(t, cut[c], cut[c + 1], in0[c], d0[c], em[c]); else span_pass2_scalar(t, cut[c], cut[c + 1], in0[c], d0[c], em[c]);
   });
+  if (getenv("CCHOST_TIMING")) {
+    const auto T2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cchost]     locate: pass 1 %.1f ms, pass 2 %.1f ms on %u threads (%s)\n", std::chrono::duration<double, std::milli>(T1 - T0).count(),
+            std::chrono::duration<double, std::milli>(T2 - T1).count(), nt, simd ? "AVX2" : "scalar");
+  }
   std::vector<size_t> o, e;
   bool ended = false;
   for (unsigned c = 0; c < nt && !ended; c++) {
-    if (bad[c]) return false;
-    o.insert(o.end(), opens[c].begin(), opens[c].end());
-    e.insert(e.end(), closes[c].begin(), closes[c].end());
-    if (list_end[c] != (size_t)-1) ended = true;
+    if (em[c].bad) return false;
+    o.insert(o.end(), em[c].opens.begin(), em[c].opens.end());
+    e.insert(e.end(), em[c].closes.begin(), em[c].closes.end());
+    if (em[c].list_end != (size_t)-1) ended = true;
   }
   if (!ended || o.size() != e.size()) return false;
   out.reserve(o.size());
@@ -456,9 +546,13 @@ static void node_into(Node *dst, std::string_view item, bool dom_only) {
 template <class T, class F> static ObjList<T> parse_list(const char *text, F one) {
   ObjList<T> out;
   if (!text || !*text) return out;
+  const bool timing = getenv("CCHOST_TIMING") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
   const size_t n = strlen(text);
   std::vector<std::pair<size_t, size_t>> spans;
-  if (!item_spans(text, n, spans)) {   // not a list of items we can locate: DOM of the whole document, items re-serialised for `one`
+  const bool located = item_spans(text, n, spans);
+  if (timing) fprintf(stderr, "[cchost]   ingest/locate %zu items in %.1f MB: %.3f s\n", spans.size(), n / 1e6, std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
+  if (!located) {   // not a list of items we can locate: DOM of the whole document, items re-serialised for `one`
     std::vector<Json> items = items_of(text);
     T *p = out.allocate_raw(items.size());
     std::exception_ptr err;

@@ -308,3 +308,37 @@ def test_pending_pods_are_left_out_and_reported(built):
     cc.SyncWithClient(helpers.list_client(fw, nodes, [p for p in pods if p["spec"].get("nodeName")], None))
     assert cc.Warnings() == []
     cc.Close()
+
+
+def test_simd_item_location_equals_scalar_and_serial(built, tmp_path):
+    """The AVX2 block-mask passes of item_spans_parallel against the scalar passes and the serial scan, on documents whose strings are
+    full of brackets, quotes and backslash runs, for several chunkings (the thread count moves the chunk cuts): one digest for all."""
+    import hashlib, os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import hashlib, importlib, json, sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import helpers
+        fw = importlib.import_module("cluster-capacity_b200.framework")
+        nodes, pods = helpers.random_cluster(33, n_nodes=200, n_pods=7000)
+        bs = chr(92)
+        nasty = ['}]{[', 'a"b', bs, bs * 2 + '"', '"]},{"', bs * 3, '[[[[', '\\n\\t"', 'x' * 31 + bs, 'y' * 30 + bs * 2, '{' * 33, '"' * 5, bs + '"' + bs, 'z' * 64 + '}' ]
+        for j, p in enumerate(pods):
+            p["metadata"]["annotations"] = {"k%%d" %% q: nasty[(j + q) %% len(nasty)] * (1 + (j + 3 * q) %% 4) + "#" * ((j * 13 + q * 5) %% 97) for q in range(7)}
+        for i, n in enumerate(nodes):
+            n["metadata"]["annotations"] = {"n": nasty[i %% len(nasty)] * 2}
+        assert len(json.dumps(pods)) > (4 << 20)
+        cc = fw.New(None, None, helpers.template("spread_two"), 0, [])
+        cc.SyncWithClient(helpers.list_client(fw, nodes, pods, "spread_two"))
+        e = cc.EncodedSnapshot()
+        e["template_hex"] = e["template_hex"][:-16]
+        e["templates_hex"] = [x[:-16] for x in e["templates_hex"]]
+        assert sum(e["nodes"]["npods"]) > 1000
+        print("DIGEST", hashlib.sha256(json.dumps(e, sort_keys=True).encode()).hexdigest())
+    ''') % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for name, env in (("serial", {"CCHOST_SERIAL_SPANS": "1"}), ("scalar-8", {"CCHOST_NO_SIMD": "1", "CCHOST_THREADS": "8"}), ("simd-2", {"CCHOST_THREADS": "2"}),
+                      ("simd-3", {"CCHOST_THREADS": "3"}), ("simd-8", {"CCHOST_THREADS": "8"}), ("simd-13", {"CCHOST_THREADS": "13"}), ("simd-64", {"CCHOST_THREADS": "64"})):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CCSIM_NO_REBUILD="1", **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "DIGEST" in r.stdout, name + ": " + r.stdout[-1500:] + r.stderr[-1500:]
+        digests[name] = r.stdout.split("DIGEST")[1].split()[0]
+    assert len(set(digests.values())) == 1, digests
