@@ -353,7 +353,7 @@ struct SpanEmit { std::vector<size_t> opens, closes; char bad = 0; size_t list_e
 static inline bool span_pass2_byte(const char *t, size_t &q, int &in, long long &d, SpanEmit &e) {
   const char ch = t[q];
   if (ch == '\\') { q++; return true; }
-  if (ch == '"') { in ^= 1; return true; }
+  if (ch == '"') { if (!in && d == 0) e.bad = 1; in ^= 1; return true; }      // (a string item: not ours either)
   if (in) return true;
   if (ch == '{' || ch == '[') { if (d == 0) { if (ch == '{') e.opens.push_back(q); else e.bad = 1; } d++; }
   else if (ch == '}' || ch == ']') {
@@ -532,7 +532,9 @@ static void pod_into(Pod *dst, std::string_view item, bool dom_only) {
     try { if (fast::pod(item, *dst)) return; } catch (...) { dst->~Pod(); throw; }
     dst->~Pod();
   }
-  new (dst) Pod(Pod::parse(parse_json(item)));
+  const Json j = parse_json(item);
+  if (!j.is_object()) throw std::runtime_error("json: a list item is not an object");      // (the reference's decoder rejects such a PodList too)
+  new (dst) Pod(Pod::parse(j));
 }
 static void node_into(Node *dst, std::string_view item, bool dom_only) {
   if (!dom_only) {
@@ -540,7 +542,9 @@ static void node_into(Node *dst, std::string_view item, bool dom_only) {
     try { if (fast::node(item, *dst)) return; } catch (...) { dst->~Node(); throw; }
     dst->~Node();
   }
-  new (dst) Node(Node::parse(parse_json(item)));
+  const Json j = parse_json(item);
+  if (!j.is_object()) throw std::runtime_error("json: a list item is not an object");
+  new (dst) Node(Node::parse(j));
 }
 
 template <class T, class F> static ObjList<T> parse_list(const char *text, F one) {

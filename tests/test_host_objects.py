@@ -342,3 +342,22 @@ def test_simd_item_location_equals_scalar_and_serial(built, tmp_path):
         assert r.returncode == 0 and "DIGEST" in r.stdout, name + ": " + r.stdout[-1500:] + r.stderr[-1500:]
         digests[name] = r.stdout.split("DIGEST")[1].split()[0]
     assert len(set(digests.values())) == 1, digests
+
+
+def test_list_items_that_are_not_objects_are_rejected(built, monkeypatch):
+    """A NodeList / PodList whose items are not objects fails like the reference's decoder would (small documents, large ones through
+    the parallel item location, and the serial scan)."""
+    import ctypes as C
+    L = fw.lib()
+    tmpl = json.dumps(helpers.template("plain", 1)).encode()
+    for doc in (json.dumps({"items": ["x" * 50] * 120000}), json.dumps(["s", 3]), json.dumps({"items": [{"metadata": {"name": "n"}}, 7]})):
+        for serial in (False, True):
+            if serial:
+                monkeypatch.setenv("CCHOST_SERIAL_SPANS", "1")
+            else:
+                monkeypatch.delenv("CCHOST_SERIAL_SPANS", raising=False)
+            h = C.c_void_p()
+            assert L.cc_new(None, tmpl, 0, None, 0, C.byref(h)) == 0
+            assert L.cc_sync_with_objects(h, doc.encode(), b"[]", None) != 0
+            assert b"not an object" in L.cc_last_error(h)
+            L.cc_close(h)
